@@ -1,0 +1,147 @@
+// Shared declarations for the b2det CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b2det.h"
+
+void b2d_set_error(const char* fmt, ...);
+
+#define B2D_CUDA(x)                                                                          \
+    do {                                                                                     \
+        cudaError_t e__ = (x);                                                               \
+        if (e__ != cudaSuccess) {                                                            \
+            b2d_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e__)); \
+            return -2;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+#define B2D_CHECK(cond, ...)                 \
+    do {                                     \
+        if (!(cond)) {                       \
+            b2d_set_error(__VA_ARGS__);      \
+            return -1;                       \
+        }                                    \
+    } while (0)
+
+#define B2D_LAUNCH_CHECK() B2D_CUDA(cudaGetLastError())
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------
+// tcgen05 implicit-GEMM convolution (conv_tc.cu)
+// ---------------------------------------------------------------------------------------
+struct __align__(64) ConvTcParams {
+    CUtensorMap tmA[4];   // [0]: stride-1 activation map; [py*2+px]: the four stride-2 phase maps
+    CUtensorMap tmB;      // packed weights [cout_pad][taps*cin], K contiguous
+    const float* bias;    // [cout_pad]
+    void* out;            // dst buffer base (bf16 or f32, NHWC)
+    const __nv_bfloat16* res;  // residual buffer base or nullptr
+    int out_cs, out_c0;   // dst channel count of the whole buffer / channel offset of the slice
+    int res_cs, res_c0;
+    int W, H;             // output spatial size
+    int cin, cout;        // true channel counts
+    int n_tile, n_tiles_n;
+    int kc, chunks;       // channels per K chunk (16/32/64), chunks per tap
+    int ksz, taps, stride;
+    int bw, bh, bn;       // M tile = bw x bh pixels x bn images = 128 rows
+    int tiles_x, tiles_y;
+    int act, out_f32;
+    int stages;
+    uint32_t a_bytes, b_bytes, b_tx_bytes;   // smem bytes per stage (padded), TMA bytes of B
+    uint32_t swizzle_bytes;                  // 128 / 64 / 32
+    uint32_t tmem_cols;
+    uint32_t idesc;
+};
+
+struct ConvTcPlan {
+    ConvTcParams p;
+    size_t smem_bytes;
+    int sm_count;
+    __nv_bfloat16* w_dev;   // packed weights (owned)
+    float* bias_dev;        // owned
+};
+
+int conv_tc_supported(int cin, int ksz, int stride);
+int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch,
+                 const __nv_bfloat16* src, int src_h, int src_w, int src_cs, int src_c0, int cin,
+                 void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32,
+                 int ksz, int stride, int act, const float* w_host, const float* b_host,
+                 const __nv_bfloat16* res, int res_cs, int res_c0);
+int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream);
+void conv_tc_free(ConvTcPlan* plan);
+int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen);
+
+// ---------------------------------------------------------------------------------------
+// CUDA-core kernels (conv_simt.cu): stem conv, depthwise conv, pools, upsample
+// ---------------------------------------------------------------------------------------
+struct ConvSimtPlan {
+    const __nv_bfloat16* src; int src_h, src_w, src_cs, src_c0, cin;
+    void* dst; int dst_h, dst_w, dst_cs, dst_c0, cout, dst_f32;
+    int ksz, stride, act;
+    const __nv_bfloat16* res; int res_cs, res_c0;
+    float* w_dev;      // [taps][cin][cout_pad16] fp32 (bf16-rounded values)
+    float* bias_dev;   // [cout_pad16]
+    int cout_pad;
+};
+int conv_simt_plan(ConvSimtPlan* plan, const __nv_bfloat16* src, int src_h, int src_w, int src_cs, int src_c0, int cin,
+                   int cin_w, void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32,
+                   int ksz, int stride, int act, const float* w_host, const float* b_host,
+                   const __nv_bfloat16* res, int res_cs, int res_c0);
+int conv_simt_launch(const ConvSimtPlan* plan, int n, cudaStream_t stream);
+void conv_simt_free(ConvSimtPlan* plan);
+
+struct DwConvPlan {
+    const __nv_bfloat16* src; int h, w, src_cs, src_c0;
+    __nv_bfloat16* dst; int dst_cs, dst_c0, c, act;
+    float* w_dev;      // [9][c]
+    float* bias_dev;   // [c]
+};
+int dwconv_plan(DwConvPlan* plan, const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
+                __nv_bfloat16* dst, int dst_cs, int dst_c0, int c, int act, const float* w_host, const float* b_host);
+int dwconv_launch(const DwConvPlan* plan, int n, cudaStream_t stream);
+void dwconv_free(DwConvPlan* plan);
+
+int maxpool_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
+                   __nv_bfloat16* dst, int oh, int ow, int dst_cs, int dst_c0, int c, int k, int stride,
+                   int n, cudaStream_t stream);
+int upsample2x_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
+                      __nv_bfloat16* dst, int dst_cs, int dst_c0, int c, int n, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------
+// pre / post processing
+// ---------------------------------------------------------------------------------------
+struct ResizeTables {     // device tables for one (mode, in_h, in_w, out)
+    int mode, in_h, in_w, out_h, out_w, left, top;   // left/top: letterbox placement
+    int ksize_x, ksize_y;
+    int32_t* xb; int32_t* xk;   // PIL: bounds [out][2], coeffs [out][ksize]; cv2: ofs [out][2], coef [out][2]
+    int32_t* yb; int32_t* yk;
+    uint8_t* tmp; size_t tmp_bytes;   // PIL horizontal-pass temporary
+};
+int preprocess_launch(const ResizeTables* t, const uint8_t* src, int n, int pitch, long long img_stride,
+                      int bgr, int out_kind, void* dst, int out_size, cudaStream_t stream);
+
+int input_from_f32_launch(const float* src, int n, int h, int w, void* dst, cudaStream_t stream);
+
+struct HeadLevel { const float* buf; int hw, c, stride, nc, kind; float anchors[6]; int row0; };
+struct HeadDesc { HeadLevel lv[3]; int nlevels; int kind; int nc; int rows_total; };
+
+int decode_rows_launch(const HeadDesc* h, int n, float* rows, cudaStream_t stream);
+int candidates_from_head_launch(const HeadDesc* h, int n, float thr, int inclusive, b2d_det* cand, int* cand_count,
+                                int cand_cap, cudaStream_t stream);
+int candidates_from_rows_launch(const float* rows, int n, int num_rows, int ncol, float thr, int inclusive,
+                                b2d_det* cand, int* cand_count, int cand_cap, cudaStream_t stream);
+int select_launch(const b2d_det* cand, const int* cand_count, int cand_cap, int n, unsigned long long* keys_scratch,
+                  float iou_thr, int top_k, int max_det, b2d_det* out, int* out_count, int cap, cudaStream_t stream);
+int georef_launch(const b2d_det* dets, const int* counts, int n, int cap, int mode, const double* params,
+                  b2d_geodet* out, cudaStream_t stream);
+int dedup_launch(const double* x, const double* y, const float* conf, int count, double thr, int inclusive,
+                 uint8_t* keep, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t dedup_scratch_bytes(int count);
+int utm_forward_launch(const double* lon, const double* lat, int count, int zone, int north, double* x, double* y,
+                       cudaStream_t stream);
+int cut_windows_launch(const uint8_t* mosaic, int mh, int mw, long long pitch, const int32_t* origins, int n, int win,
+                       int fill, uint8_t* dst, cudaStream_t stream);

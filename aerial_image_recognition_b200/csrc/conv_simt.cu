@@ -1,0 +1,338 @@
+// CUDA-core kernels of the detector graph (K3 in SURVEY.md section 2.2):
+//   * direct convolution for the stem (Cin = 3, K = 27: not a tensor-core shape) -- also the
+//     in-library cross-check for the tcgen05 path (B2D_CONV_SIMT);
+//   * depthwise 3x3 + bias + SiLU (Ultralytics 8.3.x cls branch);
+//   * max-pool k x k (SPPF 5/1, SPPCSPC 5-9-13/1, YOLOv7 MP 2/2);
+//   * nearest 2x upsample written straight into the consumer's concat slice.
+// All are HBM/L2-bound elementwise-style kernels: NHWC bf16, 16-byte vector accesses along
+// the channel axis, one thread per (pixel, 8-channel group).
+#include "common.cuh"
+
+#include <string.h>
+#include <vector>
+
+namespace {
+
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f[2 * j] = __uint_as_float(w[j] << 16);
+        f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        w[j] = *(uint32_t*)&h;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- direct conv: thread = (output pixel, group of 16 output channels) --------------------
+constexpr int kCoutPerThread = 16;
+
+__global__ void __launch_bounds__(128) conv_simt_kernel(ConvSimtPlan p, int n) {
+    const int groups = p.cout_pad / kCoutPerThread;
+    const long long total = (long long)n * p.dst_h * p.dst_w * groups;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % groups);
+    long long pix = idx / groups;
+    const int ox = (int)(pix % p.dst_w);
+    const int oy = (int)((pix / p.dst_w) % p.dst_h);
+    const int img = (int)(pix / ((long long)p.dst_w * p.dst_h));
+    const int pad = p.ksz >> 1;
+    float acc[kCoutPerThread];
+#pragma unroll
+    for (int j = 0; j < kCoutPerThread; ++j) acc[j] = 0.f;
+    for (int kh = 0; kh < p.ksz; ++kh) {
+        const int iy = oy * p.stride + kh - pad;
+        if (iy < 0 || iy >= p.src_h) continue;
+        for (int kw = 0; kw < p.ksz; ++kw) {
+            const int ix = ox * p.stride + kw - pad;
+            if (ix < 0 || ix >= p.src_w) continue;
+            const __nv_bfloat16* sp = p.src + (((long long)img * p.src_h + iy) * p.src_w + ix) * p.src_cs + p.src_c0;
+            const float* wp = p.w_dev + ((size_t)(kh * p.ksz + kw) * p.cin) * p.cout_pad + g * kCoutPerThread;
+            for (int c = 0; c < p.cin; ++c) {
+                const float a = __bfloat162float(sp[c]);
+                const float4* w4 = (const float4*)(wp + (size_t)c * p.cout_pad);
+#pragma unroll
+                for (int j = 0; j < kCoutPerThread / 4; ++j) {
+                    const float4 w = __ldg(w4 + j);
+                    acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]);
+                    acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
+                    acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]);
+                    acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
+                }
+            }
+        }
+    }
+    const int ch0 = g * kCoutPerThread;
+    for (int j = 0; j < kCoutPerThread; ++j) {
+        const int ch = ch0 + j;
+        if (ch >= p.cout) break;
+        float v = acc[j] + p.bias_dev[ch];
+        if (p.act) v = silu_f(v);
+        if (p.res) v += __bfloat162float(p.res[pix * p.res_cs + p.res_c0 + ch]);
+        if (p.dst_f32) ((float*)p.dst)[pix * p.dst_cs + p.dst_c0 + ch] = v;
+        else ((__nv_bfloat16*)p.dst)[pix * p.dst_cs + p.dst_c0 + ch] = __float2bfloat16_rn(v);
+    }
+}
+
+// ---- stem: 3x3 stride-s conv on the NHWC4 input, all output channels per thread -----------
+// Weights [tap][4][COUT] fp32 live in shared memory (broadcast reads); each thread owns one
+// output pixel and COUT accumulators, reads nine 8-byte pixels and writes COUT*2 contiguous bytes.
+template <int COUT>
+__global__ void __launch_bounds__(128) stem_kernel(ConvSimtPlan p, int n) {
+    __shared__ float ws[9 * 4 * COUT];
+    __shared__ float bs[COUT];
+    for (int i = threadIdx.x; i < 9 * 4 * COUT; i += blockDim.x) {
+        const int tap = i / (4 * COUT), r = i % (4 * COUT), c = r / COUT, o = r % COUT;
+        ws[i] = (c < p.cin) ? p.w_dev[((size_t)tap * p.cin + c) * p.cout_pad + o] : 0.f;
+    }
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = p.bias_dev[i];
+    __syncthreads();
+    const long long total = (long long)n * p.dst_h * p.dst_w;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= total) return;
+    const int ox = (int)(pix % p.dst_w);
+    const int oy = (int)((pix / p.dst_w) % p.dst_h);
+    const int img = (int)(pix / ((long long)p.dst_w * p.dst_h));
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = bs[j];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int iy = oy * p.stride + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ix = ox * p.stride + kw - 1;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            if (iy >= 0 && iy < p.src_h && ix >= 0 && ix < p.src_w) {
+                const uint2 u = __ldg((const uint2*)(p.src + (((long long)img * p.src_h + iy) * p.src_w + ix) * 4));
+                a[0] = __uint_as_float(u.x << 16);
+                a[1] = __uint_as_float(u.x & 0xFFFF0000u);
+                a[2] = __uint_as_float(u.y << 16);
+            }
+            const float* w = ws + (kh * 3 + kw) * 4 * COUT;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) acc[j] = fmaf(a[c], w[c * COUT + j], acc[j]);
+        }
+    }
+    __nv_bfloat16* op = (__nv_bfloat16*)p.dst + pix * p.dst_cs + p.dst_c0;
+#pragma unroll
+    for (int j = 0; j < COUT; j += 8) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = p.act ? silu_f(acc[j + i]) : acc[j + i];
+        *(uint4*)(op + j) = pack8(f);
+    }
+}
+
+// ---- depthwise 3x3, stride 1: thread = (pixel, 8 channels) ---------------------------------
+__global__ void __launch_bounds__(256) dwconv_kernel(DwConvPlan p, int n) {
+    const int groups = p.c / 8;
+    const long long total = (long long)n * p.h * p.w * groups;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int x = (int)(pix % p.w);
+    const int y = (int)((pix / p.w) % p.h);
+    const int img = (int)(pix / ((long long)p.w * p.h));
+    const int c0 = g * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = p.bias_dev[c0 + j];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int iy = y + kh - 1;
+        if (iy < 0 || iy >= p.h) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ix = x + kw - 1;
+            if (ix < 0 || ix >= p.w) continue;
+            const uint4 u = __ldg((const uint4*)(p.src + (((long long)img * p.h + iy) * p.w + ix) * p.src_cs + p.src_c0 + c0));
+            float a[8];
+            unpack8(u, a);
+            const float* w = p.w_dev + (size_t)(kh * 3 + kw) * p.c + c0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(a[j], __ldg(w + j), acc[j]);
+        }
+    }
+    if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = silu_f(acc[j]);
+    }
+    *(uint4*)(p.dst + pix * p.dst_cs + p.dst_c0 + c0) = pack8(acc);
+}
+
+// ---- max-pool k x k, padding k/2 for stride 1 / none for stride 2 (-inf padding) -------------
+__global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
+                                                       __nv_bfloat16* dst, int oh, int ow, int dst_cs, int dst_c0, int c,
+                                                       int k, int stride, int n) {
+    const int groups = c / 8;
+    const long long total = (long long)n * oh * ow * groups;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int x = (int)(pix % ow);
+    const int y = (int)((pix / ow) % oh);
+    const int img = (int)(pix / ((long long)ow * oh));
+    const int pad = (stride == 1) ? (k >> 1) : 0;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int kh = 0; kh < k; ++kh) {
+        const int iy = y * stride + kh - pad;
+        if (iy < 0 || iy >= h) continue;
+        for (int kw = 0; kw < k; ++kw) {
+            const int ix = x * stride + kw - pad;
+            if (ix < 0 || ix >= w) continue;
+            const uint4 u = __ldg((const uint4*)(src + (((long long)img * h + iy) * w + ix) * src_cs + src_c0 + g * 8));
+            float a[8];
+            unpack8(u, a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], a[j]);
+        }
+    }
+    *(uint4*)(dst + pix * dst_cs + dst_c0 + g * 8) = pack8(m);
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
+                                                          __nv_bfloat16* dst, int dst_cs, int dst_c0, int c, int n) {
+    const int groups = c / 8;
+    const int oh = 2 * h, ow = 2 * w;
+    const long long total = (long long)n * oh * ow * groups;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int x = (int)(pix % ow);
+    const int y = (int)((pix / ow) % oh);
+    const int img = (int)(pix / ((long long)ow * oh));
+    const uint4 u = __ldg((const uint4*)(src + (((long long)img * h + (y >> 1)) * w + (x >> 1)) * src_cs + src_c0 + g * 8));
+    *(uint4*)(dst + pix * dst_cs + dst_c0 + g * 8) = u;
+}
+
+float bf16_round(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u = (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+}  // namespace
+
+int conv_simt_plan(ConvSimtPlan* plan, const __nv_bfloat16* src, int src_h, int src_w, int src_cs, int src_c0, int cin,
+                   int cin_w, void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32, int ksz,
+                   int stride, int act, const float* w_host, const float* b_host, const __nv_bfloat16* res, int res_cs,
+                   int res_c0) {
+    memset(plan, 0, sizeof(*plan));
+    plan->src = src; plan->src_h = src_h; plan->src_w = src_w; plan->src_cs = src_cs; plan->src_c0 = src_c0; plan->cin = cin_w;
+    plan->dst = dst; plan->dst_h = dst_h; plan->dst_w = dst_w; plan->dst_cs = dst_cs; plan->dst_c0 = dst_c0;
+    plan->cout = cout; plan->dst_f32 = dst_f32; plan->ksz = ksz; plan->stride = stride; plan->act = act;
+    plan->res = res; plan->res_cs = res_cs; plan->res_c0 = res_c0;
+    (void)cin;
+    const int taps = ksz * ksz;
+    const int cout_pad = ceil_div(cout, 16) * 16;
+    plan->cout_pad = cout_pad;
+    // cin_w = channels present in the weight tensor (3 for the stem whose buffer has 4)
+    std::vector<float> wp((size_t)taps * cin_w * cout_pad, 0.f), bp(cout_pad, 0.f);
+    for (int o = 0; o < cout; ++o) {
+        for (int c = 0; c < cin_w; ++c)
+            for (int t = 0; t < taps; ++t)
+                wp[((size_t)t * cin_w + c) * cout_pad + o] = bf16_round(w_host[((size_t)o * cin_w + c) * taps + t]);
+        bp[o] = b_host ? b_host[o] : 0.f;
+    }
+    B2D_CUDA(cudaMalloc(&plan->w_dev, wp.size() * 4));
+    B2D_CUDA(cudaMemcpy(plan->w_dev, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
+    B2D_CUDA(cudaMalloc(&plan->bias_dev, bp.size() * 4));
+    B2D_CUDA(cudaMemcpy(plan->bias_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int conv_simt_launch(const ConvSimtPlan* plan, int n, cudaStream_t stream) {
+    const bool stem = plan->src_cs == 4 && plan->cin == 3 && plan->ksz == 3 && !plan->dst_f32 && plan->res == nullptr &&
+                      plan->dst_cs % 8 == 0 && plan->dst_c0 % 8 == 0;
+    if (stem && (plan->cout == 48 || plan->cout == 32)) {
+        const long long total = (long long)n * plan->dst_h * plan->dst_w;
+        const int blocks = (int)((total + 127) / 128);
+        if (plan->cout == 48) stem_kernel<48><<<blocks, 128, 0, stream>>>(*plan, n);
+        else stem_kernel<32><<<blocks, 128, 0, stream>>>(*plan, n);
+    } else {
+        const long long total = (long long)n * plan->dst_h * plan->dst_w * (plan->cout_pad / kCoutPerThread);
+        const int blocks = (int)((total + 127) / 128);
+        conv_simt_kernel<<<blocks, 128, 0, stream>>>(*plan, n);
+    }
+    B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+void conv_simt_free(ConvSimtPlan* plan) {
+    if (plan->w_dev) cudaFree(plan->w_dev);
+    if (plan->bias_dev) cudaFree(plan->bias_dev);
+    plan->w_dev = nullptr; plan->bias_dev = nullptr;
+}
+
+int dwconv_plan(DwConvPlan* plan, const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* dst,
+                int dst_cs, int dst_c0, int c, int act, const float* w_host, const float* b_host) {
+    memset(plan, 0, sizeof(*plan));
+    B2D_CHECK(c % 8 == 0 && src_cs % 8 == 0 && src_c0 % 8 == 0 && dst_cs % 8 == 0 && dst_c0 % 8 == 0,
+              "dwconv: channel counts/offsets must be multiples of 8");
+    plan->src = src; plan->h = h; plan->w = w; plan->src_cs = src_cs; plan->src_c0 = src_c0;
+    plan->dst = dst; plan->dst_cs = dst_cs; plan->dst_c0 = dst_c0; plan->c = c; plan->act = act;
+    std::vector<float> wp((size_t)9 * c), bp(c);
+    for (int ch = 0; ch < c; ++ch) {
+        for (int t = 0; t < 9; ++t) wp[(size_t)t * c + ch] = bf16_round(w_host[(size_t)ch * 9 + t]);
+        bp[ch] = b_host ? b_host[ch] : 0.f;
+    }
+    B2D_CUDA(cudaMalloc(&plan->w_dev, wp.size() * 4));
+    B2D_CUDA(cudaMemcpy(plan->w_dev, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
+    B2D_CUDA(cudaMalloc(&plan->bias_dev, bp.size() * 4));
+    B2D_CUDA(cudaMemcpy(plan->bias_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int dwconv_launch(const DwConvPlan* plan, int n, cudaStream_t stream) {
+    const long long total = (long long)n * plan->h * plan->w * (plan->c / 8);
+    dwconv_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(*plan, n);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+void dwconv_free(DwConvPlan* plan) {
+    if (plan->w_dev) cudaFree(plan->w_dev);
+    if (plan->bias_dev) cudaFree(plan->bias_dev);
+    plan->w_dev = nullptr; plan->bias_dev = nullptr;
+}
+
+int maxpool_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* dst, int oh, int ow,
+                   int dst_cs, int dst_c0, int c, int k, int stride, int n, cudaStream_t stream) {
+    B2D_CHECK(c % 8 == 0 && src_cs % 8 == 0 && src_c0 % 8 == 0 && dst_cs % 8 == 0 && dst_c0 % 8 == 0,
+              "maxpool: channel counts/offsets must be multiples of 8");
+    const long long total = (long long)n * oh * ow * (c / 8);
+    maxpool_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, h, w, src_cs, src_c0, dst, oh, ow, dst_cs, dst_c0, c, k,
+                                                                   stride, n);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+int upsample2x_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* dst, int dst_cs,
+                      int dst_c0, int c, int n, cudaStream_t stream) {
+    B2D_CHECK(c % 8 == 0 && src_cs % 8 == 0 && src_c0 % 8 == 0 && dst_cs % 8 == 0 && dst_c0 % 8 == 0,
+              "upsample: channel counts/offsets must be multiples of 8");
+    const long long total = (long long)n * 4 * h * w * (c / 8);
+    upsample2x_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, h, w, src_cs, src_c0, dst, dst_cs, dst_c0, c, n);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}

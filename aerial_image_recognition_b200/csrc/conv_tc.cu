@@ -1,0 +1,511 @@
+// K2 -- implicit-GEMM convolution + bias + SiLU (+ residual, + channel-offset write) on the
+// 5th-generation tensor cores: tcgen05.mma with the accumulator in TMEM, both operands staged
+// in shared memory by TMA, one elected thread issuing the MMAs.
+//
+// Replaces every Conv(+folded BN)+Sigmoid*Mul node onnxruntime executes inside
+// `session.run` (reference call sites simple_detector.py:474, :666; _script/gpu_handler.py:165).
+//
+// GEMM view:  D[M = pixels, N = Cout] = sum over taps (kh,kw) and channel chunks of
+//             A_tap[M, kc] * W_tap[N, kc]^T
+//   * activations are NHWC bf16; an M tile is a box of bw x bh pixels of bn images (= 128 rows).
+//     For tap (kh,kw) the A operand is the *same box shifted by the tap offset*, fetched by one
+//     4-D TMA tiled load; the zero padding of the convolution is TMA's out-of-bounds fill, so
+//     there is no im2col buffer and no halo branch anywhere.
+//   * stride-2 3x3 convs read through four "phase" tensor maps (even/odd rows x even/odd
+//     columns of the input), each of which is again a dense tiled map.
+//   * weights are pre-packed [Cout][kh][kw][Cin] (K contiguous) and fetched by a 2-D TMA load.
+//   * both operands are K-major in shared memory with the hardware swizzle matching the chunk
+//     width: 64 channels -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B.
+//   * the epilogue reads the fp32 accumulator from TMEM (tcgen05.ld 32x32b), adds the bias,
+//     applies SiLU, adds the residual, rounds to bf16 and writes at a channel offset of the
+//     destination buffer -- Concat / Split never run as ops.
+//
+// Kernel shape: persistent, one CTA per SM, 256 threads = 8 warps:
+//   warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warp 3 idle |
+//   warps 4-7 epilogue (warp%4 selects the TMEM lane quarter).
+// Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator
+// stages (tmem_full/tmem_empty) between MMA and epilogue, so tile i's epilogue overlaps
+// tile i+1's main loop.
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+#include <string.h>
+#include <vector>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t swizzle_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                   // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8u * swizzle_bytes) >> 4) << 32;         // stride byte offset: 8 rows of one swizzle span
+    d |= (uint64_t)1 << 46;                                   // descriptor version (Blackwell)
+    uint64_t layout = swizzle_bytes == 128 ? 2 : (swizzle_bytes == 64 ? 4 : 6);
+    d |= layout << 61;
+    return d;
+}
+
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+struct TileCoord { int nt, x0, y0, n0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
+    TileCoord c;
+    c.nt = t % p.n_tiles_n;
+    int m = t / p.n_tiles_n;
+    int tx = m % p.tiles_x;
+    m /= p.tiles_x;
+    int ty = m % p.tiles_y;
+    int tg = m / p.tiles_y;
+    c.x0 = tx * p.bw;
+    c.y0 = ty * p.bh;
+    c.n0 = tg * p.bn;
+    return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages x (A | B)] then barriers
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tiles_m = p.tiles_x * p.tiles_y * ((nimg + p.bn - 1) / p.bn);
+    const int total_tiles = tiles_m * p.n_tiles_n;
+    const int ksteps = p.taps * p.chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA[0]);
+        if (p.stride == 2) {
+            tma_prefetch_desc(&p.tmA[1]);
+            tma_prefetch_desc(&p.tmA[2]);
+            tma_prefetch_desc(&p.tmA[3]);
+        }
+        tma_prefetch_desc(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int pad = p.ksz >> 1;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(p, t);
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int kh = tap / p.ksz, kw = tap - kh * p.ksz;
+                    const CUtensorMap* mapA;
+                    int cx, cy;
+                    if (p.stride == 1) {
+                        mapA = &p.tmA[0];
+                        cx = tc.x0 + kw - pad;
+                        cy = tc.y0 + kh - pad;
+                    } else {
+                        // input pixel = 2*o + d, d in {-1,0,1}: odd phase for d = +-1, even for 0
+                        const int dy = kh - 1, dx = kw - 1;
+                        const int py = dy & 1, px = dx & 1;
+                        mapA = &p.tmA[py * 2 + px];
+                        cx = tc.x0 + (dx - px) / 2;
+                        cy = tc.y0 + (dy - py) / 2;
+                    }
+                    for (int ch = 0; ch < p.chunks; ++ch) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        uint8_t* sb = sa + p.a_bytes;
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)(kTileM * p.kc * 2) + p.b_tx_bytes);
+                        tma_load_4d(mapA, &full_bar[stage], sa, ch * p.kc, cx, cy, tc.n0);
+                        tma_load_2d(&p.tmB, &full_bar[stage], sb, tap * p.cin + ch * p.kc, tc.nt * p.n_tile);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        const int ksub = p.kc >> 4;   // UMMA_K = 16 for bf16
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.n_tile);
+            for (int ks = 0; ks < ksteps; ++ks) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + p.a_bytes;
+                    for (int k = 0; k < ksub; ++k) {
+                        const uint64_t ad = make_smem_desc(sa + k * 32, p.swizzle_bytes);
+                        const uint64_t bd = make_smem_desc(sb + k * 32, p.swizzle_bytes);
+                        umma_bf16(d_tmem, ad, bd, p.idesc, (ks | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+                    if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                  // TMEM lane quarter owned by this warp
+        const int row = q * 32 + lane;           // accumulator row = pixel inside the tile
+        const int lx = row % p.bw;
+        const int ly = (row / p.bw) % p.bh;
+        const int ln = row / (p.bw * p.bh);
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const TileCoord tc = decode_tile(p, t);
+            const int ox = tc.x0 + lx, oy = tc.y0 + ly, img = tc.n0 + ln;
+            const bool valid = (ox < p.W) && (oy < p.H) && (img < nimg);
+            const long long pix = ((long long)img * p.H + oy) * p.W + ox;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.n_tile);
+            const int ch_base = tc.nt * p.n_tile;
+            for (int c = 0; c < p.n_tile; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c, r);
+                tmem_ld_wait();
+                const int ch0 = ch_base + c;
+                if (!valid || ch0 >= p.cout) continue;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float a = __uint_as_float(r[j]) + __ldg(&p.bias[ch0 + j]);
+                    v[j] = p.act ? silu(a) : a;
+                }
+                const bool full16 = (ch0 + 16 <= p.cout);
+                if (p.res != nullptr) {
+                    const __nv_bfloat16* rp = p.res + pix * p.res_cs + p.res_c0 + ch0;
+                    if (full16) {
+                        uint4 a = __ldg((const uint4*)rp), b = __ldg((const uint4*)rp + 1);
+                        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            v[2 * j] += __uint_as_float(w[j] << 16);
+                            v[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                        }
+                    } else {
+                        for (int j = 0; j < 16 && ch0 + j < p.cout; ++j) v[j] += __bfloat162float(rp[j]);
+                    }
+                }
+                if (p.out_f32) {
+                    float* op = (float*)p.out + pix * p.out_cs + p.out_c0 + ch0;
+                    if (full16) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ((float4*)op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+                        for (int j = 0; j < 16 && ch0 + j < p.cout; ++j) op[j] = v[j];
+                    }
+                } else {
+                    __nv_bfloat16* op = (__nv_bfloat16*)p.out + pix * p.out_cs + p.out_c0 + ch0;
+                    if (full16) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            w[j] = *(uint32_t*)&h;
+                        }
+                        ((uint4*)op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        ((uint4*)op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    } else {
+                        for (int j = 0; j < 16 && ch0 + j < p.cout; ++j) op[j] = __float2bfloat16_rn(v[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+    }
+    return fn;
+}
+
+int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, uint32_t swizzle_bytes) {
+    auto enc = get_encode();
+    B2D_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B2D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu box %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return 0;
+}
+
+uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u = (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+    return (uint16_t)u;
+}
+
+// pick (bw, bh, bn), bw*bh*bn == 128, maximising useful rows; ties -> squarer spatial box, smaller bn
+void pick_tile(int W, int H, int N, int* bw, int* bh, int* bn) {
+    double best = -1.0;
+    int best_halo = 1 << 30;
+    for (int w = 1; w <= 128; w *= 2)
+        for (int h = 1; w * h <= 128; h *= 2) {
+            int n = 128 / (w * h);
+            long long tiles = (long long)ceil_div(W, w) * ceil_div(H, h) * ceil_div(N, n);
+            double eff = (double)W * H * N / (double)(tiles * 128);
+            int halo = (w + 2) * (h + 2) * n;
+            if (eff > best + 1e-9 || (eff > best - 1e-9 && halo < best_halo)) {
+                best = eff; best_halo = halo; *bw = w; *bh = h; *bn = n;
+            }
+        }
+}
+
+}  // namespace
+
+int conv_tc_supported(int cin, int ksz, int stride) {
+    if (cin % 16 != 0) return 0;
+    if (!((ksz == 1 && stride == 1) || (ksz == 3 && (stride == 1 || stride == 2)))) return 0;
+    return 1;
+}
+
+int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloat16* src, int src_h, int src_w, int src_cs,
+                 int src_c0, int cin, void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32, int ksz,
+                 int stride, int act, const float* w_host, const float* b_host, const __nv_bfloat16* res, int res_cs,
+                 int res_c0) {
+    memset(plan, 0, sizeof(*plan));
+    B2D_CHECK(conv_tc_supported(cin, ksz, stride), "conv_tc: unsupported shape cin=%d k=%d s=%d", cin, ksz, stride);
+    B2D_CHECK(src_cs % 8 == 0 && src_c0 % 8 == 0, "conv_tc: source slice must be 16-byte aligned (cs=%d c0=%d)", src_cs, src_c0);
+    B2D_CHECK(stride == 1 || (src_h % 2 == 0 && src_w % 2 == 0), "conv_tc: stride-2 input must have even size");
+    ConvTcParams& p = plan->p;
+    plan->sm_count = sm_count;
+    p.W = dst_w; p.H = dst_h; p.cin = cin; p.cout = cout;
+    p.ksz = ksz; p.taps = ksz * ksz; p.stride = stride;
+    p.act = act; p.out_f32 = dst_f32;
+    p.out = dst; p.out_cs = dst_cs; p.out_c0 = dst_c0;
+    p.res = res; p.res_cs = res_cs; p.res_c0 = res_c0;
+    p.kc = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+    p.chunks = cin / p.kc;
+    p.swizzle_bytes = p.kc * 2;
+    const int cout_pad = ceil_div(cout, 16) * 16;
+    int split = 1;
+    while (cout_pad % split != 0 || (cout_pad / split) % 16 != 0 || cout_pad / split > 256) ++split;
+    p.n_tile = cout_pad / split;
+    p.n_tiles_n = split;
+    pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn);
+    p.tiles_x = ceil_div(dst_w, p.bw);
+    p.tiles_y = ceil_div(dst_h, p.bh);
+    p.a_bytes = kTileM * p.kc * 2;
+    p.b_tx_bytes = p.n_tile * p.kc * 2;
+    p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    const uint32_t budget = 200 * 1024;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    const int ksteps = p.taps * p.chunks;
+    if (stages > ksteps * 2) stages = ksteps * 2;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.n_tile)) cols *= 2;
+    p.tmem_cols = cols;
+    // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+    // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin] ----
+    const size_t ktot = (size_t)p.taps * cin;
+    std::vector<uint16_t> wp((size_t)cout_pad * ktot, 0);
+    for (int o = 0; o < cout; ++o)
+        for (int c = 0; c < cin; ++c)
+            for (int t = 0; t < p.taps; ++t)
+                wp[(size_t)o * ktot + (size_t)t * cin + c] = f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
+    std::vector<float> bp(cout_pad, 0.f);
+    for (int o = 0; o < cout; ++o) bp[o] = b_host ? b_host[o] : 0.f;
+    B2D_CUDA(cudaMalloc(&plan->w_dev, wp.size() * 2));
+    B2D_CUDA(cudaMemcpy(plan->w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+    B2D_CUDA(cudaMalloc(&plan->bias_dev, bp.size() * 4));
+    B2D_CUDA(cudaMemcpy(plan->bias_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+    p.bias = plan->bias_dev;
+
+    // ---- tensor maps ----
+    {
+        uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout_pad};
+        uint64_t str[1] = {(uint64_t)ktot * 2};
+        uint32_t box[2] = {(uint32_t)p.kc, (uint32_t)p.n_tile};
+        if (encode_map(&p.tmB, plan->w_dev, 2, dims, str, box, p.swizzle_bytes)) return -1;
+    }
+    const uint32_t boxA[4] = {(uint32_t)p.kc, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    if (stride == 1) {
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)src_w, (uint64_t)src_h, (uint64_t)max_batch};
+        uint64_t str[3] = {(uint64_t)src_cs * 2, (uint64_t)src_w * src_cs * 2, (uint64_t)src_h * src_w * src_cs * 2};
+        if (encode_map(&p.tmA[0], (void*)(src + src_c0), 4, dims, str, boxA, p.swizzle_bytes)) return -1;
+    } else {
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                uint64_t dims[4] = {(uint64_t)cin, (uint64_t)src_w / 2, (uint64_t)src_h / 2, (uint64_t)max_batch};
+                uint64_t str[3] = {(uint64_t)2 * src_cs * 2, (uint64_t)2 * src_w * src_cs * 2,
+                                   (uint64_t)src_h * src_w * src_cs * 2};
+                const __nv_bfloat16* base = src + ((size_t)py * src_w + px) * src_cs + src_c0;
+                if (encode_map(&p.tmA[py * 2 + px], (void*)base, 4, dims, str, boxA, p.swizzle_bytes)) return -1;
+            }
+    }
+    B2D_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    return 0;
+}
+
+int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
+    const ConvTcParams& p = plan->p;
+    const int tiles = p.tiles_x * p.tiles_y * ceil_div(n, p.bn) * p.n_tiles_n;
+    int grid = tiles < plan->sm_count ? tiles : plan->sm_count;
+    if (grid < 1) return 0;
+    conv_tc_kernel<<<grid, kThreads, plan->smem_bytes, stream>>>(p, n);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+void conv_tc_free(ConvTcPlan* plan) {
+    if (plan->w_dev) cudaFree(plan->w_dev);
+    if (plan->bias_dev) cudaFree(plan->bias_dev);
+    plan->w_dev = nullptr;
+    plan->bias_dev = nullptr;
+}
+
+int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
+    const ConvTcParams& p = plan->p;
+    return snprintf(buf, buflen,
+                    "tcgen05 conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d n_tile %d x%d kc %d (SW%u) stages %d tmem %u smem %zu",
+                    p.ksz, p.stride, p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.n_tile, p.n_tiles_n, p.kc, p.swizzle_bytes,
+                    p.stages, p.tmem_cols, plan->smem_bytes);
+}

@@ -1,0 +1,186 @@
+// K5' -- greedy centre-distance dedup in a metric CRS, and the WGS84 -> UTM forward projection
+// that feeds it.
+//
+// Reference: SimpleDetector._remove_duplicates (simple_detector.py:540-596): sort by confidence
+// (stable, descending), keep a detection iff no already-kept one lies within `thr` metres
+// (`dx*dx + dy*dy <= thr*thr`, float64, :585-587); variant ResultsManager.remove_duplicates
+// (_script/utils.py:229-256) with a strict `<`.
+//
+// The sequential greedy pass is restated as a fixed point that gives the *same* keep set:
+//   a point is REMOVED as soon as one higher-priority neighbour is KEPT,
+//   a point is KEPT   as soon as every higher-priority neighbour is REMOVED.
+// Priority is the reference's total order (confidence descending, input index ascending), so
+// the result does not depend on thread scheduling.  Neighbours come from a hashed uniform grid
+// with cell size `thr` (3x3 cells), built with one atomicExch per point -- no sort.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace {
+
+struct DedupTable {
+    long long* cell_key;   // [cap] hashed cell id, -1 = empty  (stored as (cx<<32)|(cy & 0xffffffff))
+    int* cell_head;        // [cap] head of the linked list of points in the cell
+    int* next;             // [n]
+    uint8_t* state;        // [n] 0 undecided, 1 kept, 2 removed
+    int* flag;             // [1] number of points still undecided after a round
+    unsigned cap_mask;
+};
+
+__device__ __forceinline__ unsigned long long pack_cell(long long cx, long long cy) {
+    return ((unsigned long long)(unsigned)(int)cx << 32) | (unsigned long long)(unsigned)(int)cy;
+}
+__device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (unsigned)k;
+}
+
+__global__ void dedup_init_kernel(DedupTable t, int n, unsigned cap) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) { t.cell_key[i] = -1; t.cell_head[i] = -1; }
+    if (i < (unsigned)n) { t.state[i] = 0; t.next[i] = -1; }
+    if (i == 0) *t.flag = 0;
+}
+
+__global__ void dedup_build_kernel(DedupTable t, const double* __restrict__ x, const double* __restrict__ y, int n, double inv_cell) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = pack_cell((long long)floor(x[i] * inv_cell), (long long)floor(y[i] * inv_cell));
+    unsigned slot = hash_cell(key) & t.cap_mask;
+    while (true) {
+        const long long prev = atomicCAS((unsigned long long*)&t.cell_key[slot], (unsigned long long)-1LL, key);
+        if (prev == -1LL || (unsigned long long)prev == key) break;
+        slot = (slot + 1) & t.cap_mask;
+    }
+    t.next[i] = atomicExch(&t.cell_head[slot], i);
+}
+
+__global__ void dedup_round_kernel(DedupTable t, const double* __restrict__ x, const double* __restrict__ y,
+                                   const float* __restrict__ conf, int n, double inv_cell, double thr2, int inclusive) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (((volatile uint8_t*)t.state)[i] != 0) return;
+    const double xi = x[i], yi = y[i];
+    const float ci = conf[i];
+    const long long cx = (long long)floor(xi * inv_cell), cy = (long long)floor(yi * inv_cell);
+    bool removed = false, wait = false;
+    for (int dx = -1; dx <= 1 && !removed; ++dx)
+        for (int dy = -1; dy <= 1 && !removed; ++dy) {
+            const unsigned long long key = pack_cell(cx + dx, cy + dy);
+            unsigned slot = hash_cell(key) & t.cap_mask;
+            int head = -1;
+            while (true) {
+                const long long k = t.cell_key[slot];
+                if (k == -1LL) break;
+                if ((unsigned long long)k == key) { head = t.cell_head[slot]; break; }
+                slot = (slot + 1) & t.cap_mask;
+            }
+            for (int j = head; j >= 0; j = t.next[j]) {
+                if (j == i) continue;
+                const float cj = conf[j];
+                if (!(cj > ci || (cj == ci && j < i))) continue;       // only higher-priority points matter
+                const double ddx = __dsub_rn(xi, x[j]), ddy = __dsub_rn(yi, y[j]);
+                const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                if (!(inclusive ? (d2 <= thr2) : (d2 < thr2))) continue;
+                const uint8_t sj = ((volatile uint8_t*)t.state)[j];
+                if (sj == 1) { removed = true; break; }
+                if (sj == 0) wait = true;
+            }
+        }
+    if (removed) t.state[i] = 2;
+    else if (!wait) t.state[i] = 1;
+    else atomicAdd(t.flag, 1);
+}
+
+__global__ void dedup_finish_kernel(DedupTable t, int n, uint8_t* keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keep[i] = (t.state[i] == 1) ? 1 : 0;
+}
+
+// WGS84 -> UTM, Krueger series to n^4 (same formulation as oracle/postproc.py::utm_forward)
+__global__ void utm_forward_kernel(const double* __restrict__ lon, const double* __restrict__ lat, int n, double lon0, int north,
+                                   double* __restrict__ xo, double* __restrict__ yo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = 6378137.0, f = 1.0 / 298.257223563;
+    const double nn = f / (2.0 - f);
+    const double A = a / (1.0 + nn) * (1.0 + nn * nn / 4.0 + nn * nn * nn * nn / 64.0);
+    const double n2 = nn * nn, n3 = n2 * nn, n4 = n3 * nn;
+    const double al[4] = {nn / 2 - 2 * n2 / 3 + 5 * n3 / 16 + 41 * n4 / 180, 13 * n2 / 48 - 3 * n3 / 5 + 557 * n4 / 1440,
+                          61 * n3 / 240 - 103 * n4 / 140, 49561 * n4 / 161280};
+    const double d2r = 0.017453292519943295;
+    const double phi = lat[i] * d2r, lam = lon[i] * d2r - lon0;
+    const double e = sqrt(f * (2.0 - f));
+    const double s = sin(phi);
+    const double tt = sinh(atanh(s) - e * atanh(e * s));
+    const double xi = atan2(tt, cos(lam));
+    const double eta = atanh(sin(lam) / sqrt(1.0 + tt * tt));
+    double X = eta, Y = xi;
+    for (int j = 1; j <= 4; ++j) {
+        X += al[j - 1] * cos(2 * j * xi) * sinh(2 * j * eta);
+        Y += al[j - 1] * sin(2 * j * xi) * cosh(2 * j * eta);
+    }
+    xo[i] = 500000.0 + 0.9996 * A * X;
+    yo[i] = 0.9996 * A * Y + (north ? 0.0 : 10000000.0);
+}
+
+unsigned table_cap(int n) {
+    unsigned cap = 1024;
+    while (cap < (unsigned)(2 * n)) cap <<= 1;
+    return cap;
+}
+
+}  // namespace
+
+size_t dedup_scratch_bytes(int count) {
+    const unsigned cap = table_cap(count);
+    return (size_t)cap * 8 + (size_t)cap * 4 + (size_t)count * 4 + (size_t)((count + 15) & ~15) + 64;
+}
+
+int dedup_launch(const double* x, const double* y, const float* conf, int count, double thr, int inclusive, uint8_t* keep,
+                 void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    if (count <= 0) return 0;
+    B2D_CHECK(scratch_bytes >= dedup_scratch_bytes(count), "dedup: scratch too small");
+    const unsigned cap = table_cap(count);
+    DedupTable t;
+    uint8_t* p = (uint8_t*)scratch;
+    t.cell_key = (long long*)p; p += (size_t)cap * 8;
+    t.cell_head = (int*)p; p += (size_t)cap * 4;
+    t.next = (int*)p; p += (size_t)count * 4;
+    t.flag = (int*)p; p += 16;
+    t.state = p;
+    t.cap_mask = cap - 1;
+    const double cell = thr > 0.0 ? thr : 1.0;
+    const double inv_cell = 1.0 / cell;
+    const double thr2 = thr * thr;
+    const int threads = 256;
+    const unsigned m = cap > (unsigned)count ? cap : (unsigned)count;
+    dedup_init_kernel<<<(m + threads - 1) / threads, threads, 0, stream>>>(t, count, cap);
+    dedup_build_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, x, y, count, inv_cell);
+    B2D_LAUNCH_CHECK();
+    // Rounds: every round decides at least the highest-priority undecided point, so the loop ends;
+    // real data needs a handful of rounds.  The host reads the undecided count back every 4 rounds.
+    int h_flag = 1;
+    for (int round = 0; h_flag != 0; ++round) {
+        B2D_CUDA(cudaMemsetAsync(t.flag, 0, sizeof(int), stream));
+        dedup_round_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, x, y, conf, count, inv_cell, thr2, inclusive);
+        B2D_LAUNCH_CHECK();
+        if ((round & 3) == 3 || count < 4096) {
+            B2D_CUDA(cudaMemcpyAsync(&h_flag, t.flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            B2D_CUDA(cudaStreamSynchronize(stream));
+        }
+        B2D_CHECK(round <= count + 8, "dedup: did not converge");
+    }
+    dedup_finish_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, count, keep);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+int utm_forward_launch(const double* lon, const double* lat, int count, int zone, int north, double* x, double* y,
+                       cudaStream_t stream) {
+    if (count <= 0) return 0;
+    const double lon0 = ((zone - 1) * 6 - 180 + 3) * 0.017453292519943295;
+    utm_forward_kernel<<<(count + 255) / 256, 256, 0, stream>>>(lon, lat, count, lon0, north, x, y);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}

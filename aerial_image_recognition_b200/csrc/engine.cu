@@ -1,0 +1,475 @@
+// The C ABI (include/b2det.h): engine lifetime, plan building and stage entry points.
+//
+// An engine owns one GPU's buffers, packed weights, tensor maps and scratch.  The plan is the
+// graph the reference gives onnxruntime as an .onnx file (_script/gpu_handler.py:61-65); here it
+// is built op by op through b2d_plan_* and executed by b2d_forward as a fixed launch sequence.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+static thread_local std::string g_last_error;
+
+void b2d_set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+namespace {
+
+struct Buffer {
+    int h, w, c, f32;
+    void* ptr;
+    size_t bytes;
+};
+
+enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_MAXPOOL, OP_UPSAMPLE };
+
+struct OpDesc {   // what the caller asked for (resolved into a plan at finalize)
+    int kind_req;     // 0 conv, 1 dwconv, 2 maxpool, 3 upsample
+    int src, src_c0, cin, dst, dst_c0, cout, k, stride, act, res, res_c0, impl;
+    std::vector<float> w, b;
+};
+
+struct Op {
+    OpKind kind;
+    ConvTcPlan tc;
+    ConvSimtPlan simt;
+    DwConvPlan dw;
+    // pool / upsample
+    const __nv_bfloat16* src; __nv_bfloat16* dst;
+    int h, w, src_cs, src_c0, oh, ow, dst_cs, dst_c0, c, k, stride;
+};
+
+struct TableEntry { ResizeTables t; int canvas; };
+
+}  // namespace
+
+struct b2d_engine {
+    int device = 0;
+    int max_batch = 0;
+    int sm_count = 0;
+    bool finalized = false;
+    std::vector<Buffer> bufs;
+    std::vector<OpDesc> descs;
+    std::vector<Op> ops;
+    HeadDesc head{};
+    int head_levels = 0;
+    std::vector<TableEntry> tables;
+    // post-processing scratch
+    b2d_det* cand = nullptr;
+    int* cand_count = nullptr;
+    unsigned long long* keys = nullptr;
+    int cand_cap = 0;
+    int cand_tiles = 0;
+    void* dedup_scratch = nullptr;
+    size_t dedup_scratch_bytes = 0;
+};
+
+namespace {
+
+int ensure_cand(b2d_engine* e, int n, int rows) {
+    int cap = rows < 32768 ? rows : 32768;
+    if (e->cand && e->cand_cap >= cap && e->cand_tiles >= n) return 0;
+    if (e->cand) { cudaFree(e->cand); cudaFree(e->cand_count); cudaFree(e->keys); }
+    int tiles = n > e->max_batch ? n : e->max_batch;
+    int stride = 1;
+    while (stride < cap) stride <<= 1;
+    B2D_CUDA(cudaMalloc(&e->cand, (size_t)tiles * cap * sizeof(b2d_det)));
+    B2D_CUDA(cudaMalloc(&e->cand_count, (size_t)tiles * sizeof(int)));
+    B2D_CUDA(cudaMalloc(&e->keys, (size_t)tiles * stride * sizeof(unsigned long long)));
+    e->cand_cap = cap;
+    e->cand_tiles = tiles;
+    return 0;
+}
+
+int upload_i32(int32_t** dst, const std::vector<int32_t>& v) {
+    B2D_CUDA(cudaMalloc(dst, v.size() * sizeof(int32_t)));
+    B2D_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int get_tables(b2d_engine* e, int mode, int h, int w, int out, int n, const ResizeTables** result) {
+    for (auto& te : e->tables)
+        if (te.t.mode == mode && te.t.in_h == h && te.t.in_w == w && te.canvas == out) {
+            ResizeTables& t = te.t;
+            if (mode == B2D_RESIZE_PIL_BICUBIC && t.in_w != t.out_w) {
+                const size_t need = (size_t)n * t.in_h * t.out_w * 3;
+                if (need > t.tmp_bytes) {
+                    if (t.tmp) cudaFree(t.tmp);
+                    B2D_CUDA(cudaMalloc(&t.tmp, need));
+                    t.tmp_bytes = need;
+                }
+            }
+            *result = &t;
+            return 0;
+        }
+    ResizeTables t;
+    memset(&t, 0, sizeof(t));
+    t.mode = mode; t.in_h = h; t.in_w = w; t.out_h = out; t.out_w = out;
+    if (mode == B2D_RESIZE_IDENTITY) {
+        B2D_CHECK(h == out && w == out, "preprocess: identity mode needs %dx%d input, got %dx%d", out, out, h, w);
+    } else {
+        int tmode = mode;
+        if (mode == B2D_RESIZE_LETTERBOX) {
+            // Ultralytics LetterBox(auto=False, scaleup=True, center=True); Python round() = rint()
+            const double r = fmin((double)out / h, (double)out / w);
+            t.out_w = (int)rint(w * r);
+            t.out_h = (int)rint(h * r);
+            const double dw = (out - t.out_w) / 2.0, dh = (out - t.out_h) / 2.0;
+            t.left = (int)rint(dw - 0.1);
+            t.top = (int)rint(dh - 0.1);
+            tmode = B2D_RESIZE_CV2_LINEAR;
+        }
+        int kx = 0, ky = 0;
+        b2d_resize_table(tmode, w, t.out_w, nullptr, nullptr, &kx);
+        b2d_resize_table(tmode, h, t.out_h, nullptr, nullptr, &ky);
+        t.ksize_x = kx; t.ksize_y = ky;
+        std::vector<int32_t> xb(2 * (size_t)t.out_w), xk((size_t)kx * t.out_w), yb(2 * (size_t)t.out_h), yk((size_t)ky * t.out_h);
+        B2D_CHECK(b2d_resize_table(tmode, w, t.out_w, xb.data(), xk.data(), &kx) == 0, "resize table failed");
+        B2D_CHECK(b2d_resize_table(tmode, h, t.out_h, yb.data(), yk.data(), &ky) == 0, "resize table failed");
+        if (upload_i32(&t.xb, xb) || upload_i32(&t.xk, xk) || upload_i32(&t.yb, yb) || upload_i32(&t.yk, yk)) return -2;
+        if (mode == B2D_RESIZE_PIL_BICUBIC && t.in_w != t.out_w) {
+            t.tmp_bytes = (size_t)n * t.in_h * t.out_w * 3;
+            B2D_CUDA(cudaMalloc(&t.tmp, t.tmp_bytes));
+        }
+    }
+    e->tables.push_back({t, out});
+    *result = &e->tables.back().t;
+    return 0;
+}
+
+int launch_op(b2d_engine* e, const Op& op, int n, cudaStream_t s) {
+    (void)e;
+    switch (op.kind) {
+        case OP_CONV_TC: return conv_tc_launch(&op.tc, n, s);
+        case OP_CONV_SIMT: return conv_simt_launch(&op.simt, n, s);
+        case OP_DWCONV: return dwconv_launch(&op.dw, n, s);
+        case OP_MAXPOOL:
+            return maxpool_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.dst, op.oh, op.ow, op.dst_cs, op.dst_c0, op.c, op.k,
+                                  op.stride, n, s);
+        case OP_UPSAMPLE: return upsample2x_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.dst, op.dst_cs, op.dst_c0, op.c, n, s);
+    }
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2d_last_error(void) { return g_last_error.c_str(); }
+int b2d_version(void) { return B2D_VERSION; }
+
+int b2d_create(int device, int max_batch, b2d_engine** out) {
+    B2D_CHECK(out != nullptr && max_batch > 0, "b2d_create: bad arguments");
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    B2D_CHECK(err == cudaSuccess && count > 0, "b2d_create: no CUDA device (%s) -- this engine has no CPU fallback",
+              cudaGetErrorString(err));
+    B2D_CHECK(device >= 0 && device < count, "b2d_create: device %d out of range (%d devices)", device, count);
+    cudaDeviceProp prop;
+    B2D_CUDA(cudaGetDeviceProperties(&prop, device));
+    B2D_CHECK(prop.major == 10, "b2d_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+              prop.minor);
+    B2D_CUDA(cudaSetDevice(device));
+    b2d_engine* e = new b2d_engine();
+    e->device = device;
+    e->max_batch = max_batch;
+    e->sm_count = prop.multiProcessorCount;
+    *out = e;
+    return 0;
+}
+
+void b2d_destroy(b2d_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (auto& op : e->ops) {
+        if (op.kind == OP_CONV_TC) conv_tc_free(&op.tc);
+        if (op.kind == OP_CONV_SIMT) conv_simt_free(&op.simt);
+        if (op.kind == OP_DWCONV) dwconv_free(&op.dw);
+    }
+    for (auto& b : e->bufs)
+        if (b.ptr) cudaFree(b.ptr);
+    for (auto& te : e->tables) {
+        if (te.t.xb) cudaFree(te.t.xb);
+        if (te.t.xk) cudaFree(te.t.xk);
+        if (te.t.yb) cudaFree(te.t.yb);
+        if (te.t.yk) cudaFree(te.t.yk);
+        if (te.t.tmp) cudaFree(te.t.tmp);
+    }
+    if (e->cand) { cudaFree(e->cand); cudaFree(e->cand_count); cudaFree(e->keys); }
+    if (e->dedup_scratch) cudaFree(e->dedup_scratch);
+    delete e;
+}
+
+int b2d_device_sm_count(b2d_engine* e) { return e ? e->sm_count : -1; }
+
+int b2d_plan_buffer(b2d_engine* e, int h, int w, int c, int is_f32) {
+    B2D_CHECK(e && !e->finalized, "plan_buffer: engine finalized or null");
+    B2D_CHECK(h > 0 && w > 0 && c > 0, "plan_buffer: bad shape");
+    Buffer b{h, w, c, is_f32, nullptr, 0};
+    b.bytes = (size_t)e->max_batch * h * w * c * (is_f32 ? 4 : 2);
+    B2D_CUDA(cudaSetDevice(e->device));
+    B2D_CUDA(cudaMalloc(&b.ptr, b.bytes));
+    B2D_CUDA(cudaMemset(b.ptr, 0, b.bytes));
+    e->bufs.push_back(b);
+    return (int)e->bufs.size() - 1;
+}
+
+static int check_ref(b2d_engine* e, int buf, int c0, int c, const char* what) {
+    B2D_CHECK(buf >= 0 && buf < (int)e->bufs.size(), "%s: buffer %d out of range", what, buf);
+    B2D_CHECK(c0 >= 0 && c > 0 && c0 + c <= e->bufs[buf].c, "%s: slice [%d,%d) outside buffer with %d channels", what, c0, c0 + c,
+              e->bufs[buf].c);
+    return 0;
+}
+
+int b2d_plan_conv(b2d_engine* e, int src, int src_c0, int cin, int dst, int dst_c0, int cout, int k, int stride, int act,
+                  const float* weight_host, const float* bias_host, int res, int res_c0, int impl) {
+    B2D_CHECK(e && !e->finalized, "plan_conv: engine finalized or null");
+    if (check_ref(e, src, src_c0, src == 0 ? e->bufs[0].c : cin, "plan_conv src") || check_ref(e, dst, dst_c0, cout, "plan_conv dst")) return -1;
+    if (res >= 0 && check_ref(e, res, res_c0, cout, "plan_conv res")) return -1;
+    B2D_CHECK(weight_host != nullptr, "plan_conv: weights missing");
+    const Buffer& sb = e->bufs[src];
+    const Buffer& db = e->bufs[dst];
+    B2D_CHECK((sb.h + 2 * (k / 2) - k) / stride + 1 == db.h && (sb.w + 2 * (k / 2) - k) / stride + 1 == db.w,
+              "plan_conv: %dx%d -k%d s%d-> %dx%d does not match", sb.h, sb.w, k, stride, db.h, db.w);
+    B2D_CHECK(!sb.f32, "plan_conv: source must be bf16");
+    B2D_CHECK(res < 0 || (!e->bufs[res].f32 && e->bufs[res].h == db.h && e->bufs[res].w == db.w), "plan_conv: bad residual buffer");
+    OpDesc d{};
+    d.kind_req = 0; d.src = src; d.src_c0 = src_c0; d.cin = cin; d.dst = dst; d.dst_c0 = dst_c0; d.cout = cout;
+    d.k = k; d.stride = stride; d.act = act; d.res = res; d.res_c0 = res_c0; d.impl = impl;
+    d.w.assign(weight_host, weight_host + (size_t)cout * cin * k * k);
+    if (bias_host) d.b.assign(bias_host, bias_host + cout);
+    else d.b.assign(cout, 0.f);
+    e->descs.push_back(std::move(d));
+    return (int)e->descs.size() - 1;
+}
+
+int b2d_plan_dwconv(b2d_engine* e, int src, int src_c0, int dst, int dst_c0, int c, int act, const float* weight_host,
+                    const float* bias_host) {
+    B2D_CHECK(e && !e->finalized, "plan_dwconv: engine finalized or null");
+    if (check_ref(e, src, src_c0, c, "plan_dwconv src") || check_ref(e, dst, dst_c0, c, "plan_dwconv dst")) return -1;
+    B2D_CHECK(e->bufs[src].h == e->bufs[dst].h && e->bufs[src].w == e->bufs[dst].w, "plan_dwconv: shape mismatch");
+    B2D_CHECK(!e->bufs[src].f32 && !e->bufs[dst].f32, "plan_dwconv: buffers must be bf16");
+    OpDesc d{};
+    d.kind_req = 1; d.src = src; d.src_c0 = src_c0; d.cin = c; d.dst = dst; d.dst_c0 = dst_c0; d.cout = c; d.k = 3; d.stride = 1;
+    d.act = act; d.res = -1;
+    d.w.assign(weight_host, weight_host + (size_t)c * 9);
+    if (bias_host) d.b.assign(bias_host, bias_host + c);
+    else d.b.assign(c, 0.f);
+    e->descs.push_back(std::move(d));
+    return (int)e->descs.size() - 1;
+}
+
+int b2d_plan_maxpool(b2d_engine* e, int src, int src_c0, int dst, int dst_c0, int c, int k, int stride) {
+    B2D_CHECK(e && !e->finalized, "plan_maxpool: engine finalized or null");
+    if (check_ref(e, src, src_c0, c, "plan_maxpool src") || check_ref(e, dst, dst_c0, c, "plan_maxpool dst")) return -1;
+    const Buffer& sb = e->bufs[src];
+    const Buffer& db = e->bufs[dst];
+    const int oh = (stride == 1) ? sb.h : sb.h / stride;
+    B2D_CHECK(oh == db.h && !sb.f32 && !db.f32, "plan_maxpool: shape/type mismatch");
+    OpDesc d{};
+    d.kind_req = 2; d.src = src; d.src_c0 = src_c0; d.cin = c; d.dst = dst; d.dst_c0 = dst_c0; d.cout = c; d.k = k; d.stride = stride; d.res = -1;
+    e->descs.push_back(std::move(d));
+    return (int)e->descs.size() - 1;
+}
+
+int b2d_plan_upsample2x(b2d_engine* e, int src, int src_c0, int dst, int dst_c0, int c) {
+    B2D_CHECK(e && !e->finalized, "plan_upsample: engine finalized or null");
+    if (check_ref(e, src, src_c0, c, "plan_upsample src") || check_ref(e, dst, dst_c0, c, "plan_upsample dst")) return -1;
+    B2D_CHECK(e->bufs[src].h * 2 == e->bufs[dst].h && !e->bufs[src].f32 && !e->bufs[dst].f32, "plan_upsample: shape/type mismatch");
+    OpDesc d{};
+    d.kind_req = 3; d.src = src; d.src_c0 = src_c0; d.cin = c; d.dst = dst; d.dst_c0 = dst_c0; d.cout = c; d.res = -1;
+    e->descs.push_back(std::move(d));
+    return (int)e->descs.size() - 1;
+}
+
+int b2d_plan_head_level(b2d_engine* e, int kind, int buf, int stride, int nc, const float* anchors_px) {
+    B2D_CHECK(e && !e->finalized, "plan_head_level: engine finalized or null");
+    B2D_CHECK(buf >= 0 && buf < (int)e->bufs.size() && e->bufs[buf].f32, "plan_head_level: head buffer must be an fp32 buffer");
+    B2D_CHECK(e->head_levels < 3, "plan_head_level: at most 3 levels");
+    B2D_CHECK(e->head_levels == 0 || (e->head.kind == kind && e->head.nc == nc), "plan_head_level: inconsistent head");
+    const Buffer& b = e->bufs[buf];
+    HeadLevel& L = e->head.lv[e->head_levels];
+    L.buf = (const float*)b.ptr; L.hw = b.h; L.c = b.c; L.stride = stride; L.nc = nc; L.kind = kind;
+    for (int i = 0; i < 6; ++i) L.anchors[i] = anchors_px ? anchors_px[i] : 0.f;
+    const int per = (kind == B2D_HEAD_V7_ANCHOR) ? 3 : 1;
+    L.row0 = e->head.rows_total;
+    B2D_CHECK(b.c >= (kind == B2D_HEAD_V7_ANCHOR ? 3 * (nc + 5) : 64 + nc), "plan_head_level: head buffer too narrow");
+    e->head.rows_total += per * b.h * b.w;
+    e->head.kind = kind; e->head.nc = nc;
+    e->head_levels += 1;
+    e->head.nlevels = e->head_levels;
+    return 0;
+}
+
+int b2d_plan_finalize(b2d_engine* e) {
+    B2D_CHECK(e && !e->finalized, "plan_finalize: engine finalized or null");
+    B2D_CUDA(cudaSetDevice(e->device));
+    e->ops.resize(e->descs.size());
+    for (size_t i = 0; i < e->descs.size(); ++i) {
+        OpDesc& d = e->descs[i];
+        Op& op = e->ops[i];
+        const Buffer& sb = e->bufs[d.src];
+        const Buffer& db = e->bufs[d.dst];
+        if (d.kind_req == 0) {
+            const __nv_bfloat16* res = d.res >= 0 ? (const __nv_bfloat16*)e->bufs[d.res].ptr : nullptr;
+            const int res_cs = d.res >= 0 ? e->bufs[d.res].c : 0;
+            bool tc = conv_tc_supported(d.cin, d.k, d.stride) && sb.c % 8 == 0 && d.src_c0 % 8 == 0;
+            if (d.impl == B2D_CONV_SIMT) tc = false;
+            B2D_CHECK(!(d.impl == B2D_CONV_TCGEN05 && !tc), "plan_finalize: op %zu cannot run on the tcgen05 path", i);
+            if (tc) {
+                op.kind = OP_CONV_TC;
+                if (conv_tc_plan(&op.tc, e->sm_count, e->max_batch, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin,
+                                 db.ptr, db.h, db.w, db.c, d.dst_c0, d.cout, db.f32, d.k, d.stride, d.act, d.w.data(), d.b.data(), res,
+                                 res_cs, d.res_c0))
+                    return -1;
+            } else {
+                op.kind = OP_CONV_SIMT;
+                if (conv_simt_plan(&op.simt, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin, d.cin, db.ptr, db.h, db.w,
+                                   db.c, d.dst_c0, d.cout, db.f32, d.k, d.stride, d.act, d.w.data(), d.b.data(), res, res_cs, d.res_c0))
+                    return -1;
+            }
+        } else if (d.kind_req == 1) {
+            op.kind = OP_DWCONV;
+            if (dwconv_plan(&op.dw, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, (__nv_bfloat16*)db.ptr, db.c, d.dst_c0,
+                            d.cout, d.act, d.w.data(), d.b.data()))
+                return -1;
+        } else {
+            op.kind = d.kind_req == 2 ? OP_MAXPOOL : OP_UPSAMPLE;
+            op.src = (const __nv_bfloat16*)sb.ptr; op.dst = (__nv_bfloat16*)db.ptr;
+            op.h = sb.h; op.w = sb.w; op.src_cs = sb.c; op.src_c0 = d.src_c0;
+            op.oh = db.h; op.ow = db.w; op.dst_cs = db.c; op.dst_c0 = d.dst_c0; op.c = d.cout; op.k = d.k; op.stride = d.stride;
+        }
+        d.w.clear(); d.w.shrink_to_fit();
+    }
+    e->finalized = true;
+    return 0;
+}
+
+void* b2d_buffer_ptr(b2d_engine* e, int buf) { return (e && buf >= 0 && buf < (int)e->bufs.size()) ? e->bufs[buf].ptr : nullptr; }
+size_t b2d_buffer_bytes(b2d_engine* e, int buf) { return (e && buf >= 0 && buf < (int)e->bufs.size()) ? e->bufs[buf].bytes : 0; }
+int b2d_num_anchors(b2d_engine* e) { return e ? e->head.rows_total : -1; }
+int b2d_num_ops(b2d_engine* e) { return e ? (int)e->ops.size() : -1; }
+int b2d_num_kernels_per_forward(b2d_engine* e) { return e ? (int)e->ops.size() : -1; }
+
+int b2d_describe_op(b2d_engine* e, int i, char* buf, int buflen) {
+    B2D_CHECK(e && e->finalized && i >= 0 && i < (int)e->ops.size(), "describe_op: bad index");
+    const Op& op = e->ops[i];
+    switch (op.kind) {
+        case OP_CONV_TC: return conv_tc_describe(&op.tc, buf, buflen);
+        case OP_CONV_SIMT:
+            return snprintf(buf, buflen, "simt conv k%d s%d cin %d cout %d -> %dx%d", op.simt.ksz, op.simt.stride, op.simt.cin,
+                            op.simt.cout, op.simt.dst_h, op.simt.dst_w);
+        case OP_DWCONV: return snprintf(buf, buflen, "depthwise 3x3 c %d @ %dx%d", op.dw.c, op.dw.h, op.dw.w);
+        case OP_MAXPOOL: return snprintf(buf, buflen, "maxpool k%d s%d c %d @ %dx%d", op.k, op.stride, op.c, op.h, op.w);
+        case OP_UPSAMPLE: return snprintf(buf, buflen, "upsample2x c %d @ %dx%d", op.c, op.h, op.w);
+    }
+    return 0;
+}
+
+int b2d_run_op(b2d_engine* e, int i, int n, void* stream) {
+    B2D_CHECK(e && e->finalized && i >= 0 && i < (int)e->ops.size(), "run_op: bad index");
+    B2D_CHECK(n > 0 && n <= e->max_batch, "run_op: n=%d outside [1,%d]", n, e->max_batch);
+    return launch_op(e, e->ops[i], n, (cudaStream_t)stream);
+}
+
+int b2d_forward(b2d_engine* e, int n, void* stream) {
+    B2D_CHECK(e && e->finalized, "forward: plan not finalized");
+    B2D_CHECK(n > 0 && n <= e->max_batch, "forward: n=%d outside [1,%d]", n, e->max_batch);
+    for (const Op& op : e->ops)
+        if (int r = launch_op(e, op, n, (cudaStream_t)stream)) return r;
+    return 0;
+}
+
+int b2d_preprocess(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, int pitch, long long img_stride, int mode, int bgr,
+                   int out_kind, void* dst_dev, void* stream) {
+    B2D_CHECK(e && src_dev && n > 0, "preprocess: bad arguments");
+    B2D_CHECK(pitch >= w * 3, "preprocess: pitch %d < row bytes %d", pitch, w * 3);
+    int out = 640;
+    if (!e->bufs.empty()) out = e->bufs[0].h;
+    if (dst_dev == nullptr) {
+        B2D_CHECK(out_kind == B2D_OUT_BF16_NHWC4 && !e->bufs.empty() && e->bufs[0].c == 4 && !e->bufs[0].f32,
+                  "preprocess: dst NULL needs the planned bf16 NHWC4 input buffer");
+        B2D_CHECK(n <= e->max_batch, "preprocess: n=%d exceeds max_batch %d", n, e->max_batch);
+        dst_dev = e->bufs[0].ptr;
+    }
+    const ResizeTables* t = nullptr;
+    if (get_tables(e, mode, h, w, out, n, &t)) return -1;
+    return preprocess_launch(t, src_dev, n, pitch, img_stride, bgr, out_kind, dst_dev, out, (cudaStream_t)stream);
+}
+
+int b2d_set_input_f32(b2d_engine* e, const float* src_dev, int n, void* stream) {
+    B2D_CHECK(e && src_dev && n > 0 && n <= e->max_batch, "set_input_f32: bad arguments");
+    B2D_CHECK(!e->bufs.empty() && e->bufs[0].c == 4 && !e->bufs[0].f32, "set_input_f32: no planned bf16 NHWC4 input buffer");
+    return input_from_f32_launch(src_dev, n, e->bufs[0].h, e->bufs[0].w, e->bufs[0].ptr, (cudaStream_t)stream);
+}
+
+int b2d_decode_rows(b2d_engine* e, int n, float* rows_dev, void* stream) {
+    B2D_CHECK(e && e->finalized && e->head_levels > 0, "decode_rows: no head planned");
+    B2D_CHECK(n > 0 && n <= e->max_batch && rows_dev, "decode_rows: bad arguments");
+    return decode_rows_launch(&e->head, n, rows_dev, (cudaStream_t)stream);
+}
+
+int b2d_postprocess(b2d_engine* e, int n, float conf_thr, int inclusive, float iou_thr, int top_k, int max_det, b2d_det* dets_dev,
+                    int32_t* counts_dev, int cap, void* stream) {
+    B2D_CHECK(e && e->finalized && e->head_levels > 0, "postprocess: no head planned");
+    B2D_CHECK(n > 0 && n <= e->max_batch && dets_dev && counts_dev && cap > 0, "postprocess: bad arguments");
+    if (ensure_cand(e, n, e->head.rows_total)) return -2;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (candidates_from_head_launch(&e->head, n, conf_thr, inclusive, e->cand, e->cand_count, e->cand_cap, s)) return -2;
+    return select_launch(e->cand, e->cand_count, e->cand_cap, n, e->keys, iou_thr, top_k, max_det, dets_dev, counts_dev, cap, s);
+}
+
+int b2d_postprocess_rows(b2d_engine* e, const float* rows_dev, int n, int num_rows, int ncol, float conf_thr, int inclusive,
+                         float iou_thr, int top_k, int max_det, b2d_det* dets_dev, int32_t* counts_dev, int cap, void* stream) {
+    B2D_CHECK(e && rows_dev && n > 0 && num_rows > 0 && ncol >= 5 && dets_dev && counts_dev && cap > 0, "postprocess_rows: bad arguments");
+    if (ensure_cand(e, n, num_rows)) return -2;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (candidates_from_rows_launch(rows_dev, n, num_rows, ncol, conf_thr, inclusive, e->cand, e->cand_count, e->cand_cap, s)) return -2;
+    return select_launch(e->cand, e->cand_count, e->cand_cap, n, e->keys, iou_thr, top_k, max_det, dets_dev, counts_dev, cap, s);
+}
+
+int b2d_georef(b2d_engine* e, const b2d_det* dets_dev, const int32_t* counts_dev, int n, int cap, int mode, const double* params_dev,
+               b2d_geodet* out_dev, void* stream) {
+    B2D_CHECK(e && dets_dev && counts_dev && params_dev && out_dev, "georef: bad arguments");
+    B2D_CHECK(mode >= 0 && mode <= 2, "georef: unknown mode %d", mode);
+    return georef_launch(dets_dev, counts_dev, n, cap, mode, params_dev, out_dev, (cudaStream_t)stream);
+}
+
+int b2d_dedup(b2d_engine* e, const double* x_dev, const double* y_dev, const float* conf_dev, int count, double thr, int inclusive,
+              uint8_t* keep_dev, void* stream) {
+    B2D_CHECK(e && (count == 0 || (x_dev && y_dev && conf_dev && keep_dev)), "dedup: bad arguments");
+    if (count == 0) return 0;
+    const size_t need = dedup_scratch_bytes(count);
+    if (need > e->dedup_scratch_bytes) {
+        if (e->dedup_scratch) cudaFree(e->dedup_scratch);
+        B2D_CUDA(cudaMalloc(&e->dedup_scratch, need));
+        e->dedup_scratch_bytes = need;
+    }
+    return dedup_launch(x_dev, y_dev, conf_dev, count, thr, inclusive, keep_dev, e->dedup_scratch, e->dedup_scratch_bytes,
+                        (cudaStream_t)stream);
+}
+
+int b2d_utm_forward(b2d_engine* e, const double* lon_dev, const double* lat_dev, int count, int zone, int north, double* x_dev,
+                    double* y_dev, void* stream) {
+    B2D_CHECK(e && (count == 0 || (lon_dev && lat_dev && x_dev && y_dev)), "utm_forward: bad arguments");
+    B2D_CHECK(zone >= 1 && zone <= 60, "utm_forward: zone %d", zone);
+    return utm_forward_launch(lon_dev, lat_dev, count, zone, north, x_dev, y_dev, (cudaStream_t)stream);
+}
+
+int b2d_cut_windows(b2d_engine* e, const uint8_t* mosaic_dev, int mh, int mw, long long pitch, const int32_t* origins_dev, int n,
+                    int win, int fill, uint8_t* dst_dev, void* stream) {
+    B2D_CHECK(e && mosaic_dev && origins_dev && dst_dev && n > 0, "cut_windows: bad arguments");
+    return cut_windows_launch(mosaic_dev, mh, mw, pitch, origins_dev, n, win, fill, dst_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

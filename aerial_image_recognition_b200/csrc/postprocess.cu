@@ -1,0 +1,469 @@
+// K4 / K4' / K5 / K6 -- everything between the raw head maps and georeferenced detections.
+//
+//   decode      v8: DFL softmax-expectation + anchor decode + sigmoid (Ultralytics Detect [EXT],
+//                   SURVEY.md section 8a row a5);  v7: in-graph sigmoid/grid/anchor decode (Appendix A.4).
+//   filter      `boxes[boxes[:,4] >= thr]`           simple_detector.py:479-481, :672-673;
+//                                                    _script/gpu_handler.py:166-170 (top-10 at :173)
+//   select      per-tile ordering + (optional) greedy IoU-NMS with Ultralytics' arithmetic
+//               (class-offset boxes, suppress iff IoU > thr, max_det)  -- `model(window)` at
+//               x_arch/02_analyze_images:1 (cell 6)
+//   georef      pixel centre -> lon/lat or CRS metres in fp64 without FMA contraction:
+//               simple_detector.py:484-502, _script/gpu_handler.py:178-190, pixel_to_geo
+//
+// Layout: head maps are NHWC fp32 so one anchor's logits are contiguous; the decode kernels give
+// each anchor to 4 lanes (one per box side) so a warp reads 8 anchors x 256 B = 2 KB contiguous.
+// Candidates are compacted with warp ballots + one atomic per warp; determinism comes from the
+// per-tile sort in `select` (key = confidence, anchor index), never from arrival order.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace {
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- v8: one anchor handled by 4 consecutive lanes; returns the decoded row on every lane ----
+struct Row { float cx, cy, w, h, conf; int cls; };
+
+__device__ __forceinline__ float dfl_side(const float* p) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 q = __ldg((const float4*)p + j);
+        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+    }
+    float m = v[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
+    float s = 0.f, e = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float t = expf(v[j] - m);
+        s += t;
+        e += t * (float)j;
+    }
+    return e / s;
+}
+
+__device__ __forceinline__ void v8_scores(const float* pix, int nc, float* conf, int* cls) {
+    float best = -1.f;
+    int bi = 0;
+    for (int k = 0; k < nc; ++k) {
+        const float s = sigmoid_f(__ldg(pix + 64 + k));
+        if (s > best) { best = s; bi = k; }
+    }
+    *conf = best; *cls = bi;
+}
+
+__device__ __forceinline__ Row v8_box(float side, int lane_side, int gx, int gy, float stride, unsigned mask, int base_lane) {
+    // gather l,t,r,b from the 4 lanes of this anchor
+    const float l = __shfl_sync(mask, side, base_lane + 0);
+    const float t = __shfl_sync(mask, side, base_lane + 1);
+    const float r = __shfl_sync(mask, side, base_lane + 2);
+    const float b = __shfl_sync(mask, side, base_lane + 3);
+    (void)lane_side;
+    const float ax = (float)gx + 0.5f, ay = (float)gy + 0.5f;
+    const float x1 = __fsub_rn(ax, l), y1 = __fsub_rn(ay, t), x2 = __fadd_rn(ax, r), y2 = __fadd_rn(ay, b);
+    Row o;
+    o.cx = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), stride);
+    o.cy = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), stride);
+    o.w = __fmul_rn(__fsub_rn(x2, x1), stride);
+    o.h = __fmul_rn(__fsub_rn(y2, y1), stride);
+    o.conf = 0.f; o.cls = 0;
+    return o;
+}
+
+// ---- v7: one thread per (anchor box, cell) ------------------------------------------------------
+__device__ __forceinline__ Row v7_row(const float* cell, int nc, int gx, int gy, float stride, float aw, float ah) {
+    Row o;
+    const float sx = sigmoid_f(__ldg(cell + 0)), sy = sigmoid_f(__ldg(cell + 1));
+    const float sw = sigmoid_f(__ldg(cell + 2)), sh = sigmoid_f(__ldg(cell + 3));
+    o.cx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), (float)gx), stride);
+    o.cy = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), (float)gy), stride);
+    const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
+    o.w = __fmul_rn(__fmul_rn(tw, tw), aw);
+    o.h = __fmul_rn(__fmul_rn(th, th), ah);
+    o.conf = sigmoid_f(__ldg(cell + 4));
+    float best = -1.f; int bi = 0;
+    for (int k = 0; k < nc; ++k) {
+        const float s = sigmoid_f(__ldg(cell + 5 + k));
+        if (s > best) { best = s; bi = k; }
+    }
+    o.cls = bi;
+    return o;
+}
+
+__device__ __forceinline__ bool passes(float conf, float thr, int inclusive) { return inclusive ? (conf >= thr) : (conf > thr); }
+
+// Shared body: MODE 0 = dense rows, MODE 1 = thresholded candidates.
+template <int MODE>
+__global__ void __launch_bounds__(256) head_kernel(HeadDesc h, int n, float thr, int inclusive, float* rows, b2d_det* cand,
+                                                   int* cand_count, int cand_cap) {
+    const int tile = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    if (h.kind == B2D_HEAD_V8_DFL) {
+        // 4 lanes per anchor
+        const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;    // anchor index inside the tile
+        const int side = threadIdx.x & 3;
+        const bool in_range = a < h.rows_total;
+        int lvl = 0;
+        if (in_range) { while (lvl + 1 < h.nlevels && a >= h.lv[lvl + 1].row0) ++lvl; }
+        const HeadLevel& L = h.lv[lvl];
+        const int cell = in_range ? a - L.row0 : 0;
+        const int gy = cell / L.hw, gx = cell - gy * L.hw;
+        const float* pix = L.buf + ((size_t)tile * L.hw * L.hw + cell) * L.c;
+        float conf = 0.f; int cls = 0;
+        bool want = in_range;
+        if (in_range) {
+            v8_scores(pix, h.nc, &conf, &cls);
+            if (MODE == 1) want = passes(conf, thr, inclusive);
+        }
+        // the 4 lanes of an anchor agree on `want`; decode only where some anchor of the warp needs it
+        const unsigned any = __ballot_sync(0xffffffffu, want);
+        if (any == 0) return;
+        float sidev = 0.f;
+        if (want) sidev = dfl_side(pix + side * 16);
+        Row r = v8_box(sidev, side, gx, gy, (float)L.stride, 0xffffffffu, lane & ~3);
+        r.conf = conf; r.cls = cls;
+        if (MODE == 0) {
+            if (in_range && side == 0) {
+                float* o = rows + ((size_t)tile * h.rows_total + a) * 6;
+                o[0] = r.cx; o[1] = r.cy; o[2] = r.w; o[3] = r.h; o[4] = r.conf; o[5] = (float)r.cls;
+            }
+        } else {
+            const bool emit = want && side == 0;
+            const unsigned em = __ballot_sync(0xffffffffu, emit);
+            if (em) {
+                int base = 0;
+                const int leader = __ffs(em) - 1;
+                if (lane == leader) base = atomicAdd(&cand_count[tile], __popc(em));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (emit) {
+                    const int slot = base + __popc(em & ((1u << lane) - 1));
+                    if (slot < cand_cap) {
+                        b2d_det d;
+                        d.cx = r.cx; d.cy = r.cy; d.w = r.w; d.h = r.h; d.conf = r.conf; d.cls = r.cls; d.tile = tile; d.anchor = a;
+                        cand[(size_t)tile * cand_cap + slot] = d;
+                    }
+                }
+            }
+        }
+    } else {
+        const int a = blockIdx.x * blockDim.x + threadIdx.x;   // row index inside the tile
+        const bool in_range = a < h.rows_total;
+        int lvl = 0;
+        if (in_range) { while (lvl + 1 < h.nlevels && a >= h.lv[lvl + 1].row0) ++lvl; }
+        const HeadLevel& L = h.lv[lvl];
+        const int no = h.nc + 5;
+        const int rel = in_range ? a - L.row0 : 0;
+        const int cells = L.hw * L.hw;
+        const int ai = rel / cells, cell = rel - ai * cells;     // rows ordered anchor, y, x inside a level
+        const int gy = cell / L.hw, gx = cell - gy * L.hw;
+        Row r; r.conf = -1.f;
+        if (in_range) {
+            const float* p = L.buf + ((size_t)tile * cells + cell) * L.c + ai * no;
+            r = v7_row(p, h.nc, gx, gy, (float)L.stride, L.anchors[2 * ai], L.anchors[2 * ai + 1]);
+        }
+        if (MODE == 0) {
+            if (in_range) {
+                float* o = rows + ((size_t)tile * h.rows_total + a) * 6;
+                o[0] = r.cx; o[1] = r.cy; o[2] = r.w; o[3] = r.h; o[4] = r.conf; o[5] = (float)r.cls;
+            }
+        } else {
+            const bool emit = in_range && passes(r.conf, thr, inclusive);
+            const unsigned em = __ballot_sync(0xffffffffu, emit);
+            if (em) {
+                int base = 0;
+                const int leader = __ffs(em) - 1;
+                if (lane == leader) base = atomicAdd(&cand_count[tile], __popc(em));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (emit) {
+                    const int slot = base + __popc(em & ((1u << lane) - 1));
+                    if (slot < cand_cap) {
+                        b2d_det d;
+                        d.cx = r.cx; d.cy = r.cy; d.w = r.w; d.h = r.h; d.conf = r.conf; d.cls = r.cls; d.tile = tile; d.anchor = a;
+                        cand[(size_t)tile * cand_cap + slot] = d;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// candidates from already-decoded rows [n][num_rows][ncol]
+__global__ void __launch_bounds__(256) rows_filter_kernel(const float* __restrict__ rows, int num_rows, int ncol, float thr,
+                                                           int inclusive, b2d_det* cand, int* cand_count, int cand_cap) {
+    const int tile = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in_range = a < num_rows;
+    const float* p = rows + ((size_t)tile * num_rows + (in_range ? a : 0)) * ncol;
+    const float conf = in_range ? __ldg(p + 4) : -1.f;
+    const bool emit = in_range && passes(conf, thr, inclusive);
+    const unsigned em = __ballot_sync(0xffffffffu, emit);
+    if (!em) return;
+    int base = 0;
+    const int leader = __ffs(em) - 1;
+    if (lane == leader) base = atomicAdd(&cand_count[tile], __popc(em));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (emit) {
+        const int slot = base + __popc(em & ((1u << lane) - 1));
+        if (slot < cand_cap) {
+            b2d_det d;
+            d.cx = __ldg(p); d.cy = __ldg(p + 1); d.w = __ldg(p + 2); d.h = __ldg(p + 3); d.conf = conf;
+            d.cls = (ncol > 5) ? (int)__ldg(p + 5) : 0;
+            d.tile = tile; d.anchor = a;
+            cand[(size_t)tile * cand_cap + slot] = d;
+        }
+    }
+}
+
+// ---- select: per-tile sort (+ NMS) ----------------------------------------------------------------
+constexpr int kSelThreads = 256;
+constexpr int kSmemKeys = 2048;
+constexpr int kMaxDet = 512;
+
+__device__ void bitonic_sort(unsigned long long* keys, int n2) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& b, float ab, float thr) {
+    // torchvision nms arithmetic: inter / (area_a + area_b - inter) > thr, fp32, no contraction
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+    return ovr > thr;
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __restrict__ cand, const int* __restrict__ cand_count,
+                                                              int cand_cap, unsigned long long* keys_scratch, int keys_stride,
+                                                              float iou_thr, int top_k, int max_det, b2d_det* out, int* out_count,
+                                                              int cap) {
+    __shared__ unsigned long long skeys[kSmemKeys];
+    __shared__ float4 kbox[kMaxDet];
+    __shared__ float karea[kMaxDet];
+    __shared__ float4 cbox[kSelThreads];
+    __shared__ float carea[kSelThreads];
+    __shared__ unsigned long long cmask[kSelThreads][kSelThreads / 64];
+    __shared__ unsigned int alive_w[kSelThreads / 32];
+    __shared__ int keep_slot[kSelThreads];
+    __shared__ int s_nk;
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    int cnt = cand_count[tile];
+    if (cnt > cand_cap) cnt = cand_cap;
+    const b2d_det* tc = cand + (size_t)tile * cand_cap;
+    b2d_det* to = out + (size_t)tile * cap;
+    if (cnt == 0) {
+        if (tid == 0) out_count[tile] = 0;
+        return;
+    }
+    int n2 = 1;
+    while (n2 < cnt) n2 <<= 1;
+    unsigned long long* keys = (n2 <= kSmemKeys) ? skeys : (keys_scratch + (size_t)tile * keys_stride);
+    const bool by_conf = (iou_thr > 0.f) || (top_k > 0);
+    for (int i = tid; i < n2; i += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (i < cnt) {
+            const unsigned a = (unsigned)tc[i].anchor & 0x1FFFFu;
+            const unsigned long long lo = ((unsigned long long)a << 15) | (unsigned long long)(i & 0x7FFF);
+            if (by_conf) k = ((unsigned long long)(~__float_as_uint(tc[i].conf)) << 32) | lo;   // conf desc, anchor asc
+            else k = lo;                                                                     // row order
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    bitonic_sort(keys, n2);
+
+    if (!(iou_thr > 0.f)) {
+        int m = cnt;
+        if (top_k > 0 && m > top_k) m = top_k;
+        if (m > cap) m = cap;
+        for (int i = tid; i < m; i += blockDim.x) to[i] = tc[(int)(keys[i] & 0x7FFF)];
+        if (tid == 0) out_count[tile] = m;
+        return;
+    }
+
+    // ---- greedy NMS over the sorted list, 256 candidates at a time ----
+    if (max_det > kMaxDet) max_det = kMaxDet;
+    if (max_det > cap) max_det = cap;
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+    for (int base = 0; base < cnt; base += kSelThreads) {
+        const int nk = s_nk;
+        if (nk >= max_det) break;
+        const int i = base + tid;
+        const int chunk_n = min(kSelThreads, cnt - base);
+        const bool valid = i < cnt;
+        b2d_det d;
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ar = 0.f;
+        if (valid) {
+            d = tc[(int)(keys[i] & 0x7FFF)];
+            // xywh2xyxy then + cls * max_wh, as Ultralytics
+            const float hw = __fmul_rn(d.w, 0.5f), hh = __fmul_rn(d.h, 0.5f);
+            const float off = __fmul_rn((float)d.cls, 7680.0f);
+            bx.x = __fadd_rn(__fsub_rn(d.cx, hw), off);
+            bx.y = __fadd_rn(__fsub_rn(d.cy, hh), off);
+            bx.z = __fadd_rn(__fadd_rn(d.cx, hw), off);
+            bx.w = __fadd_rn(__fadd_rn(d.cy, hh), off);
+            ar = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+        }
+        cbox[tid] = bx;
+        carea[tid] = ar;
+        bool alive = valid;
+        for (int k = 0; k < nk && alive; ++k)
+            if (iou_gt(kbox[k], karea[k], bx, ar, iou_thr)) alive = false;
+        __syncthreads();
+        // which later candidates of this chunk does `tid` suppress?
+#pragma unroll
+        for (int w = 0; w < kSelThreads / 64; ++w) {
+            unsigned long long m = 0;
+            if (valid) {
+                for (int jj = 0; jj < 64; ++jj) {
+                    const int j = w * 64 + jj;
+                    if (j > tid && j < chunk_n && iou_gt(bx, ar, cbox[j], carea[j], iou_thr)) m |= (1ull << jj);
+                }
+            }
+            cmask[tid][w] = m;
+        }
+        const unsigned al = __ballot_sync(0xffffffffu, alive);
+        if ((tid & 31) == 0) alive_w[tid >> 5] = al;
+        keep_slot[tid] = -1;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long removed[kSelThreads / 64] = {0, 0, 0, 0};
+            int k = nk;
+            for (int j = 0; j < chunk_n && k < max_det; ++j) {
+                const bool a = (alive_w[j >> 5] >> (j & 31)) & 1u;
+                if (!a || ((removed[j >> 6] >> (j & 63)) & 1ull)) continue;
+                keep_slot[j] = k++;
+#pragma unroll
+                for (int w = 0; w < kSelThreads / 64; ++w) removed[w] |= cmask[j][w];
+            }
+            s_nk = k;
+        }
+        __syncthreads();
+        const int slot = keep_slot[tid];
+        if (slot >= 0) {
+            kbox[slot] = bx;
+            karea[slot] = ar;
+            to[slot] = d;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out_count[tile] = s_nk;
+}
+
+// ---- georef -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) georef_kernel(const b2d_det* __restrict__ dets, const int* __restrict__ counts, int cap, int mode,
+                                                      const double* __restrict__ params, b2d_geodet* __restrict__ out) {
+    const int tile = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[tile] || i >= cap) return;
+    const b2d_det d = dets[(size_t)tile * cap + i];
+    const double* P = params + (size_t)tile * B2D_GEO_PARAMS;
+    b2d_geodet g;
+    g.conf = d.conf; g.tile = tile; g.x_yolo = d.cx; g.y_yolo = d.cy; g.x_img = 0.f; g.y_img = 0.f;
+    const double x = (double)d.cx, y = (double)d.cy;
+    if (mode == B2D_GEO_BOUNDS) {
+        // simple_detector.py:487-494 -- P = west, east, south, north, crop_size, model_size
+        const double ms = P[5] > 0.0 ? P[5] : 640.0;
+        const double xf = __ddiv_rn(x, ms), yf = __ddiv_rn(y, ms);
+        g.x_img = (float)__dmul_rn(xf, P[4]);
+        g.y_img = (float)__dmul_rn(yf, P[4]);
+        g.x = __dadd_rn(P[0], __dmul_rn(xf, __dsub_rn(P[1], P[0])));
+        g.y = __dsub_rn(P[3], __dmul_rn(yf, __dsub_rn(P[3], P[2])));
+    } else if (mode == B2D_GEO_GPUHANDLER) {
+        // gpu_handler.py:182-190 -- P = lon_min, lat_min, lon_max, lat_max; keeps the *864/864 round trip
+        const double x864 = __dmul_rn(__ddiv_rn(x, 640.0), 864.0), y864 = __dmul_rn(__ddiv_rn(y, 640.0), 864.0);
+        g.x_img = (float)x864; g.y_img = (float)y864;
+        g.x = __dadd_rn(P[0], __dmul_rn(__ddiv_rn(x864, 864.0), __dsub_rn(P[2], P[0])));
+        g.y = __dsub_rn(P[3], __dmul_rn(__ddiv_rn(y864, 864.0), __dsub_rn(P[3], P[1])));
+    } else {
+        // Ultralytics scale_boxes (fp32) then the notebook's centroid + pixel_to_geo (fp64)
+        // P = gt[0..5], win_x, win_y, pad_x, pad_y, gain, w0, h0
+        const float hw = __fmul_rn(d.w, 0.5f), hh = __fmul_rn(d.h, 0.5f);
+        float x1 = __fsub_rn(d.cx, hw), y1 = __fsub_rn(d.cy, hh), x2 = __fadd_rn(d.cx, hw), y2 = __fadd_rn(d.cy, hh);
+        const float px = (float)P[8], py = (float)P[9], gain = (float)P[10], w0 = (float)P[11], h0 = (float)P[12];
+        x1 = __fdiv_rn(__fsub_rn(x1, px), gain); x2 = __fdiv_rn(__fsub_rn(x2, px), gain);
+        y1 = __fdiv_rn(__fsub_rn(y1, py), gain); y2 = __fdiv_rn(__fsub_rn(y2, py), gain);
+        x1 = fminf(fmaxf(x1, 0.f), w0); x2 = fminf(fmaxf(x2, 0.f), w0);
+        y1 = fminf(fmaxf(y1, 0.f), h0); y2 = fminf(fmaxf(y2, 0.f), h0);
+        // (x1 + x2) is an fp32 add; "/ 2" and "+= x" promote to float64 under the reference's NumPy 1.26
+        const double cxp = __dadd_rn(__ddiv_rn((double)__fadd_rn(x1, x2), 2.0), P[6]);
+        const double cyp = __dadd_rn(__ddiv_rn((double)__fadd_rn(y1, y2), 2.0), P[7]);
+        g.x_img = (float)cxp; g.y_img = (float)cyp;
+        g.x = __dadd_rn(__dadd_rn(P[0], __dmul_rn(cxp, P[1])), __dmul_rn(cyp, P[2]));
+        g.y = __dadd_rn(__dadd_rn(P[3], __dmul_rn(cxp, P[4])), __dmul_rn(cyp, P[5]));
+    }
+    out[(size_t)tile * cap + i] = g;
+}
+
+}  // namespace
+
+int decode_rows_launch(const HeadDesc* h, int n, float* rows, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    const int per = (h->kind == B2D_HEAD_V8_DFL) ? 4 : 1;
+    dim3 grid(ceil_div(h->rows_total * per, 256), n);
+    head_kernel<0><<<grid, 256, 0, stream>>>(*h, n, 0.f, 1, rows, nullptr, nullptr, 0);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+int candidates_from_head_launch(const HeadDesc* h, int n, float thr, int inclusive, b2d_det* cand, int* cand_count, int cand_cap,
+                                cudaStream_t stream) {
+    if (n <= 0) return 0;
+    B2D_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * n, stream));
+    const int per = (h->kind == B2D_HEAD_V8_DFL) ? 4 : 1;
+    dim3 grid(ceil_div(h->rows_total * per, 256), n);
+    head_kernel<1><<<grid, 256, 0, stream>>>(*h, n, thr, inclusive, nullptr, cand, cand_count, cand_cap);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+int candidates_from_rows_launch(const float* rows, int n, int num_rows, int ncol, float thr, int inclusive, b2d_det* cand,
+                                int* cand_count, int cand_cap, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    B2D_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * n, stream));
+    dim3 grid(ceil_div(num_rows, 256), n);
+    rows_filter_kernel<<<grid, 256, 0, stream>>>(rows, num_rows, ncol, thr, inclusive, cand, cand_count, cand_cap);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+int select_launch(const b2d_det* cand, const int* cand_count, int cand_cap, int n, unsigned long long* keys_scratch, float iou_thr,
+                  int top_k, int max_det, b2d_det* out, int* out_count, int cap, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    B2D_CHECK(cand_cap <= 32768, "select: candidate capacity %d exceeds the 15-bit slot field", cand_cap);
+    int stride = 1;
+    while (stride < cand_cap) stride <<= 1;
+    select_kernel<<<n, kSelThreads, 0, stream>>>(cand, cand_count, cand_cap, keys_scratch, stride, iou_thr, top_k, max_det, out,
+                                                 out_count, cap);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+int georef_launch(const b2d_det* dets, const int* counts, int n, int cap, int mode, const double* params, b2d_geodet* out,
+                  cudaStream_t stream) {
+    if (n <= 0 || cap <= 0) return 0;
+    dim3 grid(ceil_div(cap, 256), n);
+    georef_kernel<<<grid, 256, 0, stream>>>(dets, counts, cap, mode, params, out);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,68 @@
+"""Synthetic orthophoto tiles and mosaics.
+
+Stand-in for the network tile sources ``_script/wms_handler.py:196-249`` and
+``_script/xyz_handler.py:228-248`` (out of scope: they are HTTP clients).  The
+generator is procedural in ``(seed, block_y, block_x)`` so any rank can
+materialise any part of a mosaic without host traffic, and the same function is
+used for single tiles (BASELINE config C2/C3) and the sliding-window mosaic (C4).
+
+Statistics follow the reference's own imagery: per-channel mean ~90-145 and std
+~45-55 (``img/srodmiescie.tiff.aux.xml`` band stats; ``test_tile.jpg``
+mean 144 / std 48), low-frequency background plus car-sized bright/dark
+rectangles (~45x20 px at 10 cm/px, i.e. ``tile_size_meters 64`` / 640 px,
+``_script/config.py:13``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BLOCK = 512  # mosaic generation granularity (px)
+
+
+def _lowfreq(rng, h, w, cells=8):
+    gh, gw = h // cells + 2, w // cells + 2
+    coarse = rng.normal(0.0, 1.0, size=(gh, gw, 3)).astype(np.float32)
+    ys = (np.arange(h, dtype=np.float32) + 0.5) / cells
+    xs = (np.arange(w, dtype=np.float32) + 0.5) / cells
+    y0 = np.floor(ys).astype(np.int64); x0 = np.floor(xs).astype(np.int64)
+    fy = (ys - y0)[:, None, None]; fx = (xs - x0)[None, :, None]
+    a = coarse[y0][:, x0]; b = coarse[y0][:, x0 + 1]
+    c = coarse[y0 + 1][:, x0]; d = coarse[y0 + 1][:, x0 + 1]
+    return (a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy
+
+
+def make_block(seed: int, by: int, bx: int, h: int = BLOCK, w: int = BLOCK, cars: int = 24) -> np.ndarray:
+    """uint8 [h, w, 3] block, deterministic in (seed, by, bx)."""
+    rng = np.random.default_rng([1234, seed, by, bx])
+    base = np.array([118.0, 121.0, 112.0], dtype=np.float32)
+    img = base + 38.0 * _lowfreq(rng, h, w, 64) + 22.0 * _lowfreq(rng, h, w, 8)
+    img += rng.normal(0.0, 9.0, size=(h, w, 3)).astype(np.float32)
+    for _ in range(cars):
+        cw, ch = (45, 20) if rng.random() < 0.5 else (20, 45)
+        cw += int(rng.integers(-4, 5)); ch += int(rng.integers(-3, 4))
+        x = int(rng.integers(0, max(1, w - cw))); y = int(rng.integers(0, max(1, h - ch)))
+        col = rng.choice([25.0, 60.0, 200.0, 235.0]) + rng.normal(0, 8.0, size=3)
+        img[y:y + ch, x:x + cw] = col.astype(np.float32)
+        img[y + ch // 4:y + 3 * ch // 4, x + cw // 4:x + 3 * cw // 4] *= 0.8
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def make_tiles(n: int, size: int = 640, seed: int = 0) -> np.ndarray:
+    """uint8 [n, size, size, 3] independent tiles (BASELINE configs C2 / C3)."""
+    out = np.empty((n, size, size, 3), dtype=np.uint8)
+    for i in range(n):
+        out[i] = make_block(seed, 1_000_000 + i, 0, size, size, cars=max(4, (size * size * 24) // (512 * 512)))
+    return out
+
+
+def make_mosaic(height: int, width: int, seed: int = 0, y0: int = 0, y1: int | None = None) -> np.ndarray:
+    """uint8 rows [y0, y1) of a ``height x width`` mosaic assembled from 512-px blocks."""
+    y1 = height if y1 is None else y1
+    out = np.empty((y1 - y0, width, 3), dtype=np.uint8)
+    for by in range(y0 // BLOCK, (y1 + BLOCK - 1) // BLOCK):
+        ys, ye = max(y0, by * BLOCK), min(y1, (by + 1) * BLOCK)
+        for bx in range((width + BLOCK - 1) // BLOCK):
+            xs, xe = bx * BLOCK, min(width, (bx + 1) * BLOCK)
+            blk = make_block(seed, by, bx)
+            out[ys - y0:ye - y0, xs:xe] = blk[ys - by * BLOCK:ye - by * BLOCK, :xe - xs]
+    return out

@@ -1,0 +1,175 @@
+/*
+ * b2det -- C ABI of the B200-native tile-detection engine.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * jacgeborys/aerial_image_recognition.  The reference has no
+ * FFI of its own: its hot path is Python calling into the onnxruntime / OpenCV /
+ * Pillow wheels.  Each entry point below therefore cites the *Python call site* it
+ * replaces (file:line relative to the reference root); the ctypes binding a
+ * maintainer would add is shown in INTEGRATION.md and shipped as
+ * aerial_image_recognition_b200/_lib.py.
+ *
+ * Conventions: plain C, no C++ or torch types.  Every function returns 0 on success
+ * and a negative code on failure; b2d_last_error() gives the message (thread-local).
+ * Pointers named *_dev are CUDA device pointers on the engine's device, *_host are
+ * host pointers.  `stream` is a cudaStream_t passed as void*.  An engine belongs to
+ * one GPU and one owner thread (the reference issues all inference from one thread,
+ * SURVEY.md section 8b "Threading").
+ */
+#ifndef B2DET_H
+#define B2DET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_VERSION 100
+
+typedef struct b2d_engine b2d_engine;
+
+/* ---- records ------------------------------------------------------------------------- */
+
+/* One candidate / detection in model-input pixel space (32 bytes). */
+typedef struct b2d_det {
+    float cx, cy, w, h;   /* box centre and size, input pixels (reference rows cols 0-3)   */
+    float conf;           /* reference rows col 4 (v7: objectness; v8 adapter: max class)  */
+    int32_t cls;          /* best class (v8) / 0                                           */
+    int32_t tile;         /* index of the tile inside the batch                            */
+    int32_t anchor;       /* row index inside the tile's output (stable tie-break key)     */
+} b2d_det;
+
+/* One georeferenced detection (40 bytes). */
+typedef struct b2d_geodet {
+    double x, y;          /* lon/lat, or CRS metres for the affine form                    */
+    float conf;
+    float x_img, y_img;   /* SimpleDetector's 'image' {x,y} (simple_detector.py:490-491)   */
+    float x_yolo, y_yolo; /* SimpleDetector's 'yolo'  {x,y} (simple_detector.py:500)       */
+    int32_t tile;
+} b2d_geodet;
+
+/* ---- enums ----------------------------------------------------------------------------- */
+enum { B2D_ACT_NONE = 0, B2D_ACT_SILU = 1 };
+enum { B2D_CONV_AUTO = 0, B2D_CONV_TCGEN05 = 1, B2D_CONV_SIMT = 2 };
+/* resize modes of b2d_preprocess */
+enum {
+    B2D_RESIZE_IDENTITY = 0,     /* input already model-sized (BASELINE configs C2/C3)            */
+    B2D_RESIZE_CV2_LINEAR = 1,   /* cv2.resize(img,(640,640))      -- _script/gpu_handler.py:74-76 */
+    B2D_RESIZE_PIL_BICUBIC = 2,  /* PIL Image.resize((640,640))    -- simple_detector.py:463, :655 */
+    B2D_RESIZE_LETTERBOX = 3     /* Ultralytics LetterBox, pad 114 -- x_arch/02_analyze_images:1 (cell 6) */
+};
+enum { B2D_OUT_BF16_NHWC4 = 0, B2D_OUT_F32_NCHW = 1, B2D_OUT_U8_NHWC = 2 };
+enum { B2D_HEAD_V8_DFL = 0, B2D_HEAD_V7_ANCHOR = 1 };
+/* georeferencing forms */
+enum {
+    B2D_GEO_BOUNDS = 0,      /* simple_detector.py:487-494 : params = west,east,south,north,crop_size   */
+    B2D_GEO_GPUHANDLER = 1,  /* _script/gpu_handler.py:182-190 : params = lon_min,lat_min,lon_max,lat_max */
+    B2D_GEO_AFFINE = 2       /* x_arch/02_analyze_images:1 (cell 6) pixel_to_geo: params = gt[6], win_x, win_y,
+                                pad_x, pad_y, gain, w0, h0 (letterbox undo = Ultralytics scale_boxes) */
+};
+#define B2D_GEO_PARAMS 16    /* doubles per tile in every form */
+
+/* ---- engine lifetime ------------------------------------------------------------------- */
+/* Replaces ort.InferenceSession(...) at _script/gpu_handler.py:61-65 and
+ * simple_detector.py:39-46.  Fails (does not fall back) when no sm_100 device exists. */
+int b2d_create(int device, int max_batch, b2d_engine** out);
+void b2d_destroy(b2d_engine* e);
+const char* b2d_last_error(void);
+int b2d_version(void);
+int b2d_device_sm_count(b2d_engine* e);
+
+/* ---- plan building: the graph onnxruntime would have read from the .onnx file ---------- */
+/* Buffers are NHWC; id 0 must be the network input [max_batch, H, W, 4] bf16.            */
+int b2d_plan_buffer(b2d_engine* e, int h, int w, int c, int is_f32);
+/* weight_host: fp32 [cout][cin][k][k] (deploy form, BN folded); bias_host: fp32 [cout].  */
+int b2d_plan_conv(b2d_engine* e, int src, int src_c0, int cin, int dst, int dst_c0, int cout,
+                  int k, int stride, int act, const float* weight_host, const float* bias_host,
+                  int res, int res_c0, int impl);
+int b2d_plan_dwconv(b2d_engine* e, int src, int src_c0, int dst, int dst_c0, int c, int act,
+                    const float* weight_host, const float* bias_host);
+int b2d_plan_maxpool(b2d_engine* e, int src, int src_c0, int dst, int dst_c0, int c, int k, int stride);
+int b2d_plan_upsample2x(b2d_engine* e, int src, int src_c0, int dst, int dst_c0, int c);
+/* head level: fp32 buffer `buf` [.,hw,hw,c]; anchors_px: 6 floats (v7) or NULL (v8).     */
+int b2d_plan_head_level(b2d_engine* e, int kind, int buf, int stride, int nc, const float* anchors_px);
+int b2d_plan_finalize(b2d_engine* e);
+void* b2d_buffer_ptr(b2d_engine* e, int buf);
+size_t b2d_buffer_bytes(b2d_engine* e, int buf);
+int b2d_num_anchors(b2d_engine* e);
+int b2d_num_kernels_per_forward(b2d_engine* e);
+
+/* ---- stages ---------------------------------------------------------------------------- */
+/* Resize + normalise (/255, IEEE division) + layout.  Replaces simple_detector.py:463-467,
+ * :655-659 and _script/gpu_handler.py:67-92 (and the BGR variant :142-149 via `bgr`).
+ * src_dev: n images uint8 HWC RGB, row pitch `pitch` bytes, image stride `img_stride`.
+ * dst_dev == NULL writes the engine's own input buffer (B2D_OUT_BF16_NHWC4 only).          */
+int b2d_preprocess(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, int pitch,
+                   long long img_stride, int mode, int bgr, int out_kind, void* dst_dev, void* stream);
+
+/* Load the tensor the reference hands to session.run -- float32 [n,3,H,W] in [0,1], RGB
+ * (simple_detector.py:466-467, :474) -- into the engine's bf16 NHWC4 input buffer.              */
+int b2d_set_input_f32(b2d_engine* e, const float* src_dev, int n, void* stream);
+
+/* The network: replaces session.run at simple_detector.py:474, :666 and
+ * _script/gpu_handler.py:165.  Reads buffer 0, leaves raw head maps in the head buffers.   */
+int b2d_forward(b2d_engine* e, int n, void* stream);
+
+/* Dense decode to the layout the reference indexes: rows_dev fp32 [n][A][6]
+ * (cx,cy,w,h,conf,cls) -- outputs[0][0] at simple_detector.py:479 (v7: in-graph decode,
+ * conf = objectness; v8: DFL decode, conf = max class, an adapter -- SURVEY.md section 8b).         */
+int b2d_decode_rows(b2d_engine* e, int n, float* rows_dev, void* stream);
+
+/* Fused decode + confidence filter + compaction (+ IoU-NMS when iou_thr > 0).
+ *  - reference filter: `rows[:,4] >= thr` (inclusive=1), simple_detector.py:480, output in
+ *    row order; top_k > 0 keeps the k best per tile (gpu_handler.py:173);
+ *  - iou_thr > 0: Ultralytics NMS [EXT] (class-offset boxes, suppress iff IoU > thr, at most
+ *    max_det per tile, output in descending confidence).
+ * dets_dev: [n][cap]; counts_dev: int32 [n] (number written per tile, <= cap).               */
+int b2d_postprocess(b2d_engine* e, int n, float conf_thr, int inclusive, float iou_thr, int top_k,
+                    int max_det, b2d_det* dets_dev, int32_t* counts_dev, int cap, void* stream);
+
+/* Same as above but from caller-supplied rows [n][A][ncol>=6] (tests; YOLOv7-style graphs
+ * whose decode is in the exported model).                                                    */
+int b2d_postprocess_rows(b2d_engine* e, const float* rows_dev, int n, int num_rows, int ncol,
+                         float conf_thr, int inclusive, float iou_thr, int top_k, int max_det,
+                         b2d_det* dets_dev, int32_t* counts_dev, int cap, void* stream);
+
+/* Pixel -> CRS.  params_dev: double [n][B2D_GEO_PARAMS] per tile.  fp64, no FMA contraction.
+ * Replaces simple_detector.py:484-502, gpu_handler.py:178-190, pixel_to_geo.                 */
+int b2d_georef(b2d_engine* e, const b2d_det* dets_dev, const int32_t* counts_dev, int n, int cap,
+               int mode, const double* params_dev, b2d_geodet* out_dev, void* stream);
+
+/* Greedy centre-distance dedup in a metric CRS.  Replaces SimpleDetector._remove_duplicates
+ * (simple_detector.py:558-596, inclusive=1) and ResultsManager.remove_duplicates
+ * (_script/utils.py:229-256, inclusive=0).  Priority = conf desc, then input index asc.
+ * keep_dev: uint8 [count].                                                                    */
+int b2d_dedup(b2d_engine* e, const double* x_dev, const double* y_dev, const float* conf_dev,
+              int count, double thr, int inclusive, uint8_t* keep_dev, void* stream);
+
+/* WGS84 lon/lat -> UTM metres (replaces pyproj at simple_detector.py:551-556).              */
+int b2d_utm_forward(b2d_engine* e, const double* lon_dev, const double* lat_dev, int count,
+                    int zone, int north, double* x_dev, double* y_dev, void* stream);
+
+/* Cut model-sized windows out of a device-resident mosaic (sliding window of
+ * x_arch/02_analyze_images:1 (cell 6)); out-of-mosaic pixels are filled with `fill`.
+ * origins_dev: int32 [n][4] = (x0, y0, w0, h0): the clipped window is centred in the tile
+ * as Ultralytics LetterBox does, no resampling.  dst: uint8 [n][win][win][3].                */
+int b2d_cut_windows(b2d_engine* e, const uint8_t* mosaic_dev, int mh, int mw, long long pitch,
+                    const int32_t* origins_dev, int n, int win, int fill, uint8_t* dst_dev, void* stream);
+
+/* Host-only: the integer coefficient table one axis of b2d_preprocess uses (mode PIL_BICUBIC or
+ * CV2_LINEAR).  bounds_out int32 [out][2], coef_out int32 [out][ksize]; pass NULLs to query ksize. */
+int b2d_resize_table(int mode, int in_size, int out_size, int32_t* bounds_out, int32_t* coef_out, int* ksize_out);
+
+/* Debug / test hooks ---------------------------------------------------------------------- */
+/* Run a single planned op (index in plan order) -- used by the per-layer parity tests.      */
+int b2d_run_op(b2d_engine* e, int op_index, int n, void* stream);
+int b2d_num_ops(b2d_engine* e);
+/* Describe op i: writes a short text (kernel, tile shape, stages) into buf.                 */
+int b2d_describe_op(b2d_engine* e, int op_index, char* buf, int buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2DET_H */
