@@ -136,42 +136,71 @@ __global__ void __launch_bounds__(128) stem_kernel(ConvSimtPlan p, int n) {
     }
 }
 
-// ---- depthwise 3x3, stride 1: thread = (pixel, 8 channels) ---------------------------------
+// ---- depthwise 3x3, stride 1: thread = (8 channels, 4 consecutive output pixels of a row) ------
+// 18 16-byte activation loads and 20 16-byte weight/bias loads produce 32 outputs, so the kernel
+// is bound by HBM/L2 rather than by load-instruction issue.
+constexpr int kDwPix = 4;
 __global__ void __launch_bounds__(256) dwconv_kernel(DwConvPlan p, int n) {
     const int groups = p.c / 8;
-    const long long total = (long long)n * p.h * p.w * groups;
+    const int xt = (p.w + kDwPix - 1) / kDwPix;
+    const long long total = (long long)n * p.h * xt * groups;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int g = (int)(idx % groups);
-    const long long pix = idx / groups;
-    const int x = (int)(pix % p.w);
-    const int y = (int)((pix / p.w) % p.h);
-    const int img = (int)(pix / ((long long)p.w * p.h));
+    long long r = idx / groups;
+    const int x0 = (int)(r % xt) * kDwPix;
+    r /= xt;
+    const int y = (int)(r % p.h);
+    const int img = (int)(r / p.h);
     const int c0 = g * 8;
-    float acc[8];
+    float acc[kDwPix][8];
+    {
+        const float4 b0 = __ldg((const float4*)(p.bias_dev + c0)), b1 = __ldg((const float4*)(p.bias_dev + c0) + 1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = p.bias_dev[c0 + j];
+        for (int i = 0; i < kDwPix; ++i) {
+            acc[i][0] = b0.x; acc[i][1] = b0.y; acc[i][2] = b0.z; acc[i][3] = b0.w;
+            acc[i][4] = b1.x; acc[i][5] = b1.y; acc[i][6] = b1.z; acc[i][7] = b1.w;
+        }
+    }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
         const int iy = y + kh - 1;
         if (iy < 0 || iy >= p.h) continue;
+        float wv[3][8];
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-            const int ix = x + kw - 1;
-            if (ix < 0 || ix >= p.w) continue;
-            const uint4 u = __ldg((const uint4*)(p.src + (((long long)img * p.h + iy) * p.w + ix) * p.src_cs + p.src_c0 + c0));
-            float a[8];
-            unpack8(u, a);
-            const float* w = p.w_dev + (size_t)(kh * 3 + kw) * p.c + c0;
+            const float4* wp = (const float4*)(p.w_dev + (size_t)(kh * 3 + kw) * p.c + c0);
+            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+            wv[kw][0] = w0.x; wv[kw][1] = w0.y; wv[kw][2] = w0.z; wv[kw][3] = w0.w;
+            wv[kw][4] = w1.x; wv[kw][5] = w1.y; wv[kw][6] = w1.z; wv[kw][7] = w1.w;
+        }
+        const __nv_bfloat16* rowp = p.src + ((long long)img * p.h + iy) * p.w * p.src_cs + p.src_c0 + c0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(a[j], __ldg(w + j), acc[j]);
+        for (int j = 0; j < kDwPix + 2; ++j) {
+            const int ix = x0 + j - 1;
+            if (ix < 0 || ix >= p.w) continue;
+            float a[8];
+            unpack8(__ldg((const uint4*)(rowp + (long long)ix * p.src_cs)), a);
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int i = j - kw;            // output pixel fed by this input through tap kw
+                if (i < 0 || i >= kDwPix) continue;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[i][q] = fmaf(a[q], wv[kw][q], acc[i][q]);
+            }
         }
     }
-    if (p.act) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = silu_f(acc[j]);
+    for (int i = 0; i < kDwPix; ++i) {
+        const int x = x0 + i;
+        if (x >= p.w) break;
+        if (p.act) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[i][q] = silu_f(acc[i][q]);
+        }
+        const long long pix = ((long long)img * p.h + y) * p.w + x;
+        *(uint4*)(p.dst + pix * p.dst_cs + p.dst_c0 + c0) = pack8(acc[i]);
     }
-    *(uint4*)(p.dst + pix * p.dst_cs + p.dst_c0 + c0) = pack8(acc);
 }
 
 // ---- max-pool k x k, padding k/2 for stride 1 / none for stride 2 (-inf padding) -------------
@@ -304,7 +333,7 @@ int dwconv_plan(DwConvPlan* plan, const __nv_bfloat16* src, int h, int w, int sr
 }
 
 int dwconv_launch(const DwConvPlan* plan, int n, cudaStream_t stream) {
-    const long long total = (long long)n * plan->h * plan->w * (plan->c / 8);
+    const long long total = (long long)n * plan->h * ((plan->w + kDwPix - 1) / kDwPix) * (plan->c / 8);
     dwconv_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(*plan, n);
     B2D_LAUNCH_CHECK();
     return 0;

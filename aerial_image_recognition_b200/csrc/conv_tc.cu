@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    float* bias_s = (float*)(tmem_slot + 4);          // [n_tile * n_tiles_n] padded bias
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+    for (int i = threadIdx.x; i < p.n_tile * p.n_tiles_n; i += kThreads) bias_s[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -195,17 +197,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             const int pad = p.ksz >> 1;
+            const int nstages = p.stages, taps = p.taps, chunks = p.chunks, ksz = p.ksz, n_tile = p.n_tile;
+            const int cin_pad = chunks * 64;
+            const uint32_t tx_bytes = (uint32_t)(kTileM * 64 * 2) + p.b_tx_bytes;
+            const uint32_t a_bytes = p.a_bytes;
+            const bool s2 = (p.stride == 2);
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(p, t);
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    const int kh = tap / p.ksz, kw = tap - kh * p.ksz;
-                    const CUtensorMap* mapA;
-                    int cx, cy;
-                    if (p.stride == 1) {
-                        mapA = &p.tmA[0];
-                        cx = tc.x0 + kw - pad;
-                        cy = tc.y0 + kh - pad;
-                    } else {
+                const int bn0 = tc.nt * n_tile;
+                int kh = 0, kw = 0;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const CUtensorMap* mapA = &p.tmA[0];
+                    int cx = tc.x0 + kw - pad, cy = tc.y0 + kh - pad;
+                    if (s2) {
                         // input pixel = 2*o + d, d in {-1,0,1}: odd phase for d = +-1, even for 0
                         const int dy = kh - 1, dx = kw - 1;
                         const int py = dy & 1, px = dx & 1;
@@ -213,46 +217,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         cx = tc.x0 + (dx - px) / 2;
                         cy = tc.y0 + (dy - py) / 2;
                     }
-                    for (int ch = 0; ch < p.chunks; ++ch) {
+                    const int kb = tap * cin_pad;
+                    for (int ch = 0; ch < chunks; ++ch) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                        uint8_t* sb = sa + p.a_bytes;
-                        mbar_expect_tx(&full_bar[stage], (uint32_t)(kTileM * p.kc * 2) + p.b_tx_bytes);
-                        tma_load_4d(mapA, &full_bar[stage], sa, ch * p.kc, cx, cy, tc.n0);
-                        tma_load_2d(&p.tmB, &full_bar[stage], sb, tap * p.cin + ch * p.kc, tc.nt * p.n_tile);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        tma_load_4d(mapA, &full_bar[stage], sa, ch * 64, cx, cy, tc.n0);
+                        tma_load_2d(&p.tmB, &full_bar[stage], sa + a_bytes, kb + ch * 64, bn0);
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
+                    if (++kw == ksz) { kw = 0; ++kh; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        const int ksub = p.kc >> 4;   // UMMA_K = 16 for bf16
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            mbar_wait(&tempty_bar[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.n_tile);
-            for (int ks = 0; ks < ksteps; ++ks) {
-                mbar_wait(&full_bar[stage], phase);
+        // ===================== MMA issuer (one elected thread runs the whole loop) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            // descriptor = {lo: start>>4 | LBO<<16, hi: SBO | version | layout}; only `lo` moves
+            const uint32_t hi = (uint32_t)(make_smem_desc(0, p.swizzle_bytes) >> 32);
+            const uint32_t lo_base = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t stage_units = stage_bytes >> 4, a_units = p.a_bytes >> 4;
+            const uint32_t idesc = p.idesc;
+            const int nstages = p.stages, n_tile = p.n_tile;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sb = sa + p.a_bytes;
-                    for (int k = 0; k < ksub; ++k) {
-                        const uint64_t ad = make_smem_desc(sa + k * 32, p.swizzle_bytes);
-                        const uint64_t bd = make_smem_desc(sb + k * 32, p.swizzle_bytes);
-                        umma_bf16(d_tmem, ad, bd, p.idesc, (ks | k) != 0);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = lo_base + (uint32_t)stage * stage_units;
+                    const uint32_t b_lo = a_lo + a_units;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {   // kc = 64 -> four K=16 MMAs, +32 B each
+                        const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + 2 * k);
+                        const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + 2 * k);
+                        umma_bf16(d_tmem, ad, bd, idesc, (k == 0) ? (uint32_t)(ks != 0) : 1u);
                     }
                     umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
                     if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -262,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int lx = row % p.bw;
         const int ly = (row / p.bw) % p.bh;
         const int ln = row / (p.bw * p.bh);
+        const int n_tile = p.n_tile, cout = p.cout, act = p.act;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int as = it & 1;
@@ -270,58 +281,70 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int ox = tc.x0 + lx, oy = tc.y0 + ly, img = tc.n0 + ln;
             const bool valid = (ox < p.W) && (oy < p.H) && (img < nimg);
             const long long pix = ((long long)img * p.H + oy) * p.W + ox;
+            const int ch_base = tc.nt * n_tile;
+            const float* bs = bias_s + ch_base;
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.n_tile);
-            const int ch_base = tc.nt * p.n_tile;
-            for (int c = 0; c < p.n_tile; c += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + c, r);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * n_tile);
+            for (int c = 0; c < n_tile; c += 32) {
+                uint32_t r[32];
+                const bool two = (c + 16 < n_tile);
+                tmem_ld16(taddr + c, *(uint32_t(*)[16])&r[0]);
+                if (two) tmem_ld16(taddr + c + 16, *(uint32_t(*)[16])&r[16]);
                 tmem_ld_wait();
-                const int ch0 = ch_base + c;
-                if (!valid || ch0 >= p.cout) continue;
-                float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float a = __uint_as_float(r[j]) + __ldg(&p.bias[ch0 + j]);
-                    v[j] = p.act ? silu(a) : a;
-                }
-                const bool full16 = (ch0 + 16 <= p.cout);
-                if (p.res != nullptr) {
-                    const __nv_bfloat16* rp = p.res + pix * p.res_cs + p.res_c0 + ch0;
-                    if (full16) {
-                        uint4 a = __ldg((const uint4*)rp), b = __ldg((const uint4*)rp + 1);
-                        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int ch0 = ch_base + c + hlf * 16;
+                    if ((hlf == 1 && !two) || !valid || ch0 >= cout) continue;
+                    float v[16];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            v[2 * j] += __uint_as_float(w[j] << 16);
-                            v[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                    for (int j = 0; j < 16; ++j) {
+                        const float a = __uint_as_float(r[hlf * 16 + j]) + bs[c + hlf * 16 + j];
+                        v[j] = act ? silu(a) : a;
+                    }
+                    const bool full16 = (ch0 + 16 <= cout);
+                    if (p.res != nullptr) {
+                        const __nv_bfloat16* rp = p.res + pix * p.res_cs + p.res_c0 + ch0;
+                        if (full16) {
+                            const uint4 a = __ldg((const uint4*)rp), b = __ldg((const uint4*)rp + 1);
+                            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                v[2 * j] += __uint_as_float(w[j] << 16);
+                                v[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (ch0 + j < cout) v[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+                    if (p.out_f32) {
+                        float* op = (float*)p.out + pix * p.out_cs + p.out_c0 + ch0;
+                        if (full16) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) ((float4*)op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (ch0 + j < cout) op[j] = v[j];
                         }
                     } else {
-                        for (int j = 0; j < 16 && ch0 + j < p.cout; ++j) v[j] += __bfloat162float(rp[j]);
-                    }
-                }
-                if (p.out_f32) {
-                    float* op = (float*)p.out + pix * p.out_cs + p.out_c0 + ch0;
-                    if (full16) {
+                        __nv_bfloat16* op = (__nv_bfloat16*)p.out + pix * p.out_cs + p.out_c0 + ch0;
+                        if (full16) {
+                            uint32_t w[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) ((float4*)op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
-                        for (int j = 0; j < 16 && ch0 + j < p.cout; ++j) op[j] = v[j];
-                    }
-                } else {
-                    __nv_bfloat16* op = (__nv_bfloat16*)p.out + pix * p.out_cs + p.out_c0 + ch0;
-                    if (full16) {
-                        uint32_t w[8];
+                            for (int j = 0; j < 8; ++j) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                                w[j] = *(uint32_t*)&h;
+                            }
+                            ((uint4*)op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            ((uint4*)op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                            w[j] = *(uint32_t*)&h;
+                            for (int j = 0; j < 16; ++j)
+                                if (ch0 + j < cout) op[j] = __float2bfloat16_rn(v[j]);
                         }
-                        ((uint4*)op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                        ((uint4*)op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                    } else {
-                        for (int j = 0; j < 16 && ch0 + j < p.cout; ++j) op[j] = __float2bfloat16_rn(v[j]);
                     }
                 }
             }
@@ -395,7 +418,7 @@ void pick_tile(int W, int H, int N, int* bw, int* bh, int* bn) {
 }  // namespace
 
 int conv_tc_supported(int cin, int ksz, int stride) {
-    if (cin % 16 != 0) return 0;
+    if (cin % 8 != 0) return 0;
     if (!((ksz == 1 && stride == 1) || (ksz == 3 && (stride == 1 || stride == 2)))) return 0;
     return 1;
 }
@@ -415,8 +438,8 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.act = act; p.out_f32 = dst_f32;
     p.out = dst; p.out_cs = dst_cs; p.out_c0 = dst_c0;
     p.res = res; p.res_cs = res_cs; p.res_c0 = res_c0;
-    p.kc = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
-    p.chunks = cin / p.kc;
+    p.kc = 64;                          // always a full 128-byte swizzle row; a short last chunk is
+    p.chunks = ceil_div(cin, 64);       // zero-filled by TMA (A) and zero-padded in the packed weights (B)
     p.swizzle_bytes = p.kc * 2;
     const int cout_pad = ceil_div(cout, 16) * 16;
     int split = 1;
@@ -430,7 +453,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.b_tx_bytes = p.n_tile * p.kc * 2;
     p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    const uint32_t budget = 200 * 1024;
+    const uint32_t budget = 200 * 1024 - (uint32_t)cout_pad * 4;
     int stages = (int)(budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     const int ksteps = p.taps * p.chunks;
@@ -442,15 +465,16 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.tmem_cols = cols;
     // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + (size_t)cout_pad * 4 /*bias*/;
 
-    // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin] ----
-    const size_t ktot = (size_t)p.taps * cin;
+    // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin_pad] (zero padded) ----
+    const int cin_pad = p.chunks * 64;
+    const size_t ktot = (size_t)p.taps * cin_pad;
     std::vector<uint16_t> wp((size_t)cout_pad * ktot, 0);
     for (int o = 0; o < cout; ++o)
         for (int c = 0; c < cin; ++c)
             for (int t = 0; t < p.taps; ++t)
-                wp[(size_t)o * ktot + (size_t)t * cin + c] = f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
+                wp[(size_t)o * ktot + (size_t)t * cin_pad + c] = f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
     std::vector<float> bp(cout_pad, 0.f);
     for (int o = 0; o < cout; ++o) bp[o] = b_host ? b_host[o] : 0.f;
     B2D_CUDA(cudaMalloc(&plan->w_dev, wp.size() * 2));

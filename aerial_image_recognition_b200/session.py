@@ -1,0 +1,86 @@
+"""``onnxruntime.InferenceSession``-shaped front of the engine.
+
+Reference code talks to its model through three calls only --
+``session.run(None, {session.get_inputs()[0].name: ndarray})`` and
+``session.get_providers()`` (``simple_detector.py:470-477``, ``:663-669``;
+``_script/gpu_handler.py:165``) -- so this object provides exactly those, backed
+by the B200 engine.  ``run`` takes the float32 ``[B,3,640,640]`` tensor the
+reference builds, and returns ``[rows]`` with ``rows`` float32 ``[B, N, 6]`` =
+``(cx, cy, w, h, conf, cls)`` so that ``outputs[0][0]`` and ``boxes[:, 4]`` keep
+their meaning (``simple_detector.py:479-480``).
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .engine import Engine
+
+
+class _Input:
+    def __init__(self, name, shape):
+        self.name = name
+        self.shape = shape
+        self.type = "tensor(float)"
+
+
+def arch_from_model_path(model_path: Optional[str]) -> str:
+    """The reference selects the network by file name only (``_script/config.py:25``,
+    ``simple_detector.py:710``)."""
+    name = os.path.basename(model_path or "").lower()
+    if "yolov8" in name or "tokyo" in name or "v8" in name:
+        return "yolov8m"
+    if "yolo7" in name or "yolov7" in name or "itcvd" in name:
+        return "yolov7"
+    return "yolov8m"
+
+
+def load_weights(model_path: Optional[str]) -> Optional[Dict[str, np.ndarray]]:
+    """``.npz`` of deploy-form tensors (``model.N....weight`` / ``.bias``) if present.
+    The reference's ``.onnx`` blobs are absent (``.MISSING_LARGE_BLOBS:2-5``); when the
+    path does not exist the engine runs seeded synthetic weights and says so."""
+    if model_path and os.path.exists(model_path) and model_path.endswith(".npz"):
+        with np.load(model_path) as z:
+            return {k: z[k] for k in z.files}
+    if model_path and os.path.exists(model_path):
+        raise NotImplementedError(
+            f"{model_path}: ONNX ingestion is the next row of the scope table (SURVEY.md section 8f-1); "
+            "convert to a deploy-form .npz for now")
+    warnings.warn(f"model file {model_path!r} not found; using seeded synthetic weights", stacklevel=3)
+    return None
+
+
+class InferenceSession:
+    def __init__(self, model_path: Optional[str] = None, sess_options=None, providers=None, *, arch: Optional[str] = None,
+                 weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 8, device: int = 0, seed: int = 0,
+                 engine: Optional[Engine] = None):
+        if engine is None:
+            arch = arch or arch_from_model_path(model_path)
+            if weights is None:
+                weights = load_weights(model_path) if model_path else None
+            engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed)
+        self.engine = engine
+        self._inputs = [_Input("images", [None, 3, engine.imgsz, engine.imgsz])]
+
+    def get_inputs(self) -> List[_Input]:
+        return self._inputs
+
+    def get_providers(self) -> List[str]:
+        # the reference only tests for 'CUDAExecutionProvider' to decide whether to synchronise
+        return ["B200ExecutionProvider", "CUDAExecutionProvider"]
+
+    def run(self, output_names, feed: Dict[str, np.ndarray]):
+        (x,) = feed.values()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        eng = self.engine
+        outs = []
+        for i in range(0, x.shape[0], eng.max_batch):
+            xb = torch.from_numpy(x[i:i + eng.max_batch]).to(eng.device, non_blocking=False)
+            eng.set_input_f32(xb)
+            eng.forward(xb.shape[0])
+            outs.append(eng.decode_rows(xb.shape[0]).cpu().numpy())
+        return [np.concatenate(outs, 0)]

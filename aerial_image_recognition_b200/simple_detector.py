@@ -1,0 +1,133 @@
+"""Drop-in for the inference half of the reference's ``simple_detector.py::SimpleDetector``
+(``:26-57`` constructor attributes, ``:456-504`` detect, ``:506-538`` _process_detections,
+``:540-596`` _remove_duplicates, ``:648-677`` detect_batch).
+
+The tile-fetching half (aiohttp XYZ client, ``:59-453``) is network I/O and out of scope;
+callers hand in PIL images plus the ``preview_info`` dict that ``get_image`` would have
+produced (``preview_info['spatial_info']['bounds']`` = west/east/south/north,
+``preview_info['image_info']['crop_size']``; ``:459-460``).
+
+What runs where:
+  PIL-bicubic resize + /255 + layout   -> K1 on device (bit-exact against Pillow)
+  session.run                          -> the engine
+  ``boxes[:, 4] >= 0.3``               -> fused decode + compaction kernel (row order kept)
+  lon/lat from the tile bounds         -> fp64 georef kernel, reference operation order
+  1 m greedy dedup in UTM              -> UTM projection + grid-hash dedup kernels
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .engine import GEO_PARAMS, Engine, geodets_to_numpy
+from .session import InferenceSession, arch_from_model_path, load_weights
+
+
+def _as_u8_hwc(img) -> np.ndarray:
+    a = np.asarray(img)
+    if a.ndim == 2:
+        a = np.repeat(a[..., None], 3, 2)
+    if a.shape[2] == 4:
+        a = a[..., :3]
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+class SimpleDetector:
+    def __init__(self, model_path, output_dir, *, arch: Optional[str] = None,
+                 weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 8, device: int = 0, seed: int = 0):
+        self.zoom = 21
+        self.model_size = 640
+        self.confidence_threshold = 0.3
+        self.output_dir = output_dir
+        if output_dir:
+            os.makedirs(output_dir, exist_ok=True)
+        earth_circumference = 40075016.686
+        self.meters_per_pixel = earth_circumference / (2 ** self.zoom) / 256
+        arch = arch or arch_from_model_path(model_path)
+        if weights is None and model_path:
+            weights = load_weights(model_path)
+        self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, imgsz=self.model_size)
+        self.model = InferenceSession(engine=self.engine)
+
+    # -- simple_detector.py:456-504 ----------------------------------------------------------
+    def detect(self, image, preview_info):
+        return self.detect_batch([image], [preview_info], batch_size=1)
+
+    # -- simple_detector.py:648-677 ----------------------------------------------------------
+    def detect_batch(self, images, preview_infos, batch_size=4):
+        """The reference loops one image at a time because its ONNX graph is fixed at batch 1
+        (``:649-652``); the result is the concatenation in input order, which a device batch
+        reproduces."""
+        eng = self.engine
+        arrs = [_as_u8_hwc(im) for im in images]
+        out: List[dict] = []
+        i = 0
+        while i < len(arrs):
+            shape = arrs[i].shape
+            j = i
+            while j < len(arrs) and j - i < eng.max_batch and arrs[j].shape == shape:
+                j += 1
+            n = j - i
+            host = torch.from_numpy(np.stack(arrs[i:j])).pin_memory()
+            tiles = host.to(eng.device, non_blocking=True)
+            mode = "identity" if shape[:2] == (self.model_size, self.model_size) else "pil_bicubic"
+            dets, counts = eng.infer(tiles, mode, False, self.confidence_threshold, True)
+            params = np.zeros((n, GEO_PARAMS), dtype=np.float64)
+            for k in range(n):
+                b = preview_infos[i + k]["spatial_info"]["bounds"]
+                params[k, :6] = (b["west"], b["east"], b["south"], b["north"],
+                                 preview_infos[i + k]["image_info"]["crop_size"], self.model_size)
+            geo = eng.georef(dets, counts, torch.from_numpy(params).to(eng.device), "bounds")
+            for g in geodets_to_numpy(geo, counts):
+                out.extend(self._records(g))
+            i = j
+        return out
+
+    @staticmethod
+    def _records(g) -> List[dict]:
+        return [{"lon": float(r["x"]), "lat": float(r["y"]), "confidence": float(r["conf"]),
+                 "image": {"x": float(r["x_img"]), "y": float(r["y_img"])},
+                 "yolo": {"x": float(r["x_yolo"]), "y": float(r["y_yolo"])}} for r in g]
+
+    # -- simple_detector.py:506-538 ----------------------------------------------------------
+    def _process_detections(self, boxes, preview_info):
+        """``boxes``: host rows ``[K, >=5]`` already produced by ``model.run``; filter + georef on
+        the device through the same kernels as ``detect``."""
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+        if boxes.ndim != 2 or boxes.shape[0] == 0:
+            return []
+        eng = self.engine
+        rows = boxes
+        if rows.shape[1] < 6:
+            rows = np.concatenate([rows, np.zeros((rows.shape[0], 6 - rows.shape[1]), np.float32)], 1)
+        rt = torch.from_numpy(rows[None]).to(eng.device)
+        dets, counts = eng.postprocess(1, self.confidence_threshold, True, rows=rt)
+        b = preview_info["spatial_info"]["bounds"]
+        params = np.zeros((1, GEO_PARAMS), dtype=np.float64)
+        params[0, :6] = (b["west"], b["east"], b["south"], b["north"], preview_info["image_info"]["crop_size"], self.model_size)
+        geo = eng.georef(dets, counts, torch.from_numpy(params).to(eng.device), "bounds")
+        return self._records(geodets_to_numpy(geo, counts)[0])
+
+    # -- simple_detector.py:540-596 ----------------------------------------------------------
+    def _remove_duplicates(self, detections, distance_threshold=1.0):
+        if not detections:
+            return []
+        eng = self.engine
+        lon = np.array([d["lon"] for d in detections], dtype=np.float64)
+        lat = np.array([d["lat"] for d in detections], dtype=np.float64)
+        # priority = position in the reference's stable descending sort (:565); passing -rank as the
+        # fp32 "confidence" makes the kernel's (conf desc, index asc) order exactly that sort
+        ranked = sorted(range(len(detections)), key=lambda i: detections[i]["confidence"], reverse=True)
+        conf = np.empty(len(detections), dtype=np.float32)
+        conf[ranked] = -np.arange(len(detections), dtype=np.float32)
+        utm_zone = int((detections[0]["lon"] + 180) / 6) + 1      # :546
+        north = detections[0]["lat"] > 0                           # :547
+        x, y = eng.utm_forward(torch.from_numpy(lon).to(eng.device), torch.from_numpy(lat).to(eng.device), utm_zone, north)
+        keep = eng.dedup(x, y, torch.from_numpy(conf).to(eng.device), float(distance_threshold), inclusive=True).cpu().numpy()
+        idx = np.nonzero(keep)[0]
+        # kept detections come back in descending-confidence order, input order among ties (:565, :590)
+        order = sorted(idx.tolist(), key=lambda i: detections[i]["confidence"], reverse=True)
+        return [detections[i] for i in order]
