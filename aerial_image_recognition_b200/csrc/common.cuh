@@ -138,8 +138,10 @@ int select_launch(const b2d_det* cand, const int* cand_count, int cand_cap, int 
                   float iou_thr, int top_k, int max_det, b2d_det* out, int* out_count, int cap, cudaStream_t stream);
 int georef_launch(const b2d_det* dets, const int* counts, int n, int cap, int mode, const double* params,
                   b2d_geodet* out, cudaStream_t stream);
-int dedup_launch(const double* x, const double* y, const float* conf, int count, double thr, int inclusive,
-                 uint8_t* keep, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+int dedup_launch(const double* x, const double* y, const float* conf, const long long* tiebreak, int count, double thr,
+                 int inclusive, uint8_t* keep, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+int closure_launch(const double* x, const double* y, int count, double thr, int inclusive, uint8_t* flag, void* scratch,
+                   size_t scratch_bytes, cudaStream_t stream);
 size_t dedup_scratch_bytes(int count);
 int utm_forward_launch(const double* lon, const double* lat, int count, int zone, int north, double* x, double* y,
                        cudaStream_t stream);

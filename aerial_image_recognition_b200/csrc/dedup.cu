@@ -56,12 +56,14 @@ __global__ void dedup_build_kernel(DedupTable t, const double* __restrict__ x, c
 }
 
 __global__ void dedup_round_kernel(DedupTable t, const double* __restrict__ x, const double* __restrict__ y,
-                                   const float* __restrict__ conf, int n, double inv_cell, double thr2, int inclusive) {
+                                   const float* __restrict__ conf, const long long* __restrict__ tiebreak, int n, double inv_cell,
+                                   double thr2, int inclusive) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (((volatile uint8_t*)t.state)[i] != 0) return;
     const double xi = x[i], yi = y[i];
     const float ci = conf[i];
+    const long long ki = tiebreak ? tiebreak[i] : (long long)i;
     const long long cx = (long long)floor(xi * inv_cell), cy = (long long)floor(yi * inv_cell);
     bool removed = false, wait = false;
     for (int dx = -1; dx <= 1 && !removed; ++dx)
@@ -78,7 +80,8 @@ __global__ void dedup_round_kernel(DedupTable t, const double* __restrict__ x, c
             for (int j = head; j >= 0; j = t.next[j]) {
                 if (j == i) continue;
                 const float cj = conf[j];
-                if (!(cj > ci || (cj == ci && j < i))) continue;       // only higher-priority points matter
+                const long long kj = tiebreak ? tiebreak[j] : (long long)j;
+                if (!(cj > ci || (cj == ci && kj < ki))) continue;     // only higher-priority points matter
                 const double ddx = __dsub_rn(xi, x[j]), ddy = __dsub_rn(yi, y[j]);
                 const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
                 if (!(inclusive ? (d2 <= thr2) : (d2 < thr2))) continue;
@@ -137,12 +140,44 @@ size_t dedup_scratch_bytes(int count) {
     return (size_t)cap * 8 + (size_t)cap * 4 + (size_t)count * 4 + (size_t)((count + 15) & ~15) + 64;
 }
 
-int dedup_launch(const double* x, const double* y, const float* conf, int count, double thr, int inclusive, uint8_t* keep,
-                 void* scratch, size_t scratch_bytes, cudaStream_t stream) {
-    if (count <= 0) return 0;
+// Seam closure: flag[i] != 0 marks detections that may interact with another shard; the closure
+// propagates the flag along the "within thr" relation until it is stable, so that every
+// connected component of the suppression graph is either entirely flagged or entirely local.
+__global__ void closure_round_kernel(DedupTable t, const double* __restrict__ x, const double* __restrict__ y, int n, double inv_cell,
+                                     double thr2, int inclusive, uint8_t* flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (((volatile uint8_t*)flag)[i]) return;
+    const double xi = x[i], yi = y[i];
+    const long long cx = (long long)floor(xi * inv_cell), cy = (long long)floor(yi * inv_cell);
+    for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy) {
+            const unsigned long long key = pack_cell(cx + dx, cy + dy);
+            unsigned slot = hash_cell(key) & t.cap_mask;
+            int head = -1;
+            while (true) {
+                const long long k = t.cell_key[slot];
+                if (k == -1LL) break;
+                if ((unsigned long long)k == key) { head = t.cell_head[slot]; break; }
+                slot = (slot + 1) & t.cap_mask;
+            }
+            for (int j = head; j >= 0; j = t.next[j]) {
+                if (j == i || !((volatile uint8_t*)flag)[j]) continue;
+                const double ddx = __dsub_rn(xi, x[j]), ddy = __dsub_rn(yi, y[j]);
+                const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                if (inclusive ? (d2 <= thr2) : (d2 < thr2)) {
+                    flag[i] = 1;
+                    atomicAdd(t.flag, 1);
+                    return;
+                }
+            }
+        }
+}
+
+static int build_table(DedupTable& t, const double* x, const double* y, int count, double thr, void* scratch, size_t scratch_bytes,
+                       cudaStream_t stream, double* inv_cell_out) {
     B2D_CHECK(scratch_bytes >= dedup_scratch_bytes(count), "dedup: scratch too small");
     const unsigned cap = table_cap(count);
-    DedupTable t;
     uint8_t* p = (uint8_t*)scratch;
     t.cell_key = (long long*)p; p += (size_t)cap * 8;
     t.cell_head = (int*)p; p += (size_t)cap * 4;
@@ -151,19 +186,47 @@ int dedup_launch(const double* x, const double* y, const float* conf, int count,
     t.state = p;
     t.cap_mask = cap - 1;
     const double cell = thr > 0.0 ? thr : 1.0;
-    const double inv_cell = 1.0 / cell;
-    const double thr2 = thr * thr;
+    *inv_cell_out = 1.0 / cell;
     const int threads = 256;
     const unsigned m = cap > (unsigned)count ? cap : (unsigned)count;
     dedup_init_kernel<<<(m + threads - 1) / threads, threads, 0, stream>>>(t, count, cap);
-    dedup_build_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, x, y, count, inv_cell);
+    dedup_build_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, x, y, count, *inv_cell_out);
     B2D_LAUNCH_CHECK();
+    return 0;
+}
+
+int closure_launch(const double* x, const double* y, int count, double thr, int inclusive, uint8_t* flag, void* scratch,
+                   size_t scratch_bytes, cudaStream_t stream) {
+    if (count <= 0) return 0;
+    DedupTable t;
+    double inv_cell;
+    if (build_table(t, x, y, count, thr, scratch, scratch_bytes, stream, &inv_cell)) return -1;
+    int h_flag = 1;
+    for (int round = 0; h_flag != 0; ++round) {
+        B2D_CUDA(cudaMemsetAsync(t.flag, 0, sizeof(int), stream));
+        closure_round_kernel<<<(count + 255) / 256, 256, 0, stream>>>(t, x, y, count, inv_cell, thr * thr, inclusive, flag);
+        B2D_LAUNCH_CHECK();
+        B2D_CUDA(cudaMemcpyAsync(&h_flag, t.flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        B2D_CUDA(cudaStreamSynchronize(stream));
+        B2D_CHECK(round <= count + 8, "closure: did not converge");
+    }
+    return 0;
+}
+
+int dedup_launch(const double* x, const double* y, const float* conf, const long long* tiebreak, int count, double thr,
+                 int inclusive, uint8_t* keep, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    if (count <= 0) return 0;
+    DedupTable t;
+    double inv_cell;
+    if (build_table(t, x, y, count, thr, scratch, scratch_bytes, stream, &inv_cell)) return -1;
+    const double thr2 = thr * thr;
+    const int threads = 256;
     // Rounds: every round decides at least the highest-priority undecided point, so the loop ends;
     // real data needs a handful of rounds.  The host reads the undecided count back every 4 rounds.
     int h_flag = 1;
     for (int round = 0; h_flag != 0; ++round) {
         B2D_CUDA(cudaMemsetAsync(t.flag, 0, sizeof(int), stream));
-        dedup_round_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, x, y, conf, count, inv_cell, thr2, inclusive);
+        dedup_round_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, x, y, conf, tiebreak, count, inv_cell, thr2, inclusive);
         B2D_LAUNCH_CHECK();
         if ((round & 3) == 3 || count < 4096) {
             B2D_CUDA(cudaMemcpyAsync(&h_flag, t.flag, sizeof(int), cudaMemcpyDeviceToHost, stream));

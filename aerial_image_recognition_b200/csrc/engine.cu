@@ -445,18 +445,31 @@ int b2d_georef(b2d_engine* e, const b2d_det* dets_dev, const int32_t* counts_dev
     return georef_launch(dets_dev, counts_dev, n, cap, mode, params_dev, out_dev, (cudaStream_t)stream);
 }
 
-int b2d_dedup(b2d_engine* e, const double* x_dev, const double* y_dev, const float* conf_dev, int count, double thr, int inclusive,
-              uint8_t* keep_dev, void* stream) {
-    B2D_CHECK(e && (count == 0 || (x_dev && y_dev && conf_dev && keep_dev)), "dedup: bad arguments");
-    if (count == 0) return 0;
+static int ensure_dedup_scratch(b2d_engine* e, int count) {
     const size_t need = dedup_scratch_bytes(count);
     if (need > e->dedup_scratch_bytes) {
         if (e->dedup_scratch) cudaFree(e->dedup_scratch);
         B2D_CUDA(cudaMalloc(&e->dedup_scratch, need));
         e->dedup_scratch_bytes = need;
     }
-    return dedup_launch(x_dev, y_dev, conf_dev, count, thr, inclusive, keep_dev, e->dedup_scratch, e->dedup_scratch_bytes,
+    return 0;
+}
+
+int b2d_dedup(b2d_engine* e, const double* x_dev, const double* y_dev, const float* conf_dev, const long long* tiebreak_dev, int count,
+              double thr, int inclusive, uint8_t* keep_dev, void* stream) {
+    B2D_CHECK(e && (count == 0 || (x_dev && y_dev && conf_dev && keep_dev)), "dedup: bad arguments");
+    if (count == 0) return 0;
+    if (ensure_dedup_scratch(e, count)) return -2;
+    return dedup_launch(x_dev, y_dev, conf_dev, tiebreak_dev, count, thr, inclusive, keep_dev, e->dedup_scratch, e->dedup_scratch_bytes,
                         (cudaStream_t)stream);
+}
+
+int b2d_seam_closure(b2d_engine* e, const double* x_dev, const double* y_dev, int count, double thr, int inclusive, uint8_t* flag_dev,
+                     void* stream) {
+    B2D_CHECK(e && (count == 0 || (x_dev && y_dev && flag_dev)), "seam_closure: bad arguments");
+    if (count == 0) return 0;
+    if (ensure_dedup_scratch(e, count)) return -2;
+    return closure_launch(x_dev, y_dev, count, thr, inclusive, flag_dev, e->dedup_scratch, e->dedup_scratch_bytes, (cudaStream_t)stream);
 }
 
 int b2d_utm_forward(b2d_engine* e, const double* lon_dev, const double* lat_dev, int count, int zone, int north, double* x_dev,

@@ -200,14 +200,26 @@ class Engine:
                                        self.stream), "georef")
         return out
 
-    def dedup(self, x: torch.Tensor, y: torch.Tensor, conf: torch.Tensor, thr: float, inclusive: bool = True) -> torch.Tensor:
+    def dedup(self, x: torch.Tensor, y: torch.Tensor, conf: torch.Tensor, thr: float, inclusive: bool = True,
+              tiebreak: Optional[torch.Tensor] = None) -> torch.Tensor:
         n = x.numel()
         keep = torch.zeros((n,), dtype=torch.uint8, device=self.device)
         if n:
             assert x.dtype == torch.float64 and y.dtype == torch.float64 and conf.dtype == torch.float32
-            _lib.check(self.lib.b2d_dedup(self.h, _ptr(x.contiguous()), _ptr(y.contiguous()), _ptr(conf.contiguous()), n, float(thr),
-                                          int(inclusive), _ptr(keep), self.stream), "dedup")
+            assert tiebreak is None or (tiebreak.dtype == torch.int64 and tiebreak.numel() == n)
+            tb = None if tiebreak is None else tiebreak.contiguous()
+            _lib.check(self.lib.b2d_dedup(self.h, _ptr(x.contiguous()), _ptr(y.contiguous()), _ptr(conf.contiguous()), _ptr(tb), n,
+                                          float(thr), int(inclusive), _ptr(keep), self.stream), "dedup")
         return keep
+
+    def seam_closure(self, x: torch.Tensor, y: torch.Tensor, flag: torch.Tensor, thr: float, inclusive: bool = True) -> torch.Tensor:
+        """In place: closes the uint8 seam flag under the within-thr relation."""
+        n = x.numel()
+        if n:
+            assert flag.dtype == torch.uint8 and flag.is_contiguous() and flag.numel() == n
+            _lib.check(self.lib.b2d_seam_closure(self.h, _ptr(x.contiguous()), _ptr(y.contiguous()), n, float(thr), int(inclusive),
+                                                 _ptr(flag), self.stream), "seam_closure")
+        return flag
 
     def utm_forward(self, lon: torch.Tensor, lat: torch.Tensor, zone: int, north: bool):
         n = lon.numel()

@@ -1,0 +1,236 @@
+"""Sliding-window detection over a large georeferenced mosaic, tile-sharded across GPUs.
+
+Ancestor in the reference: the notebook loop at ``x_arch/02_analyze_images:1 (cell 6)`` --
+``for y in range(0,h,stride): for x in range(0,w,stride): model(window)`` -> boxes with
+``conf > 0.4`` -> centroid + window origin -> ``pixel_to_geo`` -- and the production tiling
+``TileGenerator.generate_tiles`` (``_script/utils.py:26-65``) with ``tile_overlap 0.2``
+(``_script/config.py:15``) followed by the centre-distance dedup
+(``simple_detector.py:540-596``).  BASELINE config C4: 40k x 40k, window 640, stride 512.
+
+Decisions where the reference leaves a choice (stated in DESIGN.md):
+* windows are model-sized (640) so no resampling happens; edge windows are clipped like the
+  notebook's ``min()`` and centred on a 114 canvas (Ultralytics LetterBox without up-scaling);
+* the window grid is y-outer / x-inner, and that order is the global tie-break of the dedup;
+* shards are contiguous bands of window rows (fewest seams).  Each window belongs to exactly one
+  rank, so the only cross-rank interaction is the dedup of detections that sit in the overlap
+  between two bands; only those (closed under the within-threshold relation) are exchanged.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def window_grid(h: int, w: int, win: int = 640, stride: int = 512) -> np.ndarray:
+    """int32 [n, 4] = (x0, y0, w0, h0), y outer / x inner, clipped at the mosaic edge."""
+    ys = np.arange(0, h, stride, dtype=np.int64)
+    xs = np.arange(0, w, stride, dtype=np.int64)
+    yy, xx = np.meshgrid(ys, xs, indexing="ij")
+    x0 = xx.reshape(-1); y0 = yy.reshape(-1)
+    return np.stack([x0, y0, np.minimum(x0 + win, w) - x0, np.minimum(y0 + win, h) - y0], 1).astype(np.int32)
+
+
+def grid_shape(h: int, w: int, stride: int = 512) -> Tuple[int, int]:
+    return (h + stride - 1) // stride, (w + stride - 1) // stride
+
+
+def band_rows(n_rows: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous window-row bands, sizes differing by at most one (larger bands first)."""
+    base, extra = divmod(n_rows, world)
+    out, r = [], 0
+    for k in range(world):
+        m = base + (1 if k < extra else 0)
+        out.append((r, r + m))
+        r += m
+    return out
+
+
+def shard_windows(h: int, w: int, rank: int, world: int, win: int = 640, stride: int = 512):
+    """(windows of this rank int32 [m,4], global ids int64 [m], pixel-row coverage (y_lo, y_hi))."""
+    grid = window_grid(h, w, win, stride)
+    rows, cols = grid_shape(h, w, stride)
+    r0, r1 = band_rows(rows, world)[rank]
+    ids = np.arange(r0 * cols, r1 * cols, dtype=np.int64)
+    mine = grid[ids]
+    if len(mine):
+        cover = (int(mine[:, 1].min()), int((mine[:, 1] + mine[:, 3]).max()))
+    else:
+        cover = (0, 0)
+    return mine, ids, cover
+
+
+def seam_flags(py: np.ndarray, rank: int, covers: Sequence[Tuple[int, int]], margin_px: float) -> np.ndarray:
+    """uint8 flags: detection (mosaic pixel row ``py``) lies within ``margin_px`` of the pixel rows
+    covered by another rank's windows."""
+    flag = np.zeros(len(py), dtype=np.uint8)
+    for r, (lo, hi) in enumerate(covers):
+        if r == rank or hi <= lo:
+            continue
+        flag |= ((py >= lo - margin_px) & (py < hi + margin_px)).astype(np.uint8)
+    return flag
+
+
+def affine_params(windows: np.ndarray, geotransform: Sequence[float], win: int = 640) -> np.ndarray:
+    """float64 [n,16] georef parameters for B2D_GEO_AFFINE: gt[6], win_x, win_y, pad_x, pad_y, gain,
+    w0, h0 (the letterbox undo of Ultralytics ``scale_boxes``; gain is 1 for model-sized windows)."""
+    n = len(windows)
+    p = np.zeros((n, 16), dtype=np.float64)
+    p[:, 0:6] = np.asarray(geotransform, dtype=np.float64)
+    p[:, 6] = windows[:, 0]
+    p[:, 7] = windows[:, 1]
+    p[:, 8] = (win - windows[:, 2]) // 2
+    p[:, 9] = (win - windows[:, 3]) // 2
+    p[:, 10] = 1.0
+    p[:, 11] = windows[:, 2]
+    p[:, 12] = windows[:, 3]
+    return p
+
+
+# -------------------------------------------------------------------------------------------------
+# seam exchange: host-side protocol, independent of the device (tested on CPU with gloo)
+# -------------------------------------------------------------------------------------------------
+RECORD_WORDS = 6   # float64 words per exchanged record: x, y, conf, global window id, slot in window, class
+
+
+def exchange_seam(records, world: int, all_gather_counts: Callable, all_gather_padded: Callable):
+    """records: [k, RECORD_WORDS] float64 array/tensor of this rank's flagged detections.
+    Returns the concatenation over ranks in rank order (same on every rank) and the rank of origin
+    of each row.  Two collectives: counts (world x int64), then a padded payload."""
+    k = int(records.shape[0])
+    counts = all_gather_counts(k)                       # list[int], length world
+    cap = max(max(counts), 1)
+    gathered = all_gather_padded(records, cap)          # list of [cap, RECORD_WORDS]
+    parts, origin = [], []
+    for r in range(world):
+        parts.append(gathered[r][:counts[r]])
+        origin.append(np.full(counts[r], r, dtype=np.int64))
+    return parts, np.concatenate(origin) if origin else np.zeros(0, np.int64)
+
+
+class MosaicDetector:
+    """Runs config C4 on one rank; ``run`` returns this rank's share of the globally deduplicated
+    detections as a structured array (x, y, conf, cls, window, slot)."""
+
+    OUT_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("conf", "<f4"), ("cls", "<i4"), ("window", "<i8"), ("slot", "<i4")])
+
+    def __init__(self, engine, geotransform: Sequence[float], win: int = 640, stride: int = 512, conf: float = 0.4,
+                 nms_conf: float = 0.25, iou: float = 0.7, max_det: int = 300, dedup_thr: float = 1.0, fill: int = 114):
+        self.eng = engine
+        self.gt = tuple(float(v) for v in geotransform)
+        self.win, self.stride = win, stride
+        self.conf, self.nms_conf, self.iou, self.max_det = conf, nms_conf, iou, max_det
+        self.dedup_thr = dedup_thr
+        self.fill = fill
+        assert self.gt[2] == 0.0 and self.gt[4] == 0.0, "seam margins assume an axis-aligned geotransform"
+
+    # ---- per-rank detection over its windows --------------------------------------------------
+    def detect_windows(self, mosaic, windows: np.ndarray, ids: np.ndarray, y_offset: int = 0):
+        """mosaic: uint8 CUDA tensor holding pixel rows [y_offset, y_offset + H_local) of the mosaic.
+        Returns device tensors (x, y, conf, cls, window id, slot, pixel row)."""
+        import torch
+        eng = self.eng
+        dev = eng.device
+        outs = []
+        B = eng.max_batch
+        local = windows.copy()
+        local[:, 1] -= y_offset
+        params_all = affine_params(windows, self.gt, self.win)
+        for s in range(0, len(windows), B):
+            e = min(s + B, len(windows))
+            n = e - s
+            org = torch.from_numpy(local[s:e]).to(dev)
+            tiles = eng.cut_windows(mosaic, org, self.win, self.fill)
+            dets, counts = eng.infer(tiles, "identity", False, self.nms_conf, False, self.iou, 0, self.max_det)
+            geo = eng.georef(dets, counts, torch.from_numpy(params_all[s:e]).to(dev), "affine")
+            cap = dets.shape[1]
+            slot = torch.arange(cap, device=dev, dtype=torch.int32)[None, :].expand(n, cap)
+            valid = slot < counts[:, None]
+            conf = dets[..., 4]
+            valid &= conf > self.conf                        # notebook: box.conf > 0.4
+            g64 = geo.view(torch.float64).view(n, cap, 5)     # x, y, then packed floats
+            gf = geo.view(torch.float32).view(n, cap, 10)
+            wid = torch.from_numpy(ids[s:e]).to(dev)[:, None].expand(n, cap)
+            cls = dets.view(torch.int32)[..., 5]
+            outs.append((g64[..., 0][valid], g64[..., 1][valid], conf[valid], cls[valid], wid[valid], slot[valid], gf[..., 6][valid]))
+        if not outs:
+            z = torch.zeros(0, device=dev)
+            return z.double(), z.double(), z.float(), z.int(), z.long(), z.int(), z.float()
+        return tuple(torch.cat([o[k] for o in outs]) for k in range(7))
+
+    # ---- dedup with seam exchange --------------------------------------------------------------
+    @staticmethod
+    def order_key(wid, slot):
+        """Global total order among equal confidences: window order, then rank inside the window."""
+        return wid * 65536 + slot.long()
+
+    def seam_split(self, x, y, conf, cls, wid, slot, py, rank: int, covers):
+        """Dedup everything that cannot interact with another shard; return (local survivors,
+        records [k, RECORD_WORDS] float64 on device that must be exchanged)."""
+        import torch
+        eng = self.eng
+        key = self.order_key(wid, slot)
+        margin_px = self.dedup_thr / min(abs(self.gt[1]), abs(self.gt[5])) + 1.0
+        flag = torch.from_numpy(seam_flags(py.cpu().numpy(), rank, covers, margin_px)).to(eng.device)
+        eng.seam_closure(x, y, flag, self.dedup_thr, True)
+        seam = flag.bool()
+        lx, ly, lc, lk = x[~seam], y[~seam], conf[~seam], key[~seam]
+        lkeep = eng.dedup(lx, ly, lc, self.dedup_thr, True, tiebreak=lk).bool()
+        local = self._pack(lx[lkeep], ly[lkeep], lc[lkeep], cls[~seam][lkeep], wid[~seam][lkeep], slot[~seam][lkeep])
+        rec = torch.stack([x[seam], y[seam], conf[seam].double(), wid[seam].double(), slot[seam].double(), cls[seam].double()], 1)
+        return local, rec
+
+    def seam_merge(self, parts, origin: np.ndarray, rank: int) -> np.ndarray:
+        """The identical greedy pass every rank runs on the gathered seam records; returns the
+        survivors that originated on ``rank``."""
+        import torch
+        eng = self.eng
+        allrec = torch.cat([p.to(eng.device) for p in parts]) if parts else torch.zeros((0, RECORD_WORDS), dtype=torch.float64, device=eng.device)
+        self.last_seam_records = int(allrec.shape[0])
+        if not allrec.shape[0]:
+            return np.zeros(0, self.OUT_DTYPE)
+        gk = self.order_key(allrec[:, 3].long(), allrec[:, 4].long())
+        gkeep = eng.dedup(allrec[:, 0].contiguous(), allrec[:, 1].contiguous(), allrec[:, 2].float().contiguous(),
+                          self.dedup_thr, True, tiebreak=gk).bool()
+        mine = gkeep & torch.from_numpy(origin == rank).to(eng.device)
+        m = allrec[mine]
+        return self._pack(m[:, 0], m[:, 1], m[:, 2].float(), m[:, 5].int(), m[:, 3].long(), m[:, 4].int())
+
+    def dedup(self, x, y, conf, cls, wid, slot, py, rank: int, world: int, covers, group=None):
+        import torch
+        import torch.distributed as dist
+        eng = self.eng
+        if world == 1:
+            keep = eng.dedup(x, y, conf, self.dedup_thr, True, tiebreak=self.order_key(wid, slot)).bool()
+            return self._pack(x[keep], y[keep], conf[keep], cls[keep], wid[keep], slot[keep])
+        local, rec = self.seam_split(x, y, conf, cls, wid, slot, py, rank, covers)
+
+        # seam part: NCCL all-gather over NVLink (counts, then padded payload)
+        def gather_counts(k):
+            t = torch.tensor([k], dtype=torch.int64, device=eng.device)
+            out = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(out, t, group=group)
+            return [int(o.item()) for o in out]
+
+        def gather_padded(r, cap):
+            pad = torch.zeros((cap, RECORD_WORDS), dtype=torch.float64, device=eng.device)
+            pad[:r.shape[0]] = r
+            out = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(out, pad, group=group)
+            return out
+
+        parts, origin = exchange_seam(rec, world, gather_counts, gather_padded)
+        return np.concatenate([local, self.seam_merge(parts, origin, rank)])
+
+    def _pack(self, x, y, conf, cls, wid, slot) -> np.ndarray:
+        out = np.zeros(int(x.numel()), dtype=self.OUT_DTYPE)
+        out["x"] = x.cpu().numpy(); out["y"] = y.cpu().numpy(); out["conf"] = conf.cpu().numpy()
+        out["cls"] = cls.cpu().numpy(); out["window"] = wid.cpu().numpy(); out["slot"] = slot.cpu().numpy()
+        return out
+
+    def run(self, mosaic, height: int, width: int, rank: int = 0, world: int = 1, y_offset: int = 0, group=None) -> np.ndarray:
+        windows, ids, _ = shard_windows(height, width, rank, world, self.win, self.stride)
+        covers = [shard_windows(height, width, r, world, self.win, self.stride)[2] for r in range(world)]
+        x, y, conf, cls, wid, slot, py = self.detect_windows(mosaic, windows, ids, y_offset)
+        self.last_raw = int(x.numel())
+        return self.dedup(x, y, conf, cls, wid, slot, py, rank, world, covers, group)

@@ -142,10 +142,18 @@ int b2d_georef(b2d_engine* e, const b2d_det* dets_dev, const int32_t* counts_dev
 
 /* Greedy centre-distance dedup in a metric CRS.  Replaces SimpleDetector._remove_duplicates
  * (simple_detector.py:558-596, inclusive=1) and ResultsManager.remove_duplicates
- * (_script/utils.py:229-256, inclusive=0).  Priority = conf desc, then input index asc.
+ * (_script/utils.py:229-256, inclusive=0).  Priority = conf desc, then tiebreak_dev asc
+ * (int64 per detection; NULL = input index, i.e. Python's stable sort at :565).
  * keep_dev: uint8 [count].                                                                    */
 int b2d_dedup(b2d_engine* e, const double* x_dev, const double* y_dev, const float* conf_dev,
-              int count, double thr, int inclusive, uint8_t* keep_dev, void* stream);
+              const long long* tiebreak_dev, int count, double thr, int inclusive, uint8_t* keep_dev, void* stream);
+
+/* Multi-GPU seam support (no reference counterpart: the reference is single-process).  On entry
+ * flag_dev[i] != 0 marks detections within `thr` of another shard's coverage; on exit the flag is
+ * closed under the "within thr" relation, so unflagged detections can be deduplicated locally and
+ * only flagged ones need to be exchanged.                                                        */
+int b2d_seam_closure(b2d_engine* e, const double* x_dev, const double* y_dev, int count, double thr,
+                     int inclusive, uint8_t* flag_dev, void* stream);
 
 /* WGS84 lon/lat -> UTM metres (replaces pyproj at simple_detector.py:551-556).              */
 int b2d_utm_forward(b2d_engine* e, const double* lon_dev, const double* lat_dev, int count,

