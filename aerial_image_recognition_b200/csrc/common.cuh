@@ -51,6 +51,7 @@ struct __align__(64) ConvTcParams {
     int tiles_x, tiles_y;
     int act, out_f32;
     int stages;
+    int halo;             // 0: shifted-box loads; 1/3: shared halo tile (3: descriptor base_offset set)
     uint32_t a_bytes, b_bytes, b_tx_bytes;   // smem bytes per stage (padded), TMA bytes of B
     uint32_t swizzle_bytes;                  // 128 / 64 / 32
     uint32_t tmem_cols;

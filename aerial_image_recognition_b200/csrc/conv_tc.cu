@@ -29,6 +29,7 @@
 #include "common.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -143,6 +144,117 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
     c.y0 = ty * p.bh;
     c.n0 = tg * p.bn;
     return c;
+}
+
+// ===================== epilogue (warps 4-7), shared by both kernels =====================
+// One thread owns one accumulator row (= one output pixel).  Per 32-column block: two tcgen05.ld,
+// bias (smem) + SiLU (+ residual) in fp32, round to bf16, two 32-byte stores at the channel offset.
+// The residual of the whole row is fetched into registers BEFORE waiting for the accumulator, so
+// its L2/HBM latency hides behind the tile's main loop.
+constexpr int kMaxResBlocks = 6;     // residual layers have n_tile <= 192
+
+__device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int nimg, int total_tiles, uint32_t tmem_base, const float* bias_s,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, int warp, int lane) {
+    const int q = warp & 3;                  // TMEM lane quarter owned by this warp
+    const int row = q * 32 + lane;           // accumulator row = pixel inside the tile
+    const int lx = row % p.bw;
+    const int ly = (row / p.bw) % p.bh;
+    const int ln = row / (p.bw * p.bh);
+    const int n_tile = p.n_tile, cout = p.cout, act = p.act;
+    const bool has_res = (p.res != nullptr);
+    const bool out_f32 = p.out_f32 != 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const TileCoord tc = decode_tile(p, t);
+        const int ox = tc.x0 + lx, oy = tc.y0 + ly, img = tc.n0 + ln;
+        const bool valid = (ox < p.W) && (oy < p.H) && (img < nimg);
+        const long long pix = ((long long)img * p.H + oy) * p.W + ox;
+        const int ch_base = tc.nt * n_tile;
+        const float* bs = bias_s + ch_base;
+        uint4 rr[kMaxResBlocks][4];
+        if (has_res && valid) {
+            const uint4* rp = (const uint4*)(p.res + pix * p.res_cs + p.res_c0 + ch_base);
+#pragma unroll
+            for (int b = 0; b < kMaxResBlocks; ++b) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ch_base + b * 32 + j * 8 + 8 <= cout && b * 32 + j * 8 < n_tile) rr[b][j] = __ldg(rp + b * 4 + j);
+            }
+        }
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * n_tile);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int c = b * 32;
+            if (c >= n_tile) break;
+            uint32_t r[32];
+            const bool two = (c + 16 < n_tile);
+            tmem_ld16(taddr + c, *(uint32_t(*)[16])&r[0]);
+            if (two) tmem_ld16(taddr + c + 16, *(uint32_t(*)[16])&r[16]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const int ch0 = ch_base + c + hlf * 16;
+                if ((hlf == 1 && !two) || !valid || ch0 >= cout) continue;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float a = __uint_as_float(r[hlf * 16 + j]) + bs[c + hlf * 16 + j];
+                    v[j] = act ? silu(a) : a;
+                }
+                const bool full16 = (ch0 + 16 <= cout);
+                if (has_res) {
+                    if (full16 && b < kMaxResBlocks) {
+                        const int bb = b < kMaxResBlocks ? b : 0;
+                        const uint4 x0 = rr[bb][hlf * 2], x1 = rr[bb][hlf * 2 + 1];
+                        const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            v[2 * j] += __uint_as_float(w[j] << 16);
+                            v[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                        }
+                    } else {
+                        const __nv_bfloat16* rp = p.res + pix * p.res_cs + p.res_c0 + ch0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ch0 + j < cout) v[j] += __bfloat162float(rp[j]);
+                    }
+                }
+                if (out_f32) {
+                    float* op = (float*)p.out + pix * p.out_cs + p.out_c0 + ch0;
+                    if (full16) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ((float4*)op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ch0 + j < cout) op[j] = v[j];
+                    }
+                } else {
+                    __nv_bfloat16* op = (__nv_bfloat16*)p.out + pix * p.out_cs + p.out_c0 + ch0;
+                    if (full16) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            w[j] = *(uint32_t*)&h;
+                        }
+                        ((uint4*)op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        ((uint4*)op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ch0 + j < cout) op[j] = __float2bfloat16_rn(v[j]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
@@ -266,91 +378,134 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        const int q = warp & 3;                  // TMEM lane quarter owned by this warp
-        const int row = q * 32 + lane;           // accumulator row = pixel inside the tile
-        const int lx = row % p.bw;
-        const int ly = (row / p.bw) % p.bh;
-        const int ln = row / (p.bw * p.bh);
-        const int n_tile = p.n_tile, cout = p.cout, act = p.act;
-        int it = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            const TileCoord tc = decode_tile(p, t);
-            const int ox = tc.x0 + lx, oy = tc.y0 + ly, img = tc.n0 + ln;
-            const bool valid = (ox < p.W) && (oy < p.H) && (img < nimg);
-            const long long pix = ((long long)img * p.H + oy) * p.W + ox;
-            const int ch_base = tc.nt * n_tile;
-            const float* bs = bias_s + ch_base;
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * n_tile);
-            for (int c = 0; c < n_tile; c += 32) {
-                uint32_t r[32];
-                const bool two = (c + 16 < n_tile);
-                tmem_ld16(taddr + c, *(uint32_t(*)[16])&r[0]);
-                if (two) tmem_ld16(taddr + c + 16, *(uint32_t(*)[16])&r[16]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf) {
-                    const int ch0 = ch_base + c + hlf * 16;
-                    if ((hlf == 1 && !two) || !valid || ch0 >= cout) continue;
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float a = __uint_as_float(r[hlf * 16 + j]) + bs[c + hlf * 16 + j];
-                        v[j] = act ? silu(a) : a;
-                    }
-                    const bool full16 = (ch0 + 16 <= cout);
-                    if (p.res != nullptr) {
-                        const __nv_bfloat16* rp = p.res + pix * p.res_cs + p.res_c0 + ch0;
-                        if (full16) {
-                            const uint4 a = __ldg((const uint4*)rp), b = __ldg((const uint4*)rp + 1);
-                            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                v[2 * j] += __uint_as_float(w[j] << 16);
-                                v[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (ch0 + j < cout) v[j] += __bfloat162float(rp[j]);
-                        }
-                    }
-                    if (p.out_f32) {
-                        float* op = (float*)p.out + pix * p.out_cs + p.out_c0 + ch0;
-                        if (full16) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) ((float4*)op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (ch0 + j < cout) op[j] = v[j];
-                        }
-                    } else {
-                        __nv_bfloat16* op = (__nv_bfloat16*)p.out + pix * p.out_cs + p.out_c0 + ch0;
-                        if (full16) {
-                            uint32_t w[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                                w[j] = *(uint32_t*)&h;
-                            }
-                            ((uint4*)op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            ((uint4*)op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (ch0 + j < cout) op[j] = __float2bfloat16_rn(v[j]);
-                        }
+        epilogue_loop(p, nimg, total_tiles, tmem_base, bias_s, tfull_bar, tempty_bar, warp, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Halo variant for 3x3 stride-1 convs on 8 x 16 pixel tiles: the (8+2) x (16+2) input halo of a
+// 64-channel chunk is fetched ONCE (180 rows) instead of nine shifted 128-row boxes, and the nine
+// taps are nine MMAs over the same shared-memory tile whose A descriptor starts at halo row
+// kh*10 + kw with a stride of 10 rows between 8-row groups (one output row of 8 pixels each).
+// Weights stream tap by tap through the stage ring.  A-side TMA requests drop 6.4x.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHaloW = 10, kHaloH = 18;
+constexpr uint32_t kHaloBytes = 23 * 1024;       // 180 rows x 128 B = 23040, padded to 1 KiB
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = smem + 2 * kHaloBytes;                           // B stages
+    uint64_t* full_bar = (uint64_t*)(ring + (size_t)p.stages * p.b_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* hfull_bar = tempty_bar + 2;
+    uint64_t* hempty_bar = hfull_bar + 2;
+    uint32_t* tmem_slot = (uint32_t*)(hempty_bar + 2);
+    float* bias_s = (float*)(tmem_slot + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_m = p.tiles_x * p.tiles_y * nimg;                // bn == 1
+    const int total_tiles = tiles_m * p.n_tiles_n;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmB); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128);
+            mbar_init(&hfull_bar[i], 1); mbar_init(&hempty_bar[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+    for (int i = threadIdx.x; i < p.n_tile * p.n_tiles_n; i += kThreads) bias_s[i] = p.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0, hb = 0;
+            uint32_t phase = 0, hphase = 0;
+            const int nstages = p.stages, chunks = p.chunks, n_tile = p.n_tile;
+            const int cin_pad = chunks * 64;
+            const uint32_t b_tx = p.b_tx_bytes, b_bytes = p.b_bytes;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(p, t);
+                const int bn0 = tc.nt * n_tile;
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait(&hempty_bar[hb], hphase ^ 1);
+                    mbar_expect_tx(&hfull_bar[hb], (uint32_t)(kHaloW * kHaloH * 128));
+                    tma_load_4d(&p.tmA[1], &hfull_bar[hb], smem + hb * kHaloBytes, ch * 64, tc.x0 - 1, tc.y0 - 1, tc.n0);
+                    if (++hb == 2) { hb = 0; hphase ^= 1; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], b_tx);
+                        tma_load_2d(&p.tmB, &full_bar[stage], ring + (size_t)stage * b_bytes, tap * cin_pad + ch * 64, bn0);
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[as]);
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0, hb = 0, it = 0;
+            uint32_t phase = 0, hphase = 0;
+            // B: canonical SW128 K-major, 8-row groups 1024 B apart.  A: 8-row groups one halo row (10 px) apart.
+            const uint32_t hi_b = (uint32_t)(make_smem_desc(0, 128) >> 32);
+            const uint32_t hi_a0 = (hi_b & ~0x3FFFu) | (uint32_t)((kHaloW * 128) >> 4);
+            const uint32_t smem_a = smem_u32(smem), smem_b = smem_u32(ring);
+            const uint32_t b_units = p.b_bytes >> 4;
+            const uint32_t idesc = p.idesc;
+            const int nstages = p.stages, n_tile = p.n_tile, chunks = p.chunks;
+            const bool use_base_offset = (p.halo & 2) != 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait(&hfull_bar[hb], hphase);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_a + hb * kHaloBytes;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = a_base + (uint32_t)(((tap / 3) * kHaloW + (tap % 3)) * 128);
+                        uint32_t hi_a = hi_a0;
+                        if (use_base_offset) hi_a |= ((a_addr >> 7) & 7u) << 17;      // descriptor bits [49,52)
+                        const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
+                        const uint32_t b_lo = (((smem_b & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)stage * b_units;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = ((uint64_t)hi_a << 32) | (uint64_t)(a_lo + 2 * k);
+                            const uint64_t bd = ((uint64_t)hi_b << 32) | (uint64_t)(b_lo + 2 * k);
+                            umma_bf16(d_tmem, ad, bd, idesc, (k == 0) ? (uint32_t)((ch | tap) != 0) : 1u);
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&hempty_bar[hb]);                                 // halo tile free once its 36 MMAs retire
+                    if (ch == chunks - 1) umma_commit(&tfull_bar[as]);
+                    if (++hb == 2) { hb = 0; hphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        epilogue_loop(p, nimg, total_tiles, tmem_base, bias_s, tfull_bar, tempty_bar, warp, lane);
     }
 
     tc_fence_before();
@@ -466,6 +621,19 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + (size_t)cout_pad * 4 /*bias*/;
+    // halo variant: 3x3 stride 1, one image per tile, 8-pixel-wide tiles (uniform 10-row group stride)
+    p.halo = 0;
+    {
+        const char* env = getenv("B2D_HALO");       // 0 disables; 1 = verified variant (descriptor base_offset 0)
+        const int want = env ? atoi(env) : 1;
+        if (want && ksz == 3 && stride == 1 && p.bw == 8 && p.bh == 16 && p.bn == 1 && p.n_tile <= 96) {
+            p.halo = want;                                       // 1: base_offset = 0, 3: base_offset from address
+            int hs = (int)((budget - 2 * kHaloBytes) / p.b_bytes);
+            if (hs > kMaxStages) hs = kMaxStages;
+            p.stages = hs;
+            plan->smem_bytes = 2 * kHaloBytes + (size_t)hs * p.b_bytes + 1024 + 256 + (size_t)cout_pad * 4;
+        }
+    }
 
     // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin_pad] (zero padded) ----
     const int cin_pad = p.chunks * 64;
@@ -505,7 +673,14 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                 if (encode_map(&p.tmA[py * 2 + px], (void*)base, 4, dims, str, boxA, p.swizzle_bytes)) return -1;
             }
     }
+    if (p.halo) {
+        const uint32_t boxH[4] = {64u, (uint32_t)kHaloW, (uint32_t)kHaloH, 1u};
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)src_w, (uint64_t)src_h, (uint64_t)max_batch};
+        uint64_t str[3] = {(uint64_t)src_cs * 2, (uint64_t)src_w * src_cs * 2, (uint64_t)src_h * src_w * src_cs * 2};
+        if (encode_map(&p.tmA[1], (void*)(src + src_c0), 4, dims, str, boxH, 128)) return -1;
+    }
     B2D_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    B2D_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     return 0;
 }
 
@@ -514,7 +689,8 @@ int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
     const int tiles = p.tiles_x * p.tiles_y * ceil_div(n, p.bn) * p.n_tiles_n;
     int grid = tiles < plan->sm_count ? tiles : plan->sm_count;
     if (grid < 1) return 0;
-    conv_tc_kernel<<<grid, kThreads, plan->smem_bytes, stream>>>(p, n);
+    if (p.halo) conv_tc_halo_kernel<<<grid, kThreads, plan->smem_bytes, stream>>>(p, n);
+    else conv_tc_kernel<<<grid, kThreads, plan->smem_bytes, stream>>>(p, n);
     B2D_LAUNCH_CHECK();
     return 0;
 }
@@ -529,7 +705,7 @@ void conv_tc_free(ConvTcPlan* plan) {
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
     return snprintf(buf, buflen,
-                    "tcgen05 conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d n_tile %d x%d kc %d (SW%u) stages %d tmem %u smem %zu",
+                    "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d n_tile %d x%d kc %d (SW%u) stages %d tmem %u smem %zu", p.halo ? "-halo" : "",
                     p.ksz, p.stride, p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.n_tile, p.n_tiles_n, p.kc, p.swizzle_bytes,
                     p.stages, p.tmem_cols, plan->smem_bytes);
 }
