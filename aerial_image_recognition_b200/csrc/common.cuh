@@ -34,9 +34,21 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // ---------------------------------------------------------------------------------------
 // tcgen05 implicit-GEMM convolution (conv_tc.cu)
 // ---------------------------------------------------------------------------------------
+struct EpiChunk {         // one 128/64/32-byte wide column chunk of an output row (epilogue staging + TMA store)
+    uint16_t col0, cols;  // first accumulator column, number of columns
+    uint16_t span, map;   // bytes per row in the staging slab (= swizzle span), index into tmO / tmR
+    uint32_t off;         // byte offset of the chunk's 32-row slab inside a warp's staging region
+};
+constexpr int kMaxEpiChunks = 6;
+
 struct __align__(64) ConvTcParams {
     CUtensorMap tmA[4];   // [0]: stride-1 activation map; [py*2+px]: the four stride-2 phase maps
     CUtensorMap tmB;      // packed weights [cout_pad][taps*cin], K contiguous
+    CUtensorMap tmO[3];   // output slice, one warp sub-box, chunk width 128 / 64 / 32 bytes
+    CUtensorMap tmR[3];   // residual slice, same boxes
+    EpiChunk epi[kMaxEpiChunks];
+    int epi_nchunks, has_res;
+    uint32_t stg_off, bar_off;   // smem offsets (from the 1 KiB aligned base) of the staging region / barrier block
     const float* bias;    // [cout_pad]
     void* out;            // dst buffer base (bf16 or f32, NHWC)
     const __nv_bfloat16* res;  // residual buffer base or nullptr

@@ -35,7 +35,7 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;     // 4 control warps + 8 epilogue warps
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 
@@ -147,126 +147,203 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
 }
 
 // ===================== epilogue (warps 4-7), shared by both kernels =====================
-// One thread owns one accumulator row (= one output pixel).  Per 32-column block: two tcgen05.ld,
-// bias (smem) + SiLU (+ residual) in fp32, round to bf16, two 32-byte stores at the channel offset.
-// The residual of the whole row is fetched into registers BEFORE waiting for the accumulator, so
-// its L2/HBM latency hides behind the tile's main loop.
-constexpr int kMaxResBlocks = 6;     // residual layers have n_tile <= 192
+// Warp q owns accumulator rows [32q, 32q+32) = a sub-box of the tile's pixels.  Per tile it
+//   1. (residual layers) TMA-loads the residual sub-box into its staging slab,
+//   2. waits for the accumulator, reads it 32 columns at a time (tcgen05.ld 32x32b.x32),
+//      adds the bias (smem), applies SiLU, adds the residual read back from the slab, rounds to
+//      bf16 (or keeps fp32 for head outputs) and writes the slab in the TMA swizzle pattern
+//      (conflict-free 16-byte shared stores),
+//   3. releases the TMEM stage, then TMA-stores the slab at the channel offset of the
+//      destination buffer.  TMA clips partial tiles and padded channels, so there is no
+//      per-thread bounds logic and every global write is a full coalesced row.
+// A row of n_tile columns is cut into chunks of 128 / 64 / 32 bytes (EpiChunk), one tensor map
+// per chunk width.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src_smem),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_s(const CUtensorMap* map, uint32_t bar, uint32_t dst_smem, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_smem),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
-__device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int nimg, int total_tiles, uint32_t tmem_base, const float* bias_s,
-                                              uint64_t* tfull_bar, uint64_t* tempty_bar, int warp, int lane) {
-    const int q = warp & 3;                  // TMEM lane quarter owned by this warp
-    const int row = q * 32 + lane;           // accumulator row = pixel inside the tile
-    const int lx = row % p.bw;
-    const int ly = (row / p.bw) % p.bh;
-    const int ln = row / (p.bw * p.bh);
-    const int n_tile = p.n_tile, cout = p.cout, act = p.act;
-    const bool has_res = (p.res != nullptr);
-    const bool out_f32 = p.out_f32 != 0;
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+
+// 16 accumulator columns of this thread's row (already in registers) -> staging slab.
+// `piece0` is the index of the first 16-byte piece inside the chunk row, `sw_xor` the swizzle term.
+template <int ACT, int RES, int F32>
+__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t row_addr, uint32_t piece0, uint32_t sw_xor) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 b = lds_f4(bias_addr + 16 * j);
+        v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+    }
+    if (ACT) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = silu(v[i]);
+    }
+    if (F32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            sts128(row_addr + (((piece0 + j) ^ sw_xor) << 4),
+                   make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const uint32_t a0 = row_addr + (((piece0 + j) ^ sw_xor) << 4);
+            if (RES) {
+                const uint4 x = lds128(a0);
+                const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[8 * j + 2 * i] += __uint_as_float(w[i] << 16);
+                    v[8 * j + 2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+                }
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                w[i] = *(uint32_t*)&h;
+            }
+            sts128(a0, make_uint4(w[0], w[1], w[2], w[3]));
+        }
+    }
+}
+
+// Eight epilogue warps: warp w serves TMEM lane quarter q = w % 4 (a hardware rule) and, of that
+// quarter's 16-column units, the ones with unit % 2 == (w - 4) / 4.  The two warps of a quarter
+// share one staging slab and meet at a 64-thread named barrier before the slab is reused and
+// before its TMA store is issued (by lane 0 of the first warp).
+template <int ACT, int RES, int F32>
+__device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_tiles, uint32_t tmem_base, const float* bias_s,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar, uint8_t* stg_base, int warp,
+                                              int lane) {
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int n_tile = p.n_tile, nchunks = p.epi_nchunks;
+    constexpr int esize = F32 ? 4 : 2;
+    constexpr int ppu = F32 ? 4 : 2;                   // 16-byte pieces per 16-column unit
+    const uint32_t slab = smem_u32(stg_base) + (uint32_t)q * 32u * (uint32_t)(n_tile * esize);   // this quarter's staging region
+    const uint32_t rbar = smem_u32(&res_bar[q]);
+    const uint32_t bias_base = smem_u32(bias_s);
+    const bool issuer = (half == 0 && lane == 0);
+    // sub-box of the tile covered by this quarter's 32 rows
+    const int box_px = p.bw * p.bh;
+    const int yq = ((q * 32) % box_px) / p.bw, nq = (q * 32) / box_px;
+    const int nunits = n_tile >> 4;
+    uint32_t rphase = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const TileCoord tc = decode_tile(p, t);
-        const int ox = tc.x0 + lx, oy = tc.y0 + ly, img = tc.n0 + ln;
-        const bool valid = (ox < p.W) && (oy < p.H) && (img < nimg);
-        const long long pix = ((long long)img * p.H + oy) * p.W + ox;
         const int ch_base = tc.nt * n_tile;
-        const float* bs = bias_s + ch_base;
-        uint4 rr[kMaxResBlocks][4];
-        if (has_res && valid) {
-            const uint4* rp = (const uint4*)(p.res + pix * p.res_cs + p.res_c0 + ch_base);
-#pragma unroll
-            for (int b = 0; b < kMaxResBlocks; ++b) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (ch_base + b * 32 + j * 8 + 8 <= cout && b * 32 + j * 8 < n_tile) rr[b][j] = __ldg(rp + b * 4 + j);
+        const int cx = tc.x0, cy = tc.y0 + yq, cn = tc.n0 + nq;
+        if (issuer) {
+            tma_store_wait_read();                       // the previous tile's stores have drained the slab
+            if (RES) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar), "r"(32u * (uint32_t)(n_tile * 2)) : "memory");
+#pragma unroll 1
+                for (int k = 0; k < nchunks; ++k) {
+                    const EpiChunk ck = p.epi[k];
+                    tma_load_4d_s(&p.tmR[ck.map], rbar, slab + ck.off, ch_base + ck.col0, cx, cy, cn);
+                }
             }
         }
+        pair_sync(q);                                    // slab is free (and the residual load is in flight)
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
+        if (RES) {
+            mbar_wait(&res_bar[q], rphase);
+            rphase ^= 1;
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * n_tile);
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int c = b * 32;
-            if (c >= n_tile) break;
-            uint32_t r[32];
-            const bool two = (c + 16 < n_tile);
-            tmem_ld16(taddr + c, *(uint32_t(*)[16])&r[0]);
-            if (two) tmem_ld16(taddr + c + 16, *(uint32_t(*)[16])&r[16]);
+        uint32_t rbuf[2][16];
+        if (half < nunits) tmem_ld16(taddr + half * 16, rbuf[0]);
+        int k = 0;                                       // chunk holding unit u
+        int par = 0;
+#pragma unroll 1
+        for (int u = half; u < nunits; u += 2, par ^= 1) {
             tmem_ld_wait();
-#pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf) {
-                const int ch0 = ch_base + c + hlf * 16;
-                if ((hlf == 1 && !two) || !valid || ch0 >= cout) continue;
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float a = __uint_as_float(r[hlf * 16 + j]) + bs[c + hlf * 16 + j];
-                    v[j] = act ? silu(a) : a;
-                }
-                const bool full16 = (ch0 + 16 <= cout);
-                if (has_res) {
-                    if (full16 && b < kMaxResBlocks) {
-                        const int bb = b < kMaxResBlocks ? b : 0;
-                        const uint4 x0 = rr[bb][hlf * 2], x1 = rr[bb][hlf * 2 + 1];
-                        const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            v[2 * j] += __uint_as_float(w[j] << 16);
-                            v[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-                        }
-                    } else {
-                        const __nv_bfloat16* rp = p.res + pix * p.res_cs + p.res_c0 + ch0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (ch0 + j < cout) v[j] += __bfloat162float(rp[j]);
-                    }
-                }
-                if (out_f32) {
-                    float* op = (float*)p.out + pix * p.out_cs + p.out_c0 + ch0;
-                    if (full16) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) ((float4*)op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (ch0 + j < cout) op[j] = v[j];
-                    }
-                } else {
-                    __nv_bfloat16* op = (__nv_bfloat16*)p.out + pix * p.out_cs + p.out_c0 + ch0;
-                    if (full16) {
-                        uint32_t w[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                            w[j] = *(uint32_t*)&h;
-                        }
-                        ((uint4*)op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                        ((uint4*)op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (ch0 + j < cout) op[j] = __float2bfloat16_rn(v[j]);
-                    }
-                }
+            if (u + 2 < nunits) {
+                if (par) tmem_ld16(taddr + (u + 2) * 16, rbuf[0]);
+                else tmem_ld16(taddr + (u + 2) * 16, rbuf[1]);
             }
+            const int col = u * 16;
+            while (col >= p.epi[k].col0 + p.epi[k].cols) ++k;
+            const EpiChunk ck = p.epi[k];
+            const uint32_t span = ck.span;
+            const uint32_t row_addr = slab + ck.off + (uint32_t)lane * span;
+            const uint32_t sw_xor = span == 128 ? (uint32_t)(lane & 7) : span == 64 ? (uint32_t)((lane >> 1) & 3) : (uint32_t)((lane >> 2) & 1);
+            const uint32_t piece0 = (uint32_t)((col - ck.col0) >> 4) * ppu;
+            const uint32_t baddr = bias_base + (uint32_t)(ch_base + col) * 4u;
+            if (par) epi_unit<ACT, RES, F32>(rbuf[1], baddr, row_addr, piece0, sw_xor);
+            else epi_unit<ACT, RES, F32>(rbuf[0], baddr, row_addr, piece0, sw_xor);
         }
         tc_fence_before();
-        mbar_arrive(&tempty_bar[as]);
+        mbar_arrive(&tempty_bar[as]);                    // accumulator stage free: all tcgen05.ld of this tile have completed
+        fence_proxy_async();                             // generic-proxy slab writes -> visible to the TMA store
+        pair_sync(q);
+        if (issuer) {
+#pragma unroll 1
+            for (int kk = 0; kk < nchunks; ++kk) {
+                const EpiChunk ck = p.epi[kk];
+                tma_store_4d(&p.tmO[ck.map], slab + ck.off, ch_base + ck.col0, cx, cy, cn);
+            }
+            tma_store_commit();
+        }
     }
+    if (issuer) tma_store_wait_all();
 }
 
+template <int ACT, int RES, int F32>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x (A | B)] then barriers
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+    uint8_t* stg_base = smem + p.stg_off;             // epilogue staging, 4 warps x 32 rows x n_tile columns
+    uint64_t* full_bar = (uint64_t*)(smem + p.bar_off);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    uint64_t* res_bar = tempty_bar + 6;               // (+2..+5: halo barriers in the halo kernel)
+    uint32_t* tmem_slot = (uint32_t*)(res_bar + 4);
     float* bias_s = (float*)(tmem_slot + 4);          // [n_tile * n_tiles_n] padded bias
 
     const int warp = threadIdx.x >> 5;
@@ -292,8 +369,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 128);
+            mbar_init(&tempty_bar[i], 256);
         }
+        for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -378,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
         }
     } else if (warp >= 4) {
-        epilogue_loop(p, nimg, total_tiles, tmem_base, bias_s, tfull_bar, tempty_bar, warp, lane);
+        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, bias_s, tfull_bar, tempty_bar, res_bar, stg_base, warp, lane);
     }
 
     tc_fence_before();
@@ -400,17 +478,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 constexpr int kHaloW = 10, kHaloH = 18;
 constexpr uint32_t kHaloBytes = 23 * 1024;       // 180 rows x 128 B = 23040, padded to 1 KiB
 
+template <int ACT, int RES, int F32>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* ring = smem + 2 * kHaloBytes;                           // B stages
-    uint64_t* full_bar = (uint64_t*)(ring + (size_t)p.stages * p.b_bytes);
+    uint8_t* stg_base = smem + p.stg_off;
+    uint64_t* full_bar = (uint64_t*)(smem + p.bar_off);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* hfull_bar = tempty_bar + 2;
     uint64_t* hempty_bar = hfull_bar + 2;
-    uint32_t* tmem_slot = (uint32_t*)(hempty_bar + 2);
+    uint64_t* res_bar = hempty_bar + 2;
+    uint32_t* tmem_slot = (uint32_t*)(res_bar + 4);
     float* bias_s = (float*)(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5;
@@ -422,9 +503,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128);
+            mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256);
             mbar_init(&hfull_bar[i], 1); mbar_init(&hempty_bar[i], 1);
         }
+        for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -505,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             }
         }
     } else if (warp >= 4) {
-        epilogue_loop(p, nimg, total_tiles, tmem_base, bias_s, tfull_bar, tempty_bar, warp, lane);
+        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, bias_s, tfull_bar, tempty_bar, res_bar, stg_base, warp, lane);
     }
 
     tc_fence_before();
@@ -530,7 +612,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, uint32_t swizzle_bytes) {
+               const uint32_t* box, uint32_t swizzle_bytes, bool f32 = false) {
     auto enc = get_encode();
     B2D_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gd[5], gs[4];
@@ -540,7 +622,7 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
     CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B2D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu box %u %u)", (int)r, rank,
               (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
@@ -558,7 +640,7 @@ uint16_t f2bf(float f) {
 void pick_tile(int W, int H, int N, int* bw, int* bh, int* bn) {
     double best = -1.0;
     int best_halo = 1 << 30;
-    for (int w = 1; w <= 128; w *= 2)
+    for (int w = 1; w <= 32; w *= 2)
         for (int h = 1; w * h <= 128; h *= 2) {
             int n = 128 / (w * h);
             long long tiles = (long long)ceil_div(W, w) * ceil_div(H, h) * ceil_div(N, n);
@@ -608,7 +690,37 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.b_tx_bytes = p.n_tile * p.kc * 2;
     p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    const uint32_t budget = 200 * 1024 - (uint32_t)cout_pad * 4;
+    // ---- epilogue staging: a row of n_tile columns cut into 128 / 64 / 32-byte chunks ----
+    const int esize = dst_f32 ? 4 : 2;
+    B2D_CHECK(!(dst_f32 && res), "conv_tc: residual with fp32 output is not supported");
+    B2D_CHECK(((size_t)dst_cs * esize) % 16 == 0 && ((size_t)dst_c0 * esize) % 16 == 0,
+              "conv_tc: destination slice must be 16-byte aligned (cs=%d c0=%d)", dst_cs, dst_c0);
+    B2D_CHECK(!res || (res_cs % 8 == 0 && res_c0 % 8 == 0), "conv_tc: residual slice must be 16-byte aligned");
+    B2D_CHECK(p.bw <= 32 && 32 % p.bw == 0, "conv_tc: tile width %d does not divide a warp's 32 rows", p.bw);
+    const uint32_t row_bytes = (uint32_t)p.n_tile * esize;
+    const uint32_t stg_bytes = 128u * row_bytes;
+    {
+        uint32_t done = 0, off = 0;
+        int n = 0;
+        const uint32_t spans[3] = {128, 64, 32};
+        for (int si = 0; si < 3; ++si)
+            while (row_bytes - done >= spans[si]) {
+                B2D_CHECK(n < kMaxEpiChunks, "conv_tc: n_tile %d needs too many epilogue chunks", p.n_tile);
+                p.epi[n].col0 = (uint16_t)(done / esize);
+                p.epi[n].cols = (uint16_t)(spans[si] / esize);
+                p.epi[n].span = (uint16_t)spans[si];
+                p.epi[n].map = (uint16_t)si;
+                p.epi[n].off = off;
+                off += 32u * spans[si];
+                done += spans[si];
+                ++n;
+            }
+        B2D_CHECK(done == row_bytes, "conv_tc: n_tile %d is not a multiple of 32 bytes", p.n_tile);
+        p.epi_nchunks = n;
+    }
+    p.has_res = res ? 1 : 0;
+    const uint32_t tail_bytes = 256 /*barriers + tmem slot*/ + (uint32_t)cout_pad * 4 /*bias*/;
+    const uint32_t budget = 226 * 1024 - 1024 /*align slack*/ - stg_bytes - tail_bytes;
     int stages = (int)(budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     const int ksteps = p.taps * p.chunks;
@@ -620,7 +732,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.tmem_cols = cols;
     // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + (size_t)cout_pad * 4 /*bias*/;
+    uint32_t ring_bytes = (uint32_t)stages * stage_bytes;
     // halo variant: 3x3 stride 1, one image per tile, 8-pixel-wide tiles (uniform 10-row group stride)
     p.halo = 0;
     {
@@ -631,9 +743,13 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
             int hs = (int)((budget - 2 * kHaloBytes) / p.b_bytes);
             if (hs > kMaxStages) hs = kMaxStages;
             p.stages = hs;
-            plan->smem_bytes = 2 * kHaloBytes + (size_t)hs * p.b_bytes + 1024 + 256 + (size_t)cout_pad * 4;
+            ring_bytes = 2 * kHaloBytes + (uint32_t)hs * p.b_bytes;
         }
     }
+    p.stg_off = ring_bytes;                                      // 1 KiB aligned: every ring slot is a multiple of 1 KiB
+    p.bar_off = p.stg_off + stg_bytes;
+    plan->smem_bytes = (size_t)p.bar_off + tail_bytes + 1024 /*align slack*/;
+    B2D_CHECK(plan->smem_bytes <= 227 * 1024, "conv_tc: %zu bytes of shared memory needed", plan->smem_bytes);
 
     // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin_pad] (zero padded) ----
     const int cin_pad = p.chunks * 64;
@@ -679,18 +795,55 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         uint64_t str[3] = {(uint64_t)src_cs * 2, (uint64_t)src_w * src_cs * 2, (uint64_t)src_h * src_w * src_cs * 2};
         if (encode_map(&p.tmA[1], (void*)(src + src_c0), 4, dims, str, boxH, 128)) return -1;
     }
-    B2D_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    B2D_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    {   // output / residual sub-box maps: one warp's 32 rows of the tile, one map per chunk width
+        const int box_px = p.bw * p.bh;
+        const uint32_t sbh = (uint32_t)(box_px >= 32 ? 32 / p.bw : p.bh);
+        const uint32_t sbn = (uint32_t)(box_px >= 32 ? 1 : 32 / box_px);
+        const uint32_t spans[3] = {128, 64, 32};
+        bool used[3] = {false, false, false};
+        for (int k = 0; k < p.epi_nchunks; ++k) used[p.epi[k].map] = true;
+        for (int si = 0; si < 3; ++si) {
+            if (!used[si]) continue;
+            const uint32_t box[4] = {spans[si] / (uint32_t)esize, (uint32_t)p.bw, sbh, sbn};
+            uint64_t dims[4] = {(uint64_t)cout, (uint64_t)dst_w, (uint64_t)dst_h, (uint64_t)max_batch};
+            uint64_t str[3] = {(uint64_t)dst_cs * esize, (uint64_t)dst_w * dst_cs * esize, (uint64_t)dst_h * dst_w * dst_cs * esize};
+            if (encode_map(&p.tmO[si], (uint8_t*)dst + (size_t)dst_c0 * esize, 4, dims, str, box, spans[si], dst_f32 != 0)) return -1;
+            if (res) {
+                uint64_t rstr[3] = {(uint64_t)res_cs * 2, (uint64_t)dst_w * res_cs * 2, (uint64_t)dst_h * dst_w * res_cs * 2};
+                if (encode_map(&p.tmR[si], (void*)(res + res_c0), 4, dims, rstr, box, spans[si], false)) return -1;
+            }
+        }
+    }
     return 0;
 }
+
+namespace {
+typedef void (*ConvKernel)(const ConvTcParams, int);
+// (halo, act, res, f32) -> instantiation; fp32 outputs never carry a residual
+ConvKernel pick_kernel(int halo, int act, int res, int f32) {
+#define B2D_PICK(K)                                                        \
+    if (f32) return act ? K<1, 0, 1> : K<0, 0, 1>;                         \
+    if (res) return act ? K<1, 1, 0> : K<0, 1, 0>;                         \
+    return act ? K<1, 0, 0> : K<0, 0, 0>;
+    if (halo) { B2D_PICK(conv_tc_halo_kernel) }
+    B2D_PICK(conv_tc_kernel)
+#undef B2D_PICK
+}
+}  // namespace
 
 int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
     const ConvTcParams& p = plan->p;
     const int tiles = p.tiles_x * p.tiles_y * ceil_div(n, p.bn) * p.n_tiles_n;
     int grid = tiles < plan->sm_count ? tiles : plan->sm_count;
     if (grid < 1) return 0;
-    if (p.halo) conv_tc_halo_kernel<<<grid, kThreads, plan->smem_bytes, stream>>>(p, n);
-    else conv_tc_kernel<<<grid, kThreads, plan->smem_bytes, stream>>>(p, n);
+    ConvKernel k = pick_kernel(p.halo, p.act, p.has_res, p.out_f32);
+    static bool attr_done[2][2][2][2];
+    bool& done = attr_done[p.halo ? 1 : 0][p.act ? 1 : 0][p.has_res ? 1 : 0][p.out_f32 ? 1 : 0];
+    if (!done) {
+        B2D_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        done = true;
+    }
+    k<<<grid, kThreads, plan->smem_bytes, stream>>>(p, n);
     B2D_LAUNCH_CHECK();
     return 0;
 }
