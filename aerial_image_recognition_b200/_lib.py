@@ -12,7 +12,7 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libb2det.so"
+LIB_PATH = Path(os.environ.get("B2D_LIB", _HERE / "libb2det.so"))   # B2D_LIB: A/B-test another build of the same library
 
 c_int, c_float, c_double, c_void_p, c_char_p, c_size_t, c_ll = (
     C.c_int, C.c_float, C.c_double, C.c_void_p, C.c_char_p, C.c_size_t, C.c_longlong)

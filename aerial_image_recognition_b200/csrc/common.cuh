@@ -48,6 +48,7 @@ struct __align__(64) ConvTcParams {
     CUtensorMap tmR[3];   // residual slice, same boxes
     EpiChunk epi[kMaxEpiChunks];
     int epi_nchunks, has_res;
+    int stg_bufs;         // 1 or 2 staging slabs per lane quarter
     uint32_t stg_off, bar_off;   // smem offsets (from the 1 KiB aligned base) of the staging region / barrier block
     const float* bias;    // [cout_pad]
     void* out;            // dst buffer base (bf16 or f32, NHWC)
@@ -68,6 +69,7 @@ struct __align__(64) ConvTcParams {
     uint32_t swizzle_bytes;                  // 128 / 64 / 32
     uint32_t tmem_cols;
     uint32_t idesc;
+    long long* trace;     // debug only (B2D_TRACE=1): per-role clock64 stamps of CTA 0, else nullptr
 };
 
 struct ConvTcPlan {
@@ -76,6 +78,7 @@ struct ConvTcPlan {
     int sm_count;
     __nv_bfloat16* w_dev;   // packed weights (owned)
     float* bias_dev;        // owned
+    long long* trace_dev;   // owned, debug only
 };
 
 int conv_tc_supported(int cin, int ksz, int stride);

@@ -63,6 +63,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t"
         "}" ::"r"(addr), "r"(parity) : "memory");
 }
+// 32-bit shared-address forms for the warp-uniform producer / MMA loops
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+// one lane of a converged warp (always the same one for a full mask)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -78,6 +104,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_s(const CUtensorMap* map, uint32_t bar, uint32_t dst_smem, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -91,6 +123,9 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -128,9 +163,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t swiz
     return d;
 }
 
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
-
 struct TileCoord { int nt, x0, y0, n0; };
+
+// Debug trace (B2D_TRACE=1): CTA 0 records clock64() at role events of its first kTraceTiles tiles.
+constexpr int kTraceTiles = 24, kTraceEvents = 4, kTraceRoles = 3;   // roles: 0 producer, 1 MMA, 2 epilogue warp 4
+__device__ __forceinline__ void trace(const ConvTcParams& p, int role, int it, int ev) {
+#ifdef B2D_ENABLE_TRACE     // compiled out of product builds: even a predicted-off branch in the MMA issue loop costs
+    if (p.trace && blockIdx.x == 0 && it < kTraceTiles) p.trace[(role * kTraceTiles + it) * kTraceEvents + ev] = clock64();
+#endif
+}
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
     TileCoord c;
@@ -182,6 +223,7 @@ __device__ __forceinline__ void tma_load_4d_s(const CUtensorMap* map, uint32_t b
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
@@ -199,10 +241,27 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a) {
 }
 __device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
 
+// SiLU with one MUFU op per element: e = 2^(-v log2 e) on the SFU, 1/(1+e) on the FMA pipe
+// (bit-trick seed, two Newton steps: relative error 6e-6, far below the bf16 rounding that
+// follows).  The SFU (16 lanes/clk/SM) is the scarce pipe of the epilogue: 2 MUFU per output
+// element made the memory-bound 1x1 layers epilogue-bound.
+__device__ __forceinline__ float silu(float v) {
+#ifdef B2D_SILU_MUFU2
+    return __fdividef(v, 1.0f + __expf(-v));
+#endif
+    float y = fminf(v * -1.4426950408889634f, 64.0f), e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y));
+    const float d = 1.0f + e;
+    float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
+    r = fmaf(r, fmaf(-d, r, 1.0f), r);
+    r = fmaf(r, fmaf(-d, r, 1.0f), r);
+    return v * r;
+}
+
 // 16 accumulator columns of this thread's row (already in registers) -> staging slab.
-// `piece0` is the index of the first 16-byte piece inside the chunk row, `sw_xor` the swizzle term.
+// `base` is the swizzled address of the unit's first 16-byte piece; the others are base ^ (j << 4).
 template <int ACT, int RES, int F32>
-__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t row_addr, uint32_t piece0, uint32_t sw_xor) {
+__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base) {
     float v[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -219,12 +278,12 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_
     if (F32) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            sts128(row_addr + (((piece0 + j) ^ sw_xor) << 4),
+            sts128(base ^ (uint32_t)(j << 4),
                    make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
     } else {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const uint32_t a0 = row_addr + (((piece0 + j) ^ sw_xor) << 4);
+            const uint32_t a0 = base ^ (uint32_t)(j << 4);
             if (RES) {
                 const uint4 x = lds128(a0);
                 const uint32_t w[4] = {x.x, x.y, x.z, x.w};
@@ -248,7 +307,9 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_
 // Eight epilogue warps: warp w serves TMEM lane quarter q = w % 4 (a hardware rule) and, of that
 // quarter's 16-column units, the ones with unit % 2 == (w - 4) / 4.  The two warps of a quarter
 // share one staging slab and meet at a 64-thread named barrier before the slab is reused and
-// before its TMA store is issued (by lane 0 of the first warp).
+// before its TMA store is issued (by lane 0 of the first warp).  Everything that does not depend
+// on the tile (slab addresses of this warp's units) is computed once, and the unit loop is fully
+// unrolled so those values live in registers.
 template <int ACT, int RES, int F32>
 __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_tiles, uint32_t tmem_base, const float* bias_s,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar, uint8_t* stg_base, int warp,
@@ -258,7 +319,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     const int n_tile = p.n_tile, nchunks = p.epi_nchunks;
     constexpr int esize = F32 ? 4 : 2;
     constexpr int ppu = F32 ? 4 : 2;                   // 16-byte pieces per 16-column unit
-    const uint32_t slab = smem_u32(stg_base) + (uint32_t)q * 32u * (uint32_t)(n_tile * esize);   // this quarter's staging region
+    const uint32_t slab0 = smem_u32(stg_base) + (uint32_t)q * 32u * (uint32_t)(n_tile * esize);   // this quarter's staging region
+    const uint32_t slab_stride = p.stg_bufs == 2 ? 128u * (uint32_t)(n_tile * esize) : 0u;         // second buffer (if any)
     const uint32_t rbar = smem_u32(&res_bar[q]);
     const uint32_t bias_base = smem_u32(bias_s);
     const bool issuer = (half == 0 && lane == 0);
@@ -266,6 +328,21 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     const int box_px = p.bw * p.bh;
     const int yq = ((q * 32) % box_px) / p.bw, nq = (q * 32) / box_px;
     const int nunits = n_tile >> 4;
+    const int my_units = (nunits - half + 1) >> 1;     // units half, half + 2, ...
+    // Swizzled slab address of this lane's row for the 16-column unit starting at byte `b` of the row.  Mirrors
+    // the host's chunking (conv_tc_plan): full 128-byte chunks first, then one 64-byte, then one 32-byte chunk.
+    const uint32_t row_bytes = (uint32_t)(n_tile * esize);
+    const uint32_t n128 = row_bytes >> 7, has64 = (row_bytes >> 6) & 1u;
+    const uint32_t row128 = slab0 + (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
+    const uint32_t row64 = slab0 + n128 * 4096u + (uint32_t)lane * 64u, sw64 = (uint32_t)((lane >> 1) & 3);
+    const uint32_t row32 = slab0 + n128 * 4096u + has64 * 2048u + (uint32_t)lane * 32u, sw32 = (uint32_t)((lane >> 2) & 1);
+    auto unit_base = [&](uint32_t b) -> uint32_t {
+        if (b < (n128 << 7)) return row128 + (b >> 7) * 4096u + ((((b & 127u) >> 4) ^ sw128) << 4);
+        const uint32_t rem = b - (n128 << 7);
+        if (has64 && rem < 64u) return row64 + (((rem >> 4) ^ sw64) << 4);
+        return row32 + (sw32 << 4);                     // a 32-byte chunk holds exactly one bf16 unit (piece0 = 0)
+    };
+    const uint32_t ubytes = 16u * esize;               // bytes of one unit in a row
     uint32_t rphase = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -274,8 +351,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         const TileCoord tc = decode_tile(p, t);
         const int ch_base = tc.nt * n_tile;
         const int cx = tc.x0, cy = tc.y0 + yq, cn = tc.n0 + nq;
+        const uint32_t sboff = (it & 1) ? slab_stride : 0u;
+        const uint32_t slab = slab0 + sboff;
         if (issuer) {
-            tma_store_wait_read();                       // the previous tile's stores have drained the slab
+            // the stores that last read this slab have drained it (with two slabs the previous tile's may still be in flight)
+            if (slab_stride) tma_store_wait_read1(); else tma_store_wait_read();
             if (RES) {
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar), "r"(32u * (uint32_t)(n_tile * 2)) : "memory");
 #pragma unroll 1
@@ -286,38 +366,33 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
             }
         }
         pair_sync(q);                                    // slab is free (and the residual load is in flight)
+        if (warp == 4 && lane == 0) trace(p, 2, it, 0);
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
+        if (warp == 4 && lane == 0) trace(p, 2, it, 1);
         if (RES) {
             mbar_wait(&res_bar[q], rphase);
             rphase ^= 1;
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * n_tile);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * n_tile + half * 16);
+        const uint32_t baddr = bias_base + (uint32_t)(ch_base + half * 16) * 4u;
         uint32_t rbuf[2][16];
-        if (half < nunits) tmem_ld16(taddr + half * 16, rbuf[0]);
-        int k = 0;                                       // chunk holding unit u
-        int par = 0;
+        if (my_units > 0) tmem_ld16(taddr, rbuf[0]);
 #pragma unroll 1
-        for (int u = half; u < nunits; u += 2, par ^= 1) {
+        for (int i = 0; i < my_units; i += 2) {          // two units per trip: the TMEM load of the next overlaps the math of this one
             tmem_ld_wait();
-            if (u + 2 < nunits) {
-                if (par) tmem_ld16(taddr + (u + 2) * 16, rbuf[0]);
-                else tmem_ld16(taddr + (u + 2) * 16, rbuf[1]);
+            if (i + 1 < my_units) tmem_ld16(taddr + (i + 1) * 32, rbuf[1]);
+            epi_unit<ACT, RES, F32>(rbuf[0], baddr + i * 128, unit_base((uint32_t)(half + 2 * i) * ubytes) + sboff);
+            if (i + 1 < my_units) {
+                tmem_ld_wait();
+                if (i + 2 < my_units) tmem_ld16(taddr + (i + 2) * 32, rbuf[0]);
+                epi_unit<ACT, RES, F32>(rbuf[1], baddr + (i + 1) * 128, unit_base((uint32_t)(half + 2 * i + 2) * ubytes) + sboff);
             }
-            const int col = u * 16;
-            while (col >= p.epi[k].col0 + p.epi[k].cols) ++k;
-            const EpiChunk ck = p.epi[k];
-            const uint32_t span = ck.span;
-            const uint32_t row_addr = slab + ck.off + (uint32_t)lane * span;
-            const uint32_t sw_xor = span == 128 ? (uint32_t)(lane & 7) : span == 64 ? (uint32_t)((lane >> 1) & 3) : (uint32_t)((lane >> 2) & 1);
-            const uint32_t piece0 = (uint32_t)((col - ck.col0) >> 4) * ppu;
-            const uint32_t baddr = bias_base + (uint32_t)(ch_base + col) * 4u;
-            if (par) epi_unit<ACT, RES, F32>(rbuf[1], baddr, row_addr, piece0, sw_xor);
-            else epi_unit<ACT, RES, F32>(rbuf[0], baddr, row_addr, piece0, sw_xor);
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);                    // accumulator stage free: all tcgen05.ld of this tile have completed
         fence_proxy_async();                             // generic-proxy slab writes -> visible to the TMA store
+        if (warp == 4 && lane == 0) trace(p, 2, it, 2);
         pair_sync(q);
         if (issuer) {
 #pragma unroll 1
@@ -327,6 +402,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
             }
             tma_store_commit();
         }
+        if (warp == 4 && lane == 0) trace(p, 2, it, 3);
     }
     if (issuer) tma_store_wait_all();
 }
@@ -381,66 +457,78 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Both control loops run warp-uniformly (all 32 lanes take every branch) and elect one lane only
+    // around the asynchronous instructions: addresses and coordinates then live in uniform registers
+    // and each k-step is a few dozen cycles of issue instead of a long per-thread dependent chain.
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const int pad = p.ksz >> 1;
-            const int nstages = p.stages, taps = p.taps, chunks = p.chunks, ksz = p.ksz, n_tile = p.n_tile;
-            const int cin_pad = chunks * 64;
-            const uint32_t tx_bytes = (uint32_t)(kTileM * 64 * 2) + p.b_tx_bytes;
-            const uint32_t a_bytes = p.a_bytes;
-            const bool s2 = (p.stride == 2);
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(p, t);
-                const int bn0 = tc.nt * n_tile;
-                int kh = 0, kw = 0;
-                for (int tap = 0; tap < taps; ++tap) {
-                    const CUtensorMap* mapA = &p.tmA[0];
-                    int cx = tc.x0 + kw - pad, cy = tc.y0 + kh - pad;
-                    if (s2) {
-                        // input pixel = 2*o + d, d in {-1,0,1}: odd phase for d = +-1, even for 0
-                        const int dy = kh - 1, dx = kw - 1;
-                        const int py = dy & 1, px = dx & 1;
-                        mapA = &p.tmA[py * 2 + px];
-                        cx = tc.x0 + (dx - px) / 2;
-                        cy = tc.y0 + (dy - py) / 2;
-                    }
-                    const int kb = tap * cin_pad;
-                    for (int ch = 0; ch < chunks; ++ch) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                        mbar_expect_tx(&full_bar[stage], tx_bytes);
-                        tma_load_4d(mapA, &full_bar[stage], sa, ch * 64, cx, cy, tc.n0);
-                        tma_load_2d(&p.tmB, &full_bar[stage], sa + a_bytes, kb + ch * 64, bn0);
-                        if (++stage == nstages) { stage = 0; phase ^= 1; }
-                    }
-                    if (++kw == ksz) { kw = 0; ++kh; }
+        int stage = 0;
+        uint32_t phase = 0;
+        const int pad = p.ksz >> 1;
+        const int nstages = p.stages, taps = p.taps, chunks = p.chunks, ksz = p.ksz, n_tile = p.n_tile;
+        const int cin_pad = chunks * 64;
+        const uint32_t tx_bytes = (uint32_t)(kTileM * 64 * 2) + p.b_tx_bytes;
+        const uint32_t a_bytes = p.a_bytes;
+        const bool s2 = (p.stride == 2);
+        int pit = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++pit) {
+            const TileCoord tc = decode_tile(p, t);
+            const int bn0 = tc.nt * n_tile;
+            int kh = 0, kw = 0;
+            trace(p, 0, pit, 0);
+            for (int tap = 0; tap < taps; ++tap) {
+                const CUtensorMap* mapA = &p.tmA[0];
+                int cx = tc.x0 + kw - pad, cy = tc.y0 + kh - pad;
+                if (s2) {
+                    // input pixel = 2*o + d, d in {-1,0,1}: odd phase for d = +-1, even for 0
+                    const int dy = kh - 1, dx = kw - 1;
+                    const int py = dy & 1, px = dx & 1;
+                    mapA = &p.tmA[py * 2 + px];
+                    cx = tc.x0 + (dx - px) / 2;
+                    cy = tc.y0 + (dy - py) / 2;
                 }
+                const int kb = tap * cin_pad;
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes, fb = full_u32 + stage * 8;
+                        mbar_expect_tx_u32(fb, tx_bytes);
+                        tma_load_4d_s(mapA, fb, sa, ch * 64, cx, cy, tc.n0);
+                        tma_load_2d_s(&p.tmB, fb, sa + a_bytes, kb + ch * 64, bn0);
+                    }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+                if (++kw == ksz) { kw = 0; ++kh; }
             }
+            trace(p, 0, pit, 1);
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one elected thread runs the whole loop) =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            // descriptor = {lo: start>>4 | LBO<<16, hi: SBO | version | layout}; only `lo` moves
-            const uint32_t hi = (uint32_t)(make_smem_desc(0, p.swizzle_bytes) >> 32);
-            const uint32_t lo_base = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t stage_units = stage_bytes >> 4, a_units = p.a_bytes >> 4;
-            const uint32_t idesc = p.idesc;
-            const int nstages = p.stages, n_tile = p.n_tile;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[as], aphase ^ 1);
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        // descriptor = {lo: start>>4 | LBO<<16, hi: SBO | version | layout}; only `lo` moves
+        const uint32_t hi = (uint32_t)(make_smem_desc(0, p.swizzle_bytes) >> 32);
+        const uint32_t lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t stage_units = stage_bytes >> 4, a_units = p.a_bytes >> 4;
+        const uint32_t idesc = p.idesc;
+        const int nstages = p.stages, n_tile = p.n_tile;
+        const uint32_t tfull_u32 = smem_u32(tfull_bar), tempty_u32 = smem_u32(tempty_bar);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            trace(p, 1, it, 0);
+            mbar_wait_u32(tempty_u32 + as * 8, aphase ^ 1);
+            tc_fence_after();
+            trace(p, 1, it, 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
+            for (int ks = 0; ks < ksteps; ++ks) {
+                mbar_wait_u32(full_u32 + stage * 8, phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
+                if (ks == 0) trace(p, 1, it, 2);
+                if (elect_one()) {
                     const uint32_t a_lo = lo_base + (uint32_t)stage * stage_units;
                     const uint32_t b_lo = a_lo + a_units;
 #pragma unroll
@@ -449,11 +537,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + 2 * k);
                         umma_bf16(d_tmem, ad, bd, idesc, (k == 0) ? (uint32_t)(ks != 0) : 1u);
                     }
-                    umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
-                    if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    umma_commit_u32(empty_u32 + stage * 8);                       // frees the smem slot when these MMAs retire
+                    if (ks == ksteps - 1) umma_commit_u32(tfull_u32 + as * 8);     // accumulator complete
                 }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
+            trace(p, 1, it, 3);
         }
     } else if (warp >= 4) {
         epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, bias_s, tfull_bar, tempty_bar, res_bar, stg_base, warp, lane);
@@ -516,56 +605,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // warp-uniform control loops, one elected lane around the asynchronous instructions (see conv_tc_kernel)
+    const uint32_t smem_a = smem_u32(smem), smem_b = smem_u32(ring);
+    const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
+    const uint32_t hfull_u32 = smem_u32(hfull_bar), hempty_u32 = smem_u32(hempty_bar);
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0, hb = 0;
-            uint32_t phase = 0, hphase = 0;
-            const int nstages = p.stages, chunks = p.chunks, n_tile = p.n_tile;
-            const int cin_pad = chunks * 64;
-            const uint32_t b_tx = p.b_tx_bytes, b_bytes = p.b_bytes;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(p, t);
-                const int bn0 = tc.nt * n_tile;
-                for (int ch = 0; ch < chunks; ++ch) {
-                    mbar_wait(&hempty_bar[hb], hphase ^ 1);
-                    mbar_expect_tx(&hfull_bar[hb], (uint32_t)(kHaloW * kHaloH * 128));
-                    tma_load_4d(&p.tmA[1], &hfull_bar[hb], smem + hb * kHaloBytes, ch * 64, tc.x0 - 1, tc.y0 - 1, tc.n0);
-                    if (++hb == 2) { hb = 0; hphase ^= 1; }
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], b_tx);
-                        tma_load_2d(&p.tmB, &full_bar[stage], ring + (size_t)stage * b_bytes, tap * cin_pad + ch * 64, bn0);
-                        if (++stage == nstages) { stage = 0; phase ^= 1; }
+        int stage = 0, hb = 0;
+        uint32_t phase = 0, hphase = 0;
+        const int nstages = p.stages, chunks = p.chunks, n_tile = p.n_tile;
+        const int cin_pad = chunks * 64;
+        const uint32_t b_tx = p.b_tx_bytes, b_bytes = p.b_bytes;
+        int pit = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++pit) {
+            const TileCoord tc = decode_tile(p, t);
+            const int bn0 = tc.nt * n_tile;
+            trace(p, 0, pit, 0);
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait_u32(hempty_u32 + hb * 8, hphase ^ 1);
+                if (ch == 0) trace(p, 0, pit, 1);
+                if (elect_one()) {
+                    mbar_expect_tx_u32(hfull_u32 + hb * 8, (uint32_t)(kHaloW * kHaloH * 128));
+                    tma_load_4d_s(&p.tmA[1], hfull_u32 + hb * 8, smem_a + hb * kHaloBytes, ch * 64, tc.x0 - 1, tc.y0 - 1, tc.n0);
+                }
+                if (++hb == 2) { hb = 0; hphase ^= 1; }
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx_u32(full_u32 + stage * 8, b_tx);
+                        tma_load_2d_s(&p.tmB, full_u32 + stage * 8, smem_b + (uint32_t)stage * b_bytes, tap * cin_pad + ch * 64, bn0);
                     }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
+            trace(p, 0, pit, 2);
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0, hb = 0, it = 0;
-            uint32_t phase = 0, hphase = 0;
-            // B: canonical SW128 K-major, 8-row groups 1024 B apart.  A: 8-row groups one halo row (10 px) apart.
-            const uint32_t hi_b = (uint32_t)(make_smem_desc(0, 128) >> 32);
-            const uint32_t hi_a0 = (hi_b & ~0x3FFFu) | (uint32_t)((kHaloW * 128) >> 4);
-            const uint32_t smem_a = smem_u32(smem), smem_b = smem_u32(ring);
-            const uint32_t b_units = p.b_bytes >> 4;
-            const uint32_t idesc = p.idesc;
-            const int nstages = p.stages, n_tile = p.n_tile, chunks = p.chunks;
-            const bool use_base_offset = (p.halo & 2) != 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[as], aphase ^ 1);
+        int stage = 0, hb = 0, it = 0;
+        uint32_t phase = 0, hphase = 0;
+        // B: canonical SW128 K-major, 8-row groups 1024 B apart.  A: 8-row groups one halo row (10 px) apart.
+        const uint32_t hi_b = (uint32_t)(make_smem_desc(0, 128) >> 32);
+        const uint32_t hi_a0 = (hi_b & ~0x3FFFu) | (uint32_t)((kHaloW * 128) >> 4);
+        const uint32_t b_units = p.b_bytes >> 4;
+        const uint32_t idesc = p.idesc;
+        const int nstages = p.stages, n_tile = p.n_tile, chunks = p.chunks;
+        const bool use_base_offset = (p.halo & 2) != 0;
+        const uint32_t tfull_u32 = smem_u32(tfull_bar), tempty_u32 = smem_u32(tempty_bar);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            trace(p, 1, it, 0);
+            mbar_wait_u32(tempty_u32 + as * 8, aphase ^ 1);
+            tc_fence_after();
+            trace(p, 1, it, 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait_u32(hfull_u32 + hb * 8, hphase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
-                for (int ch = 0; ch < chunks; ++ch) {
-                    mbar_wait(&hfull_bar[hb], hphase);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_a + hb * kHaloBytes;
+                if (ch == 0) trace(p, 1, it, 2);
+                const uint32_t a_base = smem_a + hb * kHaloBytes;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait_u32(full_u32 + stage * 8, phase);
+                    tc_fence_after();
+                    if (elect_one()) {
                         const uint32_t a_addr = a_base + (uint32_t)(((tap / 3) * kHaloW + (tap % 3)) * 128);
                         uint32_t hi_a = hi_a0;
                         if (use_base_offset) hi_a |= ((a_addr >> 7) & 7u) << 17;      // descriptor bits [49,52)
@@ -577,14 +679,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
                             const uint64_t bd = ((uint64_t)hi_b << 32) | (uint64_t)(b_lo + 2 * k);
                             umma_bf16(d_tmem, ad, bd, idesc, (k == 0) ? (uint32_t)((ch | tap) != 0) : 1u);
                         }
-                        umma_commit(&empty_bar[stage]);
-                        if (++stage == nstages) { stage = 0; phase ^= 1; }
+                        umma_commit_u32(empty_u32 + stage * 8);
+                        if (tap == 8) {
+                            umma_commit_u32(hempty_u32 + hb * 8);                     // halo tile free once its 36 MMAs retire
+                            if (ch == chunks - 1) umma_commit_u32(tfull_u32 + as * 8);
+                        }
                     }
-                    umma_commit(&hempty_bar[hb]);                                 // halo tile free once its 36 MMAs retire
-                    if (ch == chunks - 1) umma_commit(&tfull_bar[as]);
-                    if (++hb == 2) { hb = 0; hphase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
+                if (++hb == 2) { hb = 0; hphase ^= 1; }
             }
+            trace(p, 1, it, 3);
         }
     } else if (warp >= 4) {
         epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, bias_s, tfull_bar, tempty_bar, res_bar, stg_base, warp, lane);
@@ -698,7 +803,14 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     B2D_CHECK(!res || (res_cs % 8 == 0 && res_c0 % 8 == 0), "conv_tc: residual slice must be 16-byte aligned");
     B2D_CHECK(p.bw <= 32 && 32 % p.bw == 0, "conv_tc: tile width %d does not divide a warp's 32 rows", p.bw);
     const uint32_t row_bytes = (uint32_t)p.n_tile * esize;
-    const uint32_t stg_bytes = 128u * row_bytes;
+    uint32_t stg_bytes = 128u * row_bytes;
+    p.stg_bufs = 1;
+    {   // a second staging slab hides the TMA store's smem read behind the next tile's math, if the ring keeps >= 4 stages
+        const uint32_t sb = p.a_bytes + p.b_bytes;
+        const char* env = getenv("B2D_STG2");
+        const int want = env ? atoi(env) : 1;
+        if (want && (226u * 1024 - 2048 - 2 * stg_bytes - (uint32_t)cout_pad * 4) / sb >= 4) { p.stg_bufs = 2; stg_bytes *= 2; }
+    }
     {
         uint32_t done = 0, off = 0;
         int n = 0;
@@ -719,6 +831,11 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         p.epi_nchunks = n;
     }
     p.has_res = res ? 1 : 0;
+    p.trace = nullptr;
+    if (getenv("B2D_TRACE")) {
+        B2D_CUDA(cudaMalloc(&plan->trace_dev, sizeof(long long) * kTraceRoles * kTraceTiles * kTraceEvents));
+        p.trace = plan->trace_dev;
+    }
     const uint32_t tail_bytes = 256 /*barriers + tmem slot*/ + (uint32_t)cout_pad * 4 /*bias*/;
     const uint32_t budget = 226 * 1024 - 1024 /*align slack*/ - stg_bytes - tail_bytes;
     int stages = (int)(budget / stage_bytes);
@@ -843,7 +960,27 @@ int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
         B2D_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         done = true;
     }
+    if (p.trace) B2D_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * kTraceRoles * kTraceTiles * kTraceEvents, stream));
     k<<<grid, kThreads, plan->smem_bytes, stream>>>(p, n);
+    if (p.trace && getenv("B2D_TRACE_DUMP")) {
+        static long long h[kTraceRoles * kTraceTiles * kTraceEvents];
+        B2D_CUDA(cudaStreamSynchronize(stream));
+        B2D_CUDA(cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost));
+        long long t0 = h[0] ? h[0] : h[kTraceTiles * kTraceEvents];
+        const char* names[kTraceRoles] = {"load", "mma ", "epi "};
+        fprintf(stderr, "trace (cycles from first stamp; load: first issue, last issue | mma: start, tmem free, first operand, last commit | epi: slab free, acc ready, math done, store issued)\n");
+        for (int it = 0; it < kTraceTiles; ++it) {
+            fprintf(stderr, "tile %2d", it);
+            for (int r = 0; r < kTraceRoles; ++r) {
+                fprintf(stderr, " | %s", names[r]);
+                for (int e = 0; e < kTraceEvents; ++e) {
+                    long long v = h[(r * kTraceTiles + it) * kTraceEvents + e];
+                    if (v) fprintf(stderr, " %7lld", v - t0); else fprintf(stderr, "       -");
+                }
+            }
+            fprintf(stderr, "\n");
+        }
+    }
     B2D_LAUNCH_CHECK();
     return 0;
 }
@@ -851,6 +988,8 @@ int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
 void conv_tc_free(ConvTcPlan* plan) {
     if (plan->w_dev) cudaFree(plan->w_dev);
     if (plan->bias_dev) cudaFree(plan->bias_dev);
+    if (plan->trace_dev) cudaFree(plan->trace_dev);
+    plan->trace_dev = nullptr;
     plan->w_dev = nullptr;
     plan->bias_dev = nullptr;
 }
