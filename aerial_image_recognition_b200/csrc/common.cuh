@@ -124,6 +124,8 @@ void dwconv_free(DwConvPlan* plan);
 int maxpool_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                    __nv_bfloat16* dst, int oh, int ow, int dst_cs, int dst_c0, int c, int k, int stride,
                    int n, cudaStream_t stream);
+int poolchain_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* const* dst, const int* dst_c0,
+                     int dst_cs, int c, int stages, int n, cudaStream_t stream);
 int upsample2x_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                       __nv_bfloat16* dst, int dst_cs, int dst_c0, int c, int n, cudaStream_t stream);
 

@@ -514,7 +514,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
         const uint32_t stage_units = stage_bytes >> 4, a_units = p.a_bytes >> 4;
         const uint32_t idesc = p.idesc;
-        const int nstages = p.stages, n_tile = p.n_tile;
+        const int nstages = p.stages, n_tile = p.n_tile, chunks = p.chunks;
+        const int last_kmmas = (p.cin - (chunks - 1) * 64 + 15) >> 4;      // K=16 MMAs that carry data in the last chunk
+        int chk = 0;
         const uint32_t tfull_u32 = smem_u32(tfull_bar), tempty_u32 = smem_u32(tempty_bar);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int as = it & 1;
@@ -528,14 +530,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 mbar_wait_u32(full_u32 + stage * 8, phase);
                 tc_fence_after();
                 if (ks == 0) trace(p, 1, it, 2);
+                const bool last_chunk = (++chk == chunks);
+                if (last_chunk) chk = 0;
                 if (elect_one()) {
                     const uint32_t a_lo = lo_base + (uint32_t)stage * stage_units;
                     const uint32_t b_lo = a_lo + a_units;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {   // kc = 64 -> four K=16 MMAs, +32 B each
-                        const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + 2 * k);
-                        const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + 2 * k);
-                        umma_bf16(d_tmem, ad, bd, idesc, (k == 0) ? (uint32_t)(ks != 0) : 1u);
+                    for (int k = 0; k < 4; ++k) {   // kc = 64 -> four K=16 MMAs, +32 B each; the zero-padded tail of the last chunk is skipped
+                        if (k == 0 || !last_chunk || k < last_kmmas) {
+                            const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + 2 * k);
+                            const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + 2 * k);
+                            umma_bf16(d_tmem, ad, bd, idesc, (k == 0) ? (uint32_t)(ks != 0) : 1u);
+                        }
                     }
                     umma_commit_u32(empty_u32 + stage * 8);                       // frees the smem slot when these MMAs retire
                     if (ks == ksteps - 1) umma_commit_u32(tfull_u32 + as * 8);     // accumulator complete
@@ -663,6 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
                 tc_fence_after();
                 if (ch == 0) trace(p, 1, it, 2);
                 const uint32_t a_base = smem_a + hb * kHaloBytes;
+                const int kmmas = (ch == chunks - 1) ? ((p.cin - ch * 64 + 15) >> 4) : 4;
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     mbar_wait_u32(full_u32 + stage * 8, phase);
@@ -675,9 +682,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
                         const uint32_t b_lo = (((smem_b & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)stage * b_units;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = ((uint64_t)hi_a << 32) | (uint64_t)(a_lo + 2 * k);
-                            const uint64_t bd = ((uint64_t)hi_b << 32) | (uint64_t)(b_lo + 2 * k);
-                            umma_bf16(d_tmem, ad, bd, idesc, (k == 0) ? (uint32_t)((ch | tap) != 0) : 1u);
+                            if (k == 0 || k < kmmas) {                            // skip the zero-padded tail of the last chunk
+                                const uint64_t ad = ((uint64_t)hi_a << 32) | (uint64_t)(a_lo + 2 * k);
+                                const uint64_t bd = ((uint64_t)hi_b << 32) | (uint64_t)(b_lo + 2 * k);
+                                umma_bf16(d_tmem, ad, bd, idesc, (k == 0) ? (uint32_t)((ch | tap) != 0) : 1u);
+                            }
                         }
                         umma_commit_u32(empty_u32 + stage * 8);
                         if (tap == 8) {

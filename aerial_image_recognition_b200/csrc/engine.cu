@@ -31,7 +31,7 @@ struct Buffer {
     size_t bytes;
 };
 
-enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_MAXPOOL, OP_UPSAMPLE };
+enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_MAXPOOL, OP_UPSAMPLE, OP_POOLCHAIN, OP_NOP };
 
 struct OpDesc {   // what the caller asked for (resolved into a plan at finalize)
     int kind_req;     // 0 conv, 1 dwconv, 2 maxpool, 3 upsample
@@ -47,6 +47,8 @@ struct Op {
     // pool / upsample
     const __nv_bfloat16* src; __nv_bfloat16* dst;
     int h, w, src_cs, src_c0, oh, ow, dst_cs, dst_c0, c, k, stride;
+    // pool chain (this op + the next chain_stages - 1 max-pools, which become OP_NOP)
+    __nv_bfloat16* chain_dst[3]; int chain_c0[3]; int chain_stages; int fused_into;
 };
 
 struct TableEntry { ResizeTables t; int canvas; };
@@ -157,6 +159,9 @@ int launch_op(b2d_engine* e, const Op& op, int n, cudaStream_t s) {
             return maxpool_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.dst, op.oh, op.ow, op.dst_cs, op.dst_c0, op.c, op.k,
                                   op.stride, n, s);
         case OP_UPSAMPLE: return upsample2x_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.dst, op.dst_cs, op.dst_c0, op.c, n, s);
+        case OP_POOLCHAIN:
+            return poolchain_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.chain_dst, op.chain_c0, op.dst_cs, op.c, op.chain_stages, n, s);
+        case OP_NOP: return 0;
     }
     return -1;
 }
@@ -351,6 +356,30 @@ int b2d_plan_finalize(b2d_engine* e) {
         }
         d.w.clear(); d.w.shrink_to_fit();
     }
+    // Fuse chains of stride-1 max-pools into one launch: SPPF (mp5 of mp5 of mp5) and SPPCSPC (mp5, mp9, mp13 of one
+    // source, which are the same three tensors because max-pooling with -inf padding composes).
+    for (size_t i = 0; i + 1 < e->ops.size(); ++i) {
+        Op& a = e->ops[i];
+        if (a.kind != OP_MAXPOOL || a.stride != 1 || a.k != 5) continue;
+        if ((size_t)a.h * a.w * 8 * 2 * 2 > 200 * 1024) continue;
+        int stages = 1;
+        a.chain_dst[0] = a.dst; a.chain_c0[0] = a.dst_c0;
+        while (stages < 3 && i + stages < e->ops.size()) {
+            const Op& b = e->ops[i + stages];
+            const Op& prev = e->ops[i + stages - 1];
+            if (b.kind != OP_MAXPOOL || b.stride != 1 || b.c != a.c || b.dst != a.dst || b.dst_cs != a.dst_cs) break;
+            const bool sppf = b.k == 5 && b.src == prev.dst && b.src_c0 == prev.dst_c0 && b.src_cs == prev.dst_cs;
+            const bool spp = b.k == 5 + 4 * stages && b.src == a.src && b.src_c0 == a.src_c0;
+            if (!sppf && !spp) break;
+            a.chain_dst[stages] = b.dst; a.chain_c0[stages] = b.dst_c0;
+            ++stages;
+        }
+        if (stages == 1) continue;
+        a.kind = OP_POOLCHAIN;
+        a.chain_stages = stages;
+        for (int j = 1; j < stages; ++j) { e->ops[i + j].kind = OP_NOP; e->ops[i + j].fused_into = (int)i; }
+        i += stages - 1;
+    }
     e->finalized = true;
     return 0;
 }
@@ -359,7 +388,12 @@ void* b2d_buffer_ptr(b2d_engine* e, int buf) { return (e && buf >= 0 && buf < (i
 size_t b2d_buffer_bytes(b2d_engine* e, int buf) { return (e && buf >= 0 && buf < (int)e->bufs.size()) ? e->bufs[buf].bytes : 0; }
 int b2d_num_anchors(b2d_engine* e) { return e ? e->head.rows_total : -1; }
 int b2d_num_ops(b2d_engine* e) { return e ? (int)e->ops.size() : -1; }
-int b2d_num_kernels_per_forward(b2d_engine* e) { return e ? (int)e->ops.size() : -1; }
+int b2d_num_kernels_per_forward(b2d_engine* e) {
+    if (!e) return -1;
+    int k = 0;
+    for (const Op& op : e->ops) k += op.kind != OP_NOP;
+    return k;
+}
 
 int b2d_describe_op(b2d_engine* e, int i, char* buf, int buflen) {
     B2D_CHECK(e && e->finalized && i >= 0 && i < (int)e->ops.size(), "describe_op: bad index");
@@ -372,6 +406,8 @@ int b2d_describe_op(b2d_engine* e, int i, char* buf, int buflen) {
         case OP_DWCONV: return snprintf(buf, buflen, "depthwise 3x3 c %d @ %dx%d", op.dw.c, op.dw.h, op.dw.w);
         case OP_MAXPOOL: return snprintf(buf, buflen, "maxpool k%d s%d c %d @ %dx%d", op.k, op.stride, op.c, op.h, op.w);
         case OP_UPSAMPLE: return snprintf(buf, buflen, "upsample2x c %d @ %dx%d", op.c, op.h, op.w);
+        case OP_POOLCHAIN: return snprintf(buf, buflen, "maxpool chain x%d (k5 s1 composed) c %d @ %dx%d", op.chain_stages, op.c, op.h, op.w);
+        case OP_NOP: return snprintf(buf, buflen, "maxpool k%d s1 c %d @ %dx%d (fused into op %d)", op.k, op.c, op.h, op.w, op.fused_into);
     }
     return 0;
 }

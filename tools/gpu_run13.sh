@@ -1,0 +1,6 @@
+timeout 200 python tools/diag.py tcops --batch 3 --imgsz 320 > gpurun_out/d_tcops.log 2>&1; echo "tcops rc=$?"
+grep -c " ok " gpurun_out/d_tcops.log; grep -c BAD gpurun_out/d_tcops.log
+timeout 200 python tools/diag.py tcops --arch yolov7 --batch 2 --imgsz 128 > gpurun_out/d_tcops_v7.log 2>&1; echo "tcops v7 rc=$?"
+grep -c " ok " gpurun_out/d_tcops_v7.log; grep -c BAD gpurun_out/d_tcops_v7.log
+B2D_LIB=tools/ubench/build/libb2det_elect2.so timeout 300 python tools/diag.py time --batch 64 > gpurun_out/d_time11_prev.log 2>&1; tail -2 gpurun_out/d_time11_prev.log | head -1
+timeout 300 python tools/diag.py time --batch 64 > gpurun_out/d_time11_new.log 2>&1; tail -2 gpurun_out/d_time11_new.log | head -1
