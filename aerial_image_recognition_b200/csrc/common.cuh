@@ -42,33 +42,38 @@ struct EpiChunk {         // one 128/64/32-byte wide column chunk of an output r
 constexpr int kMaxEpiChunks = 6;
 
 struct __align__(64) ConvTcParams {
-    CUtensorMap tmA[4];   // [0]: stride-1 activation map; [py*2+px]: the four stride-2 phase maps
-    CUtensorMap tmB;      // packed weights [cout_pad][taps*cin], K contiguous
-    CUtensorMap tmO[3];   // output slice, one warp sub-box, chunk width 128 / 64 / 32 bytes
+    CUtensorMap tmA[4];   // generic: [0] stride-1 map or [py*2+px] the four stride-2 phase maps; halo: [0] the halo box map
+    CUtensorMap tmB;      // packed weights [cout_pad][taps*cin_pad], K contiguous
+    CUtensorMap tmO[3];   // output slice, one warp quarter's sub-box, chunk width 128 / 64 / 32 bytes
     CUtensorMap tmR[3];   // residual slice, same boxes
     EpiChunk epi[kMaxEpiChunks];
     int epi_nchunks, has_res;
-    int stg_bufs;         // 1 or 2 staging slabs per lane quarter
+    int stg_bufs;         // 1 or 2 staging buffers (each mt tiles x 128 rows x n_tile columns)
     uint32_t stg_off, bar_off;   // smem offsets (from the 1 KiB aligned base) of the staging region / barrier block
     const float* bias;    // [cout_pad]
-    void* out;            // dst buffer base (bf16 or f32, NHWC)
-    const __nv_bfloat16* res;  // residual buffer base or nullptr
-    int out_cs, out_c0;   // dst channel count of the whole buffer / channel offset of the slice
-    int res_cs, res_c0;
     int W, H;             // output spatial size
     int cin, cout;        // true channel counts
     int n_tile, n_tiles_n;
-    int kc, chunks;       // channels per K chunk (16/32/64), chunks per tap
+    int chunks;           // 64-channel K chunks per tap
     int ksz, taps, stride;
-    int bw, bh, bn;       // M tile = bw x bh pixels x bn images = 128 rows
+    int bw, bh, bn;       // M tile = bw x bh pixels x bn images = 128 rows, row m = (y * bn + n) * bw + x
+    int perm;             // 1: activation maps are (C, W, N, H) (tiles spanning images), 0: (C, W, H, N)
     int tiles_x, tiles_y;
+    uint32_t rcp_nn, rcp_tx, rcp_ty;   // ceil(2^32 / d) for the tile decode (0 when d == 1)
     int act, out_f32;
     int stages;
-    int halo;             // 0: shifted-box loads; 1/3: shared halo tile (3: descriptor base_offset set)
-    uint32_t a_bytes, b_bytes, b_tx_bytes;   // smem bytes per stage (padded), TMA bytes of B
-    uint32_t swizzle_bytes;                  // 128 / 64 / 32
+    int kind;             // 0 generic (shifted boxes), 1 halo (3x3 s1, bw == 8), 2 stem (im2col gather)
+    int mt;               // M tiles per round (share B stages, one accumulator stage, one epilogue pass)
+    int halo_w;           // bw + 2
+    uint32_t halo_bytes;  // bytes of one halo buffer (1 KiB multiple)
+    uint32_t halo_kh_rows;   // halo rows between kh taps = bn * (bw + 2)
+    uint32_t a_bytes, b_bytes;       // smem bytes of one A tile / one B stage (padded to 1 KiB)
+    uint32_t a_tx_bytes, b_tx_bytes; // TMA bytes of one A box / one B box
     uint32_t tmem_cols;
     uint32_t idesc;
+    int in_h, in_w;       // input spatial size (stem)
+    const void* src_raw;  // stem: NHWC4 bf16 input
+    const void* w_raw;    // stem: packed weights [n_tile][64] bf16
     long long* trace;     // debug only (B2D_TRACE=1): per-role clock64 stamps of CTA 0, else nullptr
 };
 
@@ -82,6 +87,7 @@ struct ConvTcPlan {
 };
 
 int conv_tc_supported(int cin, int ksz, int stride);
+int conv_tc_stem_supported(int src_cs, int cin, int ksz, int stride, int cout, int dst_f32, int has_res);
 int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch,
                  const __nv_bfloat16* src, int src_h, int src_w, int src_cs, int src_c0, int cin,
                  void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32,

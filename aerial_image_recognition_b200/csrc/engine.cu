@@ -328,7 +328,8 @@ int b2d_plan_finalize(b2d_engine* e) {
         if (d.kind_req == 0) {
             const __nv_bfloat16* res = d.res >= 0 ? (const __nv_bfloat16*)e->bufs[d.res].ptr : nullptr;
             const int res_cs = d.res >= 0 ? e->bufs[d.res].c : 0;
-            bool tc = conv_tc_supported(d.cin, d.k, d.stride) && sb.c % 8 == 0 && d.src_c0 % 8 == 0;
+            bool tc = (conv_tc_supported(d.cin, d.k, d.stride) && sb.c % 8 == 0 && d.src_c0 % 8 == 0) ||
+                      (conv_tc_stem_supported(sb.c, d.cin, d.k, d.stride, d.cout, db.f32, d.res >= 0) && d.src_c0 == 0);
             if (d.impl == B2D_CONV_SIMT) tc = false;
             B2D_CHECK(!(d.impl == B2D_CONV_TCGEN05 && !tc), "plan_finalize: op %zu cannot run on the tcgen05 path", i);
             if (tc) {
