@@ -62,7 +62,7 @@ struct __align__(64) ConvTcParams {
     uint32_t rcp_nn, rcp_tx, rcp_ty;   // ceil(2^32 / d) for the tile decode (0 when d == 1)
     int act, out_f32;
     int stages;
-    int kind;             // 0 generic (shifted boxes), 1 halo (3x3 s1, bw == 8), 2 stem (im2col gather)
+    int kind;             // 0 generic (shifted boxes), 1 halo (3x3 s1, bw == 8), 2 stem (im2col gather), 3 depthwise (halo + diagonal blocks)
     int mt;               // M tiles per round (share B stages, one accumulator stage, one epilogue pass)
     int halo_w;           // bw + 2
     uint32_t halo_bytes;  // bytes of one halo buffer (1 KiB multiple)
@@ -92,7 +92,8 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch,
                  const __nv_bfloat16* src, int src_h, int src_w, int src_cs, int src_c0, int cin,
                  void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32,
                  int ksz, int stride, int act, const float* w_host, const float* b_host,
-                 const __nv_bfloat16* res, int res_cs, int res_c0);
+                 const __nv_bfloat16* res, int res_cs, int res_c0, int depthwise = 0);
+int conv_tc_dw_supported(int cin, int cout, int ksz, int stride, int dst_f32, int has_res);
 int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream);
 void conv_tc_free(ConvTcPlan* plan);
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen);

@@ -691,6 +691,122 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// depthwise kernel: 3x3 stride-1 depthwise conv (Ultralytics 8.3.x cls branch) on the tensor cores.
+// Channels are cut into groups of 16; for a group the depthwise filter is a dense 16 -> 16 conv whose
+// weight matrix per tap is diagonal, i.e. one M128 x N16 x K16 MMA per (tap, group): A = the halo
+// tile of the group's 64-channel chunk at K offset 32 B x (group % 4), B = a 16 x 16 diagonal block,
+// D = the group's 16 accumulator columns.  15/16 of the multiplies hit zeros, which is irrelevant:
+// the tensor pipe is otherwise idle here and the kernel stays bound by its output like every other
+// narrow layer, while the CUDA-core version was bound by FMA issue and L2 re-reads.
+// Weights: per 64-channel chunk one 18 KB stage = [tap][16 rows][64 k] bf16, SWIZZLE_128B: row n of tap t
+// holds the four groups' diagonal entries side by side (k = group * 16 + n), so a group's block is the
+// same 16 rows at K offset 32 B x group -- 144 full 128-byte TMA rows instead of 576 32-byte ones.
+// ---------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const Bars b = carve_bars(smem, p);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int mt = p.mt;
+    const int total_tiles = p.tiles_x * p.tiles_y * ((nimg + p.bn - 1) / p.bn) * p.n_tiles_n;
+    const int rounds = (total_tiles + mt - 1) / mt;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB); }
+    const uint32_t tmem_base = prologue(p, b, warp, lane, 1);
+    const uint32_t halo_bytes = p.halo_bytes;
+    const uint32_t smem_a = smem_u32(smem), smem_b = smem_a + 2u * (uint32_t)mt * halo_bytes;
+    const uint32_t full_u32 = smem_u32(b.full), empty_u32 = smem_u32(b.empty);
+    const uint32_t hfull_u32 = smem_u32(b.hfull), hempty_u32 = smem_u32(b.hempty);
+    const int chunks = p.chunks;                 // 64-channel chunks per n_tile
+
+    if (warp == 0) {
+        int stage = 0, hb = 0;
+        uint32_t phase = 0, hphase = 0;
+        const int nstages = p.stages;
+        const uint32_t b_tx = p.b_tx_bytes, b_bytes = p.b_bytes;
+        const bool perm = p.perm != 0;
+        int pit = 0;
+        for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++pit) {
+            const int t0 = rd * mt;
+            const int nv = min(mt, total_tiles - t0);
+            const TileCoord tc0 = decode_tile(p, t0);
+            const TileCoord tc1 = decode_tile(p, nv > 1 ? t0 + 1 : t0);
+            trace(p, 0, pit, 0);
+            for (int ch = 0; ch < chunks; ++ch) {
+                const int gch = tc0.nt * chunks + ch;                    // chunk index in the whole channel range
+                mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx_u32(full_u32 + stage * 8, b_tx);
+                    tma_load_2d(&p.tmB, full_u32 + stage * 8, smem_b + (uint32_t)stage * b_bytes, 0, gch * 144);
+                }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+                mbar_wait_u32(hempty_u32 + hb * 8, hphase ^ 1);
+                if (elect_one()) {
+                    const uint32_t hbar = hfull_u32 + hb * 8, dst = smem_a + (uint32_t)(hb * mt) * halo_bytes;
+                    mbar_expect_tx_u32(hbar, (uint32_t)nv * p.a_tx_bytes);
+                    tma_load_4d(&p.tmA[0], hbar, dst, gch * 64, tc0.x0 - 1, perm ? tc0.n0 : tc0.y0 - 1, perm ? tc0.y0 - 1 : tc0.n0);
+                    if (nv > 1) tma_load_4d(&p.tmA[0], hbar, dst + halo_bytes, gch * 64, tc1.x0 - 1, perm ? tc1.n0 : tc1.y0 - 1, perm ? tc1.y0 - 1 : tc1.n0);
+                }
+                if (++hb == 2) { hb = 0; hphase ^= 1; }
+            }
+            trace(p, 0, pit, 1);
+        }
+    } else if (warp == 1) {
+        int stage = 0, hb = 0, it = 0;
+        uint32_t phase = 0, hphase = 0;
+        const uint32_t hi_b = desc_hi(1024), hi_a = desc_hi((uint32_t)p.halo_w * 128u);
+        const uint32_t b_units = p.b_bytes >> 4;
+        const uint32_t idesc = p.idesc;                                   // M128 x N16
+        const int nstages = p.stages, n_tile = p.n_tile;
+        const uint32_t kh_bytes = p.halo_kh_rows * 128u;
+        const uint32_t tfull_u32 = smem_u32(b.tfull), tempty_u32 = smem_u32(b.tempty);
+        for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int nv = min(mt, total_tiles - rd * mt);
+            trace(p, 1, it, 0);
+            mbar_wait_u32(tempty_u32 + as * 8, aphase ^ 1);
+            tc_fence_after();
+            trace(p, 1, it, 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * mt * n_tile);
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait_u32(full_u32 + stage * 8, phase);
+                mbar_wait_u32(hfull_u32 + hb * 8, hphase);
+                tc_fence_after();
+                if (ch == 0) trace(p, 1, it, 2);
+                const uint32_t a_base = smem_a + (uint32_t)(hb * mt) * halo_bytes;
+                const int ngroups = min(4, (n_tile - ch * 64) >> 4);      // 16-channel groups in this chunk
+                if (elect_one()) {
+                    const uint32_t b_lo = desc_lo(smem_b) + (uint32_t)stage * b_units;
+                    for (int m = 0; m < nv; ++m) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t a_lo = desc_lo(a_base + (uint32_t)m * halo_bytes + (uint32_t)(tap / 3) * kh_bytes + (uint32_t)(tap % 3) * 128u);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (j < ngroups)
+                                    umma_bf16(d_tmem + (uint32_t)(m * n_tile + ch * 64 + j * 16), desc64(hi_a, a_lo + 2 * j),
+                                              desc64(hi_b, b_lo + (uint32_t)(tap * 128 + 2 * j)), idesc, (uint32_t)(tap != 0));
+                        }
+                    }
+                    umma_commit(empty_u32 + stage * 8);
+                    umma_commit(hempty_u32 + hb * 8);
+                    if (ch == chunks - 1) umma_commit(tfull_u32 + as * 8);
+                }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+                if (++hb == 2) { hb = 0; hphase ^= 1; }
+            }
+            trace(p, 1, it, 3);
+        }
+    } else if (warp >= 4) {
+        epilogue_loop<ACT, 0, 0>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.res, smem + p.stg_off, warp, lane);
+    }
+    epilogue_exit(p, tmem_base, warp);
+}
+
+// ---------------------------------------------------------------------------------------------
 // stem kernel: 3x3 (or 1x1) conv on the 4-channel network input (NHWC4 bf16, 8 bytes per pixel).
 // K = 9 taps x 4 channels = 36 is far too short for a TMA-fed pipeline, so four gather warps build
 // the im2col tiles: thread r owns row r of each of the round's mt tiles, reads its nine 8-byte input
@@ -866,13 +982,14 @@ uint16_t f2bf(float f) {
 }
 
 // pick (bw, bh, bn), bw*bh*bn == 128, maximising useful rows; ties -> squarer spatial box, smaller bn
-void pick_tile(int W, int H, int N, int* bw, int* bh, int* bn) {
+void pick_tile(int W, int H, int N, int* bw, int* bh, int* bn, bool need_w8 = false) {
     double best = -1.0;
     int best_halo = 1 << 30;
     for (int w = 1; w <= 32; w *= 2)
         for (int h = 1; w * h <= 128; h *= 2) {
             int n = 128 / (w * h);
             if (w * n < 8) continue;             // an 8-row operand group must not straddle two y rows
+            if (need_w8 && w != 8) continue;     // halo-fed kernels need 8-pixel-wide tiles
             long long tiles = (long long)ceil_div(W, w) * ceil_div(H, h) * ceil_div(N, n);
             double eff = (double)W * H * N / (double)(tiles * 128);
             int halo = (w + 2) * (h + 2) * n;
@@ -895,6 +1012,11 @@ int conv_tc_supported(int cin, int ksz, int stride) {
     return 1;
 }
 
+// depthwise 3x3 stride 1 with 16-channel groups on the tensor cores
+int conv_tc_dw_supported(int cin, int cout, int ksz, int stride, int dst_f32, int has_res) {
+    return cin == cout && cin % 16 == 0 && ksz == 3 && stride == 1 && !dst_f32 && !has_res && env_int("B2D_DW_TC", 1) != 0;
+}
+
 // the network input: 4-channel NHWC buffer of which the first `cin` (<= 4) carry weights, 3x3 or 1x1, bf16 output
 int conv_tc_stem_supported(int src_cs, int cin, int ksz, int stride, int cout, int dst_f32, int has_res) {
     return src_cs == 4 && cin <= 4 && (ksz == 3 || ksz == 1) && (stride == 1 || stride == 2) && cout <= 256 && !dst_f32 && !has_res;
@@ -903,9 +1025,11 @@ int conv_tc_stem_supported(int src_cs, int cin, int ksz, int stride, int cout, i
 int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloat16* src, int src_h, int src_w, int src_cs,
                  int src_c0, int cin, void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32, int ksz,
                  int stride, int act, const float* w_host, const float* b_host, const __nv_bfloat16* res, int res_cs,
-                 int res_c0) {
+                 int res_c0, int depthwise) {
     memset(plan, 0, sizeof(*plan));
-    const bool stem = conv_tc_stem_supported(src_cs, cin, ksz, stride, cout, dst_f32, res != nullptr) && src_c0 == 0;
+    const bool dw = depthwise != 0;
+    if (dw) B2D_CHECK(conv_tc_dw_supported(cin, cout, ksz, stride, dst_f32, res != nullptr), "conv_tc: unsupported depthwise shape");
+    const bool stem = !dw && conv_tc_stem_supported(src_cs, cin, ksz, stride, cout, dst_f32, res != nullptr) && src_c0 == 0;
     if (!stem) {
         B2D_CHECK(conv_tc_supported(cin, ksz, stride), "conv_tc: unsupported shape cin=%d k=%d s=%d", cin, ksz, stride);
         B2D_CHECK(src_cs % 8 == 0 && src_c0 % 8 == 0, "conv_tc: source slice must be 16-byte aligned (cs=%d c0=%d)", src_cs, src_c0);
@@ -920,10 +1044,11 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.chunks = stem ? 1 : ceil_div(cin, 64);       // a short last chunk is zero-filled by TMA (A) and zero-padded in the packed weights (B)
     const int cout_pad = ceil_div(cout, 16) * 16;
     int split = 1;
-    while (cout_pad % split != 0 || (cout_pad / split) % 16 != 0 || cout_pad / split > 256) ++split;
+    while (cout_pad % split != 0 || (cout_pad / split) % 16 != 0 || cout_pad / split > 256 || (dw && split > 1 && (cout_pad / split) % 64 != 0)) ++split;
     p.n_tile = cout_pad / split;
     p.n_tiles_n = split;
-    pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn);
+    if (dw) p.chunks = ceil_div(p.n_tile, 64);     // depthwise: chunks of one channel tile
+    pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn, dw);
     p.perm = p.bn > 1 ? 1 : 0;
     p.tiles_x = ceil_div(dst_w, p.bw);
     p.tiles_y = ceil_div(dst_h, p.bh);
@@ -934,7 +1059,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     const int total_tiles = p.tiles_x * p.tiles_y * ceil_div(max_batch, p.bn) * split;
     p.a_bytes = kTileM * 64 * 2;
     p.a_tx_bytes = p.a_bytes;
-    p.b_tx_bytes = p.n_tile * 64 * 2;
+    p.b_tx_bytes = dw ? 144 * 128 : p.n_tile * 64 * 2;      // depthwise: [9 taps][16 rows] x 128 B per 64-channel chunk
     p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
     const int esize = dst_f32 ? 4 : 2;
     B2D_CHECK(!(dst_f32 && res), "conv_tc: residual with fp32 output is not supported");
@@ -950,7 +1075,8 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
 
     // ---- kind, tiles per round, stages, staging buffers ----
     // halo: 3x3 stride 1 on 8-pixel-wide tiles (uniform (bw+2)-row stride between 8-row groups)
-    const bool halo_ok = !stem && ksz == 3 && stride == 1 && p.bw == 8 && env_int("B2D_HALO", 1) != 0;
+    const bool halo_ok = !stem && ksz == 3 && stride == 1 && p.bw == 8 && (dw || env_int("B2D_HALO", 1) != 0);
+    B2D_CHECK(!dw || halo_ok, "conv_tc: depthwise needs an 8-pixel-wide tile");
     p.halo_w = p.bw + 2;
     p.halo_kh_rows = (uint32_t)(p.bn * p.halo_w);
     const uint32_t halo_rows = (uint32_t)(p.halo_w * p.bn * (p.bh + 2));
@@ -962,7 +1088,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         if (mt_env > 0 && mt > mt_env) continue;
         if (mt > 1 && (split > 1 || 2 * mt * p.n_tile > 512)) continue;
         if (mt > 1 && !stem && mt_env == 0 && total_tiles < 4 * mt * sm_count) continue;   // keep enough rounds per SM for balance (B2D_MT forces)
-        for (int kind = (stem ? 2 : halo_ok ? 1 : 0); kind >= (stem ? 2 : 0) && best_kind < 0; --kind) {
+        for (int kind = (stem ? 2 : halo_ok ? 1 : 0); kind >= (stem ? 2 : dw ? 1 : 0) && best_kind < 0; --kind) {
             for (int bufs = 2; bufs >= 1 && best_kind < 0; --bufs) {
                 if (bufs == 2 && env_int("B2D_STG2", 1) == 0) continue;
                 const uint32_t stg = (uint32_t)bufs * mt * tile_stg;
@@ -974,8 +1100,9 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                     stages = (int)(room / sb);
                     const int ksteps = p.taps * p.chunks;
                     if (stages > ksteps * 2) stages = ksteps * 2;
+                    // a second staging buffer is worth more than a deep ring when a round has few k-steps (memory-bound 1x1 layers)
                     min_stages = (bufs == 2 || mt > 1) ? 4 : 2;
-                    if (ksteps * 2 < min_stages) min_stages = ksteps * 2;
+                    if (ksteps < min_stages) min_stages = ksteps < 2 ? 2 : ksteps;
                 } else if (kind == 1) {
                     const uint32_t fixed = 2u * mt * p.halo_bytes;
                     stages = room > fixed ? (int)((room - fixed) / p.b_bytes) : 0;
@@ -993,12 +1120,12 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         }
     }
     B2D_CHECK(best_kind >= 0, "conv_tc: no shared-memory configuration fits (n_tile %d)", p.n_tile);
-    p.kind = best_kind; p.mt = best_mt; p.stages = best_stages; p.stg_bufs = best_bufs;
-    if (p.kind == 1) p.a_tx_bytes = halo_rows * 128u;
+    p.kind = dw ? 3 : best_kind; p.mt = best_mt; p.stages = best_stages; p.stg_bufs = best_bufs;
+    if (best_kind == 1) p.a_tx_bytes = halo_rows * 128u;
     const uint32_t stg_bytes = (uint32_t)p.stg_bufs * p.mt * tile_stg;
     uint32_t operand_bytes;
     if (p.kind == 0) operand_bytes = (uint32_t)p.stages * ((uint32_t)p.mt * p.a_bytes + p.b_bytes);
-    else if (p.kind == 1) operand_bytes = 2u * p.mt * p.halo_bytes + (uint32_t)p.stages * p.b_bytes;
+    else if (p.kind == 1 || p.kind == 3) operand_bytes = 2u * p.mt * p.halo_bytes + (uint32_t)p.stages * p.b_bytes;
     else operand_bytes = (uint32_t)p.stages * p.mt * p.a_bytes + p.b_bytes;
     p.stg_off = operand_bytes;                                   // 1 KiB aligned: every operand slot is a multiple of 1 KiB
     p.bar_off = p.stg_off + stg_bytes;
@@ -1033,16 +1160,27 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     while (cols < (uint32_t)(2 * p.mt * p.n_tile)) cols *= 2;
     p.tmem_cols = cols;
     // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((dw ? 16 : p.n_tile) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
     // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin_pad] (zero padded) ----
     const int cin_pad = p.chunks * 64;
     const size_t ktot = stem ? 64 : (size_t)p.taps * cin_pad;     // stem: k = tap * 4 + c, one 128-byte row per output channel
-    std::vector<uint16_t> wp((size_t)cout_pad * ktot, 0);
-    for (int o = 0; o < cout; ++o)
-        for (int c = 0; c < cin; ++c)
-            for (int t = 0; t < p.taps; ++t)
-                wp[(size_t)o * ktot + (stem ? (size_t)t * 4 + c : (size_t)t * cin_pad + c)] = f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
+    const int dw_chunks = p.chunks * split;                       // depthwise: 64-channel chunks over all channels
+    std::vector<uint16_t> wp(dw ? (size_t)dw_chunks * 9 * 16 * 64 : (size_t)cout_pad * ktot, 0);
+    if (dw) {
+        // row (chunk * 9 + tap) * 16 + n, 64 k each: k = group * 16 + n carries w[chunk * 64 + group * 16 + n][tap]
+        for (int c = 0; c < cout; ++c)
+            for (int t = 0; t < 9; ++t) {
+                const int chunk = c / 64, g = (c % 64) / 16, d = c % 16;
+                const size_t row = ((size_t)chunk * 9 + t) * 16 + d;
+                wp[row * 64 + g * 16 + d] = f2bf(w_host[(size_t)c * 9 + t]);
+            }
+    } else {
+        for (int o = 0; o < cout; ++o)
+            for (int c = 0; c < cin; ++c)
+                for (int t = 0; t < p.taps; ++t)
+                    wp[(size_t)o * ktot + (stem ? (size_t)t * 4 + c : (size_t)t * cin_pad + c)] = f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
+    }
     std::vector<float> bp(cout_pad, 0.f);
     for (int o = 0; o < cout; ++o) bp[o] = b_host ? b_host[o] : 0.f;
     B2D_CUDA(cudaMalloc(&plan->w_dev, wp.size() * 2));
@@ -1055,12 +1193,19 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // ---- tensor maps ----
     const bool perm = p.perm != 0;
     if (!stem) {
-        uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout_pad};
-        uint64_t str[1] = {(uint64_t)ktot * 2};
-        uint32_t box[2] = {64u, (uint32_t)p.n_tile};
-        if (encode_map(&p.tmB, plan->w_dev, 2, dims, str, box, 128)) return -1;
+        if (dw) {
+            uint64_t dims[2] = {64u, (uint64_t)dw_chunks * 9 * 16};
+            uint64_t str[1] = {128u};
+            uint32_t box[2] = {64u, 144u};
+            if (encode_map(&p.tmB, plan->w_dev, 2, dims, str, box, 128)) return -1;
+        } else {
+            uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout_pad};
+            uint64_t str[1] = {(uint64_t)ktot * 2};
+            uint32_t box[2] = {64u, (uint32_t)p.n_tile};
+            if (encode_map(&p.tmB, plan->w_dev, 2, dims, str, box, 128)) return -1;
+        }
         const uint64_t pix = (uint64_t)src_cs * 2, rowb = (uint64_t)src_w * pix, imgb = (uint64_t)src_h * rowb;
-        if (p.kind == 1) {
+        if (p.kind == 1 || p.kind == 3) {
             if (encode_act_map(&p.tmA[0], (void*)(src + src_c0), cin, src_w, src_h, max_batch, pix, rowb, imgb, 64u, (uint32_t)p.halo_w,
                                (uint32_t)(p.bh + 2), (uint32_t)p.bn, perm, 128))
                 return -1;
@@ -1111,6 +1256,7 @@ ConvKernel pick_kernel(int kind, int act, int res, int f32) {
     if (res) return act ? K<1, 1, 0> : K<0, 1, 0>;                         \
     return act ? K<1, 0, 0> : K<0, 0, 0>;
     if (kind == 2) return act ? conv_tc_stem_kernel<1> : conv_tc_stem_kernel<0>;
+    if (kind == 3) return act ? conv_tc_dw_kernel<1> : conv_tc_dw_kernel<0>;
     if (kind == 1) { B2D_PICK(conv_tc_halo_kernel) }
     B2D_PICK(conv_tc_kernel)
 #undef B2D_PICK
@@ -1128,7 +1274,7 @@ int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
     }
     if (grid < 1) return 0;
     ConvKernel k = pick_kernel(p.kind, p.act, p.has_res, p.out_f32);
-    static bool attr_done[3][2][2][2];
+    static bool attr_done[4][2][2][2];
     bool& done = attr_done[p.kind][p.act ? 1 : 0][p.has_res ? 1 : 0][p.out_f32 ? 1 : 0];
     if (!done) {
         B2D_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1170,7 +1316,7 @@ void conv_tc_free(ConvTcPlan* plan) {
 
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
-    static const char* kinds[3] = {"", "-halo", "-stem"};
+    static const char* kinds[4] = {"", "-halo", "-stem", "-depthwise"};
     return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d stg %d tmem %u smem %zu",
                     kinds[p.kind], p.ksz, p.stride, p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages, p.stg_bufs,
                     p.tmem_cols, plan->smem_bytes);

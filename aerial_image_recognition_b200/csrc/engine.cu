@@ -344,6 +344,12 @@ int b2d_plan_finalize(b2d_engine* e) {
                                    db.c, d.dst_c0, d.cout, db.f32, d.k, d.stride, d.act, d.w.data(), d.b.data(), res, res_cs, d.res_c0))
                     return -1;
             }
+        } else if (d.kind_req == 1 && d.impl != B2D_CONV_SIMT && conv_tc_dw_supported(d.cin, d.cout, 3, 1, db.f32, 0) && sb.c % 8 == 0 &&
+                   d.src_c0 % 8 == 0) {
+            op.kind = OP_CONV_TC;
+            if (conv_tc_plan(&op.tc, e->sm_count, e->max_batch, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin, db.ptr, db.h,
+                             db.w, db.c, d.dst_c0, d.cout, 0, 3, 1, d.act, d.w.data(), d.b.data(), nullptr, 0, 0, 1))
+                return -1;
         } else if (d.kind_req == 1) {
             op.kind = OP_DWCONV;
             if (dwconv_plan(&op.dw, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, (__nv_bfloat16*)db.ptr, db.c, d.dst_c0,
