@@ -74,6 +74,7 @@ struct __align__(64) ConvTcParams {
     int in_h, in_w;       // input spatial size (stem)
     const void* src_raw;  // stem: NHWC4 bf16 input
     const void* w_raw;    // stem: packed weights [n_tile][64] bf16
+    int exp;              // timing-ablation flags (trace builds only)
     long long* trace;     // debug only (B2D_TRACE=1): per-role clock64 stamps of CTA 0, else nullptr
 };
 

@@ -191,6 +191,15 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
     return c;
 }
 
+// Ablation flags for timing experiments (trace builds only; results are wrong when set): p.exp bit 0 = the MMA warp
+// does not wait for operand barriers, bit 1 = the epilogue skips TMEM loads / math / stores, bit 2 = the producer
+// issues no TMA loads (arrives on the barriers instead).
+#ifdef B2D_ENABLE_TRACE
+#define B2D_EXP(p, bit) (((p).exp >> (bit)) & 1)
+#else
+#define B2D_EXP(p, bit) 0
+#endif
+
 // Debug trace (build with -DB2D_ENABLE_TRACE, run with B2D_TRACE=1): CTA 0 records clock64() at role
 // events of its first kTraceTiles rounds.  Compiled out of product builds.
 constexpr int kTraceTiles = 24, kTraceEvents = 4, kTraceRoles = 3;   // roles: 0 producer, 1 MMA, 2 epilogue warp 4
@@ -354,7 +363,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         const int ch_base = p.n_tiles_n > 1 ? (int)((uint32_t)t0 - __umulhi((uint32_t)t0, p.rcp_nn) * (uint32_t)p.n_tiles_n) * n_tile : 0;   // n_tiles_n > 1 implies mt == 1
         const uint32_t baddr = bias_base + (uint32_t)(ch_base + half * 16) * 4u;
 #pragma unroll 1
-        for (int m = 0; m < nv; ++m) {
+        for (int m = 0; m < (B2D_EXP(p, 1) ? 0 : nv); ++m) {
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * mt + m) * n_tile + half * 16);
             const uint32_t moff = sboff + (uint32_t)m * tile_bytes;
             uint32_t rbuf[2][16];
@@ -376,7 +385,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         fence_proxy_async();                             // generic-proxy slab writes -> visible to the TMA store
         if (warp == 4 && lane == 0) trace(p, 2, it, 2);
         pair_sync(q);
-        if (issuer) {
+        if (issuer && !B2D_EXP(p, 1)) {
 #pragma unroll
             for (int m = 0; m < kMaxMt; ++m)
                 if (m < nv)
@@ -524,9 +533,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // One lane issues; it is elected once, and the loop body is kept to a handful of instructions per MMA: the issue
+        // interval of a lone thread (~8 cycles per dependent instruction), not the tensor pipe, bounds narrow layers.
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
+        const bool leader = elect_one();
         const uint32_t hi = desc_hi(1024);
         const uint32_t lo_base = desc_lo(smem_base);
         const uint32_t stage_units = stage_bytes >> 4, a_units = p.a_bytes >> 4;
@@ -538,28 +550,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int nv = min(mt, total_tiles - rd * mt);
+            const bool two = min(mt, total_tiles - rd * mt) > 1;
             trace(p, 1, it, 0);
             mbar_wait_u32(tempty_u32 + as * 8, aphase ^ 1);
             tc_fence_after();
             trace(p, 1, it, 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * mt * n_tile);
             for (int ks = 0; ks < ksteps; ++ks) {
-                mbar_wait_u32(full_u32 + stage * 8, phase);
+                if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
                 tc_fence_after();
                 if (ks == 0) trace(p, 1, it, 2);
                 const bool last_chunk = (++chk == chunks);
                 if (last_chunk) chk = 0;
-                if (elect_one()) {
+                const int km = last_chunk ? last_kmmas : 4;                   // the zero-padded tail of the last chunk is skipped
+                if (leader) {
                     const uint32_t a_lo = lo_base + (uint32_t)stage * stage_units;
                     const uint32_t b_lo = a_lo + (uint32_t)mt * a_units;
-                    for (int m = 0; m < nv; ++m) {
+                    const uint32_t acc0 = (uint32_t)(ks != 0);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {   // four K=16 MMAs per 64-channel chunk, +32 B each; the zero-padded tail is skipped
-                            if (k == 0 || !last_chunk || k < last_kmmas)
-                                umma_bf16(d_tmem + (uint32_t)(m * n_tile), desc64(hi, a_lo + (uint32_t)m * a_units + 2 * k), desc64(hi, b_lo + 2 * k),
-                                          idesc, (k == 0) ? (uint32_t)(ks != 0) : 1u);
-                        }
+                    for (int k = 0; k < 4; ++k)     // four K=16 MMAs per 64-channel chunk, +32 B each
+                        if (k < km) umma_bf16(d_tmem, desc64(hi, a_lo + 2 * k), desc64(hi, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                    if (two) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < km) umma_bf16(d_tmem + (uint32_t)n_tile, desc64(hi, a_lo + a_units + 2 * k), desc64(hi, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
                     }
                     umma_commit(empty_u32 + stage * 8);                       // frees the smem slot when these MMAs retire
                     if (ks == ksteps - 1) umma_commit(tfull_u32 + as * 8);     // accumulators complete
@@ -616,16 +630,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
                 if (ch == 0) trace(p, 0, pit, 1);
                 if (elect_one()) {
                     const uint32_t hbar = hfull_u32 + hb * 8, dst = smem_a + (uint32_t)(hb * mt) * halo_bytes;
-                    mbar_expect_tx_u32(hbar, (uint32_t)nv * p.a_tx_bytes);
-                    tma_load_4d(&p.tmA[0], hbar, dst, ch * 64, tc0.x0 - 1, perm ? tc0.n0 : tc0.y0 - 1, perm ? tc0.y0 - 1 : tc0.n0);
-                    if (nv > 1) tma_load_4d(&p.tmA[0], hbar, dst + halo_bytes, ch * 64, tc1.x0 - 1, perm ? tc1.n0 : tc1.y0 - 1, perm ? tc1.y0 - 1 : tc1.n0);
+                    if (B2D_EXP(p, 2)) {
+                        mbar_arrive_u32(hbar);
+                    } else {
+                        mbar_expect_tx_u32(hbar, (uint32_t)nv * p.a_tx_bytes);
+                        tma_load_4d(&p.tmA[0], hbar, dst, ch * 64, tc0.x0 - 1, perm ? tc0.n0 : tc0.y0 - 1, perm ? tc0.y0 - 1 : tc0.n0);
+                        if (nv > 1) tma_load_4d(&p.tmA[0], hbar, dst + halo_bytes, ch * 64, tc1.x0 - 1, perm ? tc1.n0 : tc1.y0 - 1, perm ? tc1.y0 - 1 : tc1.n0);
+                    }
                 }
                 if (++hb == 2) { hb = 0; hphase ^= 1; }
                 for (int tap = 0; tap < 9; ++tap) {
                     mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx_u32(full_u32 + stage * 8, b_tx);
-                        tma_load_2d(&p.tmB, full_u32 + stage * 8, smem_b + (uint32_t)stage * b_bytes, tap * cin_pad + ch * 64, bn0);
+                        if (B2D_EXP(p, 2)) {
+                            mbar_arrive_u32(full_u32 + stage * 8);
+                        } else {
+                            mbar_expect_tx_u32(full_u32 + stage * 8, b_tx);
+                            tma_load_2d(&p.tmB, full_u32 + stage * 8, smem_b + (uint32_t)stage * b_bytes, tap * cin_pad + ch * 64, bn0);
+                        }
                     }
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
@@ -635,47 +657,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     } else if (warp == 1) {
         int stage = 0, hb = 0, it = 0;
         uint32_t phase = 0, hphase = 0;
+        const bool leader = elect_one();                 // elected once; see conv_tc_kernel for why the loop is this lean
         // B: canonical SW128 K-major, 8-row groups 1024 B apart.  A: 8-row groups one halo row (bw + 2 pixels) apart.
         const uint32_t hi_b = desc_hi(1024), hi_a = desc_hi((uint32_t)p.halo_w * 128u);
-        const uint32_t b_units = p.b_bytes >> 4;
+        const uint32_t b_units = p.b_bytes >> 4, halo_units = halo_bytes >> 4, kh_units = (p.halo_kh_rows * 128u) >> 4;
+        const uint32_t a_lo0 = desc_lo(smem_a), b_lo0 = desc_lo(smem_b);
         const uint32_t idesc = p.idesc;
         const int nstages = p.stages, n_tile = p.n_tile, chunks = p.chunks;
-        const uint32_t kh_bytes = p.halo_kh_rows * 128u;
+        const int last_kmmas = (p.cin - (chunks - 1) * 64 + 15) >> 4;
         const uint32_t tfull_u32 = smem_u32(b.tfull), tempty_u32 = smem_u32(b.tempty);
         for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int nv = min(mt, total_tiles - rd * mt);
+            const bool two = min(mt, total_tiles - rd * mt) > 1;
             trace(p, 1, it, 0);
             mbar_wait_u32(tempty_u32 + as * 8, aphase ^ 1);
             tc_fence_after();
             trace(p, 1, it, 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * mt * n_tile);
             for (int ch = 0; ch < chunks; ++ch) {
-                mbar_wait_u32(hfull_u32 + hb * 8, hphase);
+                if (!B2D_EXP(p, 0)) mbar_wait_u32(hfull_u32 + hb * 8, hphase);
                 tc_fence_after();
                 if (ch == 0) trace(p, 1, it, 2);
-                const uint32_t a_base = smem_a + (uint32_t)(hb * mt) * halo_bytes;
-                const int kmmas = (ch == chunks - 1) ? ((p.cin - ch * 64 + 15) >> 4) : 4;
+                const uint32_t a_lo_h = a_lo0 + (uint32_t)(hb * mt) * halo_units;
+                const int km = (ch == chunks - 1) ? last_kmmas : 4;           // skip the zero-padded tail of the last chunk
+                const bool last = ch == chunks - 1;
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    mbar_wait_u32(full_u32 + stage * 8, phase);
+                    if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t b_lo = desc_lo(smem_b) + (uint32_t)stage * b_units;
-                        for (int m = 0; m < nv; ++m) {
-                            const uint32_t a_lo = desc_lo(a_base + (uint32_t)m * halo_bytes + (uint32_t)(tap / 3) * kh_bytes + (uint32_t)(tap % 3) * 128u);
+                    if (leader) {
+                        const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_units;
+                        const uint32_t a_lo = a_lo_h + (uint32_t)(tap / 3) * kh_units + (uint32_t)(tap % 3) * 8u;
+                        const uint32_t acc0 = tap == 0 ? (uint32_t)(ch != 0) : 1u;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k == 0 || k < kmmas)                              // skip the zero-padded tail of the last chunk
-                                    umma_bf16(d_tmem + (uint32_t)(m * n_tile), desc64(hi_a, a_lo + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc,
-                                              (k == 0) ? (uint32_t)((ch | tap) != 0) : 1u);
-                            }
+                        for (int k = 0; k < 4; ++k)
+                            if (k < km) umma_bf16(d_tmem, desc64(hi_a, a_lo + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                        if (two) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < km) umma_bf16(d_tmem + (uint32_t)n_tile, desc64(hi_a, a_lo + halo_units + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
                         }
                         umma_commit(empty_u32 + stage * 8);
                         if (tap == 8) {
                             umma_commit(hempty_u32 + hb * 8);                         // halo tiles free once their MMAs retire
-                            if (ch == chunks - 1) umma_commit(tfull_u32 + as * 8);
+                            if (last) umma_commit(tfull_u32 + as * 8);
                         }
                     }
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -1151,6 +1177,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         p.epi_nchunks = n;
     }
     p.has_res = res ? 1 : 0;
+    p.exp = env_int("B2D_EXP", 0);
     p.trace = nullptr;
     if (getenv("B2D_TRACE")) {
         B2D_CUDA(cudaMalloc(&plan->trace_dev, sizeof(long long) * kTraceRoles * kTraceTiles * kTraceEvents));

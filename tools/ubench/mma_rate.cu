@@ -2,6 +2,8 @@
 // issued back to back by one elected thread (and by two warps into disjoint accumulator columns).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <string.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -14,7 +16,7 @@ __device__ __forceinline__ void commit(uint32_t bar) { asm volatile("tcgen05.com
 __device__ __forceinline__ void wait(uint32_t bar, uint32_t ph) {
     asm volatile("{\n.reg .pred P1;\nW:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra D;\nbra W;\nD:\n}" ::"r"(bar), "r"(ph) : "memory");
 }
-__global__ void __launch_bounds__(128) k(int N, int iters, int issuers, int a_stride_rows, long long* out) {
+__global__ void __launch_bounds__(384) k(int N, int iters, int issuers, int a_stride_rows, int pattern, int bg, long long* out, const __grid_constant__ CUtensorMap tmap, int tma_rows) {
     extern __shared__ __align__(1024) uint8_t raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar[2];
@@ -42,15 +44,86 @@ __global__ void __launch_bounds__(128) k(int N, int iters, int issuers, int a_st
         const uint32_t a0 = ((s32(smem) & 0x3FFFFu) >> 4) | (1u << 16);
         const uint32_t b0 = (((s32(smem) + 32768u) & 0x3FFFFu) >> 4) | (1u << 16);
         long long t0 = clock64();
-        for (int i = 0; i < iters; ++i) {
-            const uint32_t st = (uint32_t)(i & 3);
-            mma(tm + (uint32_t)(w * 256), ((uint64_t)hi_a << 32) | (a0 + st * 2), ((uint64_t)hi_b << 32) | (b0 + st * 2), idesc, 1u);
+        if (pattern >= 10) {
+            const int every = pattern - 10;     // commit to a scratch barrier after every `every` MMAs
+            int tap = 0, ks = 0, c = 0;
+            for (int i = 0; i < iters; ++i) {
+                const uint32_t aoff = (uint32_t)(((tap / 3) * 10 + tap % 3) * 8) + (uint32_t)ks * 2;
+                mma(tm + (uint32_t)(w * 256), ((uint64_t)hi_a << 32) | (a0 + aoff), ((uint64_t)hi_b << 32) | (b0 + (uint32_t)ks * 2), idesc, 1u);
+                if (++ks == 4) { ks = 0; if (++tap == 9) tap = 0; }
+                if (++c == every) { c = 0; commit(s32(&bar[1])); }
+            }
+        } else if (pattern == 0) {
+            for (int i = 0; i < iters; ++i) {
+                const uint32_t st = (uint32_t)(i & 3);
+                mma(tm + (uint32_t)(w * 256), ((uint64_t)hi_a << 32) | (a0 + st * 2), ((uint64_t)hi_b << 32) | (b0 + st * 2), idesc, 1u);
+            }
+        } else {
+            // halo-like: tap offsets (kh*10 + kw) rows over a 180-row tile, 4 K offsets, B rotating over 6 stages of N rows
+            int tap = 0, ks = 0, stg = 0;
+            for (int i = 0; i < iters; ++i) {
+                const uint32_t aoff = (uint32_t)(((tap / 3) * 10 + tap % 3) * 8) + (uint32_t)ks * 2;       // 128 B rows -> 8 x 16 B
+                const uint32_t boff = (uint32_t)stg * (uint32_t)((N * 128 + 1023) / 1024 * 64) + (uint32_t)ks * 2;
+                mma(tm + (uint32_t)(w * 256), ((uint64_t)hi_a << 32) | (a0 + aoff), ((uint64_t)hi_b << 32) | (b0 + boff), idesc, 1u);
+                if (++ks == 4) { ks = 0; if (++tap == 9) tap = 0; if (++stg == (N > 128 ? 1 : N > 64 ? 2 : 4)) stg = 0; }
+            }
         }
         long long t1 = clock64();
         commit(s32(&bar[w]));
         wait(s32(&bar[w]), 0);
         long long t2 = clock64();
         if (blockIdx.x == 0) { out[w * 2] = t1 - t0; out[w * 2 + 1] = t2 - t0; }
+    }
+    __shared__ uint64_t tbar[4];
+    __shared__ volatile int stop_flag;
+    if (threadIdx.x == 0) stop_flag = 0;
+    if (warp == 3 && lane == 0 && tma_rows > 0) {
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&tbar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t slot_bytes = (uint32_t)tma_rows * 128u;
+        long long bytes = 0;
+        uint32_t ph[4] = {0, 0, 0, 0};
+        long long t0 = clock64();
+        // keep 4 loads in flight until the MMA warp has finished (bar[0] phase flips)
+        for (int i = 0; i < 4; ++i) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&tbar[i])), "r"(slot_bytes) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s32(smem) + 49152u + i * slot_bytes), "l"(&tmap), "r"(s32(&tbar[i])), "r"(0), "r"(i * tma_rows) : "memory");
+        }
+        int i = 0, n = 0;
+        while (n < iters * 2) {
+            wait(s32(&tbar[i]), ph[i]); ph[i] ^= 1; bytes += slot_bytes;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&tbar[i])), "r"(slot_bytes) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s32(smem) + 49152u + i * slot_bytes), "l"(&tmap), "r"(s32(&tbar[i])), "r"(0), "r"((n & 63) * tma_rows) : "memory");
+            i = (i + 1) & 3; ++n;
+            if (*(volatile long long*)&out[8] != 0 && blockIdx.x == 0) {}
+        }
+        for (int j = 0; j < 4; ++j) { wait(s32(&tbar[(i + j) & 3]), ph[(i + j) & 3]); }
+        long long t1 = clock64();
+        if (blockIdx.x == 0) { out[4] = bytes; out[5] = t1 - t0; }
+    }
+    if (warp >= 4 && bg == 3) {
+        // epilogue-like TMEM reads: every warp keeps loading 16 columns of its lane quarter from the other accumulator half
+        uint32_t acc = 0;
+        const uint32_t taddr = tm + ((uint32_t)((warp & 3) * 32) << 16) + 256u;
+        for (int i = 0; i < iters; ++i) {
+            uint32_t r[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr + (uint32_t)((i & 7) * 16)) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc += r[0] + r[15];
+        }
+        if (acc == 0x12345) out[3] = acc;
+    }
+    if (warp >= 4 && bg > 0 && bg < 3) {
+        // background shared-memory traffic: bg = 1 conflict-free STS.128 stream, 2 = STS + LDS
+        const uint32_t base = s32(smem) + 65536u + (uint32_t)(threadIdx.x - 128) * 16u;
+        uint32_t acc = 0;
+        for (int i = 0; i < iters * 4; ++i) {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(base + (uint32_t)(i & 3) * 4096u), "r"(acc) : "memory");
+            if (bg > 1) { uint32_t x, y, z, q; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(q) : "r"(base + (uint32_t)((i + 1) & 3) * 4096u)); acc += x; }
+        }
+        if (acc == 0x12345) out[3] = acc;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -59,21 +132,25 @@ __global__ void __launch_bounds__(128) k(int N, int iters, int issuers, int a_st
 int main() {
     CK(cudaSetDevice(0));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
-    long long* out; CK(cudaMalloc(&out, 64)); long long h[4];
+    long long* out; CK(cudaMalloc(&out, 128)); long long h[4]; (void)h;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     const int iters = 4000;
-    for (int issuers = 1; issuers <= 2; ++issuers)
-        for (int arows : {8, 10})
-            for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) {
-                if (issuers == 2 && N > 256) continue;
-                CK(cudaMemset(out, 0, 64));
-                k<<<prop.multiProcessorCount, 128, 100 * 1024>>>(N, iters, issuers, arows, out);
-                CK(cudaDeviceSynchronize());
-                CK(cudaMemcpy(h, out, 32, cudaMemcpyDeviceToHost));
-                printf("issuers %d a-group-stride %2d rows N %3d: issue %6.1f cyc/mma, complete %6.1f cyc/mma (math floor %5.1f)", issuers, arows, N, (double)h[0] / iters,
-                       (double)h[1] / iters, N / 2.0);
-                if (issuers == 2) printf(" | warp2: issue %6.1f complete %6.1f", (double)h[2] / iters, (double)h[3] / iters);
-                printf("\n");
-            }
+    void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q));
+    auto enc = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+    uint8_t* w; CK(cudaMalloc(&w, 64 * 192 * 128)); CK(cudaMemset(w, 0, 64 * 192 * 128));
+    long long h8[8];
+    for (int every : {1, 2, 4, 8, 36})
+        for (int N : {16, 96, 192}) {
+            CUtensorMap tm; memset(&tm, 0, sizeof(tm));
+            cuuint64_t gd[2] = {64, (cuuint64_t)64 * 192}; cuuint64_t gs[1] = {128}; cuuint32_t bx[2] = {64, 8}, es[2] = {1, 1};
+            CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { printf("encode failed\n"); return 1; }
+            CK(cudaMemset(out, 0, 64));
+            k<<<prop.multiProcessorCount, 384, 100 * 1024>>>(N, iters, 1, 10, 10 + every, 0, out, tm, 0);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(h8, out, 64, cudaMemcpyDeviceToHost));
+            printf("commit every %2d MMAs, N %3d: mma %6.1f cyc (floor %5.1f)\n", every, N, (double)h8[1] / iters, N / 2.0);
+        }
     return 0;
 }
