@@ -63,6 +63,7 @@ struct __align__(64) ConvTcParams {
     int act, out_f32;
     int stages;
     int kind;             // 0 generic (shifted boxes), 1 halo (3x3 s1, bw == 8), 2 stem (im2col gather), 3 depthwise (halo + diagonal blocks)
+    int pair;             // 1: CTA-pair kernel (cta_group::2, M = 256 across two SMs)
     int mt;               // M tiles per round (share B stages, one accumulator stage, one epilogue pass)
     int halo_w;           // bw + 2
     uint32_t halo_bytes;  // bytes of one halo buffer (1 KiB multiple)

@@ -135,6 +135,60 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: one MMA spans the two SMs of a 2-CTA cluster (M = 256), each CTA holding its
+// own 128 A rows and half of the B rows; the leader (cluster rank 0) issues, barriers that gate it live in its smem.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {   // shared::cta address -> shared::cluster address in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint32_t cluster_bar, uint32_t dst_smem, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_smem),
+        "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t cluster_bar, uint32_t dst_smem, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+        "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {     // arrives on the barrier at this offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -279,7 +333,7 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_
 template <int ACT, int RES, int F32>
 __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_tiles, uint32_t tmem_base, const float* bias_s,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar, uint8_t* stg_base, int warp,
-                                              int lane) {
+                                              int lane, bool pair = false) {
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     const int n_tile = p.n_tile, nchunks = p.epi_nchunks, mt = p.mt;
@@ -320,12 +374,17 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     };
     uint32_t rphase = 0;
     int it = 0;
-    const int rounds = (total_tiles + mt - 1) / mt;
-    for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++it) {
+    // tile walk: a CTA takes rounds blockIdx.x, + gridDim.x, ... of mt tiles; in a CTA pair (mt == 1) the pair takes two
+    // consecutive tiles per round, one per CTA, and an odd last tile is computed (and stored, identically) by both
+    const uint32_t rank = pair ? cluster_ctarank() : 0u;
+    const int rounds = pair ? (total_tiles + 1) / 2 : (total_tiles + mt - 1) / mt;
+    const int rd0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, rd_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const uint32_t tempty_arrive = pair ? mapa_u32(tempty_u32, 0) : tempty_u32;   // the leader's barrier gates the pair's MMAs
+    for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        const int t0 = rd * mt;
-        const int nv = min(mt, total_tiles - t0);        // valid tiles of this round
+        const int t0 = pair ? min(2 * rd + (int)rank, total_tiles - 1) : rd * mt;
+        const int nv = pair ? 1 : min(mt, total_tiles - t0);        // valid tiles of this round
         const uint32_t sboff = (it & 1) ? buf_stride : 0u;
         // box coordinates of this quarter's rows in every tile of the round (issuer only; computed here, off the
         // math -> store critical path)
@@ -381,7 +440,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
             }
         }
         tc_fence_before();
-        mbar_arrive_u32(tempty_u32 + as * 8);            // accumulator stage free: all tcgen05.ld of this round have completed
+        if (pair) mbar_arrive_cluster(tempty_arrive + as * 8);
+        else mbar_arrive_u32(tempty_u32 + as * 8);       // accumulator stage free: all tcgen05.ld of this round have completed
         fence_proxy_async();                             // generic-proxy slab writes -> visible to the TMA store
         if (warp == 4 && lane == 0) trace(p, 2, it, 2);
         pair_sync(q);
@@ -439,6 +499,11 @@ __device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, constants to smem) overlapped the
+    // tail of the previous kernel in the stream; from here on its results are needed.  The next kernel may be scheduled
+    // as soon as SMs free up -- it will block at this same point until this grid has completed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     return *b.tmem_slot;
 }
 __device__ __forceinline__ void epilogue_exit(const ConvTcParams& p, uint32_t tmem_base, int warp) {
@@ -714,6 +779,166 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
         epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.res, smem + p.stg_off, warp, lane);
     }
     epilogue_exit(p, tmem_base, warp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair halo kernel (wide layers, n_tile >= 128): two SMs of one cluster work on two neighbouring M tiles with
+// ONE stream of MMAs (cta_group::2, M = 256) issued by the leader.  Each CTA loads its own halo and only half of
+// every weight tile, so per SM the weight fill and the B-operand reads are halved and each MMA instruction carries
+// twice the work -- what keeps the tensor pipe fed where a single SM's issue rate and smem bandwidth could not.
+// Barriers: full / hfull / tempty live in the leader (both CTAs arrive), empty / hempty / tfull are signalled in
+// both CTAs by the leader's multicast commits.
+// ---------------------------------------------------------------------------------------------
+template <int ACT, int RES, int F32>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const Bars b = carve_bars(smem, p);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int total_tiles = p.tiles_x * p.tiles_y * ((nimg + p.bn - 1) / p.bn);     // n_tiles_n == 1
+    const int rounds = (total_tiles + 1) / 2;
+    const int rd0 = (int)(blockIdx.x >> 1), rd_step = (int)(gridDim.x >> 1);
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&b.full[i], 2);                 // one arrive.expect_tx per CTA (leader's copy is the one waited on)
+            mbar_init(&b.empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&b.tfull[i], 1);
+            mbar_init(&b.tempty[i], 512);             // epilogue threads of both CTAs
+            mbar_init(&b.hfull[i], 2);
+            mbar_init(&b.hempty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&b.res[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2sm(b.tmem_slot, p.tmem_cols);
+    for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) b.bias_s[i] = p.bias[i];
+    tc_fence_before();
+    cluster_sync_all();                               // barriers of both CTAs initialised before anyone signals them
+    tc_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t tmem_base = *b.tmem_slot;
+    const uint32_t halo_bytes = p.halo_bytes;
+    const uint32_t smem_a = smem_u32(smem), smem_b = smem_a + 2u * halo_bytes;
+    const uint32_t full_u32 = smem_u32(b.full), empty_u32 = smem_u32(b.empty);
+    const uint32_t hfull_u32 = smem_u32(b.hfull), hempty_u32 = smem_u32(b.hempty);
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        int stage = 0, hb = 0;
+        uint32_t phase = 0, hphase = 0;
+        const int nstages = p.stages, chunks = p.chunks;
+        const int cin_pad = chunks * 64;
+        const uint32_t b_tx = p.b_tx_bytes, b_bytes = p.b_bytes;
+        const bool perm = p.perm != 0;
+        const uint32_t lead_full = mapa_u32(full_u32, 0), lead_hfull = mapa_u32(hfull_u32, 0);
+        const int b_row0 = (int)rank * (p.n_tile >> 1);                      // this CTA's half of the weight rows
+        for (int rd = rd0; rd < rounds; rd += rd_step) {
+            const TileCoord tc = decode_tile(p, min(2 * rd + (int)rank, total_tiles - 1));
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait_u32(hempty_u32 + hb * 8, hphase ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx_cluster(lead_hfull + hb * 8, p.a_tx_bytes);
+                    tma_load_4d_2sm(&p.tmA[0], lead_hfull + hb * 8, smem_a + (uint32_t)hb * halo_bytes, ch * 64, tc.x0 - 1, perm ? tc.n0 : tc.y0 - 1,
+                                    perm ? tc.y0 - 1 : tc.n0);
+                }
+                if (++hb == 2) { hb = 0; hphase ^= 1; }
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx_cluster(lead_full + stage * 8, b_tx);
+                        tma_load_2d_2sm(&p.tmB, lead_full + stage * 8, smem_b + (uint32_t)stage * b_bytes, tap * cin_pad + ch * 64, b_row0);
+                    }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        int stage = 0, hb = 0, it = 0;
+        uint32_t phase = 0, hphase = 0;
+        const bool leader = elect_one();
+        const uint32_t hi_b = desc_hi(1024), hi_a = desc_hi((uint32_t)p.halo_w * 128u);
+        const uint32_t b_units = p.b_bytes >> 4, halo_units = halo_bytes >> 4, kh_units = (p.halo_kh_rows * 128u) >> 4;
+        const uint32_t a_lo0 = desc_lo(smem_a), b_lo0 = desc_lo(smem_b);
+        const uint32_t idesc = p.idesc;                                   // M = 256
+        const int nstages = p.stages, n_tile = p.n_tile, chunks = p.chunks;
+        const int last_kmmas = (p.cin - (chunks - 1) * 64 + 15) >> 4;
+        const uint32_t tfull_u32 = smem_u32(b.tfull), tempty_u32 = smem_u32(b.tempty);
+        for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            trace(p, 1, it, 0);
+            mbar_wait_u32(tempty_u32 + as * 8, aphase ^ 1);
+            tc_fence_after();
+            trace(p, 1, it, 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
+#ifdef B2D_ENABLE_TRACE
+            long long wait_b = 0, wait_h = 0, w0;
+#endif
+            for (int ch = 0; ch < chunks; ++ch) {
+#ifdef B2D_ENABLE_TRACE
+                w0 = clock64();
+#endif
+                if (!B2D_EXP(p, 0)) mbar_wait_u32(hfull_u32 + hb * 8, hphase);
+#ifdef B2D_ENABLE_TRACE
+                wait_h += clock64() - w0;
+#endif
+                tc_fence_after();
+                if (ch == 0) trace(p, 1, it, 2);
+                const uint32_t a_lo_h = a_lo0 + (uint32_t)hb * halo_units;
+                const int km = (ch == chunks - 1) ? last_kmmas : 4;
+                const bool last = ch == chunks - 1;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+#ifdef B2D_ENABLE_TRACE
+                    w0 = clock64();
+#endif
+                    if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
+                    tc_fence_after();
+#ifdef B2D_ENABLE_TRACE
+                    wait_b += clock64() - w0;
+#endif
+                    if (leader) {
+                        const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_units;
+                        const uint32_t a_lo = a_lo_h + (uint32_t)(tap / 3) * kh_units + (uint32_t)(tap % 3) * 8u;
+                        const uint32_t acc0 = tap == 0 ? (uint32_t)(ch != 0) : 1u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < km) umma_bf16_2sm(d_tmem, desc64(hi_a, a_lo + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                        umma_commit_2sm(empty_u32 + stage * 8);
+                        if (tap == 8) {
+                            umma_commit_2sm(hempty_u32 + hb * 8);
+                            if (last) umma_commit_2sm(tfull_u32 + as * 8);
+                        }
+                    }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+                if (++hb == 2) { hb = 0; hphase ^= 1; }
+            }
+            trace(p, 1, it, 3);
+#ifdef B2D_ENABLE_TRACE
+            if (p.trace && blockIdx.x == 0 && it < kTraceTiles && lane == 0) {      // reported as offsets from the first stamp: halo / weight wait cycles
+                p.trace[(0 * kTraceTiles + it) * kTraceEvents + 2] = wait_h + p.trace[kTraceTiles * kTraceEvents];
+                p.trace[(0 * kTraceTiles + it) * kTraceEvents + 3] = wait_b + p.trace[kTraceTiles * kTraceEvents];
+            }
+#endif
+        }
+    } else if (warp >= 4) {
+        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.res, smem + p.stg_off, warp, lane, true);
+    }
+    tc_fence_before();
+    cluster_sync_all();                               // the peer may still signal this CTA's barriers / read its smem until here
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, p.tmem_cols);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1147,6 +1372,18 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     }
     B2D_CHECK(best_kind >= 0, "conv_tc: no shared-memory configuration fits (n_tile %d)", p.n_tile);
     p.kind = dw ? 3 : best_kind; p.mt = best_mt; p.stages = best_stages; p.stg_bufs = best_bufs;
+    // CTA pairs for wide halo layers: weight stages shrink to half a tile per CTA (so the ring gets deeper)
+    p.pair = 0;
+    if (p.kind == 1 && split == 1 && p.n_tile >= env_int("B2D_PAIR_MIN_N", 128) && p.n_tile % 32 == 0 && (total_tiles >= 2 * sm_count || env_int("B2D_PAIR", 1) == 2) && env_int("B2D_PAIR", 1) != 0) {
+        p.pair = 1;
+        p.mt = 1;
+        p.b_tx_bytes = (uint32_t)(p.n_tile / 2) * 128u;
+        p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
+        if (avail > 2u * tile_stg + 2u * p.halo_bytes + 6u * p.b_bytes && env_int("B2D_STG2", 1) != 0) p.stg_bufs = 2;
+        const uint32_t room = avail - (uint32_t)p.stg_bufs * tile_stg - 2u * p.halo_bytes;
+        int st = (int)(room / p.b_bytes);
+        p.stages = st > kMaxStages ? kMaxStages : st;
+    }
     if (best_kind == 1) p.a_tx_bytes = halo_rows * 128u;
     const uint32_t stg_bytes = (uint32_t)p.stg_bufs * p.mt * tile_stg;
     uint32_t operand_bytes;
@@ -1187,7 +1424,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     while (cols < (uint32_t)(2 * p.mt * p.n_tile)) cols *= 2;
     p.tmem_cols = cols;
     // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((dw ? 16 : p.n_tile) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((dw ? 16 : p.n_tile) >> 3) << 17) | ((uint32_t)((p.pair ? 2 * kTileM : kTileM) >> 4) << 24);
 
     // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin_pad] (zero padded) ----
     const int cin_pad = p.chunks * 64;
@@ -1228,7 +1465,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         } else {
             uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout_pad};
             uint64_t str[1] = {(uint64_t)ktot * 2};
-            uint32_t box[2] = {64u, (uint32_t)p.n_tile};
+            uint32_t box[2] = {64u, (uint32_t)(p.pair ? p.n_tile / 2 : p.n_tile)};
             if (encode_map(&p.tmB, plan->w_dev, 2, dims, str, box, 128)) return -1;
         }
         const uint64_t pix = (uint64_t)src_cs * 2, rowb = (uint64_t)src_w * pix, imgb = (uint64_t)src_h * rowb;
@@ -1277,13 +1514,14 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
 namespace {
 typedef void (*ConvKernel)(const ConvTcParams, int);
 // (kind, act, res, f32) -> instantiation; fp32 outputs never carry a residual
-ConvKernel pick_kernel(int kind, int act, int res, int f32) {
+ConvKernel pick_kernel(int kind, int pair, int act, int res, int f32) {
 #define B2D_PICK(K)                                                        \
     if (f32) return act ? K<1, 0, 1> : K<0, 0, 1>;                         \
     if (res) return act ? K<1, 1, 0> : K<0, 1, 0>;                         \
     return act ? K<1, 0, 0> : K<0, 0, 0>;
     if (kind == 2) return act ? conv_tc_stem_kernel<1> : conv_tc_stem_kernel<0>;
     if (kind == 3) return act ? conv_tc_dw_kernel<1> : conv_tc_dw_kernel<0>;
+    if (kind == 1 && pair) { B2D_PICK(conv_tc_halo2_kernel) }
     if (kind == 1) { B2D_PICK(conv_tc_halo_kernel) }
     B2D_PICK(conv_tc_kernel)
 #undef B2D_PICK
@@ -1300,15 +1538,41 @@ int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
         if (cap > 0 && grid > cap) grid = cap;
     }
     if (grid < 1) return 0;
-    ConvKernel k = pick_kernel(p.kind, p.act, p.has_res, p.out_f32);
-    static bool attr_done[4][2][2][2];
-    bool& done = attr_done[p.kind][p.act ? 1 : 0][p.has_res ? 1 : 0][p.out_f32 ? 1 : 0];
+    if (p.pair) {
+        const int prs = ceil_div(tiles, 2);
+        grid = 2 * (prs < plan->sm_count / 2 ? prs : plan->sm_count / 2);
+    }
+    ConvKernel k = pick_kernel(p.kind, p.pair, p.act, p.has_res, p.out_f32);
+    static bool attr_done[5][2][2][2];
+    bool& done = attr_done[p.pair ? 4 : p.kind][p.act ? 1 : 0][p.has_res ? 1 : 0][p.out_f32 ? 1 : 0];
     if (!done) {
         B2D_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         done = true;
     }
     if (p.trace) B2D_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * kTraceRoles * kTraceTiles * kTraceEvents, stream));
-    k<<<grid, p.kind == 2 ? kStemThreads : kThreads, plan->smem_bytes, stream>>>(p, n);
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(p.kind == 2 ? kStemThreads : kThreads);
+        cfg.dynamicSmemBytes = plan->smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        static const int pdl = env_int("B2D_PDL", 0);   // measured neutral to slightly negative on B200 for this kernel chain
+        if (pdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        if (p.pair) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        B2D_CUDA(cudaLaunchKernelEx(&cfg, k, p, n));
+    }
     if (p.trace && getenv("B2D_TRACE_DUMP")) {
         static long long h[kTraceRoles * kTraceTiles * kTraceEvents];
         B2D_CUDA(cudaStreamSynchronize(stream));
@@ -1343,8 +1607,8 @@ void conv_tc_free(ConvTcPlan* plan) {
 
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
-    static const char* kinds[4] = {"", "-halo", "-stem", "-depthwise"};
+    static const char* kinds[5] = {"", "-halo", "-stem", "-depthwise", "-halo-pair"};
     return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d stg %d tmem %u smem %zu",
-                    kinds[p.kind], p.ksz, p.stride, p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages, p.stg_bufs,
+                    kinds[p.pair ? 4 : p.kind], p.ksz, p.stride, p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages, p.stg_bufs,
                     p.tmem_cols, plan->smem_bytes);
 }
