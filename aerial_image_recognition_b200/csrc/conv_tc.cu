@@ -197,6 +197,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -280,11 +286,11 @@ __device__ __forceinline__ float silu(float v) {
 // ===================== epilogue (warps 4-11), shared by all kernels =====================
 // 16 accumulator columns of this thread's row (already in registers) -> staging slab.
 // `base` is the swizzled address of the unit's first 16-byte piece; the others are base ^ (j << 4).
-template <int ACT, int RES, int F32>
+template <int ACT, int RES, int F32, int NC = 16>
 __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base) {
-    float v[16];
+    float v[NC];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NC / 4; ++j) {
         const float4 b = lds_f4(bias_addr + 16 * j);
         v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
         v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
@@ -293,16 +299,16 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_
     }
     if (ACT) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = silu(v[i]);
+        for (int i = 0; i < NC; ++i) v[i] = silu(v[i]);
     }
     if (F32) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NC / 4; ++j)
             sts128(base ^ (uint32_t)(j << 4),
                    make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
     } else {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < NC / 8; ++j) {
             const uint32_t a0 = base ^ (uint32_t)(j << 4);
             if (RES) {
                 const uint4 x = lds128(a0);
@@ -350,8 +356,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     const int rows_per_y = p.bw * p.bn;
     const int dy = rows_per_y >= 32 ? (q * 32) / rows_per_y : q * (32 / rows_per_y);
     const int dn = rows_per_y >= 32 ? ((q * 32) % rows_per_y) / p.bw : 0;
+    // 16-column units alternate between the two warps of a quarter; an odd last unit is split 8 + 8 so both warps carry
+    // the same load (n_tile = 16, 48, 144 would otherwise leave one warp waiting at the pair barrier)
     const int nunits = n_tile >> 4;
-    const int my_units = (nunits - half + 1) >> 1;     // units half, half + 2, ...
+    const bool split_last = (nunits & 1) != 0;
+    const int my_units = split_last ? (nunits - 1) >> 1 : (nunits - half + 1) >> 1;     // full units half, half + 2, ...
     // Swizzled slab address of this lane's row for the 16-column unit starting at byte `b` of the row.  Mirrors
     // the host's chunking (conv_tc_plan): full 128-byte chunks first, then one 64-byte, then one 32-byte chunk.
     const uint32_t n128 = row_bytes >> 7, has64 = (row_bytes >> 6) & 1u;
@@ -362,7 +371,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         if (b < (n128 << 7)) return row128 + (b >> 7) * 4096u + ((((b & 127u) >> 4) ^ sw128) << 4);
         const uint32_t rem = b - (n128 << 7);
         if (has64 && rem < 64u) return row64 + (((rem >> 4) ^ sw64) << 4);
-        return row32 + (sw32 << 4);                     // a 32-byte chunk holds exactly one bf16 unit
+        return row32 + ((((rem >> 4) & 1u) ^ sw32) << 4);
     };
     const uint32_t ubytes = 16u * esize;               // bytes of one unit in a row
     // TMA boxes of one tile's quarter slab, in the order of the host's chunk list (no table look-ups on the issue path)
@@ -437,6 +446,12 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
                     if (i + 2 < my_units) tmem_ld16(taddr + (i + 2) * 32, rbuf[0]);
                     epi_unit<ACT, RES, F32>(rbuf[1], baddr + (i + 1) * 128, unit_base((uint32_t)(half + 2 * i + 2) * ubytes) + moff);
                 }
+            }
+            if (split_last) {                            // this warp's 8 columns of the last unit
+                const int col = (nunits - 1) * 16 + half * 8;
+                tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * mt + m) * n_tile + col), rbuf[0]);
+                tmem_ld_wait();
+                epi_unit<ACT, RES, F32, 8>(rbuf[0], bias_base + (uint32_t)(ch_base + col) * 4u, unit_base((uint32_t)col * esize) + moff);
             }
         }
         tc_fence_before();

@@ -1,0 +1,4 @@
+OPS="2 0"
+python tools/one_op.py --op $OPS --reps 1 > gpurun_out/oneop_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'conv_tc' -s 90 -c 2 -o gpurun_out/prof_r1f_ops python tools/one_op.py --op $OPS --reps 1 > gpurun_out/oneop_ncu.log 2>&1
+echo "ncu full rc=$?"
