@@ -249,11 +249,43 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& 
     return ovr > thr;
 }
 
+// Sort kernel: one CTA of 1024 threads per tile builds the 64-bit keys (conf desc, anchor asc | row order) in shared
+// memory (up to 16384 keys; beyond that in the global scratch), sorts them and leaves the sorted list in the scratch.
+constexpr int kSortThreads = 1024;
+constexpr int kSortSmemKeys = 16384;
+__global__ void __launch_bounds__(kSortThreads) sort_keys_kernel(const b2d_det* __restrict__ cand, const int* __restrict__ cand_count,
+                                                                  int cand_cap, unsigned long long* keys_scratch, int keys_stride,
+                                                                  int by_conf) {
+    extern __shared__ unsigned long long dkeys[];
+    const int tile = blockIdx.x;
+    int cnt = cand_count[tile];
+    if (cnt > cand_cap) cnt = cand_cap;
+    if (cnt == 0) return;
+    const b2d_det* tc = cand + (size_t)tile * cand_cap;
+    int n2 = 1;
+    while (n2 < cnt) n2 <<= 1;
+    unsigned long long* out = keys_scratch + (size_t)tile * keys_stride;
+    unsigned long long* keys = (n2 <= kSortSmemKeys) ? dkeys : out;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (i < cnt) {
+            const unsigned a = (unsigned)tc[i].anchor & 0x1FFFFu;
+            const unsigned long long lo = ((unsigned long long)a << 15) | (unsigned long long)(i & 0x7FFF);
+            if (by_conf) k = ((unsigned long long)(~__float_as_uint(tc[i].conf)) << 32) | lo;   // conf desc, anchor asc
+            else k = lo;                                                                     // row order
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    bitonic_sort(keys, n2);
+    if (keys != out)
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) out[i] = keys[i];
+}
+
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __restrict__ cand, const int* __restrict__ cand_count,
-                                                              int cand_cap, unsigned long long* keys_scratch, int keys_stride,
+                                                              int cand_cap, const unsigned long long* __restrict__ keys_scratch, int keys_stride,
                                                               float iou_thr, int top_k, int max_det, b2d_det* out, int* out_count,
                                                               int cap) {
-    __shared__ unsigned long long skeys[kSmemKeys];
     __shared__ float4 kbox[kMaxDet];
     __shared__ float karea[kMaxDet];
     __shared__ float4 cbox[kSelThreads];
@@ -273,22 +305,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __re
         if (tid == 0) out_count[tile] = 0;
         return;
     }
-    int n2 = 1;
-    while (n2 < cnt) n2 <<= 1;
-    unsigned long long* keys = (n2 <= kSmemKeys) ? skeys : (keys_scratch + (size_t)tile * keys_stride);
-    const bool by_conf = (iou_thr > 0.f) || (top_k > 0);
-    for (int i = tid; i < n2; i += blockDim.x) {
-        unsigned long long k = ~0ull;
-        if (i < cnt) {
-            const unsigned a = (unsigned)tc[i].anchor & 0x1FFFFu;
-            const unsigned long long lo = ((unsigned long long)a << 15) | (unsigned long long)(i & 0x7FFF);
-            if (by_conf) k = ((unsigned long long)(~__float_as_uint(tc[i].conf)) << 32) | lo;   // conf desc, anchor asc
-            else k = lo;                                                                     // row order
-        }
-        keys[i] = k;
-    }
-    __syncthreads();
-    bitonic_sort(keys, n2);
+    const unsigned long long* keys = keys_scratch + (size_t)tile * keys_stride;     // sorted by sort_keys_kernel
 
     if (!(iou_thr > 0.f)) {
         int m = cnt;
@@ -329,32 +346,44 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __re
         bool alive = valid;
         for (int k = 0; k < nk && alive; ++k)
             if (iou_gt(kbox[k], karea[k], bx, ar, iou_thr)) alive = false;
-        __syncthreads();
-        // which later candidates of this chunk does `tid` suppress?
-#pragma unroll
-        for (int w = 0; w < kSelThreads / 64; ++w) {
-            unsigned long long m = 0;
-            if (valid) {
-                for (int jj = 0; jj < 64; ++jj) {
-                    const int j = w * 64 + jj;
-                    if (j > tid && j < chunk_n && iou_gt(bx, ar, cbox[j], carea[j], iou_thr)) m |= (1ull << jj);
-                }
-            }
-            cmask[tid][w] = m;
-        }
         const unsigned al = __ballot_sync(0xffffffffu, alive);
         if ((tid & 31) == 0) alive_w[tid >> 5] = al;
         keep_slot[tid] = -1;
         __syncthreads();
+        // which later, still alive candidates of this chunk does `tid` suppress?  (dead rows and dead columns are skipped:
+        // after the test against the kept boxes most of a chunk is already gone)
+#pragma unroll
+        for (int w = 0; w < kSelThreads / 64; ++w) {
+            unsigned long long m = 0;
+            if (alive) {
+                unsigned long long am = ((unsigned long long)alive_w[2 * w + 1] << 32) | (unsigned long long)alive_w[2 * w];
+                if (w * 64 <= tid) am &= (tid - w * 64 >= 63) ? 0ull : (~0ull << (tid - w * 64 + 1));      // only j > tid
+                while (am) {
+                    const int jj = __ffsll((long long)am) - 1;
+                    am &= am - 1;
+                    const int j = w * 64 + jj;
+                    if (iou_gt(bx, ar, cbox[j], carea[j], iou_thr)) m |= (1ull << jj);
+                }
+            }
+            cmask[tid][w] = m;
+        }
+        __syncthreads();
         if (tid == 0) {
             unsigned long long removed[kSelThreads / 64] = {0, 0, 0, 0};
             int k = nk;
-            for (int j = 0; j < chunk_n && k < max_det; ++j) {
-                const bool a = (alive_w[j >> 5] >> (j & 31)) & 1u;
-                if (!a || ((removed[j >> 6] >> (j & 63)) & 1ull)) continue;
-                keep_slot[j] = k++;
 #pragma unroll
-                for (int w = 0; w < kSelThreads / 64; ++w) removed[w] |= cmask[j][w];
+            for (int w = 0; w < kSelThreads / 64; ++w) {
+                unsigned long long am = ((unsigned long long)alive_w[2 * w + 1] << 32) | (unsigned long long)alive_w[2 * w];
+                while (k < max_det) {
+                    am &= ~removed[w];
+                    if (!am) break;
+                    const int jj = __ffsll((long long)am) - 1;
+                    am &= ~(1ull << jj);
+                    const int j = w * 64 + jj;
+                    keep_slot[j] = k++;
+#pragma unroll
+                    for (int v = 0; v < kSelThreads / 64; ++v) removed[v] |= cmask[j][v];
+                }
             }
             s_nk = k;
         }
@@ -453,6 +482,14 @@ int select_launch(const b2d_det* cand, const int* cand_count, int cand_cap, int 
     B2D_CHECK(cand_cap <= 32768, "select: candidate capacity %d exceeds the 15-bit slot field", cand_cap);
     int stride = 1;
     while (stride < cand_cap) stride <<= 1;
+    {
+        static bool attr = false;
+        if (!attr) { B2D_CUDA(cudaFuncSetAttribute(sort_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemKeys * 8)); attr = true; }
+        int need = 1;
+        while (need < cand_cap && need < kSortSmemKeys) need <<= 1;       // keys that can occur, capped by the smem variant
+        sort_keys_kernel<<<n, kSortThreads, (size_t)need * 8, stream>>>(cand, cand_count, cand_cap, keys_scratch, stride, (iou_thr > 0.f) || (top_k > 0));
+        B2D_LAUNCH_CHECK();
+    }
     select_kernel<<<n, kSelThreads, 0, stream>>>(cand, cand_count, cand_cap, keys_scratch, stride, iou_thr, top_k, max_det, out,
                                                  out_count, cap);
     B2D_LAUNCH_CHECK();
