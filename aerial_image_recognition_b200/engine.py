@@ -57,6 +57,7 @@ class Engine:
         self._build(w, CONV_IMPL[conv_impl])
         self.num_rows = self.lib.b2d_num_anchors(self.h)
         self.num_ops = self.lib.b2d_num_ops(self.h)
+        self.num_kernels = self.lib.b2d_num_kernels_per_forward(self.h)     # ops minus those fused into a neighbour
         self.sm_count = self.lib.b2d_device_sm_count(self.h)
 
     # ---- plan ------------------------------------------------------------------------

@@ -36,6 +36,9 @@ SIZE = 640
 CONF, IOU, MAX_DET = 0.25, 0.7, 300
 WORKLOAD = "C2: YOLOv8m-tokyo (nc=2, seeded synthetic weights), synthetic 640x640 uint8 tiles, batch 64 per step"
 CONV_GFLOP_PER_TILE = 67.43      # 2 x 33.713 GMAC
+# DRAM bytes moved by the conv_tc_* kernel family in ONE step (its 89 launches summed), from the ncu pass in
+# profiles/r1_final_kernel_shares.txt (dram__bytes_read.sum + dram__bytes_write.sum): 12.154 GB + 4.216 GB
+CONV_DRAM_BYTES_PER_STEP = 16.369e9
 
 
 def _peaks():
@@ -288,10 +291,11 @@ def main():
                        "detections_last_step": n_det},
             "e2e": {"value": total_tiles / (ms_e2e * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": BATCH * SIZE * SIZE * 3,
                     "d2h_bytes_per_step": BATCH * MAX_DET * 40 + BATCH * 4, "ms_per_step": ms_e2e / K},
-            "gpu_launches": K * (nops + 4),     # 1 preprocess + nops graph kernels + decode/compact + select/NMS + georef
+            "gpu_launches": K * (eng.num_kernels + 5),     # graph kernels + preprocess, decode/compact, key sort, select/NMS, georef
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv+bias+SiLU)",
-                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_* family (tcgen05 implicit-GEMM conv+bias+SiLU: generic, halo, halo-pair, stem, depthwise)",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": CONV_DRAM_BYTES_PER_STEP, "traffic_note": "DRAM bytes per step summed over the family's launches (ncu, profiles/r1_final_kernel_shares.txt); achieved/peak are per step too",
                          "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_per_step": n_tc, "ms_per_step_in_kernel": tc_ms,
                          "algorithmic_gflop_per_tile": tc_flops / BATCH / 1e9},

@@ -91,8 +91,24 @@ def test_session_input_path_equals_preprocess_path(eng640, tiles4):
 # ---- K2/K3: every op of the graph against torch on the engine's own inputs -------------------------
 @pytest.mark.parametrize("arch,imgsz,n", [("yolov8m", 128, 3), ("yolov8m", 320, 2), ("yolov7", 128, 2)])
 def test_every_planned_op_matches_torch(arch, imgsz, n):
+    _check_every_op(arch, imgsz, n)
+
+
+@pytest.mark.parametrize("arch,imgsz,n", [("yolov8m", 640, 2), ("yolov7", 256, 2)])
+def test_every_planned_op_large_batch_kernel_variants(arch, imgsz, n, monkeypatch):
+    """The planner only picks multi-tile rounds (mt = 2 / 4) and CTA pairs when a layer has enough tiles to
+    balance 148 SMs, i.e. at bench batch sizes.  Force them (B2D_MT, B2D_PAIR=2 are read at plan time) so the
+    kernels the benchmark runs -- halo-pair, two-tile halo/generic rounds, four-tile stem -- are the ones checked."""
+    monkeypatch.setenv("B2D_MT", "4")
+    monkeypatch.setenv("B2D_PAIR", "2")
+    seen = _check_every_op(arch, imgsz, n)
+    assert any("halo-pair" in d for d in seen) and any(" x2 " in d for d in seen) and any(" x4 " in d for d in seen), seen[:8]
+
+
+def _check_every_op(arch, imgsz, n):
     from _ir_cpu import run_graph_cpu  # noqa: F401  (same arithmetic, per-op form below)
     import torch.nn.functional as F
+    seen = []
     g = G.build(arch, imgsz=imgsz)
     w = W.make_synthetic_weights(g, 2)
     eng = _engine(arch, weights=w, max_batch=n, imgsz=imgsz, graph=g)
@@ -121,7 +137,9 @@ def test_every_planned_op_matches_torch(arch, imgsz, n):
         if op.kind in ("maxpool", "upsample2x"):
             tol = 0.0
         assert err <= tol, (i, eng.describe_op(i), err, tol)
+        seen.append(eng.describe_op(i))
     eng.close()
+    return seen
 
 
 # ---- whole network vs the oracle -------------------------------------------------------------------

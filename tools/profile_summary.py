@@ -1,0 +1,36 @@
+"""Aggregate an `ncu --metrics ... --csv` launch list of bench.py into per-kernel shares of ONE step.
+usage: python tools/profile_summary.py gpurun_out/launches_r1_metrics.csv > profiles/<name>.txt"""
+import collections, csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+h = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
+hdr = rows[h]
+ki, mi, vi, ii, ui = hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Value'), hdr.index('ID'), hdr.index('Metric Unit')
+per, order = {}, []
+for r in rows[h + 1:]:
+    if len(r) <= vi:
+        continue
+    k = int(r[ii])
+    if k not in per:
+        per[k] = {'name': r[ki].split('(')[0].replace('void ', '').replace('<unnamed>::', '')[-52:]}
+        order.append(k)
+    v = float(r[vi].replace(',', ''))
+    if r[mi].startswith('dram__bytes'):
+        v *= {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[r[ui]]
+    per[k][r[mi]] = v
+seq = [per[k] for k in order]
+idx = [i for i, d in enumerate(seq) if 'prep' in d['name']]
+step = seq[idx[0]:idx[1]]
+agg = collections.OrderedDict()
+T = 'gpu__time_duration.sum'
+for d in step:
+    a = agg.setdefault(d['name'], [0.0, 0, 0.0, 0.0, 0.0])
+    a[0] += d[T] / 1e3; a[1] += 1; a[2] += d.get('dram__bytes_read.sum', 0); a[3] += d.get('dram__bytes_write.sum', 0)
+    a[4] += d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 0) * d[T] / 1e3
+tot = sum(a[0] for a in agg.values())
+print(f"one bench step (64 tiles, YOLOv8m), {len(step)} kernel launches, {tot:.1f} us summed under ncu (cold, serialised)")
+print(f"{'time us':>9} {'n':>4} {'share':>6} {'dram rd MB':>11} {'dram wr MB':>11} {'tensor act':>10}  kernel")
+for n, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    print(f"{a[0]:9.1f} {a[1]:4d} {100 * a[0] / tot:5.1f}% {a[2] / 1e6:11.1f} {a[3] / 1e6:11.1f} {a[4] / a[0]:9.1f}%  {n}")
+conv = [a for n, a in agg.items() if n.startswith('conv_tc')]
+print(f"conv_tc_* family: {sum(a[0] for a in conv):.1f} us ({100 * sum(a[0] for a in conv) / tot:.1f}% of the step), {sum(a[1] for a in conv)} launches, "
+      f"dram read {sum(a[2] for a in conv) / 1e9:.3f} GB + write {sum(a[3] for a in conv) / 1e9:.3f} GB = {sum(a[2] + a[3] for a in conv) / 1e9:.3f} GB per step")
