@@ -228,6 +228,7 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 
 struct TileCoord { int nt, x0, y0, n0; };
+template <int V> struct KConst { static constexpr int value = V; };
 
 // t -> (nt, x tile, y tile, image group) without hardware division: q = umulhi(t, ceil(2^32 / d)) is exact
 // for t * d < 2^32 (tile counts are far below that); the reciprocals are computed on the host.
@@ -256,8 +257,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
 // issues no TMA loads (arrives on the barriers instead).
 #ifdef B2D_ENABLE_TRACE
 #define B2D_EXP(p, bit) (((p).exp >> (bit)) & 1)
+#define B2D_EXPW(p) ((p).exp)
 #else
 #define B2D_EXP(p, bit) 0
+#define B2D_EXPW(p) 0
 #endif
 
 // Debug trace (build with -DB2D_ENABLE_TRACE, run with B2D_TRACE=1): CTA 0 records clock64() at role
@@ -269,43 +272,96 @@ __device__ __forceinline__ void trace(const ConvTcParams& p, int role, int it, i
 #endif
 }
 
-// SiLU with one MUFU op per element: e = 2^(-v log2 e) on the SFU, 1/(1+e) on the FMA pipe
-// (bit-trick seed, two Newton steps: relative error 6e-6, far below the bf16 rounding that
-// follows).  The SFU (16 lanes/clk/SM) is the scarce pipe of the epilogue: 2 MUFU per output
-// element made the memory-bound layers epilogue-bound.
-__device__ __forceinline__ float silu(float v) {
-    float y = fminf(v * -1.4426950408889634f, 64.0f), e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y));
-    const float d = 1.0f + e;
-    float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
-    r = fmaf(r, fmaf(-d, r, 1.0f), r);
-    r = fmaf(r, fmaf(-d, r, 1.0f), r);
-    return v * r;
+// Packed fp32 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per instruction, each component rounded
+// exactly like the scalar op).  The epilogue is bound by the FMA pipe -- a 3-register FFMA issues every other cycle
+// per scheduler -- so bias, SiLU and the residual add run on register pairs: about 4 FMA-pipe instructions per output
+// element instead of 7, with the same results bit for bit.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void upk2u(uint64_t v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// SiLU of two values with one MUFU op per element: e = 2^(-v log2 e) on the SFU, 1/(1+e) on the FMA pipe
+// (bit-trick seed, two Newton steps: relative error 6e-6, far below the bf16 rounding that follows).  The
+// SFU (16 lanes/clk/SM) is the other scarce pipe of the epilogue: 2 MUFU per output element made the
+// memory-bound layers epilogue-bound.  nd = -(1 + e) is kept negated so the Newton residual 1 - d r is one FFMA2.
+__device__ __forceinline__ uint64_t silu2(uint64_t v) {
+    float y0, y1, e0, e1, n0, n1;
+    upk2(mul2(v, pk2(-1.4426950408889634f, -1.4426950408889634f)), y0, y1);
+    y0 = fminf(y0, 64.0f);
+    y1 = fminf(y1, 64.0f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(y0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(y1));
+    const uint64_t nd = sub2(pk2(-1.0f, -1.0f), pk2(e0, e1));
+    upk2(nd, n0, n1);
+    uint64_t r = pk2u(0xFEF311C7u - __float_as_uint(n0), 0xFEF311C7u - __float_as_uint(n1));   // 0x7EF311C7 - bits(1 + e)
+    const uint64_t one = pk2(1.0f, 1.0f);
+    r = fma2(r, fma2(nd, r, one), r);
+    r = fma2(r, fma2(nd, r, one), r);
+    return mul2(v, r);
+}
+__device__ __forceinline__ void lds_b64x2(uint32_t a, uint64_t& x, uint64_t& y) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
+}
+__device__ __forceinline__ void sts_b64x2(uint32_t a, uint64_t x, uint64_t y) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(x), "l"(y) : "memory");
 }
 
 // ===================== epilogue (warps 4-11), shared by all kernels =====================
 // 16 accumulator columns of this thread's row (already in registers) -> staging slab.
 // `base` is the swizzled address of the unit's first 16-byte piece; the others are base ^ (j << 4).
 template <int ACT, int RES, int F32, int NC = 16>
-__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base) {
-    float v[NC];
+__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base, int exp = 0) {
+    uint64_t v[NC / 2];
 #pragma unroll
     for (int j = 0; j < NC / 4; ++j) {
-        const float4 b = lds_f4(bias_addr + 16 * j);
-        v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+        uint64_t b0, b1;
+        lds_b64x2(bias_addr + 16 * j, b0, b1);
+        v[2 * j] = add2(pk2u(r[4 * j], r[4 * j + 1]), b0);
+        v[2 * j + 1] = add2(pk2u(r[4 * j + 2], r[4 * j + 3]), b1);
     }
-    if (ACT) {
+    if (ACT && !(exp & 8)) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) v[i] = silu(v[i]);
+        for (int i = 0; i < NC / 2; ++i) v[i] = silu2(v[i]);
+    }
+    if (exp & 64) {             // ablation: no staging stores (keep the values alive)
+        uint64_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < NC / 2; ++i) acc ^= v[i];
+        if (acc == 0x123456789ull) sts_b64x2(base, acc, acc);
+        return;
     }
     if (F32) {
 #pragma unroll
-        for (int j = 0; j < NC / 4; ++j)
-            sts128(base ^ (uint32_t)(j << 4),
-                   make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+        for (int j = 0; j < NC / 4; ++j) sts_b64x2(base ^ (uint32_t)(j << 4), v[2 * j], v[2 * j + 1]);
     } else {
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) {
@@ -314,15 +370,14 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_
                 const uint4 x = lds128(a0);
                 const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    v[8 * j + 2 * i] += __uint_as_float(w[i] << 16);
-                    v[8 * j + 2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
-                }
+                for (int i = 0; i < 4; ++i) v[4 * j + i] = add2(v[4 * j + i], pk2u(w[i] << 16, w[i] & 0xFFFF0000u));
             }
             uint32_t w[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                float lo, hi;
+                upk2(v[4 * j + i], lo, hi);
+                __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
                 w[i] = *(uint32_t*)&h;
             }
             sts128(a0, make_uint4(w[0], w[1], w[2], w[3]));
@@ -435,23 +490,23 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * mt + m) * n_tile + half * 16);
             const uint32_t moff = sboff + (uint32_t)m * tile_bytes;
             uint32_t rbuf[2][16];
-            if (my_units > 0) tmem_ld16(taddr, rbuf[0]);
+            if (my_units > 0 && !B2D_EXP(p, 4)) tmem_ld16(taddr, rbuf[0]);
 #pragma unroll 1
             for (int i = 0; i < my_units; i += 2) {      // two units per trip: the TMEM load of the next overlaps the math of this one
                 tmem_ld_wait();
-                if (i + 1 < my_units) tmem_ld16(taddr + (i + 1) * 32, rbuf[1]);
-                epi_unit<ACT, RES, F32>(rbuf[0], baddr + i * 128, unit_base((uint32_t)(half + 2 * i) * ubytes) + moff);
+                if (i + 1 < my_units && !B2D_EXP(p, 4)) tmem_ld16(taddr + (i + 1) * 32, rbuf[1]);
+                epi_unit<ACT, RES, F32>(rbuf[0], baddr + i * 128, unit_base((uint32_t)(half + 2 * i) * ubytes) + moff, B2D_EXPW(p));
                 if (i + 1 < my_units) {
                     tmem_ld_wait();
-                    if (i + 2 < my_units) tmem_ld16(taddr + (i + 2) * 32, rbuf[0]);
-                    epi_unit<ACT, RES, F32>(rbuf[1], baddr + (i + 1) * 128, unit_base((uint32_t)(half + 2 * i + 2) * ubytes) + moff);
+                    if (i + 2 < my_units && !B2D_EXP(p, 4)) tmem_ld16(taddr + (i + 2) * 32, rbuf[0]);
+                    epi_unit<ACT, RES, F32>(rbuf[1], baddr + (i + 1) * 128, unit_base((uint32_t)(half + 2 * i + 2) * ubytes) + moff, B2D_EXPW(p));
                 }
             }
             if (split_last) {                            // this warp's 8 columns of the last unit
                 const int col = (nunits - 1) * 16 + half * 8;
                 tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * mt + m) * n_tile + col), rbuf[0]);
                 tmem_ld_wait();
-                epi_unit<ACT, RES, F32, 8>(rbuf[0], bias_base + (uint32_t)(ch_base + col) * 4u, unit_base((uint32_t)col * esize) + moff);
+                epi_unit<ACT, RES, F32, 8>(rbuf[0], bias_base + (uint32_t)(ch_base + col) * 4u, unit_base((uint32_t)col * esize) + moff, B2D_EXPW(p));
             }
         }
         tc_fence_before();
@@ -460,7 +515,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         fence_proxy_async();                             // generic-proxy slab writes -> visible to the TMA store
         if (warp == 4 && lane == 0) trace(p, 2, it, 2);
         pair_sync(q);
-        if (issuer && !B2D_EXP(p, 1)) {
+        if (issuer && !B2D_EXP(p, 1) && !B2D_EXP(p, 5)) {
 #pragma unroll
             for (int m = 0; m < kMaxMt; ++m)
                 if (m < nv)
@@ -648,8 +703,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     const uint32_t b_lo = a_lo + (uint32_t)mt * a_units;
                     const uint32_t acc0 = (uint32_t)(ks != 0);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)     // four K=16 MMAs per 64-channel chunk, +32 B each
-                        if (k < km) umma_bf16(d_tmem, desc64(hi, a_lo + 2 * k), desc64(hi, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                    for (int k = 0; k < 4; ++k)     // four K=16 MMAs per 64-channel chunk, +32 B each (a predicated skip is cheaper here
+                        if (k < km)                 // than a specialised loop: almost every chunk of these layers is full)
+                            umma_bf16(d_tmem, desc64(hi, a_lo + 2 * k), desc64(hi, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
                     if (two) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -760,32 +816,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
                 tc_fence_after();
                 if (ch == 0) trace(p, 1, it, 2);
                 const uint32_t a_lo_h = a_lo0 + (uint32_t)(hb * mt) * halo_units;
-                const int km = (ch == chunks - 1) ? last_kmmas : 4;           // skip the zero-padded tail of the last chunk
                 const bool last = ch == chunks - 1;
+                const int km = last ? last_kmmas : 4;                        // skip the zero-padded tail of the last chunk
+                // the K-step count is a compile-time constant of the issue loop: a per-MMA `k < km` test costs ~13 cycles
+                // per MMA on the single issuing thread (tools/ubench/mma_issue.cu, variants 32 / 33)
+                auto taps = [&](auto KM) {
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
-                    tc_fence_after();
-                    if (leader) {
-                        const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_units;
-                        const uint32_t a_lo = a_lo_h + (uint32_t)(tap / 3) * kh_units + (uint32_t)(tap % 3) * 8u;
-                        const uint32_t acc0 = tap == 0 ? (uint32_t)(ch != 0) : 1u;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_units;
+                            const uint32_t a_lo = a_lo_h + (uint32_t)(tap / 3) * kh_units + (uint32_t)(tap % 3) * 8u;
+                            const uint32_t acc0 = tap == 0 ? (uint32_t)(ch != 0) : 1u;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < km) umma_bf16(d_tmem, desc64(hi_a, a_lo + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
-                        if (two) {
+                            for (int k = 0; k < decltype(KM)::value; ++k)
+                                umma_bf16(d_tmem, desc64(hi_a, a_lo + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                            if (two) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (k < km) umma_bf16(d_tmem + (uint32_t)n_tile, desc64(hi_a, a_lo + halo_units + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                                for (int k = 0; k < decltype(KM)::value; ++k)
+                                    umma_bf16(d_tmem + (uint32_t)n_tile, desc64(hi_a, a_lo + halo_units + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                            }
+                            umma_commit(empty_u32 + stage * 8);
+                            if (tap == 8) {
+                                umma_commit(hempty_u32 + hb * 8);                         // halo tiles free once their MMAs retire
+                                if (last) umma_commit(tfull_u32 + as * 8);
+                            }
                         }
-                        umma_commit(empty_u32 + stage * 8);
-                        if (tap == 8) {
-                            umma_commit(hempty_u32 + hb * 8);                         // halo tiles free once their MMAs retire
-                            if (last) umma_commit(tfull_u32 + as * 8);
-                        }
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
-                }
+                };
+                if (km == 4) taps(KConst<4>{});
+                else if (km == 3) taps(KConst<3>{});
+                else if (km == 2) taps(KConst<2>{});
+                else taps(KConst<1>{});
                 if (++hb == 2) { hb = 0; hphase ^= 1; }
             }
             trace(p, 1, it, 3);
@@ -910,31 +974,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
                 const uint32_t a_lo_h = a_lo0 + (uint32_t)hb * halo_units;
                 const int km = (ch == chunks - 1) ? last_kmmas : 4;
                 const bool last = ch == chunks - 1;
+                auto taps = [&](auto KM) {
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < 9; ++tap) {
 #ifdef B2D_ENABLE_TRACE
-                    w0 = clock64();
+                        w0 = clock64();
 #endif
-                    if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
-                    tc_fence_after();
+                        if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
+                        tc_fence_after();
 #ifdef B2D_ENABLE_TRACE
-                    wait_b += clock64() - w0;
+                        wait_b += clock64() - w0;
 #endif
-                    if (leader) {
-                        const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_units;
-                        const uint32_t a_lo = a_lo_h + (uint32_t)(tap / 3) * kh_units + (uint32_t)(tap % 3) * 8u;
-                        const uint32_t acc0 = tap == 0 ? (uint32_t)(ch != 0) : 1u;
+                        if (leader) {
+                            const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_units;
+                            const uint32_t a_lo = a_lo_h + (uint32_t)(tap / 3) * kh_units + (uint32_t)(tap % 3) * 8u;
+                            const uint32_t acc0 = tap == 0 ? (uint32_t)(ch != 0) : 1u;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < km) umma_bf16_2sm(d_tmem, desc64(hi_a, a_lo + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
-                        umma_commit_2sm(empty_u32 + stage * 8);
-                        if (tap == 8) {
-                            umma_commit_2sm(hempty_u32 + hb * 8);
-                            if (last) umma_commit_2sm(tfull_u32 + as * 8);
+                            for (int k = 0; k < decltype(KM)::value; ++k)
+                                umma_bf16_2sm(d_tmem, desc64(hi_a, a_lo + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                            umma_commit_2sm(empty_u32 + stage * 8);
+                            if (tap == 8) {
+                                umma_commit_2sm(hempty_u32 + hb * 8);
+                                if (last) umma_commit_2sm(tfull_u32 + as * 8);
+                            }
                         }
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
-                }
+                };
+                if (km == 4) taps(KConst<4>{});
+                else if (km == 3) taps(KConst<3>{});
+                else if (km == 2) taps(KConst<2>{});
+                else taps(KConst<1>{});
                 if (++hb == 2) { hb = 0; hphase ^= 1; }
             }
             trace(p, 1, it, 3);
@@ -1205,8 +1275,10 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
+int env_int(const char* name, int dflt);
+
 int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, uint32_t swizzle_bytes, bool f32 = false) {
+               const uint32_t* box, uint32_t swizzle_bytes, bool f32 = false, int promo = 3) {
     auto enc = get_encode();
     B2D_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gd[5], gs[4];
@@ -1217,7 +1289,9 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
                           : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
     CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B2D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu %llu %llu box %u %u %u %u)", (int)r, rank,
               (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
               (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
@@ -1228,16 +1302,21 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
 // images keep an image's rows of one y together, see the header).
 int encode_act_map(CUtensorMap* map, void* base, int c, int w, int h, int n, uint64_t pix_bytes, uint64_t row_bytes, uint64_t img_bytes,
                    uint32_t bc, uint32_t bw, uint32_t bh, uint32_t bn, bool perm, uint32_t swizzle, bool f32 = false) {
+    // L2 promotion widens every request to an aligned 64/128/256-byte block.  On a dense tensor (the slice is the whole
+    // pixel) that is a free prefetch of the neighbouring pixel; on a channel slice of a wider concat buffer it drags in
+    // the other producers' channels -- measured 3.3x the algorithmic DRAM reads on the 48-of-192-channel slices.
+    static const int promo_slice = env_int("B2D_PROMO_SLICE", 0), promo_dense = env_int("B2D_PROMO_DENSE", 3);
+    const int promo = (uint64_t)c * (f32 ? 4u : 2u) == pix_bytes ? promo_dense : promo_slice;
     if (perm) {
         uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)n, (uint64_t)h};
         uint64_t str[3] = {pix_bytes, img_bytes, row_bytes};
         uint32_t box[4] = {bc, bw, bn, bh};
-        return encode_map(map, base, 4, dims, str, box, swizzle, f32);
+        return encode_map(map, base, 4, dims, str, box, swizzle, f32, promo);
     }
     uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     uint64_t str[3] = {pix_bytes, row_bytes, img_bytes};
     uint32_t box[4] = {bc, bw, bh, bn};
-    return encode_map(map, base, 4, dims, str, box, swizzle, f32);
+    return encode_map(map, base, 4, dims, str, box, swizzle, f32, promo);
 }
 
 uint16_t f2bf(float f) {
