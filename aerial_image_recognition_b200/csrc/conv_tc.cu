@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t idesc = p.idesc;
         const int nstages = p.stages, n_tile = p.n_tile, chunks = p.chunks;
         const int last_kmmas = (p.cin - (chunks - 1) * 64 + 15) >> 4;      // K=16 MMAs that carry data in the last chunk
-        int chk = 0;
+        const int taps = p.taps;
         const uint32_t tfull_u32 = smem_u32(b.tfull), tempty_u32 = smem_u32(b.tempty);
         for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++it) {
             const int as = it & 1;
@@ -691,30 +691,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tc_fence_after();
             trace(p, 1, it, 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * mt * n_tile);
-            for (int ks = 0; ks < ksteps; ++ks) {
+            // one (tap, chunk) step: KM K=16 MMAs per tile (+32 B each), KM a compile-time constant -- the full chunks run
+            // without any per-MMA test, only a tap's last (possibly short, zero-padded) chunk picks its count
+            int ks = 0;
+            auto step = [&](auto KM) {
                 if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
                 tc_fence_after();
                 if (ks == 0) trace(p, 1, it, 2);
-                const bool last_chunk = (++chk == chunks);
-                if (last_chunk) chk = 0;
-                const int km = last_chunk ? last_kmmas : 4;                   // the zero-padded tail of the last chunk is skipped
                 if (leader) {
                     const uint32_t a_lo = lo_base + (uint32_t)stage * stage_units;
                     const uint32_t b_lo = a_lo + (uint32_t)mt * a_units;
                     const uint32_t acc0 = (uint32_t)(ks != 0);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)     // four K=16 MMAs per 64-channel chunk, +32 B each (a predicated skip is cheaper here
-                        if (k < km)                 // than a specialised loop: almost every chunk of these layers is full)
-                            umma_bf16(d_tmem, desc64(hi, a_lo + 2 * k), desc64(hi, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                    for (int k = 0; k < decltype(KM)::value; ++k)
+                        umma_bf16(d_tmem, desc64(hi, a_lo + 2 * k), desc64(hi, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
                     if (two) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < km) umma_bf16(d_tmem + (uint32_t)n_tile, desc64(hi, a_lo + a_units + 2 * k), desc64(hi, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                        for (int k = 0; k < decltype(KM)::value; ++k)
+                            umma_bf16(d_tmem + (uint32_t)n_tile, desc64(hi, a_lo + a_units + 2 * k), desc64(hi, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
                     }
                     umma_commit(empty_u32 + stage * 8);                       // frees the smem slot when these MMAs retire
                     if (ks == ksteps - 1) umma_commit(tfull_u32 + as * 8);     // accumulators complete
                 }
+                ++ks;
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
+            };
+            for (int tap = 0; tap < taps; ++tap) {
+                for (int ch = 0; ch < chunks - 1; ++ch) step(KConst<4>{});
+                if (last_kmmas == 4) step(KConst<4>{});
+                else if (last_kmmas == 3) step(KConst<3>{});
+                else if (last_kmmas == 2) step(KConst<2>{});
+                else step(KConst<1>{});
             }
             trace(p, 1, it, 3);
         }
