@@ -242,6 +242,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
     } else {
         c.nt = 0;
     }
+    if (p.rev_last >= 0) m = (uint32_t)p.rev_last - m;     // walk the M tiles backwards (see conv_tc_launch)
     const uint32_t qx = p.tiles_x > 1 ? __umulhi(m, p.rcp_tx) : m;
     const uint32_t tx = m - qx * (uint32_t)p.tiles_x;
     const uint32_t qy = p.tiles_y > 1 ? __umulhi(qx, p.rcp_ty) : qx;
@@ -309,24 +310,18 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
     return r;
 }
 
-// SiLU of two values with one MUFU op per element: e = 2^(-v log2 e) on the SFU, 1/(1+e) on the FMA pipe
-// (bit-trick seed, two Newton steps: relative error 6e-6, far below the bf16 rounding that follows).  The
-// SFU (16 lanes/clk/SM) is the other scarce pipe of the epilogue: 2 MUFU per output element made the
-// memory-bound layers epilogue-bound.  nd = -(1 + e) is kept negated so the Newton residual 1 - d r is one FFMA2.
-__device__ __forceinline__ uint64_t silu2(uint64_t v) {
-    float y0, y1, e0, e1, n0, n1;
-    upk2(mul2(v, pk2(-1.4426950408889634f, -1.4426950408889634f)), y0, y1);
-    y0 = fminf(y0, 64.0f);
-    y1 = fminf(y1, 64.0f);
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(y0));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(y1));
-    const uint64_t nd = sub2(pk2(-1.0f, -1.0f), pk2(e0, e1));
-    upk2(nd, n0, n1);
-    uint64_t r = pk2u(0xFEF311C7u - __float_as_uint(n0), 0xFEF311C7u - __float_as_uint(n1));   // 0x7EF311C7 - bits(1 + e)
-    const uint64_t one = pk2(1.0f, 1.0f);
-    r = fma2(r, fma2(nd, r, one), r);
-    r = fma2(r, fma2(nd, r, one), r);
-    return mul2(v, r);
+// SiLU of two values, v = 2h given as h:  v * sigmoid(v) = h + h * tanh(h).  One MUFU.TANH per element plus one FFMA2 per
+// pair; the halving is folded into the bias step (h = 0.5 * acc + 0.5 * bias, exact scaling).  Measured on B200
+// (tools/ubench/silu_acc.cu, 4M points in [-16, 16] against double precision): absolute error <= 1.1e-5 everywhere,
+// relative error <= 4.3e-6 for v > 0 -- hundreds of times below the bf16 rounding that follows -- at 15.4 outputs/clk/SM
+// with eight warps, the MUFU limit, against 7.0 for exp2 + Newton reciprocal and 7.8 for exp2 + rcp
+// (tools/ubench/silu_rate.cu).  The epilogue's throughput bounds every short-K layer of the network.
+__device__ __forceinline__ uint64_t silu2_h(uint64_t h) {
+    float h0, h1, t0, t1;
+    upk2(h, h0, h1);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+    return fma2(h, pk2(t0, t1), h);
 }
 __device__ __forceinline__ void lds_b64x2(uint32_t a, uint64_t& x, uint64_t& y) {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
@@ -336,22 +331,28 @@ __device__ __forceinline__ void sts_b64x2(uint32_t a, uint64_t x, uint64_t y) {
 }
 
 // ===================== epilogue (warps 4-11), shared by all kernels =====================
-// 16 accumulator columns of this thread's row (already in registers) -> staging slab.
+// NC accumulator columns of this thread's row (already in registers) -> staging slab, in three steps so that the
+// caller can run two 16-column units side by side (sixteen independent SiLU chains in flight per thread instead of
+// eight: with only two epilogue warps per scheduler the dependent FFMA2 / MUFU latencies are otherwise exposed).
 // `base` is the swizzled address of the unit's first 16-byte piece; the others are base ^ (j << 4).
-template <int ACT, int RES, int F32, int NC = 16>
-__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base, int exp = 0) {
-    uint64_t v[NC / 2];
+template <int ACT, int NC>
+__device__ __forceinline__ void epi_bias(const uint32_t (&r)[16], uint32_t bias_addr, uint64_t (&v)[8]) {
+    const uint64_t half2 = pk2(0.5f, 0.5f);
 #pragma unroll
     for (int j = 0; j < NC / 4; ++j) {
         uint64_t b0, b1;
-        lds_b64x2(bias_addr + 16 * j, b0, b1);
-        v[2 * j] = add2(pk2u(r[4 * j], r[4 * j + 1]), b0);
-        v[2 * j + 1] = add2(pk2u(r[4 * j + 2], r[4 * j + 3]), b1);
+        lds_b64x2(bias_addr + 16 * j, b0, b1);          // ACT layers keep 0.5 * bias in shared memory (prologue)
+        if (ACT) {
+            v[2 * j] = fma2(pk2u(r[4 * j], r[4 * j + 1]), half2, b0);
+            v[2 * j + 1] = fma2(pk2u(r[4 * j + 2], r[4 * j + 3]), half2, b1);
+        } else {
+            v[2 * j] = add2(pk2u(r[4 * j], r[4 * j + 1]), b0);
+            v[2 * j + 1] = add2(pk2u(r[4 * j + 2], r[4 * j + 3]), b1);
+        }
     }
-    if (ACT && !(exp & 8)) {
-#pragma unroll
-        for (int i = 0; i < NC / 2; ++i) v[i] = silu2(v[i]);
-    }
+}
+template <int RES, int F32, int NC>
+__device__ __forceinline__ void epi_store(uint64_t (&v)[8], uint32_t base, int exp) {
     if (exp & 64) {             // ablation: no staging stores (keep the values alive)
         uint64_t acc = 0;
 #pragma unroll
@@ -383,6 +384,16 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_
             sts128(a0, make_uint4(w[0], w[1], w[2], w[3]));
         }
     }
+}
+template <int ACT, int RES, int F32, int NC = 16>
+__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base, int exp = 0) {
+    uint64_t v[8];
+    epi_bias<ACT, NC>(r, bias_addr, v);
+    if (ACT && !(exp & 8)) {
+#pragma unroll
+        for (int i = 0; i < NC / 2; ++i) v[i] = silu2_h(v[i]);
+    }
+    epi_store<RES, F32, NC>(v, base, exp);
 }
 
 // Eight epilogue warps: warp w serves TMEM lane quarter q = w % 4 (a hardware rule) and, of that
@@ -490,16 +501,35 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * mt + m) * n_tile + half * 16);
             const uint32_t moff = sboff + (uint32_t)m * tile_bytes;
             uint32_t rbuf[2][16];
-            if (my_units > 0 && !B2D_EXP(p, 4)) tmem_ld16(taddr, rbuf[0]);
+            const bool ldt = !B2D_EXP(p, 4);
+            if (my_units > 0 && ldt) tmem_ld16(taddr, rbuf[0]);
+            if (my_units > 1 && ldt) tmem_ld16(taddr + 32, rbuf[1]);
 #pragma unroll 1
-            for (int i = 0; i < my_units; i += 2) {      // two units per trip: the TMEM load of the next overlaps the math of this one
+            for (int i = 0; i < my_units; i += 2) {      // two units per trip, side by side; the TMEM loads of the next two overlap the math
+                const bool both = i + 1 < my_units;
+                uint64_t v0[8], v1[8];
                 tmem_ld_wait();
-                if (i + 1 < my_units && !B2D_EXP(p, 4)) tmem_ld16(taddr + (i + 1) * 32, rbuf[1]);
-                epi_unit<ACT, RES, F32>(rbuf[0], baddr + i * 128, unit_base((uint32_t)(half + 2 * i) * ubytes) + moff, B2D_EXPW(p));
-                if (i + 1 < my_units) {
-                    tmem_ld_wait();
-                    if (i + 2 < my_units && !B2D_EXP(p, 4)) tmem_ld16(taddr + (i + 2) * 32, rbuf[0]);
-                    epi_unit<ACT, RES, F32>(rbuf[1], baddr + (i + 1) * 128, unit_base((uint32_t)(half + 2 * i + 2) * ubytes) + moff, B2D_EXPW(p));
+                epi_bias<ACT, 16>(rbuf[0], baddr + i * 128, v0);
+                if (both) epi_bias<ACT, 16>(rbuf[1], baddr + (i + 1) * 128, v1);
+                if (i + 2 < my_units && ldt) tmem_ld16(taddr + (i + 2) * 32, rbuf[0]);      // rbuf is dead from here on
+                if (i + 3 < my_units && ldt) tmem_ld16(taddr + (i + 3) * 32, rbuf[1]);
+                const uint32_t base0 = unit_base((uint32_t)(half + 2 * i) * ubytes) + moff;
+                if (both) {
+                    if (ACT && !B2D_EXP(p, 3)) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            v0[k] = silu2_h(v0[k]);
+                            v1[k] = silu2_h(v1[k]);
+                        }
+                    }
+                    epi_store<RES, F32, 16>(v0, base0, B2D_EXPW(p));
+                    epi_store<RES, F32, 16>(v1, unit_base((uint32_t)(half + 2 * i + 2) * ubytes) + moff, B2D_EXPW(p));
+                } else {
+                    if (ACT && !B2D_EXP(p, 3)) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v0[k] = silu2_h(v0[k]);
+                    }
+                    epi_store<RES, F32, 16>(v0, base0, B2D_EXPW(p));
                 }
             }
             if (split_last) {                            // this warp's 8 columns of the last unit
@@ -565,7 +595,7 @@ __device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& 
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(b.tmem_slot, p.tmem_cols);
-    for (int i = threadIdx.x; i < p.n_tile * p.n_tiles_n; i += blockDim.x) b.bias_s[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.n_tile * p.n_tiles_n; i += blockDim.x) b.bias_s[i] = p.act ? 0.5f * p.bias[i] : p.bias[i];   // see epi_bias
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -903,7 +933,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_2sm(b.tmem_slot, p.tmem_cols);
-    for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) b.bias_s[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) b.bias_s[i] = p.act ? 0.5f * p.bias[i] : p.bias[i];
     tc_fence_before();
     cluster_sync_all();                               // barriers of both CTAs initialised before anyone signals them
     tc_fence_after();
@@ -1630,8 +1660,11 @@ ConvKernel pick_kernel(int kind, int pair, int act, int res, int f32) {
 }  // namespace
 
 int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
-    const ConvTcParams& p = plan->p;
+    ConvTcParams p = plan->p;
     const int tiles = p.tiles_x * p.tiles_y * ceil_div(n, p.bn) * p.n_tiles_n;
+    // Every other op of the graph walks its tiles backwards: what the previous kernel wrote last (the part of its output
+    // still resident in the 126 MB L2) is what this kernel reads first, before its own traffic evicts it.
+    p.rev_last = p.rev ? tiles / p.n_tiles_n - 1 : -1;
     const int rounds = ceil_div(tiles, p.mt);
     int grid = rounds < plan->sm_count ? rounds : plan->sm_count;
     {   // debug: B2D_GRID caps the number of CTAs (per-SM vs chip-wide bottleneck experiments)

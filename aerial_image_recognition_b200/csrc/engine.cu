@@ -362,6 +362,10 @@ int b2d_plan_finalize(b2d_engine* e) {
             op.oh = db.h; op.ow = db.w; op.dst_cs = db.c; op.dst_c0 = d.dst_c0; op.c = d.cout; op.k = d.k; op.stride = d.stride;
         }
         d.w.clear(); d.w.shrink_to_fit();
+        if (op.kind == OP_CONV_TC) {        // B2D_REV: 1 (default) odd ops walk backwards, 0 nobody, 2 everybody
+            static const int rev_mode = getenv("B2D_REV") ? atoi(getenv("B2D_REV")) : 1;
+            op.tc.p.rev = rev_mode == 2 ? 1 : rev_mode == 1 ? (int)(i & 1) : 0;
+        }
     }
     // Fuse chains of stride-1 max-pools into one launch: SPPF (mp5 of mp5 of mp5) and SPPCSPC (mp5, mp9, mp13 of one
     // source, which are the same three tensors because max-pooling with -inf padding composes).
