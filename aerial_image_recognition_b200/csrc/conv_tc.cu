@@ -396,40 +396,127 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_
     epi_store<RES, F32, NC>(v, base, exp);
 }
 
-// Eight epilogue warps: warp w serves TMEM lane quarter q = w % 4 (a hardware rule) and, of that
-// quarter's 16-column units, the ones with unit % 2 == (w - 4) / 4.  The two warps of a quarter
-// share the quarter's staging slabs and meet at a 64-thread named barrier before the slabs are
-// reused and before their TMA stores are issued (by lane 0 of the first warp).  A round's mt tiles
-// are drained back to back between one pair of barriers.  A tile row of n_tile columns is cut into
-// chunks of 128 / 64 / 32 bytes (EpiChunk, one tensor map per width), 32 rows x chunk per store.
+// Geometry of the staging slabs, shared by the epilogue warps and the store warp.  A tile row of n_tile columns is cut
+// into chunks of 128 / 64 / 32 bytes (one tensor map per width); a quarter's slab of one tile holds 32 rows x chunk for
+// every chunk, full 128-byte chunks first, then one 64-byte, then one 32-byte chunk (mirrors conv_tc_plan).
+template <int F32>
+struct EpiGeom {
+    static constexpr int esize = F32 ? 4 : 2;
+    uint32_t row_bytes, tile_bytes, slab0, buf_stride, n128, has64, has32;
+    int dy, dn, nb;
+    __device__ __forceinline__ EpiGeom(const ConvTcParams& p, uint8_t* stg_base, int q) {
+        row_bytes = (uint32_t)(p.n_tile * esize);
+        tile_bytes = 128u * row_bytes;                                          // staging bytes of one M tile
+        slab0 = smem_u32(stg_base) + (uint32_t)q * 32u * row_bytes;             // this quarter's slab of tile 0, buffer 0
+        nb = p.stg_bufs;
+        buf_stride = nb == 2 ? (uint32_t)p.mt * tile_bytes : 0u;
+        n128 = row_bytes >> 7; has64 = (row_bytes >> 6) & 1u; has32 = (row_bytes >> 5) & 1u;
+        // sub-box of a tile covered by this quarter's 32 rows (row m = (y * bn + n) * bw + x)
+        const int rows_per_y = p.bw * p.bn;
+        dy = rows_per_y >= 32 ? (q * 32) / rows_per_y : q * (32 / rows_per_y);
+        dn = rows_per_y >= 32 ? ((q * 32) % rows_per_y) / p.bw : 0;
+    }
+    // TMA boxes of one tile's quarter slab: fn(map index, byte offset in the slab, first column)
+    template <typename Fn>
+    __device__ __forceinline__ void for_each_chunk(Fn&& fn) const {
+        constexpr int cols128 = 128 / esize, cols64 = 64 / esize;
+        for (uint32_t k = 0; k < n128; ++k) fn(0, k * 4096u, (int)k * cols128);
+        if (has64) fn(1, n128 * 4096u, (int)n128 * cols128);
+        if (has32) fn(2, n128 * 4096u + has64 * 2048u, (int)n128 * cols128 + (int)has64 * cols64);
+    }
+};
+
+// Store warp (warp 3): lane q < 4 serves TMEM lane quarter q.  The quarter's staging area is a ring of
+// S = stg_bufs * mt one-tile slabs.  For every tile, in the order the epilogue produces them, the lane waits for the slab
+// to be written (sfull), issues the tile's TMA stores, waits until the TMA unit has read the slab, hands it back (sempty)
+// and -- for residual layers -- starts the residual loads of the tile that will use this slab next, so they have S tiles
+// of time to land.  Issuing a TMA instruction costs its thread ~200 cycles; taking that, the slab wait and the residual
+// latency out of the epilogue warps' loop is what the layers with epilogue-bound rounds needed.
+template <int RES, int F32>
+__device__ __forceinline__ void store_loop(const ConvTcParams& p, int total_tiles, uint64_t* sfull_bar, uint64_t* sempty_bar,
+                                           uint64_t* res_bar, uint8_t* stg_base, int lane, bool pair = false) {
+    if (lane >= 4) return;
+    const int q = lane;
+    const EpiGeom<F32> g(p, stg_base, q);
+    const int mt = p.mt, n_tile = p.n_tile;
+    const int S = g.nb * mt, s_shift = 31 - __clz(S);                          // S is 1, 2, 4 or 8
+    const uint32_t sfull_u32 = smem_u32(sfull_bar) + (uint32_t)(q * S) * 8u, sempty_u32 = smem_u32(sempty_bar) + (uint32_t)(q * S) * 8u;
+    const uint32_t rbar_u32 = smem_u32(res_bar) + (uint32_t)(q * S) * 8u;
+    const uint32_t rank = pair ? cluster_ctarank() : 0u;
+    const int rounds = pair ? (total_tiles + 1) / 2 : (total_tiles + mt - 1) / mt;
+    const int rd0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, rd_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const bool no_store = B2D_EXP(p, 1) || B2D_EXP(p, 5);
+    auto first_tile = [&](int rd) { return pair ? min(2 * rd + (int)rank, total_tiles - 1) : rd * mt; };
+    auto valid_tiles = [&](int rd) { return pair ? 1 : min(mt, total_tiles - rd * mt); };
+    // TMA boxes of this quarter's rows of tile t: residual loads into / stores out of slab `slab`
+    auto tile_io = [&](int t, int slab, bool load) {
+        const TileCoord tc = decode_tile(p, t);
+        const int c0 = tc.nt * n_tile, c1 = tc.x0;
+        const int c2 = p.perm ? tc.n0 + g.dn : tc.y0 + g.dy, c3 = p.perm ? tc.y0 + g.dy : tc.n0 + g.dn;
+        const uint32_t sa = g.slab0 + (uint32_t)slab * g.tile_bytes;
+        if (load) {
+            const uint32_t bar = rbar_u32 + (uint32_t)slab * 8u;
+            mbar_expect_tx_u32(bar, 32u * (uint32_t)(n_tile * 2));
+            g.for_each_chunk([&](int map, uint32_t off, int col0) { tma_load_4d(&p.tmR[map], bar, sa + off, c0 + col0, c1, c2, c3); });
+        } else {
+            g.for_each_chunk([&](int map, uint32_t off, int col0) { tma_store_4d(&p.tmO[map], sa + off, c0 + col0, c1, c2, c3); });
+        }
+    };
+    if (RES) {                                                                 // the first S tiles' residuals: every slab is free
+        for (int c = 0; c < S; ++c) {
+            const int rd = rd0 + (c / mt) * rd_step, m = c % mt;
+            if (rd < rounds && m < valid_tiles(rd)) tile_io(first_tile(rd) + m, c, true);
+        }
+    }
+    int it = 0;
+    for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
+        const int t0 = first_tile(rd), nv = valid_tiles(rd);
+        const int rdn = rd + g.nb * rd_step;                                   // the round whose tile m reuses tile m's slab
+        const int nvn = rdn < rounds ? valid_tiles(rdn) : 0;
+        for (int m = 0; m < nv; ++m) {
+            const int c = it * mt + m, slab = c & (S - 1);
+            const uint32_t use = (uint32_t)(c >> s_shift);
+            mbar_wait_u32(sfull_u32 + (uint32_t)slab * 8u, use & 1u);
+            if (!no_store) {
+                tile_io(t0 + m, slab, false);
+                tma_store_commit();
+                tma_store_wait_read0();                  // the TMA unit has read the slab
+            }
+            mbar_arrive_u32(sempty_u32 + (uint32_t)slab * 8u);
+            if (RES && m < nvn) tile_io(first_tile(rdn) + m, slab, true);
+        }
+    }
+    tma_store_wait_all();
+}
+
+// Eight epilogue warps: warp w serves TMEM lane quarter q = w % 4 (a hardware rule) and, of that quarter's
+// 16-column units, the ones with unit % 2 == (w - 4) / 4.  The two warps of a quarter share the quarter's ring of
+// one-tile staging slabs; a slab is handed to the store warp and back through the sfull / sempty mbarriers (no named
+// barriers, no TMA instruction on this path).  A round's mt tiles are drained back to back as one flat list of work
+// items, the TMEM load of the next item always in flight behind the math of the current one.
 template <int ACT, int RES, int F32>
 __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_tiles, uint32_t tmem_base, const float* bias_s,
-                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar, uint8_t* stg_base, int warp,
-                                              int lane, bool pair = false) {
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* sfull_bar, uint64_t* sempty_bar,
+                                              uint64_t* res_bar, uint8_t* stg_base, int warp, int lane, bool pair = false) {
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    const int n_tile = p.n_tile, nchunks = p.epi_nchunks, mt = p.mt;
+    const EpiGeom<F32> g(p, stg_base, q);
     constexpr int esize = F32 ? 4 : 2;
-    const uint32_t row_bytes = (uint32_t)(n_tile * esize);
-    const uint32_t tile_bytes = 128u * row_bytes;                               // staging bytes of one M tile
-    const uint32_t slab0 = smem_u32(stg_base) + (uint32_t)q * 32u * row_bytes;   // this quarter's slab of tile 0, buffer 0
-    const uint32_t buf_stride = p.stg_bufs == 2 ? (uint32_t)mt * tile_bytes : 0u;
-    const uint32_t rbar = smem_u32(&res_bar[q]);
+    const int n_tile = p.n_tile, mt = p.mt;
+    const int S = g.nb * mt, s_shift = 31 - __clz(S);
+    const uint32_t tile_bytes = g.tile_bytes, slab0 = g.slab0;
+    const uint32_t sfull_u32 = smem_u32(sfull_bar) + (uint32_t)(q * S) * 8u, sempty_u32 = smem_u32(sempty_bar) + (uint32_t)(q * S) * 8u;
+    const uint32_t rbar_u32 = smem_u32(res_bar) + (uint32_t)(q * S) * 8u;
     const uint32_t bias_base = smem_u32(bias_s);
     const uint32_t tfull_u32 = smem_u32(tfull_bar), tempty_u32 = smem_u32(tempty_bar);
-    const bool issuer = (half == 0 && lane == 0);
-    // sub-box of a tile covered by this quarter's 32 rows (row m = (y * bn + n) * bw + x)
-    const int rows_per_y = p.bw * p.bn;
-    const int dy = rows_per_y >= 32 ? (q * 32) / rows_per_y : q * (32 / rows_per_y);
-    const int dn = rows_per_y >= 32 ? ((q * 32) % rows_per_y) / p.bw : 0;
     // 16-column units alternate between the two warps of a quarter; an odd last unit is split 8 + 8 so both warps carry
-    // the same load (n_tile = 16, 48, 144 would otherwise leave one warp waiting at the pair barrier)
+    // the same load (n_tile = 16, 48, 144 would otherwise leave one warp idle for a unit)
     const int nunits = n_tile >> 4;
     const bool split_last = (nunits & 1) != 0;
     const int my_units = split_last ? (nunits - 1) >> 1 : (nunits - half + 1) >> 1;     // full units half, half + 2, ...
-    // Swizzled slab address of this lane's row for the 16-column unit starting at byte `b` of the row.  Mirrors
-    // the host's chunking (conv_tc_plan): full 128-byte chunks first, then one 64-byte, then one 32-byte chunk.
-    const uint32_t n128 = row_bytes >> 7, has64 = (row_bytes >> 6) & 1u;
+    const int ipt = my_units + (split_last ? 1 : 0);                                    // work items per tile
+    // Swizzled slab address of this lane's row for the 16-column unit starting at byte `b` of the row.
+    const uint32_t n128 = g.n128, has64 = g.has64;
     const uint32_t row128 = slab0 + (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
     const uint32_t row64 = slab0 + n128 * 4096u + (uint32_t)lane * 64u, sw64 = (uint32_t)((lane >> 1) & 3);
     const uint32_t row32 = slab0 + n128 * 4096u + has64 * 2048u + (uint32_t)lane * 32u, sw32 = (uint32_t)((lane >> 2) & 1);
@@ -440,14 +527,6 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         return row32 + ((((rem >> 4) & 1u) ^ sw32) << 4);
     };
     const uint32_t ubytes = 16u * esize;               // bytes of one unit in a row
-    // TMA boxes of one tile's quarter slab, in the order of the host's chunk list (no table look-ups on the issue path)
-    const int cols128 = 128 / esize, cols64 = 64 / esize;
-    auto for_each_chunk = [&](auto&& fn) {
-        for (uint32_t k = 0; k < n128; ++k) fn(0, k * 4096u, (int)k * cols128);
-        if (has64) fn(1, n128 * 4096u, (int)n128 * cols128);
-        if (row_bytes & 32u) fn(2, n128 * 4096u + has64 * 2048u, (int)n128 * cols128 + (int)has64 * cols64);
-    };
-    uint32_t rphase = 0;
     int it = 0;
     // tile walk: a CTA takes rounds blockIdx.x, + gridDim.x, ... of mt tiles; in a CTA pair (mt == 1) the pair takes two
     // consecutive tiles per round, one per CTA, and an odd last tile is computed (and stored, identically) by both
@@ -455,113 +534,71 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     const int rounds = pair ? (total_tiles + 1) / 2 : (total_tiles + mt - 1) / mt;
     const int rd0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, rd_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const uint32_t tempty_arrive = pair ? mapa_u32(tempty_u32, 0) : tempty_u32;   // the leader's barrier gates the pair's MMAs
+    const bool ldt = !B2D_EXP(p, 4);
+    const int split_col = (nunits - 1) * 16 + half * 8;
     for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const int t0 = pair ? min(2 * rd + (int)rank, total_tiles - 1) : rd * mt;
         const int nv = pair ? 1 : min(mt, total_tiles - t0);        // valid tiles of this round
-        const uint32_t sboff = (it & 1) ? buf_stride : 0u;
-        // box coordinates of this quarter's rows in every tile of the round (issuer only; computed here, off the
-        // math -> store critical path)
-        int cc0[kMaxMt], cc1[kMaxMt], cc2[kMaxMt], cc3[kMaxMt];
-        if (issuer) {
-#pragma unroll
-            for (int m = 0; m < kMaxMt; ++m) {
-                const TileCoord tc = decode_tile(p, t0 + (m < nv ? m : 0));
-                cc0[m] = tc.nt * n_tile;
-                cc1[m] = tc.x0;
-                cc2[m] = p.perm ? tc.n0 + dn : tc.y0 + dy;
-                cc3[m] = p.perm ? tc.y0 + dy : tc.n0 + dn;
-            }
-            // the stores that last read these slabs have drained them (with two buffers the previous round's may still be in flight)
-            if (buf_stride) tma_store_wait_read1(); else tma_store_wait_read0();
-            if (RES) {
-                mbar_expect_tx_u32(rbar, (uint32_t)nv * 32u * (uint32_t)(n_tile * 2));
-#pragma unroll
-                for (int m = 0; m < kMaxMt; ++m)
-                    if (m < nv)
-                        for_each_chunk([&](int map, uint32_t off, int col0) {
-                            tma_load_4d(&p.tmR[map], rbar, slab0 + sboff + (uint32_t)m * tile_bytes + off, cc0[m] + col0, cc1[m], cc2[m], cc3[m]);
-                        });
-            }
-        }
-        pair_sync(q);                                    // slabs are free (and the residual loads are in flight)
         if (warp == 4 && lane == 0) trace(p, 2, it, 0);
         mbar_wait_u32(tfull_u32 + as * 8, aphase);
         tc_fence_after();
         if (warp == 4 && lane == 0) trace(p, 2, it, 1);
-        if (RES) {
-            mbar_wait_u32(rbar, rphase);
-            rphase ^= 1;
-        }
         const int ch_base = p.n_tiles_n > 1 ? (int)((uint32_t)t0 - __umulhi((uint32_t)t0, p.rcp_nn) * (uint32_t)p.n_tiles_n) * n_tile : 0;   // n_tiles_n > 1 implies mt == 1
         const uint32_t baddr = bias_base + (uint32_t)(ch_base + half * 16) * 4u;
-#pragma unroll 1
-        for (int m = 0; m < (B2D_EXP(p, 1) ? 0 : nv); ++m) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * mt + m) * n_tile + half * 16);
-            const uint32_t moff = sboff + (uint32_t)m * tile_bytes;
-            uint32_t rbuf[2][16];
-            const bool ldt = !B2D_EXP(p, 4);
-            if (my_units > 0 && ldt) tmem_ld16(taddr, rbuf[0]);
-            if (my_units > 1 && ldt) tmem_ld16(taddr + 32, rbuf[1]);
-#pragma unroll 1
-            for (int i = 0; i < my_units; i += 2) {      // two units per trip, side by side; the TMEM loads of the next two overlap the math
-                const bool both = i + 1 < my_units;
-                uint64_t v0[8], v1[8];
-                tmem_ld_wait();
-                epi_bias<ACT, 16>(rbuf[0], baddr + i * 128, v0);
-                if (both) epi_bias<ACT, 16>(rbuf[1], baddr + (i + 1) * 128, v1);
-                if (i + 2 < my_units && ldt) tmem_ld16(taddr + (i + 2) * 32, rbuf[0]);      // rbuf is dead from here on
-                if (i + 3 < my_units && ldt) tmem_ld16(taddr + (i + 3) * 32, rbuf[1]);
-                const uint32_t base0 = unit_base((uint32_t)(half + 2 * i) * ubytes) + moff;
-                if (both) {
-                    if (ACT && !B2D_EXP(p, 3)) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            v0[k] = silu2_h(v0[k]);
-                            v1[k] = silu2_h(v1[k]);
-                        }
-                    }
-                    epi_store<RES, F32, 16>(v0, base0, B2D_EXPW(p));
-                    epi_store<RES, F32, 16>(v1, unit_base((uint32_t)(half + 2 * i + 2) * ubytes) + moff, B2D_EXPW(p));
-                } else {
-                    if (ACT && !B2D_EXP(p, 3)) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) v0[k] = silu2_h(v0[k]);
-                    }
-                    epi_store<RES, F32, 16>(v0, base0, B2D_EXPW(p));
-                }
+        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * mt * n_tile);
+        const int c_base = it * mt;
+        auto item_ld = [&](int m, int u, uint32_t (&rb)[16]) {
+            if (!ldt) return;
+            if (u < my_units) tmem_ld16(tq + (uint32_t)(m * n_tile + half * 16 + u * 32), rb);
+            else tmem_ld8(tq + (uint32_t)(m * n_tile + split_col), rb);
+        };
+        auto item_do = [&](int m, int u, const uint32_t (&rb)[16]) {
+            const int c = c_base + m, slab = c & (S - 1);
+            const uint32_t use = (uint32_t)(c >> s_shift);
+            if (u == 0) {                                                      // first item of a tile: its slab must be free (and the residual in it)
+                mbar_wait_u32(sempty_u32 + (uint32_t)slab * 8u, (use & 1u) ^ 1u);
+                if (RES) mbar_wait_u32(rbar_u32 + (uint32_t)slab * 8u, use & 1u);
             }
-            if (split_last) {                            // this warp's 8 columns of the last unit
-                const int col = (nunits - 1) * 16 + half * 8;
-                tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * mt + m) * n_tile + col), rbuf[0]);
+            const uint32_t moff = (uint32_t)slab * tile_bytes;
+            if (u < my_units) epi_unit<ACT, RES, F32, 16>(rb, baddr + u * 128, unit_base((uint32_t)(half + 2 * u) * ubytes) + moff, B2D_EXPW(p));
+            else epi_unit<ACT, RES, F32, 8>(rb, bias_base + (uint32_t)(ch_base + split_col) * 4u, unit_base((uint32_t)split_col * esize) + moff, B2D_EXPW(p));
+            if (u == ipt - 1) {                                                // last item: hand the slab to the store warp (64 arrivals per quarter)
+                fence_proxy_async();                                           // generic-proxy slab writes -> visible to the TMA store
+                mbar_arrive_u32(sfull_u32 + (uint32_t)slab * 8u);
+            }
+        };
+        const int nitems = nv * ipt;
+        uint32_t rbuf[2][16];
+        int m0 = 0, u0 = 0;
+        item_ld(0, 0, rbuf[0]);
+#pragma unroll 1
+        for (int j = 0; j < nitems; j += 2) {
+            int m1 = m0, u1 = u0 + 1;
+            if (u1 == ipt) { u1 = 0; ++m1; }
+            tmem_ld_wait();
+            if (j + 1 < nitems) item_ld(m1, u1, rbuf[1]);
+            item_do(m0, u0, rbuf[0]);
+            if (j + 1 < nitems) {
+                int m2 = m1, u2 = u1 + 1;
+                if (u2 == ipt) { u2 = 0; ++m2; }
                 tmem_ld_wait();
-                epi_unit<ACT, RES, F32, 8>(rbuf[0], bias_base + (uint32_t)(ch_base + col) * 4u, unit_base((uint32_t)col * esize) + moff, B2D_EXPW(p));
+                if (j + 2 < nitems) item_ld(m2, u2, rbuf[0]);
+                item_do(m1, u1, rbuf[1]);
+                m0 = m2; u0 = u2;
             }
         }
         tc_fence_before();
         if (pair) mbar_arrive_cluster(tempty_arrive + as * 8);
         else mbar_arrive_u32(tempty_u32 + as * 8);       // accumulator stage free: all tcgen05.ld of this round have completed
-        fence_proxy_async();                             // generic-proxy slab writes -> visible to the TMA store
         if (warp == 4 && lane == 0) trace(p, 2, it, 2);
-        pair_sync(q);
-        if (issuer && !B2D_EXP(p, 1) && !B2D_EXP(p, 5)) {
-#pragma unroll
-            for (int m = 0; m < kMaxMt; ++m)
-                if (m < nv)
-                    for_each_chunk([&](int map, uint32_t off, int col0) {
-                        tma_store_4d(&p.tmO[map], slab0 + sboff + (uint32_t)m * tile_bytes + off, cc0[m] + col0, cc1[m], cc2[m], cc3[m]);
-                    });
-            tma_store_commit();
-        }
-        if (warp == 4 && lane == 0) trace(p, 2, it, 3);
     }
-    if (issuer) tma_store_wait_all();
 }
 
 // barrier block shared by all kernels (offsets in 8-byte units from bar_off)
 struct Bars {
-    uint64_t *full, *empty, *tfull, *tempty, *hfull, *hempty, *res;
+    uint64_t *full, *empty, *tfull, *tempty, *hfull, *hempty, *res, *sfull, *sempty;   // res / sfull / sempty: [quarter][slab], stg_bufs * mt one-tile slabs per quarter
     uint32_t* tmem_slot;
     float* bias_s;
 };
@@ -574,7 +611,10 @@ __device__ __forceinline__ Bars carve_bars(uint8_t* smem, const ConvTcParams& p)
     b.hfull = b.tempty + 2;
     b.hempty = b.hfull + 2;
     b.res = b.hempty + 2;
-    b.tmem_slot = (uint32_t*)(b.res + 4);
+    const int nslab = 4 * p.stg_bufs * p.mt;            // [quarter][slab]; the residual barriers exist only for residual layers
+    b.sfull = b.res + (p.has_res ? nslab : 0);
+    b.sempty = b.sfull + nslab;
+    b.tmem_slot = (uint32_t*)(b.sempty + nslab);
     b.bias_s = (float*)(b.tmem_slot + 4);
     return b;
 }
@@ -591,7 +631,11 @@ __device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& 
             mbar_init(&b.hfull[i], 1);
             mbar_init(&b.hempty[i], 1);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(&b.res[i], 1);
+        for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
+            if (p.has_res) mbar_init(&b.res[i], 1);
+            mbar_init(&b.sfull[i], 64);
+            mbar_init(&b.sempty[i], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(b.tmem_slot, p.tmem_cols);
@@ -755,8 +799,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             trace(p, 1, it, 3);
         }
+    } else if (warp == 3) {
+        store_loop<RES, F32>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
     } else if (warp >= 4) {
-        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.res, smem + p.stg_off, warp, lane);
+        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
     }
     epilogue_exit(p, tmem_base, warp);
 }
@@ -891,8 +937,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             }
             trace(p, 1, it, 3);
         }
+    } else if (warp == 3) {
+        store_loop<RES, F32>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
     } else if (warp >= 4) {
-        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.res, smem + p.stg_off, warp, lane);
+        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
     }
     epilogue_exit(p, tmem_base, warp);
 }
@@ -929,7 +977,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
             mbar_init(&b.hfull[i], 2);
             mbar_init(&b.hempty[i], 1);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(&b.res[i], 1);
+        for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
+            if (p.has_res) mbar_init(&b.res[i], 1);
+            mbar_init(&b.sfull[i], 64);
+            mbar_init(&b.sempty[i], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_2sm(b.tmem_slot, p.tmem_cols);
@@ -1052,8 +1104,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
             }
 #endif
         }
+    } else if (warp == 3) {
+        store_loop<RES, F32>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane, true);
     } else if (warp >= 4) {
-        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.res, smem + p.stg_off, warp, lane, true);
+        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane, true);
     }
     tc_fence_before();
     cluster_sync_all();                               // the peer may still signal this CTA's barriers / read its smem until here
@@ -1173,8 +1227,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
             }
             trace(p, 1, it, 3);
         }
+    } else if (warp == 3) {
+        store_loop<0, 0>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
     } else if (warp >= 4) {
-        epilogue_loop<ACT, 0, 0>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.res, smem + p.stg_off, warp, lane);
+        epilogue_loop<ACT, 0, 0>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
     }
     epilogue_exit(p, tmem_base, warp);
 }
@@ -1293,8 +1349,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_tc_stem_kernel(const __g
             if (r == 0) trace(p, 0, git, 3);
             if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
+    } else if (warp == 3) {
+        store_loop<0, 0>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
     } else if (warp >= 4) {
-        epilogue_loop<ACT, 0, 0>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.res, smem + p.stg_off, warp, lane);
+        epilogue_loop<ACT, 0, 0>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
     }
     epilogue_exit(p, tmem_base, warp);
 }
@@ -1452,8 +1510,10 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     B2D_CHECK(!stem || split == 1, "conv_tc: stem with %d output channels", cout);
     const uint32_t row_bytes = (uint32_t)p.n_tile * esize;
     const uint32_t tile_stg = 128u * row_bytes;
-    const uint32_t tail_bytes = 256 /*barriers + tmem slot*/ + (uint32_t)cout_pad * 4 /*bias*/;
-    const uint32_t avail = 226 * 1024 - 1024 /*align slack*/ - tail_bytes;
+    const uint32_t tail_fixed = 256 /*pipeline barriers + tmem slot*/ + (uint32_t)cout_pad * 4 /*bias*/;
+    // slab hand-off barriers: sfull + sempty (+ residual) per quarter and one-tile slab
+    auto slab_bars = [&](int mt, int bufs) { return (uint32_t)((res ? 3 : 2) * 4 * mt * bufs * 8); };
+    const uint32_t avail = 226 * 1024 - 1024 /*align slack*/ - tail_fixed;
 
     // ---- kind, tiles per round, stages, staging buffers ----
     // halo: 3x3 stride 1 on 8-pixel-wide tiles (uniform (bw+2)-row stride between 8-row groups)
@@ -1473,7 +1533,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         for (int kind = (stem ? 2 : halo_ok ? 1 : 0); kind >= (stem ? 2 : dw ? 1 : 0) && best_kind < 0; --kind) {
             for (int bufs = 2; bufs >= 1 && best_kind < 0; --bufs) {
                 if (bufs == 2 && env_int("B2D_STG2", 1) == 0) continue;
-                const uint32_t stg = (uint32_t)bufs * mt * tile_stg;
+                const uint32_t stg = (uint32_t)bufs * mt * tile_stg + slab_bars(mt, bufs);
                 if (stg + 4096 > avail) continue;
                 const uint32_t room = avail - stg;
                 int stages = 0, min_stages = 0;
@@ -1510,8 +1570,8 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         p.mt = 1;
         p.b_tx_bytes = (uint32_t)(p.n_tile / 2) * 128u;
         p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
-        if (avail > 2u * tile_stg + 2u * p.halo_bytes + 6u * p.b_bytes && env_int("B2D_STG2", 1) != 0) p.stg_bufs = 2;
-        const uint32_t room = avail - (uint32_t)p.stg_bufs * tile_stg - 2u * p.halo_bytes;
+        if (avail > 2u * tile_stg + 2u * p.halo_bytes + 6u * p.b_bytes + slab_bars(1, 2) && env_int("B2D_STG2", 1) != 0) p.stg_bufs = 2;
+        const uint32_t room = avail - (uint32_t)p.stg_bufs * tile_stg - 2u * p.halo_bytes - slab_bars(1, p.stg_bufs);
         int st = (int)(room / p.b_bytes);
         p.stages = st > kMaxStages ? kMaxStages : st;
     }
@@ -1523,7 +1583,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     else operand_bytes = (uint32_t)p.stages * p.mt * p.a_bytes + p.b_bytes;
     p.stg_off = operand_bytes;                                   // 1 KiB aligned: every operand slot is a multiple of 1 KiB
     p.bar_off = p.stg_off + stg_bytes;
-    plan->smem_bytes = (size_t)p.bar_off + tail_bytes + 1024 /*align slack*/;
+    plan->smem_bytes = (size_t)p.bar_off + tail_fixed + slab_bars(p.mt, p.stg_bufs) + 1024 /*align slack*/;
     B2D_CHECK(plan->smem_bytes <= 227 * 1024, "conv_tc: %zu bytes of shared memory needed", plan->smem_bytes);
     {   // epilogue chunks: a row of n_tile columns cut into 128 / 64 / 32-byte pieces
         uint32_t done = 0, off = 0;
