@@ -75,6 +75,7 @@ struct __align__(64) ConvTcParams {
     int in_h, in_w;       // input spatial size (stem)
     const void* src_raw;  // stem: NHWC4 bf16 input
     const void* w_raw;    // stem: packed weights [n_tile][64] bf16
+    int b_res;            // halo kernel: 1 = all 9 * chunks weight boxes stay resident in the stage slots (loaded once per CTA)
     int rev;              // 1: this op walks its M tiles in descending order (set per op by the engine)
     int rev_last;         // per launch: index of the last M tile when walking backwards, else -1
     int exp;              // timing-ablation flags (trace builds only)

@@ -46,7 +46,7 @@ namespace {
 constexpr int kThreads = 384;         // 4 control warps + 8 epilogue warps
 constexpr int kStemThreads = 512;     // + 4 gather warps
 constexpr int kTileM = 128;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 9;         // 9: a 3x3 layer with one K chunk keeps all nine weight taps resident (b_res)
 constexpr int kMaxMt = 4;
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -858,6 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
                     }
                 }
                 if (++hb == 2) { hb = 0; hphase ^= 1; }
+                if (p.b_res && pit > 0) continue;        // resident weights: the ring holds every (chunk, tap) and is filled once
                 for (int tap = 0; tap < 9; ++tap) {
                     mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
                     if (elect_one()) {
@@ -889,6 +890,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const bool two = min(mt, total_tiles - rd * mt) > 1;
+            const bool b_res = p.b_res != 0, b_wait = !b_res || it == 0;
             trace(p, 1, it, 0);
             mbar_wait_u32(tempty_u32 + as * 8, aphase ^ 1);
             tc_fence_after();
@@ -906,8 +908,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
                 auto taps = [&](auto KM) {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
-                        tc_fence_after();
+                        if (b_wait) {                    // resident weights: only the first round waits for (and never releases) a stage
+                            if (!B2D_EXP(p, 0)) mbar_wait_u32(full_u32 + stage * 8, phase);
+                            tc_fence_after();
+                        }
                         if (leader) {
                             const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_units;
                             const uint32_t a_lo = a_lo_h + (uint32_t)(tap / 3) * kh_units + (uint32_t)(tap % 3) * 8u;
@@ -920,7 +924,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
                                 for (int k = 0; k < decltype(KM)::value; ++k)
                                     umma_bf16(d_tmem + (uint32_t)n_tile, desc64(hi_a, a_lo + halo_units + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
                             }
-                            umma_commit(empty_u32 + stage * 8);
+                            if (!b_res) umma_commit(empty_u32 + stage * 8);
                             if (tap == 8) {
                                 umma_commit(hempty_u32 + hb * 8);                         // halo tiles free once their MMAs retire
                                 if (last) umma_commit(tfull_u32 + as * 8);
@@ -1525,7 +1529,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.halo_bytes = (halo_rows * 128u + 1023u) & ~1023u;
     const int mt_env = env_int("B2D_MT", 0);
     const int mt_cap = stem ? 4 : 2;
-    int best_kind = -1, best_mt = 1, best_stages = 0, best_bufs = 1;
+    int best_kind = -1, best_mt = 1, best_stages = 0, best_bufs = 1, best_bres = 0;
     for (int mt = mt_cap; mt >= 1 && best_kind < 0; mt >>= 1) {
         if (mt_env > 0 && mt > mt_env) continue;
         if (mt > 1 && (split > 1 || 2 * mt * p.n_tile > 512)) continue;
@@ -1537,6 +1541,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                 if (stg + 4096 > avail) continue;
                 const uint32_t room = avail - stg;
                 int stages = 0, min_stages = 0;
+                bool bres = false;
                 if (kind == 0) {
                     const uint32_t sb = (uint32_t)mt * p.a_bytes + p.b_bytes;
                     stages = (int)(room / sb);
@@ -1549,6 +1554,10 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                     const uint32_t fixed = 2u * mt * p.halo_bytes;
                     stages = room > fixed ? (int)((room - fixed) / p.b_bytes) : 0;
                     min_stages = (bufs == 2 || mt > 1) ? 4 : 3;
+                    // resident weights: every (chunk, tap) weight box gets its own stage, loaded once per CTA.  The narrow 3x3
+                    // layers are bound by the TMA unit's request rate and the per-round weight refetch was a third of it.
+                    bres = !dw && split == 1 && 9 * p.chunks <= kMaxStages && stages >= 9 * p.chunks && env_int("B2D_BRES", 1) != 0;
+                    if (bres) stages = 9 * p.chunks;
                 } else {
                     const uint32_t sb = (uint32_t)mt * p.a_bytes;
                     stages = room > p.b_bytes ? (int)((room - p.b_bytes) / sb) : 0;
@@ -1557,17 +1566,18 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                 }
                 if (stages > kMaxStages) stages = kMaxStages;
                 if (stages < min_stages) continue;
-                best_kind = kind; best_mt = mt; best_stages = stages; best_bufs = bufs;
+                best_kind = kind; best_mt = mt; best_stages = stages; best_bufs = bufs; best_bres = bres ? 1 : 0;
             }
         }
     }
     B2D_CHECK(best_kind >= 0, "conv_tc: no shared-memory configuration fits (n_tile %d)", p.n_tile);
-    p.kind = dw ? 3 : best_kind; p.mt = best_mt; p.stages = best_stages; p.stg_bufs = best_bufs;
+    p.kind = dw ? 3 : best_kind; p.mt = best_mt; p.stages = best_stages; p.stg_bufs = best_bufs; p.b_res = best_bres;
     // CTA pairs for wide halo layers: weight stages shrink to half a tile per CTA (so the ring gets deeper)
     p.pair = 0;
     if (p.kind == 1 && split == 1 && p.n_tile >= env_int("B2D_PAIR_MIN_N", 128) && p.n_tile % 32 == 0 && (total_tiles >= 2 * sm_count || env_int("B2D_PAIR", 1) == 2) && env_int("B2D_PAIR", 1) != 0) {
         p.pair = 1;
         p.mt = 1;
+        p.b_res = 0;
         p.b_tx_bytes = (uint32_t)(p.n_tile / 2) * 128u;
         p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
         if (avail > 2u * tile_stg + 2u * p.halo_bytes + 6u * p.b_bytes + slab_bars(1, 2) && env_int("B2D_STG2", 1) != 0) p.stg_bufs = 2;
@@ -1802,7 +1812,7 @@ void conv_tc_free(ConvTcPlan* plan) {
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
     static const char* kinds[5] = {"", "-halo", "-stem", "-depthwise", "-halo-pair"};
-    return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d stg %d tmem %u smem %zu",
-                    kinds[p.pair ? 4 : p.kind], p.ksz, p.stride, p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages, p.stg_bufs,
-                    p.tmem_cols, plan->smem_bytes);
+    return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d%s stg %d tmem %u smem %zu",
+                    kinds[p.pair ? 4 : p.kind], p.ksz, p.stride, p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
+                    p.b_res ? " (resident)" : "", p.stg_bufs, p.tmem_cols, plan->smem_bytes);
 }

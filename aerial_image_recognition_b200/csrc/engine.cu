@@ -185,6 +185,16 @@ int b2d_create(int device, int max_batch, b2d_engine** out) {
     B2D_CHECK(prop.major == 10, "b2d_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
               prop.minor);
     B2D_CUDA(cudaSetDevice(device));
+    {   // Experiment knob: B2D_L2_FETCH = 32 / 64 / 128 sets cudaLimitMaxL2FetchGranularity (driver default 64; measured
+        // neutral for this kernel chain, profiles/r1_l2_fetch_granularity.txt), unset leaves the default.
+        const char* g = getenv("B2D_L2_FETCH");
+        const int gran = g ? atoi(g) : 0;
+        if (gran > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        if (getenv("B2D_VERBOSE")) fprintf(stderr, "b2det: L2 fetch granularity %zu bytes\n", got);
+        cudaGetLastError();
+    }
     b2d_engine* e = new b2d_engine();
     e->device = device;
     e->max_batch = max_batch;

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .graph import ACT_SILU, Graph, build
+from .graph import ACT_SILU, Graph, build, op_weights
 from .weights import make_synthetic_weights
 
 RESIZE = {"identity": 0, "cv2_linear": 1, "pil_bicubic": 2, "letterbox": 3}
@@ -71,8 +71,9 @@ class Engine:
         for op in g.ops:
             s, d = op.src, op.dst
             if op.kind in ("conv", "dwconv"):
-                wt = np.ascontiguousarray(w[op.weight + ".weight"], dtype=np.float32)
-                bs = np.ascontiguousarray(w[op.weight + ".bias"], dtype=np.float32)
+                wt, bs = op_weights(op, w)             # the model's weights in the buffers' channel order
+                wt = np.ascontiguousarray(wt, dtype=np.float32)
+                bs = np.ascontiguousarray(bs, dtype=np.float32)
                 cout, cing, k, groups = g.wshapes[op.weight]
                 assert wt.shape == (cout, cing, k, k), (op.weight, wt.shape)
                 wp, bp = wt.ctypes.data_as(C.c_void_p), bs.ctypes.data_as(C.c_void_p)

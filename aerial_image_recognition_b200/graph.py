@@ -65,6 +65,11 @@ class Op:
     weight: Optional[str] = None   # weight name (conv / dwconv)
     res: Optional[Ref] = None      # residual added after the activation
     tag: str = ""
+    # Channel placement: the buffers may hold a concat's segments in another order than the model's
+    # (see _c2f).  out_perm[j] / in_perm[j] = the model's output / input channel that lives at
+    # channel j of the destination / source slice; None = the model's own order.
+    out_perm: Optional[List[int]] = None
+    in_perm: Optional[List[int]] = None
 
 
 @dataclass
@@ -85,7 +90,7 @@ class Graph:
         self.bufs[name] = Buf(name, h, w, c, f32)
         return name
 
-    def conv(self, name, src: Ref, dst: Ref, k=1, s=1, act=ACT_SILU, res=None, groups=1):
+    def conv(self, name, src: Ref, dst: Ref, k=1, s=1, act=ACT_SILU, res=None, groups=1, out_perm=None, in_perm=None):
         sb, db = self.bufs[src.buf], self.bufs[dst.buf]
         pad = k // 2
         assert (sb.h + 2 * pad - k) // s + 1 == db.h, (name, sb.h, db.h)
@@ -93,7 +98,7 @@ class Graph:
         if groups == 1:
             cin = 3 if (src.buf == "input") else src.c
             self.wshapes[name] = (dst.c, cin, k, 1)
-            self.ops.append(Op("conv", src, dst, k, s, act, name, res, name))
+            self.ops.append(Op("conv", src, dst, k, s, act, name, res, name, out_perm, in_perm))
         else:
             assert groups == src.c == dst.c and k == 3 and s == 1
             self.wshapes[name] = (dst.c, 1, k, groups)
@@ -122,22 +127,45 @@ class Graph:
         return n + (16 if self.arch == "yolov8m" else 0)  # + the DFL arange conv
 
 
-def _c2f(g: Graph, name, src: Ref, dst: Ref, n, shortcut, hw):
+def op_weights(op: Op, w) -> Tuple:
+    """(weight [Cout, Cin/g, k, k], bias [Cout]) of a conv op in the channel order of the buffers it
+    reads and writes: the model's weights with the op's channel placement applied."""
+    wt, bs = w[op.weight + ".weight"], w[op.weight + ".bias"]
+    if op.out_perm is not None:
+        wt, bs = wt[op.out_perm], bs[op.out_perm]
+    if op.in_perm is not None:
+        wt = wt[:, op.in_perm]
+    return wt, bs
+
+
+def _c2f(g: Graph, name, src: Ref, dst: Ref, n, shortcut, hw, order=None):
     """Ultralytics C2f with the concat realised as channel offsets.
 
-    cat = [y0 | y1 | m0(y1) | m1(m0) ...]; cv1 writes [0,2c), bottleneck i reads
-    [(i+1)c,(i+2)c) and writes [(i+2)c,(i+3)c).
+    The model's cat = [y0 | y1 | m0(y1) | m1(m0) ...]: cv1 produces [y0 | y1], bottleneck i reads
+    segment i+1 and writes segment i+2, cv2 reads everything.  ``order[j]`` = the segment stored in
+    slot j of the buffer (default: the model's order).  The placement matters when a segment is
+    narrower than a 128-byte L2 line: TMA fetches whole lines, so a 96-byte (48-channel) segment
+    that straddles two lines costs 2.7x its bytes in DRAM reads (measured, profiles/), one that sits
+    inside a line 1.3x.  cv1's output rows and cv2's input columns are permuted to match
+    (``Op.out_perm`` / ``Op.in_perm``); results are identical.
     """
     c = dst.c // 2
+    order = list(range(n + 2)) if order is None else list(order)
+    assert sorted(order) == list(range(n + 2))
+    slot = {seg: j for j, seg in enumerate(order)}
+    assert abs(slot[0] - slot[1]) == 1, "cv1 writes y0 and y1 with one store: they must be neighbours"
     cat = g.buf(f"{name}.cat", hw, hw, (2 + n) * c)
     tmp = g.buf(f"{name}.tmp", hw, hw, c)
-    g.conv(f"{name}.cv1", src, Ref(cat, 0, 2 * c), 1, 1)
+    swap = slot[1] < slot[0]
+    g.conv(f"{name}.cv1", src, Ref(cat, min(slot[0], slot[1]) * c, 2 * c), 1, 1,
+           out_perm=(list(range(c, 2 * c)) + list(range(c))) if swap else None)
     for i in range(n):
-        x = Ref(cat, (i + 1) * c, c)
+        x = Ref(cat, slot[i + 1] * c, c)
         g.conv(f"{name}.m.{i}.cv1", x, Ref(tmp, 0, c), 3, 1)
-        g.conv(f"{name}.m.{i}.cv2", Ref(tmp, 0, c), Ref(cat, (i + 2) * c, c), 3, 1,
+        g.conv(f"{name}.m.{i}.cv2", Ref(tmp, 0, c), Ref(cat, slot[i + 2] * c, c), 3, 1,
                res=x if shortcut else None)
-    g.conv(f"{name}.cv2", Ref(cat, 0, (2 + n) * c), dst, 1, 1)
+    in_perm = None if order == list(range(n + 2)) else [seg * c + k for seg in order for k in range(c)]
+    g.conv(f"{name}.cv2", Ref(cat, 0, (2 + n) * c), dst, 1, 1, in_perm=in_perm)
 
 
 def build_yolov8m(nc: int = 2, imgsz: int = 640) -> Graph:
@@ -157,7 +185,8 @@ def build_yolov8m(nc: int = 2, imgsz: int = 640) -> Graph:
     x1 = g.buf("x1", s2, s2, 96)
     g.conv("model.1", Ref(x0, 0, 48), Ref(x1, 0, 96), 3, 2)
     x2 = g.buf("x2", s2, s2, 96)
-    _c2f(g, "model.2", Ref(x1, 0, 96), Ref(x2, 0, 96), 2, True, s2)
+    # 48-channel segments (96 B): y1 and m0, the two that are read as slices, go to the ends of the 384-byte pixel
+    _c2f(g, "model.2", Ref(x1, 0, 96), Ref(x2, 0, 96), 2, True, s2, order=(1, 0, 3, 2))
     x3 = g.buf("x3", s3, s3, 192)
     g.conv("model.3", Ref(x2, 0, 96), Ref(x3, 0, 192), 3, 2)
     p4 = Ref(cat14, 384, 192)                               # layer 4 output

@@ -20,7 +20,7 @@ from typing import Dict
 
 import numpy as np
 
-from .graph import Graph
+from .graph import Graph, op_weights
 
 def round_to_bf16(x: np.ndarray) -> np.ndarray:
     """Round-to-nearest-even fp32 -> bf16 -> fp32 (NaN-free inputs)."""
@@ -104,13 +104,12 @@ def _lsuv(graph: Graph, w: Dict[str, np.ndarray], seed: int) -> None:
             if op.kind in ("conv", "dwconv"):
                 if op.src.buf == "input":
                     src = src[:, :3]
-                wt = torch.from_numpy(w[op.weight + ".weight"])
-                b = torch.from_numpy(w[op.weight + ".bias"])
+                wt, b = (torch.from_numpy(np.ascontiguousarray(a)) for a in op_weights(op, w))    # buffer channel order
                 groups = g.wshapes[op.weight][3]
                 y = F.conv2d(src, wt, None, stride=op.s, padding=op.k // 2, groups=groups)
                 sc = _quantised_scale(1.0 / float(y.std()))
                 wt = torch.from_numpy(round_to_bf16((wt * sc).numpy()))
-                w[op.weight + ".weight"] = wt.numpy()
+                w[op.weight + ".weight"] = round_to_bf16((torch.from_numpy(w[op.weight + ".weight"]) * sc).numpy())   # model order
                 y = F.conv2d(src, wt, b, stride=op.s, padding=op.k // 2, groups=groups)
                 if op.act:
                     y = y * torch.sigmoid(y)

@@ -4,6 +4,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from aerial_image_recognition_b200.graph import op_weights
+
 
 def run_graph_cpu(g, weights, x_nchw, emulate_bf16=False):
     B = x_nchw.shape[0]
@@ -13,8 +15,7 @@ def run_graph_cpu(g, weights, x_nchw, emulate_bf16=False):
     for op in g.ops:
         src = bufs[op.src.buf][:, op.src.c0:op.src.c0 + op.src.c]
         if op.kind in ("conv", "dwconv"):
-            w = torch.from_numpy(weights[op.weight + ".weight"]).float()
-            b = torch.from_numpy(weights[op.weight + ".bias"]).float()
+            w, b = (torch.from_numpy(np.ascontiguousarray(a)).float() for a in op_weights(op, weights))
             groups = g.wshapes[op.weight][3]
             if op.src.buf == "input":
                 src = src[:, :3]

@@ -120,7 +120,8 @@ def _check_every_op(arch, imgsz, n):
         if op.kind in ("conv", "dwconv"):
             if op.src.buf == "input":
                 src = src[:, :3]
-            y = F.conv2d(src, torch.from_numpy(w[op.weight + ".weight"]), torch.from_numpy(w[op.weight + ".bias"]),
+            wt, bs = (torch.from_numpy(np.ascontiguousarray(a)) for a in G.op_weights(op, w))
+            y = F.conv2d(src, wt, bs,
                          stride=op.s, padding=op.k // 2, groups=g.wshapes[op.weight][3])
             if op.act:
                 y = y * torch.sigmoid(y)

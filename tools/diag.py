@@ -74,7 +74,8 @@ def _cpu_op(g, op, w, bufs_cpu, emulate=True):
     import torch.nn.functional as F
     src = bufs_cpu[op.src.buf][..., op.src.c0:op.src.c0 + op.src.c].permute(0, 3, 1, 2).float()
     if op.kind in ("conv", "dwconv"):
-        wt = torch.from_numpy(w[op.weight + ".weight"]); b = torch.from_numpy(w[op.weight + ".bias"])
+        from aerial_image_recognition_b200.graph import op_weights
+        wt, b = (torch.from_numpy(np.ascontiguousarray(a)) for a in op_weights(op, w))
         groups = g.wshapes[op.weight][3]
         if op.src.buf == "input":
             src = src[:, :3]
