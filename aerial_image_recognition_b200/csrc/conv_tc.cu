@@ -830,11 +830,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     const uint32_t hfull_u32 = smem_u32(b.hfull), hempty_u32 = smem_u32(b.hempty);
 
     if (warp == 0) {
-        int stage = 0, hb = 0;
-        uint32_t phase = 0, hphase = 0;
+        // ===================== weight producer: nine boxes per chunk through the stage ring =====================
+        int stage = 0;
+        uint32_t phase = 0;
         const int nstages = p.stages, chunks = p.chunks, n_tile = p.n_tile;
         const int cin_pad = chunks * 64;
         const uint32_t b_tx = p.b_tx_bytes, b_bytes = p.b_bytes;
+        int pit = 0;
+        for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++pit) {
+            if (p.b_res && pit > 0) break;               // resident weights: the ring holds every (chunk, tap) and is filled once
+            const int bn0 = decode_tile(p, rd * mt).nt * n_tile;
+            for (int ch = 0; ch < chunks; ++ch) {
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                    if (elect_one()) {
+                        if (B2D_EXP(p, 2)) {
+                            mbar_arrive_u32(full_u32 + stage * 8);
+                        } else {
+                            mbar_expect_tx_u32(full_u32 + stage * 8, b_tx);
+                            tma_load_2d(&p.tmB, full_u32 + stage * 8, smem_b + (uint32_t)stage * b_bytes, tap * cin_pad + ch * 64, bn0);
+                        }
+                    }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== halo producer (the TMEM allocator warp, idle after the prologue) =====================
+        // Its own warp, so the next round's halos are requested the moment a halo buffer frees up instead of queueing
+        // behind the weight ring: the MMA warp used to wait ~2000 cycles per round for its first operand.
+        int hb = 0;
+        uint32_t hphase = 0;
+        const int chunks = p.chunks;
         const bool perm = p.perm != 0;
         int pit = 0;
         for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++pit) {
@@ -842,7 +869,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             const int nv = min(mt, total_tiles - t0);
             const TileCoord tc0 = decode_tile(p, t0);
             const TileCoord tc1 = decode_tile(p, nv > 1 ? t0 + 1 : t0);
-            const int bn0 = tc0.nt * n_tile;
             trace(p, 0, pit, 0);
             for (int ch = 0; ch < chunks; ++ch) {
                 mbar_wait_u32(hempty_u32 + hb * 8, hphase ^ 1);
@@ -858,19 +884,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
                     }
                 }
                 if (++hb == 2) { hb = 0; hphase ^= 1; }
-                if (p.b_res && pit > 0) continue;        // resident weights: the ring holds every (chunk, tap) and is filled once
-                for (int tap = 0; tap < 9; ++tap) {
-                    mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
-                    if (elect_one()) {
-                        if (B2D_EXP(p, 2)) {
-                            mbar_arrive_u32(full_u32 + stage * 8);
-                        } else {
-                            mbar_expect_tx_u32(full_u32 + stage * 8, b_tx);
-                            tma_load_2d(&p.tmB, full_u32 + stage * 8, smem_b + (uint32_t)stage * b_bytes, tap * cin_pad + ch * 64, bn0);
-                        }
-                    }
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
-                }
             }
             trace(p, 0, pit, 2);
         }
@@ -1002,15 +1015,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
     const uint32_t hfull_u32 = smem_u32(b.hfull), hempty_u32 = smem_u32(b.hempty);
 
     if (warp == 0) {
-        // ===================== TMA producer (both CTAs) =====================
-        int stage = 0, hb = 0;
-        uint32_t phase = 0, hphase = 0;
+        // ===================== weight producer (both CTAs): this CTA's half of every weight box =====================
+        int stage = 0;
+        uint32_t phase = 0;
         const int nstages = p.stages, chunks = p.chunks;
         const int cin_pad = chunks * 64;
         const uint32_t b_tx = p.b_tx_bytes, b_bytes = p.b_bytes;
-        const bool perm = p.perm != 0;
-        const uint32_t lead_full = mapa_u32(full_u32, 0), lead_hfull = mapa_u32(hfull_u32, 0);
+        const uint32_t lead_full = mapa_u32(full_u32, 0);
         const int b_row0 = (int)rank * (p.n_tile >> 1);                      // this CTA's half of the weight rows
+        for (int rd = rd0; rd < rounds; rd += rd_step) {
+            for (int ch = 0; ch < chunks; ++ch) {
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx_cluster(lead_full + stage * 8, b_tx);
+                        tma_load_2d_2sm(&p.tmB, lead_full + stage * 8, smem_b + (uint32_t)stage * b_bytes, tap * cin_pad + ch * 64, b_row0);
+                    }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== halo producer (both CTAs; the TMEM allocator warp, idle after the prologue) =====================
+        int hb = 0;
+        uint32_t hphase = 0;
+        const int chunks = p.chunks;
+        const bool perm = p.perm != 0;
+        const uint32_t lead_hfull = mapa_u32(hfull_u32, 0);
         for (int rd = rd0; rd < rounds; rd += rd_step) {
             const TileCoord tc = decode_tile(p, min(2 * rd + (int)rank, total_tiles - 1));
             for (int ch = 0; ch < chunks; ++ch) {
@@ -1021,14 +1052,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
                                     perm ? tc.y0 - 1 : tc.n0);
                 }
                 if (++hb == 2) { hb = 0; hphase ^= 1; }
-                for (int tap = 0; tap < 9; ++tap) {
-                    mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx_cluster(lead_full + stage * 8, b_tx);
-                        tma_load_2d_2sm(&p.tmB, lead_full + stage * 8, smem_b + (uint32_t)stage * b_bytes, tap * cin_pad + ch * 64, b_row0);
-                    }
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
-                }
             }
         }
     } else if (warp == 1 && rank == 0) {
