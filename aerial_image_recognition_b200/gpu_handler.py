@@ -49,7 +49,7 @@ class GPUHandler:
         self._setup_gpu()
         arch = arch or arch_from_model_path(model_path)
         if weights is None and model_path:
-            weights = load_weights(model_path)
+            weights = load_weights(model_path, arch)
         self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed)
         self.session = InferenceSession(engine=self.engine)
 

@@ -39,17 +39,25 @@ def arch_from_model_path(model_path: Optional[str]) -> str:
     return "yolov8m"
 
 
-def load_weights(model_path: Optional[str]) -> Optional[Dict[str, np.ndarray]]:
-    """``.npz`` of deploy-form tensors (``model.N....weight`` / ``.bias``) if present.
-    The reference's ``.onnx`` blobs are absent (``.MISSING_LARGE_BLOBS:2-5``); when the
-    path does not exist the engine runs seeded synthetic weights and says so."""
-    if model_path and os.path.exists(model_path) and model_path.endswith(".npz"):
-        with np.load(model_path) as z:
-            return {k: z[k] for k in z.files}
+def load_weights(model_path: Optional[str], arch: Optional[str] = None) -> Optional[Dict[str, np.ndarray]]:
+    """Deploy-form tensors (``model.N....weight`` / ``.bias``) from ``model_path``:
+
+    * ``.onnx`` -- what the reference loads (``_script/config.py:25``, ``simple_detector.py:710``): the
+      convolution weights are read straight from the protobuf (``onnx_reader.py``, no ``onnx`` package)
+      and checked against the engine's graph for ``arch``;
+    * ``.npz`` -- the same tensors saved with ``numpy.savez``.
+
+    The reference's own blobs are absent (``.MISSING_LARGE_BLOBS:2-5``): when the path does not exist the
+    engine runs seeded synthetic weights of the right architecture and says so."""
     if model_path and os.path.exists(model_path):
-        raise NotImplementedError(
-            f"{model_path}: ONNX ingestion is the next row of the scope table (SURVEY.md section 8f-1); "
-            "convert to a deploy-form .npz for now")
+        if model_path.endswith(".npz"):
+            with np.load(model_path) as z:
+                return {k: z[k] for k in z.files}
+        if model_path.endswith(".onnx"):
+            from .graph import build
+            from .onnx_reader import load_onnx_weights
+            return load_onnx_weights(model_path, build(arch or arch_from_model_path(model_path)))
+        raise ValueError(f"{model_path}: unknown model file type (expected .onnx or .npz)")
     warnings.warn(f"model file {model_path!r} not found; using seeded synthetic weights", stacklevel=3)
     return None
 
@@ -61,7 +69,7 @@ class InferenceSession:
         if engine is None:
             arch = arch or arch_from_model_path(model_path)
             if weights is None:
-                weights = load_weights(model_path) if model_path else None
+                weights = load_weights(model_path, arch) if model_path else None
             engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed)
         self.engine = engine
         self._inputs = [_Input("images", [None, 3, engine.imgsz, engine.imgsz])]

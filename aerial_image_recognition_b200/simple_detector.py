@@ -48,7 +48,7 @@ class SimpleDetector:
         self.meters_per_pixel = earth_circumference / (2 ** self.zoom) / 256
         arch = arch or arch_from_model_path(model_path)
         if weights is None and model_path:
-            weights = load_weights(model_path)
+            weights = load_weights(model_path, arch)
         self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, imgsz=self.model_size)
         self.model = InferenceSession(engine=self.engine)
 

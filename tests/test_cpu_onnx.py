@@ -1,0 +1,67 @@
+"""ONNX weight ingestion: the reference loads its model by ``.onnx`` path
+(``_script/gpu_handler.py:61-65``, ``simple_detector.py:39-46``).  No real checkpoint exists here
+(``.MISSING_LARGE_BLOBS``), so the files are written by ``onnx_reader.write_conv_onnx`` in the layout of
+an Ultralytics export and read back with the package-free protobuf walker."""
+import numpy as np
+import pytest
+
+from aerial_image_recognition_b200 import graph as G, onnx_reader as R, session as S, weights as W
+
+
+@pytest.fixture(scope="module")
+def v8():
+    g = G.build("yolov8m", imgsz=64)
+    return g, W.make_synthetic_weights(g, 5, calibrate=False)
+
+
+@pytest.mark.parametrize("named,half", [(True, False), (False, False), (True, True)])
+def test_roundtrip_by_name_by_order_and_fp16(tmp_path, v8, named, half):
+    g, w = v8
+    path = str(tmp_path / "yolov8_tokyo_checkpoint.onnx")
+    R.write_conv_onnx(path, g, w, named=named, half=half)
+    got = R.load_onnx_weights(path, g)
+    assert set(got) == set(w)
+    for k in w:
+        ref = w[k].astype(np.float16).astype(np.float32) if half else w[k]
+        assert got[k].dtype == np.float32 and np.array_equal(got[k], ref), k
+
+
+def test_nodes_and_initializers_are_parsed(tmp_path, v8):
+    g, w = v8
+    path = str(tmp_path / "m.onnx")
+    R.write_conv_onnx(path, g, w)
+    nodes, inits = R.read_onnx(path)
+    convs = [n for n in nodes if n.op_type == "Conv"]
+    assert len(convs) == 89 + 1                                   # 83 dense + 6 depthwise + the DFL arange conv
+    assert convs[0].name == "/model/0/conv/Conv" and convs[0].inputs[1] == "model.0.conv.weight"
+    assert inits["model.0.conv.weight"].shape == (48, 3, 3, 3)
+    assert inits["model.22.cv3.0.0.0.conv.weight"].shape == (192, 1, 3, 3)       # depthwise cls branch (Ultralytics 8.3.x)
+    assert np.array_equal(inits["model.22.dfl.conv.weight"].ravel(), np.arange(16, dtype=np.float32))
+
+
+def test_wrong_architecture_fails_loudly(tmp_path, v8):
+    g, w = v8
+    path = str(tmp_path / "m.onnx")
+    R.write_conv_onnx(path, g, w, named=False)
+    with pytest.raises(ValueError, match="Conv nodes|expects"):
+        R.load_onnx_weights(path, G.build("yolov7", imgsz=64))
+    w2 = dict(w)
+    w2["model.1.weight"] = w["model.1.weight"][:, :, :1, :1]
+    R.write_conv_onnx(path, g, w2)
+    with pytest.raises(ValueError, match="expects"):
+        R.load_onnx_weights(path, g)
+
+
+def test_session_load_weights_dispatches_on_extension(tmp_path, v8):
+    g, w = v8
+    path = str(tmp_path / "yolov8_tokyo_checkpoint.onnx")
+    R.write_conv_onnx(path, g, w)
+    got = S.load_weights(path)
+    assert np.array_equal(got["model.21.cv2.weight"], w["model.21.cv2.weight"])
+    np.savez(str(tmp_path / "m.npz"), **w)
+    assert np.array_equal(S.load_weights(str(tmp_path / "m.npz"))["model.0.bias"], w["model.0.bias"])
+    with pytest.warns(UserWarning, match="synthetic"):
+        assert S.load_weights(str(tmp_path / "absent.onnx")) is None
+    (tmp_path / "m.bin").write_bytes(b"x")
+    with pytest.raises(ValueError):
+        S.load_weights(str(tmp_path / "m.bin"))

@@ -478,3 +478,25 @@ def test_full_batch_determinism_and_batch_invariance():
     for i in range(5):
         assert torch.equal(d3[i, :int(c3[i]), :6], d1[i, :int(c3[i]), :6])
     eng.close()
+
+
+# ---- the model arrives as an .onnx path, as in the reference ---------------------------------------
+def test_detector_built_from_onnx_file_equals_detector_built_from_tensors(tmp_path):
+    """``SimpleDetector(model_path)`` / ``GPUHandler(model_path)`` with a real file at the path
+    (``simple_detector.py:710``, ``_script/config.py:25``): weights read from the ONNX protobuf give
+    bit-identical rows to the same tensors handed over directly."""
+    from aerial_image_recognition_b200 import onnx_reader as R
+    from aerial_image_recognition_b200.gpu_handler import GPUHandler
+    from aerial_image_recognition_b200.simple_detector import SimpleDetector
+    g = G.build("yolov8m")
+    w = W.make_synthetic_weights(g, 3)
+    path = str(tmp_path / "yolov8_tokyo_checkpoint.onnx")
+    R.write_conv_onnx(path, g, w, named=False)                  # anonymous initializers: matched by graph order
+    x = (synth.make_tiles(2, 640, 8).astype(np.float32) / 255.0).transpose(0, 3, 1, 2)
+    a = SimpleDetector(path, None, max_batch=2)
+    b = SimpleDetector("absent.onnx", None, weights=w, max_batch=2)
+    ra = a.model.run(None, {"images": x})[0]
+    rb = b.model.run(None, {"images": x})[0]
+    assert ra.shape == (2, 8400, 6) and np.array_equal(ra, rb)
+    h = GPUHandler(path, max_batch=2)
+    assert np.array_equal(h.session.run(None, {"images": x})[0], rb)
