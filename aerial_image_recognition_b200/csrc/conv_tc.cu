@@ -619,17 +619,18 @@ __device__ __forceinline__ Bars carve_bars(uint8_t* smem, const ConvTcParams& p)
     return b;
 }
 // common prologue: barrier init (warp 1), TMEM allocation (warp 2), bias to smem (everyone)
-__device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& b, int warp, int lane, uint32_t full_count) {
+__device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& b, int warp, int lane, uint32_t full_count,
+                                             uint32_t issuers = 1) {
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&b.full[i], full_count);
-            mbar_init(&b.empty[i], 1);
+            mbar_init(&b.empty[i], issuers);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&b.tfull[i], 1);
+            mbar_init(&b.tfull[i], issuers);
             mbar_init(&b.tempty[i], 256);
             mbar_init(&b.hfull[i], 1);
-            mbar_init(&b.hempty[i], 1);
+            mbar_init(&b.hempty[i], issuers);
         }
         for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
@@ -1168,7 +1169,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
     const int rounds = (total_tiles + mt - 1) / mt;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB); }
-    const uint32_t tmem_base = prologue(p, b, warp, lane, 1);
+    const uint32_t tmem_base = prologue(p, b, warp, lane, 1, 2);
     const uint32_t halo_bytes = p.halo_bytes;
     const uint32_t smem_a = smem_u32(smem), smem_b = smem_a + 2u * (uint32_t)mt * halo_bytes;
     const uint32_t full_u32 = smem_u32(b.full), empty_u32 = smem_u32(b.empty);
@@ -1207,7 +1208,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
             }
             trace(p, 0, pit, 1);
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 2) {
+        // Two MMA issuers (warps 1 and 2, the latter idle after allocating TMEM): an N = 16 MMA occupies its issuing
+        // thread for ~55 cycles whatever its size, two threads together sustain one per ~39 (tools/ubench/mma_rate.cu).
+        // Issuer i takes the 16-channel groups j with j % 2 == i -- disjoint accumulator columns, no ordering between
+        // them -- and commits for its own MMAs; empty / hempty / tfull therefore expect two arrivals in this kernel.
+        const int isu = warp - 1;
         int stage = 0, hb = 0, it = 0;
         uint32_t phase = 0, hphase = 0;
         const uint32_t hi_b = desc_hi(1024), hi_a = desc_hi((uint32_t)p.halo_w * 128u);
@@ -1220,16 +1226,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int nv = min(mt, total_tiles - rd * mt);
-            trace(p, 1, it, 0);
+            if (isu == 0) trace(p, 1, it, 0);
             mbar_wait_u32(tempty_u32 + as * 8, aphase ^ 1);
             tc_fence_after();
-            trace(p, 1, it, 1);
+            if (isu == 0) trace(p, 1, it, 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * mt * n_tile);
             for (int ch = 0; ch < chunks; ++ch) {
                 mbar_wait_u32(full_u32 + stage * 8, phase);
                 mbar_wait_u32(hfull_u32 + hb * 8, hphase);
                 tc_fence_after();
-                if (ch == 0) trace(p, 1, it, 2);
+                if (ch == 0 && isu == 0) trace(p, 1, it, 2);
                 const uint32_t a_base = smem_a + (uint32_t)(hb * mt) * halo_bytes;
                 const int ngroups = min(4, (n_tile - ch * 64) >> 4);      // 16-channel groups in this chunk
                 if (elect_one()) {
@@ -1240,7 +1246,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
                             const uint32_t a_lo = desc_lo(a_base + (uint32_t)m * halo_bytes + (uint32_t)(tap / 3) * kh_bytes + (uint32_t)(tap % 3) * 128u);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                if (j < ngroups)
+                                if (j < ngroups && (j & 1) == isu)
                                     umma_bf16(d_tmem + (uint32_t)(m * n_tile + ch * 64 + j * 16), desc64(hi_a, a_lo + 2 * j),
                                               desc64(hi_b, b_lo + (uint32_t)(tap * 128 + 2 * j)), idesc, (uint32_t)(tap != 0));
                         }
@@ -1252,7 +1258,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
                 if (++hb == 2) { hb = 0; hphase ^= 1; }
             }
-            trace(p, 1, it, 3);
+            if (isu == 0) trace(p, 1, it, 3);
         }
     } else if (warp == 3) {
         store_loop<0, 0>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
