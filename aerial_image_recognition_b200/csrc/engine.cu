@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <string>
+#include <map>
 #include <vector>
 
 static thread_local std::string g_last_error;
@@ -74,6 +75,10 @@ struct b2d_engine {
     int cand_tiles = 0;
     void* dedup_scratch = nullptr;
     size_t dedup_scratch_bytes = 0;
+    // forward() as a CUDA graph per batch size: the ~94 launches of a step replay without per-launch driver work
+    std::map<int, cudaGraphExec_t> fwd_graphs;
+    std::map<int, int> fwd_calls;
+    cudaStream_t cap_stream = nullptr;      // capture happens here (the caller's stream may be the legacy default stream)
 };
 
 namespace {
@@ -222,6 +227,8 @@ void b2d_destroy(b2d_engine* e) {
     }
     if (e->cand) { cudaFree(e->cand); cudaFree(e->cand_count); cudaFree(e->keys); }
     if (e->dedup_scratch) cudaFree(e->dedup_scratch);
+    for (auto& kv : e->fwd_graphs) cudaGraphExecDestroy(kv.second);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     delete e;
 }
 
@@ -442,9 +449,42 @@ int b2d_run_op(b2d_engine* e, int i, int n, void* stream) {
 int b2d_forward(b2d_engine* e, int n, void* stream) {
     B2D_CHECK(e && e->finalized, "forward: plan not finalized");
     B2D_CHECK(n > 0 && n <= e->max_batch, "forward: n=%d outside [1,%d]", n, e->max_batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    static const bool use_graph = (getenv("B2D_GRAPH") ? atoi(getenv("B2D_GRAPH")) != 0 : true) && !getenv("B2D_TRACE");
+    auto it = e->fwd_graphs.find(n);
+    if (use_graph && it != e->fwd_graphs.end()) {
+        B2D_CUDA(cudaGraphLaunch(it->second, st));
+        return 0;
+    }
+    // the first call of a batch size runs eagerly (function attributes, lazy module loading); the second is captured
+    const bool capture = use_graph && e->fwd_calls[n]++ >= 1;
+    if (capture) {
+        if (!e->cap_stream) B2D_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+        B2D_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    }
+    int rc = 0;
     for (const Op& op : e->ops)
-        if (int r = launch_op(e, op, n, (cudaStream_t)stream)) return r;
-    return 0;
+        if ((rc = launch_op(e, op, n, capture ? e->cap_stream : st)) != 0) break;
+    if (capture) {
+        cudaGraph_t g = nullptr;
+        cudaError_t err = cudaStreamEndCapture(e->cap_stream, &g);
+        if (rc == 0 && err == cudaSuccess && g) {
+            cudaGraphExec_t ex = nullptr;
+            if (cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) {
+                e->fwd_graphs[n] = ex;
+                cudaGraphDestroy(g);
+                B2D_CUDA(cudaGraphLaunch(ex, st));
+                return 0;
+            }
+        }
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        B2D_CHECK(rc == 0, "forward: launch failed during graph capture");
+        for (const Op& op : e->ops)                     // capture or instantiation failed: plain launches
+            if (int r = launch_op(e, op, n, st)) return r;
+        return 0;
+    }
+    return rc;
 }
 
 int b2d_preprocess(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, int pitch, long long img_stride, int mode, int bgr,
