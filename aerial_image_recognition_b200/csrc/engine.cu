@@ -79,6 +79,8 @@ struct b2d_engine {
     std::map<int, cudaGraphExec_t> fwd_graphs;
     std::map<int, int> fwd_calls;
     cudaStream_t cap_stream = nullptr;      // capture happens here (the caller's stream may be the legacy default stream)
+    std::vector<cudaStream_t> side_streams; // further capture streams: independent ops become parallel graph branches
+    std::vector<cudaEvent_t> cap_events;    // one per op + fork / join events (capture only)
 };
 
 namespace {
@@ -171,6 +173,87 @@ int launch_op(b2d_engine* e, const Op& op, int n, cudaStream_t s) {
     return -1;
 }
 
+// Launches every op of the plan into the capture: op i goes to the stream of the dependency it continues, or to another
+// capture stream when that one has moved on, with event edges for every read-after-write, write-after-read and
+// write-after-write between channel ranges of the same buffer.  Independent chains -- the six branches of the
+// detect head, head level 0 against the rest of the PAN path -- become parallel branches of the graph, so one
+// kernel's CTAs start on the SMs another kernel's tail has already left (each persistent kernel holds a whole SM, so
+// nothing else can hide the ~6 us of prologue and tail per launch).  B2D_STREAMS=1 keeps a single chain.
+struct Range { int buf, c0, c1; };
+static bool overlaps(const Range& a, const Range& b) { return a.buf == b.buf && a.buf >= 0 && a.c0 < b.c1 && b.c0 < a.c1; }
+
+int capture_ops(b2d_engine* e, int n) {
+    const int nops = (int)e->ops.size();
+    static const int ns_env = getenv("B2D_STREAMS") ? atoi(getenv("B2D_STREAMS")) : 3;
+    const int ns = ns_env < 1 ? 1 : (ns_env > 8 ? 8 : ns_env);
+    while ((int)e->side_streams.size() < ns - 1) {
+        cudaStream_t s;
+        B2D_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        e->side_streams.push_back(s);
+    }
+    while ((int)e->cap_events.size() < nops + 2 * ns) {
+        cudaEvent_t ev;
+        B2D_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->cap_events.push_back(ev);
+    }
+    auto stream_of = [&](int k) { return k == 0 ? e->cap_stream : e->side_streams[k - 1]; };
+    // reads / writes of every launched op (a fused pool chain writes its followers' outputs too)
+    std::vector<std::vector<Range>> rd(nops), wr(nops);
+    for (int i = 0; i < nops; ++i) {
+        const OpDesc& d = e->descs[i];
+        const int owner = e->ops[i].kind == OP_NOP ? e->ops[i].fused_into : i;
+        const int cin = d.kind_req == 0 ? d.cin : d.cout;
+        if (owner == i) rd[i].push_back({d.src, d.src_c0, d.src_c0 + cin});
+        if (d.res >= 0) rd[owner].push_back({d.res, d.res_c0, d.res_c0 + d.cout});
+        wr[owner].push_back({d.dst, d.dst_c0, d.dst_c0 + d.cout});
+    }
+    std::vector<int> where(nops, -1), last_on(ns, -1);
+    std::vector<bool> joined(ns, false);
+    joined[0] = true;
+    cudaEvent_t fork_ev = e->cap_events[nops];
+    B2D_CUDA(cudaEventRecord(fork_ev, e->cap_stream));
+    for (int i = 0; i < nops; ++i) {
+        if (e->ops[i].kind == OP_NOP) continue;
+        std::vector<int> deps;
+        for (int j = 0; j < i; ++j) {
+            if (where[j] < 0) continue;
+            bool dep = false;
+            for (const Range& w : wr[j]) {
+                for (const Range& r : rd[i]) dep = dep || overlaps(w, r);
+                for (const Range& w2 : wr[i]) dep = dep || overlaps(w, w2);
+            }
+            for (const Range& r : rd[j])
+                for (const Range& w2 : wr[i]) dep = dep || overlaps(r, w2);
+            if (dep) deps.push_back(j);
+        }
+        int k = -1;
+        for (int j : deps)                                   // continue the chain of the latest dependency that is still the tail of its stream
+            if (last_on[where[j]] == j) k = where[j];
+        if (k < 0) {                                         // otherwise the stream that has been idle longest
+            k = 0;
+            for (int t = 1; t < ns; ++t)
+                if (last_on[t] < last_on[k]) k = t;
+        }
+        cudaStream_t s = stream_of(k);
+        if (!joined[k]) {
+            B2D_CUDA(cudaStreamWaitEvent(s, fork_ev, 0));
+            joined[k] = true;
+        }
+        for (int j : deps)
+            if (where[j] != k) B2D_CUDA(cudaStreamWaitEvent(s, e->cap_events[j], 0));
+        if (int r = launch_op(e, e->ops[i], n, s)) return r;
+        B2D_CUDA(cudaEventRecord(e->cap_events[i], s));
+        where[i] = k;
+        last_on[k] = i;
+    }
+    for (int t = 1; t < ns; ++t)
+        if (joined[t]) {
+            B2D_CUDA(cudaEventRecord(e->cap_events[nops + 1 + t], stream_of(t)));
+            B2D_CUDA(cudaStreamWaitEvent(e->cap_stream, e->cap_events[nops + 1 + t], 0));
+        }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -229,6 +312,8 @@ void b2d_destroy(b2d_engine* e) {
     if (e->dedup_scratch) cudaFree(e->dedup_scratch);
     for (auto& kv : e->fwd_graphs) cudaGraphExecDestroy(kv.second);
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    for (auto st : e->side_streams) cudaStreamDestroy(st);
+    for (auto ev : e->cap_events) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -463,8 +548,12 @@ int b2d_forward(b2d_engine* e, int n, void* stream) {
         B2D_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
     }
     int rc = 0;
-    for (const Op& op : e->ops)
-        if ((rc = launch_op(e, op, n, capture ? e->cap_stream : st)) != 0) break;
+    if (!capture) {
+        for (const Op& op : e->ops)
+            if ((rc = launch_op(e, op, n, st)) != 0) break;
+    } else {
+        rc = capture_ops(e, n);
+    }
     if (capture) {
         cudaGraph_t g = nullptr;
         cudaError_t err = cudaStreamEndCapture(e->cap_stream, &g);
