@@ -135,28 +135,34 @@ class MosaicDetector:
         B = eng.max_batch
         local = windows.copy()
         local[:, 1] -= y_offset
-        params_all = affine_params(windows, self.gt, self.win)
+        # every per-window table goes to the device once; the batch loop below queues kernels only (no host
+        # synchronisation: a boolean-mask gather per batch would stall the launch queue ~100 times per mosaic)
+        params_all = torch.from_numpy(affine_params(windows, self.gt, self.win)).to(dev)
+        org_all = torch.from_numpy(local).to(dev)
+        ids_all = torch.from_numpy(ids).to(dev)
         for s in range(0, len(windows), B):
             e = min(s + B, len(windows))
             n = e - s
-            org = torch.from_numpy(local[s:e]).to(dev)
-            tiles = eng.cut_windows(mosaic, org, self.win, self.fill)
+            tiles = eng.cut_windows(mosaic, org_all[s:e], self.win, self.fill)
             dets, counts = eng.infer(tiles, "identity", False, self.nms_conf, False, self.iou, 0, self.max_det)
-            geo = eng.georef(dets, counts, torch.from_numpy(params_all[s:e]).to(dev), "affine")
-            cap = dets.shape[1]
-            slot = torch.arange(cap, device=dev, dtype=torch.int32)[None, :].expand(n, cap)
-            valid = slot < counts[:, None]
-            conf = dets[..., 4]
-            valid &= conf > self.conf                        # notebook: box.conf > 0.4
-            g64 = geo.view(torch.float64).view(n, cap, 5)     # x, y, then packed floats
-            gf = geo.view(torch.float32).view(n, cap, 10)
-            wid = torch.from_numpy(ids[s:e]).to(dev)[:, None].expand(n, cap)
-            cls = dets.view(torch.int32)[..., 5]
-            outs.append((g64[..., 0][valid], g64[..., 1][valid], conf[valid], cls[valid], wid[valid], slot[valid], gf[..., 6][valid]))
+            geo = eng.georef(dets, counts, params_all[s:e], "affine")
+            outs.append((geo, dets, counts, ids_all[s:e]))
         if not outs:
             z = torch.zeros(0, device=dev)
             return z.double(), z.double(), z.float(), z.int(), z.long(), z.int(), z.float()
-        return tuple(torch.cat([o[k] for o in outs]) for k in range(7))
+        geo = torch.cat([o[0] for o in outs])
+        dets = torch.cat([o[1] for o in outs])
+        counts = torch.cat([o[2] for o in outs])
+        wid_n = torch.cat([o[3] for o in outs])
+        n, cap = dets.shape[0], dets.shape[1]
+        slot = torch.arange(cap, device=dev, dtype=torch.int32)[None, :].expand(n, cap)
+        conf = dets[..., 4]
+        valid = (slot < counts[:, None]) & (conf > self.conf)            # notebook: box.conf > 0.4
+        g64 = geo.view(torch.float64).view(n, cap, 5)                     # x, y, then packed floats
+        gf = geo.view(torch.float32).view(n, cap, 10)
+        wid = wid_n[:, None].expand(n, cap)
+        cls = dets.view(torch.int32)[..., 5]
+        return (g64[..., 0][valid], g64[..., 1][valid], conf[valid], cls[valid], wid[valid], slot[valid], gf[..., 6][valid])
 
     # ---- dedup with seam exchange --------------------------------------------------------------
     @staticmethod
