@@ -1,0 +1,96 @@
+"""Host side of SURVEY.md section 8f-2 / 8f-3: UTM tiling (``_script/utils.py:17-65``), checkpoint and result
+files (``:68-146``, ``:181-292``), the synthetic tile source.  No GPU: the kernels these classes call are
+covered by ``tests/test_gpu_parity.py``."""
+import json
+import math
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from aerial_image_recognition_b200 import geo, utils as U
+from aerial_image_recognition_b200.config import DEFAULT_CONFIG
+from aerial_image_recognition_b200.tile_source import SyntheticTileHandler
+from oracle import postproc as OP
+
+
+def test_utm_forward_matches_oracle_and_inverse_round_trips():
+    rng = np.random.default_rng(0)
+    for zone, north in [(34, True), (31, True), (11, True), (56, False), (33, False)]:
+        lon0 = (zone - 1) * 6 - 180 + 3
+        lon = lon0 + rng.uniform(-3, 3, 200); lat = rng.uniform(1, 70, 200) * (1 if north else -1)
+        e, n = geo.utm_forward(lon, lat, zone, north)
+        eo, no = OP.utm_forward(lon, lat, zone, north)
+        assert np.array_equal(e, eo) and np.array_equal(n, no)          # the same series, term for term
+        lo2, la2 = geo.utm_inverse(e, n, zone, north)
+        assert np.abs(lo2 - lon).max() < 1e-10 and np.abs(la2 - lat).max() < 1e-10      # < 0.02 mm
+    # on the central meridian the easting is the false easting and the northing k0 * meridian arc
+    e, n = geo.utm_forward(21.0, 52.2, 34, True)
+    assert e == 500000.0 and abs(n - 5783283.16) < 0.01
+    assert geo.utm_epsg(4.9, 52.37) == "EPSG:32631" and geo.utm_epsg(151.2, -33.86) == "EPSG:32756"
+
+
+def test_generate_tiles_order_size_and_overlap():
+    bounds = (20.999, 52.199, 21.003, 52.2012)           # ~270 m x 245 m near Warsaw
+    tiles = U.TileGenerator.generate_tiles(bounds, 64.0, 0.2)
+    zone = geo.utm_zone_of(21.001)
+    (x0, x1), (y0, y1) = geo.utm_forward([bounds[0], bounds[2]], [bounds[1], bounds[3]], zone, True)
+    ref = OP.generate_tiles_metric(float(x0), float(y0), float(x1), float(y1), 64.0, 0.2)      # the reference's loop in metres
+    assert len(tiles) == len(ref) > 20
+    for (lo0, la0, lo1, la1), (rx0, ry0, rx1, ry1) in zip(tiles, ref):
+        (ex0, ex1), (ny0, ny1) = geo.utm_forward([lo0, lo1], [la0, la1], zone, True)
+        assert abs(ex0 - rx0) < 1e-6 and abs(ny0 - ry0) < 1e-6 and abs(ex1 - rx1) < 1e-6 and abs(ny1 - ry1) < 1e-6
+    nx = sum(1 for t in ref if t[1] == ref[0][1])        # x runs fastest
+    assert ref[1][0] - ref[0][0] == pytest.approx(51.2) and ref[nx][1] - ref[0][1] == pytest.approx(51.2)
+    assert ref[nx - 1][2] > float(x1)                    # the last column is not clipped (utils.py:49-54)
+    assert U.TileGenerator.generate_tiles((21.0, 52.0, 21.0, 52.0), 64.0, 0.2) == []
+    assert U.TileGenerator.get_utm_epsg(21.0, 52.0) == "EPSG:32634"
+
+
+def test_shapefile_header_bounds(tmp_path):
+    p = tmp_path / "frame.shp"
+    head = struct.pack(">i", 9994) + b"\0" * 20 + struct.pack(">i", 50) + struct.pack("<ii", 1000, 5)
+    head += struct.pack("<4d", 4.85, 52.33, 4.95, 52.41) + struct.pack("<4d", 0, 0, 0, 0)
+    p.write_bytes(head)
+    assert U.shapefile_bounds(str(p)) == (4.85, 52.33, 4.95, 52.41)
+    (tmp_path / "bad.shp").write_bytes(b"\0" * 100)
+    with pytest.raises(ValueError):
+        U.shapefile_bounds(str(tmp_path / "bad.shp"))
+
+
+def test_geojson_checkpoint_round_trip(tmp_path):
+    dets = [{'lon': 21.0 + 1e-5 * i, 'lat': 52.2 - 2e-5 * i, 'confidence': 0.3 + 0.01 * i} for i in range(5)]
+    cm = U.CheckpointManager(str(tmp_path))
+    assert cm.load_checkpoint() == (0, [])
+    cm.save_checkpoint(processed_count=128, detections=dets + [("image", "bbox")], total_tiles=400)   # stray tuples are skipped (:131-133)
+    state = json.load(open(cm.state_file))
+    assert set(state) == {'processed_count', 'total_tiles', 'timestamp'} and state['processed_count'] == 128 and state['total_tiles'] == 400
+    fc = json.load(open(cm.data_file))
+    assert fc["type"] == "FeatureCollection" and fc["crs"]["properties"]["name"].endswith("CRS84") and len(fc["features"]) == 5
+    assert fc["features"][2] == {"type": "Feature", "properties": {"confidence": dets[2]['confidence']},
+                                 "geometry": {"type": "Point", "coordinates": [dets[2]['lon'], dets[2]['lat']]}}
+    n, back = cm.load_checkpoint()
+    assert n == 128 and back == dets
+    assert os.path.basename(cm.state_file) == "processing_state.json" and os.path.basename(cm.data_file) == "latest_detections.geojson"
+    assert os.path.basename(U.CheckpointManager(str(tmp_path), "x").state_file) == "x_processing_state.json"
+    # create_geodataframe: the three accepted shapes of utils.py:153-168
+    fc = U.create_geodataframe([{'geometry': (1.0, 2.0), 'confidence': 0.5}, {'lon': 3.0, 'lat': 4.0}, {'foo': 1}, 7])
+    assert [f["geometry"]["coordinates"] for f in fc["features"]] == [[1.0, 2.0], [3.0, 4.0]] and fc["features"][1]["properties"]["confidence"] == 0.0
+
+
+def test_results_manager_paths_and_no_cpu_fallback(tmp_path):
+    rm = U.ResultsManager(str(tmp_path / "out"), prefix="detections", duplicate_distance=2.0)
+    assert rm.output_file.endswith("detections_results.geojson") and os.path.isdir(tmp_path / "out")
+    assert rm.process_results([]) == [] and rm.remove_duplicates([]) == []
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rm.remove_duplicates([{'lon': 21.0, 'lat': 52.0, 'confidence': 0.5}])
+
+
+def test_synthetic_tile_source_shape_and_determinism():
+    h = SyntheticTileHandler(size=64)
+    a = h.fetch_batch([(21.0, 52.0, 21.001, 52.0006), (21.001, 52.0, 21.002, 52.0006)])
+    assert isinstance(a[0], list) and len(a[0]) == 1 and a[0][0][0].size == (64, 64) and a[0][0][1] == (21.0, 52.0, 21.001, 52.0006)
+    b = h.get_single_image((21.0, 52.0, 21.001, 52.0006))
+    assert np.array_equal(np.asarray(a[0][0][0]), np.asarray(b[0][0])) and not np.array_equal(np.asarray(a[0][0][0]), np.asarray(a[1][0][0]))
+    assert DEFAULT_CONFIG['tile_size_meters'] == 64.0 and DEFAULT_CONFIG['tile_overlap'] == 0.2 and DEFAULT_CONFIG['batch_size'] == 64

@@ -521,3 +521,65 @@ def test_graph_replay_with_parallel_branches_equals_eager_forward(arch, imgsz):
         for a, b in zip(outs[0], outs[k]):
             assert torch.equal(a, b)
     eng.close()
+
+
+# ---- the production loop and its files ---------------------------------------------------------
+def test_results_manager_remove_duplicates_matches_reference_semantics(eng640, tmp_path):
+    """``ResultsManager.remove_duplicates`` (``_script/utils.py:212-274``): zone from the mean longitude, strict ``<``,
+    survivors in descending confidence with coordinates out of a UTM round trip."""
+    from aerial_image_recognition_b200 import geo, utils as U
+    rng = np.random.default_rng(3)
+    base = np.array([21.0, 52.2])
+    pts = base + rng.uniform(0, 0.002, (400, 2))
+    pts = np.concatenate([pts, pts[:120] + rng.normal(0, 4e-6, (120, 2))])          # near-duplicates within ~0.5 m
+    conf = rng.uniform(0.3, 0.95, len(pts)).astype(np.float32)
+    dets = [{'lon': float(p[0]), 'lat': float(p[1]), 'confidence': float(c)} for p, c in zip(pts, conf)]
+    rm = U.ResultsManager(str(tmp_path), duplicate_distance=2.0, engine=eng640)
+    got = rm.remove_duplicates(dets)
+    zone = geo.utm_zone_of(float(pts[:, 0].mean()))
+    x, y = geo.utm_forward(pts[:, 0], pts[:, 1], zone, True)
+    order = np.argsort(-conf, kind="stable")
+    keep = OP.dedup_greedy(x[order], y[order], conf[order], 2.0, inclusive=False)
+    ref_idx = order[keep]
+    assert len(got) == len(ref_idx) < len(dets)
+    assert [g['confidence'] for g in got] == [float(conf[i]) for i in ref_idx]
+    for g, i in zip(got, ref_idx):
+        assert abs(g['lon'] - pts[i, 0]) < 1e-9 and abs(g['lat'] - pts[i, 1]) < 1e-9     # round trip: ~1e-12 deg
+    rm0 = U.ResultsManager(str(tmp_path), duplicate_distance=0, engine=eng640)                # the default: nothing removed
+    assert len(rm0.remove_duplicates(dets)) == len(dets)
+
+
+def test_car_detector_production_loop(tmp_path):
+    """``CarDetector(base_dir, custom_config).detect()`` (``_script/detector.py:156-237``) against the same steps done
+    by hand: tiles in generation order, batches of ``batch_size``, final duplicate removal, results GeoJSON; then a
+    resume from a checkpoint."""
+    import json
+    from aerial_image_recognition_b200 import utils as U
+    from aerial_image_recognition_b200.detector import CarDetector
+    g = G.build("yolov7")
+    w = W.make_synthetic_weights(g, 0)
+    cfg = {'frame_path': 'testframe.shp', 'frame_bounds': (20.9990, 52.1990, 21.0022, 52.2008), 'batch_size': 8,
+           'duplicate_distance': 1.5, 'engine_options': {'weights': w}}
+    det = CarDetector(str(tmp_path), cfg)
+    assert det.output_dir == os.path.join(str(tmp_path), 'output', 'testframe') and det.model_path.endswith(
+        os.path.join('models', 'car_aerial_detection_yolo7_ITCVD_deepness.onnx'))
+    out = det.detect(interactive=False, force_restart=True)
+    tiles = U.TileGenerator.generate_tiles(cfg['frame_bounds'], 64.0, 0.2)
+    assert det.stats['total_tiles'] == len(tiles) > 16
+    manual = []
+    for s in range(0, len(tiles), 8):
+        manual.extend(det.gpu_handler.process_batch(det.tile_handler.fetch_batch(tiles[s:s + 8])))
+    ref = det.results_manager.remove_duplicates(det.results_manager.remove_duplicates(manual))      # periodic + final pass, as the loop does
+    assert len(manual) > 0 and out == ref
+    fc = json.load(open(det.results_manager.output_file))
+    assert os.path.basename(det.results_manager.output_file) == "detections_results.geojson"
+    assert [(f["geometry"]["coordinates"], f["properties"]["confidence"]) for f in fc["features"]] == [([d['lon'], d['lat']], d['confidence']) for d in out]
+    # resume: a checkpoint at tile 16 with the detections of the first 16 tiles continues to the same raw set
+    first = []
+    for s in range(0, 16, 8):
+        first.extend(det.gpu_handler.process_batch(det.tile_handler.fetch_batch(tiles[s:s + 8])))
+    det.checkpoint_manager.save_checkpoint(16, first, len(tiles))
+    det2 = CarDetector(str(tmp_path), cfg)
+    out2 = det2.detect(interactive=False, force_restart=False)
+    assert det2.stats['start'] == 16 and len(out2) == len(out)
+    assert [d['confidence'] for d in out2] == [d['confidence'] for d in out]
