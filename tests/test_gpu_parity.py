@@ -583,3 +583,38 @@ def test_car_detector_production_loop(tmp_path):
     out2 = det2.detect(interactive=False, force_restart=False)
     assert det2.stats['start'] == 16 and len(out2) == len(out)
     assert [d['confidence'] for d in out2] == [d['confidence'] for d in out]
+
+
+# ---- BASELINE size (C2: batch 64 at 640x640): size-independent properties ---------------------------------------------
+def test_full_batch_is_permutation_equivariant_and_matches_small_batches():
+    """At the benchmark's own size the oracle is too slow to be the checker, so the check is structural: tiles are
+    independent, therefore (a) permuting the 64 tiles of a batch permutes the detections and changes nothing else --
+    which exercises the M tiles that span several images (8 x 8 x 2 at 40^2, 4 x 4 x 8 at 20^2), the CTA pairs and
+    the multi-tile rounds the planner only picks at this size -- and (b) a tile gives bit-identical detections in a
+    batch of 64 and in a batch of 4 (different tile shapes, kernels and grid sizes)."""
+    from aerial_image_recognition_b200.engine import dets_to_numpy
+    g = G.build("yolov8m")
+    w = W.make_synthetic_weights(g, 0)
+    big = _engine("yolov8m", weights=w, max_batch=64, graph=g)
+    base = synth.make_tiles(16, 640, 77)
+    idx = (np.arange(64) * 5 + 3) % 16
+    tiles = base[idx]
+    perm = np.random.default_rng(1).permutation(64)
+    a = dets_to_numpy(*big.infer(torch.from_numpy(tiles).cuda(), "identity", conf_thr=0.25, inclusive=False, iou_thr=0.7, max_det=300))
+    b = dets_to_numpy(*big.infer(torch.from_numpy(tiles[perm]).cuda(), "identity", conf_thr=0.25, inclusive=False, iou_thr=0.7, max_det=300))
+    fields = ("cx", "cy", "w", "h", "conf", "cls", "anchor")
+    for k in range(64):
+        assert len(a[perm[k]]) == len(b[k]) > 0
+        for f in fields:
+            assert np.array_equal(a[perm[k]][f], b[k][f]), (k, f)
+    # equal tiles inside one batch give equal detections
+    for k in range(16, 64):
+        j = int(np.nonzero(idx[:16] == idx[k])[0][0])
+        assert np.array_equal(a[k]["conf"], a[j]["conf"]) and np.array_equal(a[k]["cx"], a[j]["cx"])
+    big.close()
+    small = _engine("yolov8m", weights=w, max_batch=4, graph=g)
+    c = dets_to_numpy(*small.infer(torch.from_numpy(tiles[:4]).cuda(), "identity", conf_thr=0.25, inclusive=False, iou_thr=0.7, max_det=300))
+    for k in range(4):
+        for f in fields:
+            assert np.array_equal(a[k][f], c[k][f]), (k, f)
+    small.close()
