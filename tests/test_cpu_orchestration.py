@@ -94,3 +94,25 @@ def test_synthetic_tile_source_shape_and_determinism():
     b = h.get_single_image((21.0, 52.0, 21.001, 52.0006))
     assert np.array_equal(np.asarray(a[0][0][0]), np.asarray(b[0][0])) and not np.array_equal(np.asarray(a[0][0][0]), np.asarray(a[1][0][0]))
     assert DEFAULT_CONFIG['tile_size_meters'] == 64.0 and DEFAULT_CONFIG['tile_overlap'] == 0.2 and DEFAULT_CONFIG['batch_size'] == 64
+
+
+def test_default_config_equals_the_reference_module():
+    """``tests/golden/default_config.json`` is ``DEFAULT_CONFIG`` imported from the reference's own ``_script/config.py``
+    (``tests/golden/make_golden.py``); the drop-in keeps every key and default."""
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "default_config.json")))
+    ours = {k: (list(v) if isinstance(v, tuple) else v) for k, v in DEFAULT_CONFIG.items()}
+    assert ours == ref
+
+
+def test_reference_tile_fixture_and_its_reference_resizes():
+    """The committed PNG holds the decoded pixels of the reference's ``test_tile.jpg``; the two resizes the reference
+    applies to it (PIL bicubic, cv2 linear) are reproduced bit for bit by the host-side tables the device kernels use
+    (``resample.py``; the kernels themselves are checked against these libraries in the GPU tests)."""
+    import zlib
+    from PIL import Image
+    from aerial_image_recognition_b200 import resample as RS
+    st = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "test_tile_stats.json")))
+    a = np.array(Image.open(os.path.join(os.path.dirname(__file__), "golden", "test_tile_864.png")).convert("RGB"))
+    assert list(a.shape) == st["size"] == [864, 864, 3] and zlib.crc32(a.tobytes()) == st["crc32"]
+    assert zlib.crc32(RS.emulate_pil_bicubic(a, 640, 640).tobytes()) == st["pil_bicubic_640_crc32"]
+    assert zlib.crc32(RS.emulate_cv2_linear(a, 640, 640).tobytes()) == st["cv2_linear_640_crc32"]
