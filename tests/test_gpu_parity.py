@@ -163,6 +163,13 @@ def test_forward_against_bf16_emulating_and_fp32_oracle(eng640, tiles4):
         assert np.median(db) < 0.5, (emu, np.median(db))
         agree = np.mean((rows[..., 4] >= 0.3) == sel)
         assert agree > 0.99, agree
+    # The deviation from the fp32 reference is the bf16 storage format's, not the kernels': a CPU model that only
+    # rounds its activations to bf16 (same places, torch's own arithmetic) is just as far from fp32 as the engine is.
+    f32 = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", eng640._weights, False).forward(x)])
+    emu = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", eng640._weights, True).forward(x)])
+    d_eng, d_emu = np.abs(rows[..., 4] - f32[..., 4]), np.abs(emu[..., 4] - f32[..., 4])
+    assert d_eng.mean() < 1.25 * d_emu.mean() + 1e-5 and np.quantile(d_eng, 0.99) < 1.25 * np.quantile(d_emu, 0.99) + 1e-4, (
+        d_eng.mean(), d_emu.mean(), np.quantile(d_eng, 0.99), np.quantile(d_emu, 0.99))
 
 
 def test_decode_kernel_matches_oracle_decode_on_identical_head_maps(eng640, tiles4):
