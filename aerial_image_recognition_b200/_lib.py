@@ -25,6 +25,8 @@ SIGNATURES = {
     "b2d_last_error": (c_char_p, []),
     "b2d_version": (c_int, []),
     "b2d_device_sm_count": (c_int, [c_void_p]),
+    "b2d_set_precision": (c_int, [c_void_p, c_int]),
+    "b2d_get_precision": (c_int, [c_void_p]),
     "b2d_plan_buffer": (c_int, [c_void_p, c_int, c_int, c_int, c_int]),
     "b2d_plan_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_int, c_int, c_int]),

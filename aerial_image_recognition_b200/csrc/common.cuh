@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -75,6 +76,7 @@ struct __align__(64) ConvTcParams {
     int in_h, in_w;       // input spatial size (stem)
     const void* src_raw;  // stem: NHWC4 bf16 input
     const void* w_raw;    // stem: packed weights [n_tile][64] bf16
+    int f16;              // 16-bit activation / weight format: 0 bf16, 1 fp16 (B2D_PREC_FP16)
     int b_res;            // halo kernel: 1 = all 9 * chunks weight boxes stay resident in the stage slots (loaded once per CTA)
     int rev;              // 1: this op walks its M tiles in descending order (set per op by the engine)
     int rev_last;         // per launch: index of the last M tile when walking backwards, else -1
@@ -97,7 +99,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch,
                  const __nv_bfloat16* src, int src_h, int src_w, int src_cs, int src_c0, int cin,
                  void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32,
                  int ksz, int stride, int act, const float* w_host, const float* b_host,
-                 const __nv_bfloat16* res, int res_cs, int res_c0, int depthwise = 0);
+                 const __nv_bfloat16* res, int res_cs, int res_c0, int depthwise = 0, int f16 = 0);
 int conv_tc_dw_supported(int cin, int cout, int ksz, int stride, int dst_f32, int has_res);
 int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream);
 void conv_tc_free(ConvTcPlan* plan);
@@ -135,9 +137,9 @@ void dwconv_free(DwConvPlan* plan);
 
 int maxpool_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                    __nv_bfloat16* dst, int oh, int ow, int dst_cs, int dst_c0, int c, int k, int stride,
-                   int n, cudaStream_t stream);
+                   int n, cudaStream_t stream, int f16 = 0);
 int poolchain_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* const* dst, const int* dst_c0,
-                     int dst_cs, int c, int stages, int n, cudaStream_t stream);
+                     int dst_cs, int c, int stages, int n, cudaStream_t stream, int f16 = 0);
 int upsample2x_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                       __nv_bfloat16* dst, int dst_cs, int dst_c0, int c, int n, cudaStream_t stream);
 
@@ -154,7 +156,7 @@ struct ResizeTables {     // device tables for one (mode, in_h, in_w, out)
 int preprocess_launch(const ResizeTables* t, const uint8_t* src, int n, int pitch, long long img_stride,
                       int bgr, int out_kind, void* dst, int out_size, cudaStream_t stream);
 
-int input_from_f32_launch(const float* src, int n, int h, int w, void* dst, cudaStream_t stream);
+int input_from_f32_launch(const float* src, int n, int h, int w, void* dst, cudaStream_t stream, int f16 = 0);
 
 struct HeadLevel { const float* buf; int hw, c, stride, nc, kind; float anchors[6]; int row0; };
 struct HeadDesc { HeadLevel lv[3]; int nlevels; int kind; int nc; int rows_total; };

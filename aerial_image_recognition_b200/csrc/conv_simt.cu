@@ -33,6 +33,26 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// the same for fp16 activations (B2D_PREC_FP16)
+__device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 v = __half22float2(*(const __half2*)&w[j]);
+        f[2 * j] = v.x;
+        f[2 * j + 1] = v.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+        w[j] = *(uint32_t*)&h;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ---- direct conv: thread = (output pixel, group of 16 output channels) --------------------
 constexpr int kCoutPerThread = 16;
 
@@ -206,7 +226,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwConvPlan p, int n) {
 // ---- max-pool k x k, padding k/2 for stride 1 / none for stride 2 (-inf padding) -------------
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                                                        __nv_bfloat16* dst, int oh, int ow, int dst_cs, int dst_c0, int c,
-                                                       int k, int stride, int n) {
+                                                       int k, int stride, int n, int f16) {
     const int groups = c / 8;
     const long long total = (long long)n * oh * ow * groups;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,12 +248,12 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* src, 
             if (ix < 0 || ix >= w) continue;
             const uint4 u = __ldg((const uint4*)(src + (((long long)img * h + iy) * w + ix) * src_cs + src_c0 + g * 8));
             float a[8];
-            unpack8(u, a);
+            if (f16) unpack8h(u, a); else unpack8(u, a);
 #pragma unroll
             for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], a[j]);
         }
     }
-    *(uint4*)(dst + pix * dst_cs + dst_c0 + g * 8) = pack8(m);
+    *(uint4*)(dst + pix * dst_cs + dst_c0 + g * 8) = f16 ? pack8h(m) : pack8(m);
 }
 
 // thread = (source pixel, 8-channel group): one 16-byte load, four 16-byte stores
@@ -264,7 +284,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* sr
 template <int CG>
 __global__ void __launch_bounds__(256) poolchain_kernel(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                                                          __nv_bfloat16* d0, __nv_bfloat16* d1, __nv_bfloat16* d2, int dst_cs,
-                                                         int c0_0, int c0_1, int c0_2, int c, int stages) {
+                                                         int c0_0, int c0_1, int c0_2, int c, int stages, int f16) {
     extern __shared__ uint4 pool_smem[];
     constexpr int V = CG / 8;                          // 16-byte vectors per pixel
     uint4* cur = pool_smem;
@@ -276,8 +296,16 @@ __global__ void __launch_bounds__(256) poolchain_kernel(const __nv_bfloat16* src
     const __nv_bfloat16* sp = src + img * h * w * src_cs + src_c0 + g * CG;
     for (int i = threadIdx.x; i < items; i += blockDim.x) cur[i] = __ldg((const uint4*)(sp + (long long)(i / V) * src_cs) + (i % V));
     __syncthreads();
-    auto vmax = [](uint4 a, uint4 b) {
+    auto vmax = [f16](uint4 a, uint4 b) {
         uint4 r;
+        if (f16) {
+            __half2 t;
+            t = __hmax2(*(__half2*)&a.x, *(__half2*)&b.x); r.x = *(uint32_t*)&t;
+            t = __hmax2(*(__half2*)&a.y, *(__half2*)&b.y); r.y = *(uint32_t*)&t;
+            t = __hmax2(*(__half2*)&a.z, *(__half2*)&b.z); r.z = *(uint32_t*)&t;
+            t = __hmax2(*(__half2*)&a.w, *(__half2*)&b.w); r.w = *(uint32_t*)&t;
+            return r;
+        }
         __nv_bfloat162 t;
         t = __hmax2(*(__nv_bfloat162*)&a.x, *(__nv_bfloat162*)&b.x); r.x = *(uint32_t*)&t;
         t = __hmax2(*(__nv_bfloat162*)&a.y, *(__nv_bfloat162*)&b.y); r.y = *(uint32_t*)&t;
@@ -403,12 +431,12 @@ void dwconv_free(DwConvPlan* plan) {
 }
 
 int maxpool_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* dst, int oh, int ow,
-                   int dst_cs, int dst_c0, int c, int k, int stride, int n, cudaStream_t stream) {
+                   int dst_cs, int dst_c0, int c, int k, int stride, int n, cudaStream_t stream, int f16) {
     B2D_CHECK(c % 8 == 0 && src_cs % 8 == 0 && src_c0 % 8 == 0 && dst_cs % 8 == 0 && dst_c0 % 8 == 0,
               "maxpool: channel counts/offsets must be multiples of 8");
     const long long total = (long long)n * oh * ow * (c / 8);
     maxpool_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, h, w, src_cs, src_c0, dst, oh, ow, dst_cs, dst_c0, c, k,
-                                                                   stride, n);
+                                                                   stride, n, f16);
     B2D_LAUNCH_CHECK();
     return 0;
 }
@@ -426,7 +454,7 @@ int upsample2x_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int sr
 // Stride-1 5x5 max-pool applied `stages` (<= 3) times in a chain; stage s is written to dst[s] at channel offset c0[s].
 // Returns 1 (and launches nothing) when the plane does not fit in shared memory: the caller then runs the pools one by one.
 int poolchain_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* const* dst, const int* dst_c0,
-                     int dst_cs, int c, int stages, int n, cudaStream_t stream) {
+                     int dst_cs, int c, int stages, int n, cudaStream_t stream, int f16) {
     B2D_CHECK(stages >= 1 && stages <= 3, "poolchain: 1..3 stages");
     B2D_CHECK(c % 8 == 0 && src_cs % 8 == 0 && src_c0 % 8 == 0 && dst_cs % 8 == 0, "poolchain: channel counts/offsets must be multiples of 8");
     const int cg = (c % 32 == 0 && (size_t)h * w * 32 * 2 * 2 <= 96 * 1024) ? 32 : 8;
@@ -439,11 +467,11 @@ int poolchain_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src
     if (cg == 32) {
         static bool attr32 = false;
         if (!attr32) { B2D_CUDA(cudaFuncSetAttribute(poolchain_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr32 = true; }
-        poolchain_kernel<32><<<blocks, 256, smem, stream>>>(src, h, w, src_cs, src_c0, d[0], d[1], d[2], dst_cs, c0[0], c0[1], c0[2], c, stages);
+        poolchain_kernel<32><<<blocks, 256, smem, stream>>>(src, h, w, src_cs, src_c0, d[0], d[1], d[2], dst_cs, c0[0], c0[1], c0[2], c, stages, f16);
     } else {
         static bool attr8 = false;
         if (!attr8) { B2D_CUDA(cudaFuncSetAttribute(poolchain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr8 = true; }
-        poolchain_kernel<8><<<blocks, 256, smem, stream>>>(src, h, w, src_cs, src_c0, d[0], d[1], d[2], dst_cs, c0[0], c0[1], c0[2], c, stages);
+        poolchain_kernel<8><<<blocks, 256, smem, stream>>>(src, h, w, src_cs, src_c0, d[0], d[1], d[2], dst_cs, c0[0], c0[1], c0[2], c, stages, f16);
     }
     B2D_LAUNCH_CHECK();
     return 0;

@@ -352,7 +352,7 @@ __device__ __forceinline__ void epi_bias(const uint32_t (&r)[16], uint32_t bias_
     }
 }
 template <int RES, int F32, int NC>
-__device__ __forceinline__ void epi_store(uint64_t (&v)[8], uint32_t base, int exp) {
+__device__ __forceinline__ void epi_store(uint64_t (&v)[8], uint32_t base, int exp, int f16) {
     if (exp & 64) {             // ablation: no staging stores (keep the values alive)
         uint64_t acc = 0;
 #pragma unroll
@@ -371,29 +371,41 @@ __device__ __forceinline__ void epi_store(uint64_t (&v)[8], uint32_t base, int e
                 const uint4 x = lds128(a0);
                 const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[4 * j + i] = add2(v[4 * j + i], pk2u(w[i] << 16, w[i] & 0xFFFF0000u));
+                for (int i = 0; i < 4; ++i) {
+                    if (f16) {
+                        const float2 f = __half22float2(*(const __half2*)&w[i]);
+                        v[4 * j + i] = add2(v[4 * j + i], pk2(f.x, f.y));
+                    } else {
+                        v[4 * j + i] = add2(v[4 * j + i], pk2u(w[i] << 16, w[i] & 0xFFFF0000u));
+                    }
+                }
             }
             uint32_t w[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float lo, hi;
                 upk2(v[4 * j + i], lo, hi);
-                __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-                w[i] = *(uint32_t*)&h;
+                if (f16) {
+                    __half2 h = __floats2half2_rn(lo, hi);
+                    w[i] = *(uint32_t*)&h;
+                } else {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+                    w[i] = *(uint32_t*)&h;
+                }
             }
             sts128(a0, make_uint4(w[0], w[1], w[2], w[3]));
         }
     }
 }
 template <int ACT, int RES, int F32, int NC = 16>
-__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base, int exp = 0) {
+__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base, int exp, int f16) {
     uint64_t v[8];
     epi_bias<ACT, NC>(r, bias_addr, v);
     if (ACT && !(exp & 8)) {
 #pragma unroll
         for (int i = 0; i < NC / 2; ++i) v[i] = silu2_h(v[i]);
     }
-    epi_store<RES, F32, NC>(v, base, exp);
+    epi_store<RES, F32, NC>(v, base, exp, f16);
 }
 
 // Geometry of the staging slabs, shared by the epilogue warps and the store warp.  A tile row of n_tile columns is cut
@@ -535,6 +547,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     const int rd0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, rd_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const uint32_t tempty_arrive = pair ? mapa_u32(tempty_u32, 0) : tempty_u32;   // the leader's barrier gates the pair's MMAs
     const bool ldt = !B2D_EXP(p, 4);
+    const int f16 = p.f16;
     const int split_col = (nunits - 1) * 16 + half * 8;
     for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
         const int as = it & 1;
@@ -562,8 +575,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
                 if (RES) mbar_wait_u32(rbar_u32 + (uint32_t)slab * 8u, use & 1u);
             }
             const uint32_t moff = (uint32_t)slab * tile_bytes;
-            if (u < my_units) epi_unit<ACT, RES, F32, 16>(rb, baddr + u * 128, unit_base((uint32_t)(half + 2 * u) * ubytes) + moff, B2D_EXPW(p));
-            else epi_unit<ACT, RES, F32, 8>(rb, bias_base + (uint32_t)(ch_base + split_col) * 4u, unit_base((uint32_t)split_col * esize) + moff, B2D_EXPW(p));
+            if (u < my_units) epi_unit<ACT, RES, F32, 16>(rb, baddr + u * 128, unit_base((uint32_t)(half + 2 * u) * ubytes) + moff, B2D_EXPW(p), f16);
+            else epi_unit<ACT, RES, F32, 8>(rb, bias_base + (uint32_t)(ch_base + split_col) * 4u, unit_base((uint32_t)split_col * esize) + moff, B2D_EXPW(p), f16);
             if (u == ipt - 1) {                                                // last item: hand the slab to the store warp (64 arrivals per quarter)
                 fence_proxy_async();                                           // generic-proxy slab writes -> visible to the TMA store
                 mbar_arrive_u32(sfull_u32 + (uint32_t)slab * 8u);
@@ -1447,6 +1460,13 @@ int encode_act_map(CUtensorMap* map, void* base, int c, int w, int h, int n, uin
     return encode_map(map, base, 4, dims, str, box, swizzle, f32, promo);
 }
 
+uint16_t f2h(float f) {
+    const __half h = __float2half_rn(f);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+
 uint16_t f2bf(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
@@ -1498,7 +1518,7 @@ int conv_tc_stem_supported(int src_cs, int cin, int ksz, int stride, int cout, i
 int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloat16* src, int src_h, int src_w, int src_cs,
                  int src_c0, int cin, void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32, int ksz,
                  int stride, int act, const float* w_host, const float* b_host, const __nv_bfloat16* res, int res_cs,
-                 int res_c0, int depthwise) {
+                 int res_c0, int depthwise, int f16) {
     memset(plan, 0, sizeof(*plan));
     const bool dw = depthwise != 0;
     if (dw) B2D_CHECK(conv_tc_dw_supported(cin, cout, ksz, stride, dst_f32, res != nullptr), "conv_tc: unsupported depthwise shape");
@@ -1654,7 +1674,9 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     while (cols < (uint32_t)(2 * p.mt * p.n_tile)) cols *= 2;
     p.tmem_cols = cols;
     // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((dw ? 16 : p.n_tile) >> 3) << 17) | ((uint32_t)((p.pair ? 2 * kTileM : kTileM) >> 4) << 24);
+    p.f16 = f16;
+    p.idesc = (1u << 4) | (f16 ? 0u : (1u << 7) | (1u << 10)) |        // D fp32; A / B format: 1 = bf16, 0 = fp16
+              ((uint32_t)((dw ? 16 : p.n_tile) >> 3) << 17) | ((uint32_t)((p.pair ? 2 * kTileM : kTileM) >> 4) << 24);
 
     // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin_pad] (zero padded) ----
     const int cin_pad = p.chunks * 64;
@@ -1667,13 +1689,13 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
             for (int t = 0; t < 9; ++t) {
                 const int chunk = c / 64, g = (c % 64) / 16, d = c % 16;
                 const size_t row = ((size_t)chunk * 9 + t) * 16 + d;
-                wp[row * 64 + g * 16 + d] = f2bf(w_host[(size_t)c * 9 + t]);
+                wp[row * 64 + g * 16 + d] = f16 ? f2h(w_host[(size_t)c * 9 + t]) : f2bf(w_host[(size_t)c * 9 + t]);
             }
     } else {
         for (int o = 0; o < cout; ++o)
             for (int c = 0; c < cin; ++c)
                 for (int t = 0; t < p.taps; ++t)
-                    wp[(size_t)o * ktot + (stem ? (size_t)t * 4 + c : (size_t)t * cin_pad + c)] = f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
+                    wp[(size_t)o * ktot + (stem ? (size_t)t * 4 + c : (size_t)t * cin_pad + c)] = f16 ? f2h(w_host[((size_t)o * cin + c) * p.taps + t]) : f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
     }
     std::vector<float> bp(cout_pad, 0.f);
     for (int o = 0; o < cout; ++o) bp[o] = b_host ? b_host[o] : 0.f;

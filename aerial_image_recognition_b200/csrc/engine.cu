@@ -61,6 +61,7 @@ struct b2d_engine {
     int max_batch = 0;
     int sm_count = 0;
     bool finalized = false;
+    int f16 = 0;                            // 16-bit activation / weight format: 0 bf16 (default), 1 fp16 (b2d_set_precision)
     std::vector<Buffer> bufs;
     std::vector<OpDesc> descs;
     std::vector<Op> ops;
@@ -157,17 +158,16 @@ int get_tables(b2d_engine* e, int mode, int h, int w, int out, int n, const Resi
 }
 
 int launch_op(b2d_engine* e, const Op& op, int n, cudaStream_t s) {
-    (void)e;
     switch (op.kind) {
         case OP_CONV_TC: return conv_tc_launch(&op.tc, n, s);
         case OP_CONV_SIMT: return conv_simt_launch(&op.simt, n, s);
         case OP_DWCONV: return dwconv_launch(&op.dw, n, s);
         case OP_MAXPOOL:
             return maxpool_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.dst, op.oh, op.ow, op.dst_cs, op.dst_c0, op.c, op.k,
-                                  op.stride, n, s);
+                                  op.stride, n, s, e->f16);
         case OP_UPSAMPLE: return upsample2x_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.dst, op.dst_cs, op.dst_c0, op.c, n, s);
         case OP_POOLCHAIN:
-            return poolchain_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.chain_dst, op.chain_c0, op.dst_cs, op.c, op.chain_stages, n, s);
+            return poolchain_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.chain_dst, op.chain_c0, op.dst_cs, op.c, op.chain_stages, n, s, e->f16);
         case OP_NOP: return 0;
     }
     return -1;
@@ -319,6 +319,14 @@ void b2d_destroy(b2d_engine* e) {
 
 int b2d_device_sm_count(b2d_engine* e) { return e ? e->sm_count : -1; }
 
+int b2d_set_precision(b2d_engine* e, int precision) {
+    B2D_CHECK(e && !e->finalized && e->descs.empty(), "set_precision: call right after b2d_create, before planning");
+    B2D_CHECK(precision == B2D_PREC_BF16 || precision == B2D_PREC_FP16, "set_precision: unknown precision %d", precision);
+    e->f16 = precision == B2D_PREC_FP16;
+    return 0;
+}
+int b2d_get_precision(b2d_engine* e) { return e ? (e->f16 ? B2D_PREC_FP16 : B2D_PREC_BF16) : -1; }
+
 int b2d_plan_buffer(b2d_engine* e, int h, int w, int c, int is_f32) {
     B2D_CHECK(e && !e->finalized, "plan_buffer: engine finalized or null");
     B2D_CHECK(h > 0 && w > 0 && c > 0, "plan_buffer: bad shape");
@@ -438,9 +446,10 @@ int b2d_plan_finalize(b2d_engine* e) {
                 op.kind = OP_CONV_TC;
                 if (conv_tc_plan(&op.tc, e->sm_count, e->max_batch, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin,
                                  db.ptr, db.h, db.w, db.c, d.dst_c0, d.cout, db.f32, d.k, d.stride, d.act, d.w.data(), d.b.data(), res,
-                                 res_cs, d.res_c0))
+                                 res_cs, d.res_c0, 0, e->f16))
                     return -1;
             } else {
+                B2D_CHECK(!e->f16, "plan_finalize: op %zu needs the CUDA-core fallback, which exists for bf16 only", i);
                 op.kind = OP_CONV_SIMT;
                 if (conv_simt_plan(&op.simt, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin, d.cin, db.ptr, db.h, db.w,
                                    db.c, d.dst_c0, d.cout, db.f32, d.k, d.stride, d.act, d.w.data(), d.b.data(), res, res_cs, d.res_c0))
@@ -450,9 +459,10 @@ int b2d_plan_finalize(b2d_engine* e) {
                    d.src_c0 % 8 == 0) {
             op.kind = OP_CONV_TC;
             if (conv_tc_plan(&op.tc, e->sm_count, e->max_batch, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin, db.ptr, db.h,
-                             db.w, db.c, d.dst_c0, d.cout, 0, 3, 1, d.act, d.w.data(), d.b.data(), nullptr, 0, 0, 1))
+                             db.w, db.c, d.dst_c0, d.cout, 0, 3, 1, d.act, d.w.data(), d.b.data(), nullptr, 0, 0, 1, e->f16))
                 return -1;
         } else if (d.kind_req == 1) {
+            B2D_CHECK(!e->f16, "plan_finalize: op %zu needs the CUDA-core depthwise fallback, which exists for bf16 only", i);
             op.kind = OP_DWCONV;
             if (dwconv_plan(&op.dw, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, (__nv_bfloat16*)db.ptr, db.c, d.dst_c0,
                             d.cout, d.act, d.w.data(), d.b.data()))
@@ -582,9 +592,10 @@ int b2d_preprocess(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, i
     B2D_CHECK(pitch >= w * 3, "preprocess: pitch %d < row bytes %d", pitch, w * 3);
     int out = 640;
     if (!e->bufs.empty()) out = e->bufs[0].h;
+    if (out_kind == B2D_OUT_BF16_NHWC4 && e->f16 && dst_dev == nullptr) out_kind = B2D_OUT_F16_NHWC4;   // the engine's own input format
     if (dst_dev == nullptr) {
-        B2D_CHECK(out_kind == B2D_OUT_BF16_NHWC4 && !e->bufs.empty() && e->bufs[0].c == 4 && !e->bufs[0].f32,
-                  "preprocess: dst NULL needs the planned bf16 NHWC4 input buffer");
+        B2D_CHECK((out_kind == B2D_OUT_BF16_NHWC4 || out_kind == B2D_OUT_F16_NHWC4) && !e->bufs.empty() && e->bufs[0].c == 4 && !e->bufs[0].f32,
+                  "preprocess: dst NULL needs the planned 16-bit NHWC4 input buffer");
         B2D_CHECK(n <= e->max_batch, "preprocess: n=%d exceeds max_batch %d", n, e->max_batch);
         dst_dev = e->bufs[0].ptr;
     }
@@ -596,7 +607,7 @@ int b2d_preprocess(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, i
 int b2d_set_input_f32(b2d_engine* e, const float* src_dev, int n, void* stream) {
     B2D_CHECK(e && src_dev && n > 0 && n <= e->max_batch, "set_input_f32: bad arguments");
     B2D_CHECK(!e->bufs.empty() && e->bufs[0].c == 4 && !e->bufs[0].f32, "set_input_f32: no planned bf16 NHWC4 input buffer");
-    return input_from_f32_launch(src_dev, n, e->bufs[0].h, e->bufs[0].w, e->bufs[0].ptr, (cudaStream_t)stream);
+    return input_from_f32_launch(src_dev, n, e->bufs[0].h, e->bufs[0].w, e->bufs[0].ptr, (cudaStream_t)stream, e->f16);
 }
 
 int b2d_decode_rows(b2d_engine* e, int n, float* rows_dev, void* stream) {

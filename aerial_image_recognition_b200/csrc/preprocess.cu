@@ -28,8 +28,14 @@ constexpr int PIL_BITS = 22;
 
 __device__ __forceinline__ uint8_t clip8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
-__device__ __forceinline__ uint32_t bf16x2_of(uint8_t a, uint8_t b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(__fdiv_rn((float)a, 255.0f), __fdiv_rn((float)b, 255.0f));
+// two pixels values / 255 in the engine's 16-bit activation format (bf16, or fp16 when the engine runs in B2D_PREC_FP16)
+__device__ __forceinline__ uint32_t bf16x2_of(uint8_t a, uint8_t b, int f16 = 0) {
+    const float x = __fdiv_rn((float)a, 255.0f), y = __fdiv_rn((float)b, 255.0f);
+    if (f16) {
+        __half2 h = __floats2half2_rn(x, y);
+        return *(uint32_t*)&h;
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
     return *(uint32_t*)&h;
 }
 
@@ -38,8 +44,9 @@ __device__ __forceinline__ void emit_pixel(int out_kind, void* dst, int img, int
                                            uint8_t b, int bgr) {
     if (bgr) { uint8_t t = r; r = b; b = t; }
     const long long pix = ((long long)img * oh + y) * ow + x;
-    if (out_kind == B2D_OUT_BF16_NHWC4) {
-        ((uint2*)dst)[pix] = make_uint2(bf16x2_of(r, g), bf16x2_of(b, 0));
+    if (out_kind == B2D_OUT_BF16_NHWC4 || out_kind == B2D_OUT_F16_NHWC4) {
+        const int f16 = out_kind == B2D_OUT_F16_NHWC4;
+        ((uint2*)dst)[pix] = make_uint2(bf16x2_of(r, g, f16), bf16x2_of(b, 0, f16));
     } else if (out_kind == B2D_OUT_F32_NCHW) {
         float* o = (float*)dst + (long long)img * 3 * oh * ow + (long long)y * ow + x;
         const long long plane = (long long)oh * ow;
@@ -54,7 +61,7 @@ __device__ __forceinline__ void emit_pixel(int out_kind, void* dst, int img, int
 
 // ---- identity: 16 pixels per thread, 3 x 128-bit loads -> 8 x 128-bit stores ---------------
 __global__ void __launch_bounds__(256) prep_identity_vec_kernel(const uint8_t* __restrict__ src, int n, int h, int w, int pitch,
-                                                                 long long img_stride, uint2* __restrict__ dst, int bgr) {
+                                                                 long long img_stride, uint2* __restrict__ dst, int bgr, int f16) {
     const int gw = w / 16;
     const long long total = (long long)n * h * gw;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(256) prep_identity_vec_kernel(const uint8_t* _
         uint8_t g = (uint8_t)(wd[(3 * i + 1) >> 2] >> (8 * ((3 * i + 1) & 3)));
         uint8_t bl = (uint8_t)(wd[(3 * i + 2) >> 2] >> (8 * ((3 * i + 2) & 3)));
         if (bgr) { uint8_t t = r; r = bl; bl = t; }
-        o[i] = make_uint2(bf16x2_of(r, g), bf16x2_of(bl, 0));
+        o[i] = make_uint2(bf16x2_of(r, g, f16), bf16x2_of(bl, 0, f16));
     }
     uint4* dp = (uint4*)(dst + ((long long)img * h + y) * w + gx * 16);
 #pragma unroll
@@ -192,7 +199,8 @@ __global__ void __launch_bounds__(256) cut_windows_kernel(const uint8_t* __restr
 
 
 // ---- f32 NCHW in [0,1] (the tensor the reference hands to session.run) -> bf16 NHWC4 ---------
-__global__ void __launch_bounds__(256) input_from_f32_kernel(const float* __restrict__ src, int n, int h, int w, uint2* __restrict__ dst) {
+__global__ void __launch_bounds__(256) input_from_f32_kernel(const float* __restrict__ src, int n, int h, int w, uint2* __restrict__ dst,
+                                                              int f16) {
     const long long total = (long long)n * h * w;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -200,6 +208,12 @@ __global__ void __launch_bounds__(256) input_from_f32_kernel(const float* __rest
     const int img = (int)(idx / plane);
     const long long p = idx - (long long)img * plane;
     const float* s = src + (long long)img * 3 * plane + p;
+    if (f16) {
+        __half2 a = __floats2half2_rn(__ldg(s), __ldg(s + plane));
+        __half2 b = __floats2half2_rn(__ldg(s + 2 * plane), 0.f);
+        dst[idx] = make_uint2(*(uint32_t*)&a, *(uint32_t*)&b);
+        return;
+    }
     __nv_bfloat162 a = __floats2bfloat162_rn(__ldg(s), __ldg(s + plane));
     __nv_bfloat162 b = __floats2bfloat162_rn(__ldg(s + 2 * plane), 0.f);
     dst[idx] = make_uint2(*(uint32_t*)&a, *(uint32_t*)&b);
@@ -207,10 +221,10 @@ __global__ void __launch_bounds__(256) input_from_f32_kernel(const float* __rest
 
 }  // namespace
 
-int input_from_f32_launch(const float* src, int n, int h, int w, void* dst, cudaStream_t stream) {
+int input_from_f32_launch(const float* src, int n, int h, int w, void* dst, cudaStream_t stream, int f16) {
     if (n <= 0) return 0;
     const long long total = (long long)n * h * w;
-    input_from_f32_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, n, h, w, (uint2*)dst);
+    input_from_f32_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, n, h, w, (uint2*)dst, f16);
     B2D_LAUNCH_CHECK();
     return 0;
 }
@@ -219,12 +233,12 @@ int preprocess_launch(const ResizeTables* t, const uint8_t* src, int n, int pitc
                       void* dst, int out_size, cudaStream_t stream) {
     if (n <= 0) return 0;
     if (t->mode == B2D_RESIZE_IDENTITY) {
-        const bool vec = out_kind == B2D_OUT_BF16_NHWC4 && (t->in_w % 16 == 0) && (pitch % 16 == 0) && (img_stride % 16 == 0) &&
+        const bool vec = (out_kind == B2D_OUT_BF16_NHWC4 || out_kind == B2D_OUT_F16_NHWC4) && (t->in_w % 16 == 0) && (pitch % 16 == 0) && (img_stride % 16 == 0) &&
                          (((uintptr_t)src) % 16 == 0) && (((uintptr_t)dst) % 16 == 0);
         if (vec) {
             const long long total = (long long)n * t->in_h * (t->in_w / 16);
             prep_identity_vec_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, n, t->in_h, t->in_w, pitch, img_stride,
-                                                                                      (uint2*)dst, bgr);
+                                                                                      (uint2*)dst, bgr, out_kind == B2D_OUT_F16_NHWC4);
         } else {
             const long long total = (long long)n * t->in_h * t->in_w;
             prep_identity_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, n, t->in_h, t->in_w, pitch, img_stride, dst,

@@ -21,6 +21,7 @@ from .weights import make_synthetic_weights
 RESIZE = {"identity": 0, "cv2_linear": 1, "pil_bicubic": 2, "letterbox": 3}
 GEO = {"bounds": 0, "gpuhandler": 1, "affine": 2}
 CONV_IMPL = {"auto": 0, "tcgen05": 1, "simt": 2}
+PRECISION = {"bf16": 0, "fp16": 1}
 DET_WORDS = 8          # b2d_det = 8 x 4 bytes
 GEODET_BYTES = 40
 GEO_PARAMS = 16
@@ -39,7 +40,9 @@ def _ptr(t: Optional[torch.Tensor]):
 class Engine:
     def __init__(self, arch: str = "yolov8m", weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 64,
                  device: int = 0, seed: int = 0, conv_impl: str = "auto", imgsz: int = 640, nc: Optional[int] = None,
-                 graph: Optional[Graph] = None):
+                 graph: Optional[Graph] = None, precision: str = "bf16"):
+        """``precision``: storage format of activations and weights -- "bf16" (default, the configuration BASELINE.json
+        is quoted on) or "fp16" (three more mantissa bits, same tensor-core rate; closer to the reference's fp32 results)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.B2DError("CUDA is not available: the B200 engine has no CPU fallback")
@@ -54,6 +57,8 @@ class Engine:
         handle = C.c_void_p()
         _lib.check(self.lib.b2d_create(device, self.max_batch, C.byref(handle)), "b2d_create")
         self.h = handle
+        self.precision = precision
+        _lib.check(self.lib.b2d_set_precision(self.h, PRECISION[precision]), "b2d_set_precision")
         self._build(w, CONV_IMPL[conv_impl])
         self.num_rows = self.lib.b2d_num_anchors(self.h)
         self.num_ops = self.lib.b2d_num_ops(self.h)
@@ -126,7 +131,7 @@ class Engine:
         """Zero-copy torch view [max_batch, H, W, C] of an engine buffer (tests / debugging)."""
         b = self.graph.bufs[name]
         ptr = self.lib.b2d_buffer_ptr(self.h, self.buf_id[name])
-        dt, np_dt = (torch.float32, np.float32) if b.f32 else (torch.bfloat16, np.uint16)
+        half = torch.float16 if self.precision == "fp16" else torch.bfloat16
         numel = self.max_batch * b.h * b.w * b.c
 
         class _Holder:
@@ -136,7 +141,7 @@ class Engine:
                                          "version": 3}
         t = torch.as_tensor(hold, device=self.device)
         if not b.f32:
-            t = t.view(torch.bfloat16)
+            t = t.view(half)
         t = t.view(self.max_batch, b.h, b.w, b.c)
         return t if n is None else t[:n]
 

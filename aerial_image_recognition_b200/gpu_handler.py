@@ -37,7 +37,8 @@ def _as_u8_hwc(img) -> np.ndarray:
 class GPUHandler:
     def __init__(self, model_path, max_gpu_memory=5.0, confidence_threshold=0.3, output_dir=None, *,
                  arch: Optional[str] = None, weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 64,
-                 top_k: int = 10, bgr: bool = False, device: int = 0, seed: int = 0, swallow_errors: bool = False):
+                 top_k: int = 10, bgr: bool = False, device: int = 0, seed: int = 0, swallow_errors: bool = False,
+                 precision: str = "bf16"):
         self.model_path = model_path
         self.max_gpu_memory = max_gpu_memory
         self.confidence_threshold = confidence_threshold
@@ -50,7 +51,7 @@ class GPUHandler:
         arch = arch or arch_from_model_path(model_path)
         if weights is None and model_path:
             weights = load_weights(model_path, arch)
-        self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed)
+        self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, precision=precision)
         self.session = InferenceSession(engine=self.engine)
 
     def _setup_gpu(self):

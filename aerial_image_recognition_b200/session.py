@@ -65,12 +65,12 @@ def load_weights(model_path: Optional[str], arch: Optional[str] = None) -> Optio
 class InferenceSession:
     def __init__(self, model_path: Optional[str] = None, sess_options=None, providers=None, *, arch: Optional[str] = None,
                  weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 8, device: int = 0, seed: int = 0,
-                 engine: Optional[Engine] = None):
+                 engine: Optional[Engine] = None, precision: str = "bf16"):
         if engine is None:
             arch = arch or arch_from_model_path(model_path)
             if weights is None:
                 weights = load_weights(model_path, arch) if model_path else None
-            engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed)
+            engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, precision=precision)
         self.engine = engine
         self._inputs = [_Input("images", [None, 3, engine.imgsz, engine.imgsz])]
 

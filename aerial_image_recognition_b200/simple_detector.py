@@ -37,7 +37,7 @@ def _as_u8_hwc(img) -> np.ndarray:
 
 class SimpleDetector:
     def __init__(self, model_path, output_dir, *, arch: Optional[str] = None,
-                 weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 8, device: int = 0, seed: int = 0):
+                 weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 8, device: int = 0, seed: int = 0, precision: str = "bf16"):
         self.zoom = 21
         self.model_size = 640
         self.confidence_threshold = 0.3
@@ -49,7 +49,8 @@ class SimpleDetector:
         arch = arch or arch_from_model_path(model_path)
         if weights is None and model_path:
             weights = load_weights(model_path, arch)
-        self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, imgsz=self.model_size)
+        self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, imgsz=self.model_size,
+                             precision=precision)
         self.model = InferenceSession(engine=self.engine)
 
     # -- simple_detector.py:456-504 ----------------------------------------------------------

@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--ref-tiles", type=int, default=4)
     ap.add_argument("--cpu-sample", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
+                    help="storage format of activations/weights; bf16 is the configuration BASELINE.json names")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -163,7 +165,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W_, K = max(args.warmup, 3), args.steps
-    eng = Engine("yolov8m", max_batch=BATCH, device=local_rank, seed=0)
+    eng = Engine("yolov8m", max_batch=BATCH, device=local_rank, seed=0, precision=args.precision)
     dev = eng.device
 
     # inputs: NPOOL distinct batches (> L2 in total: 4 x 78.6 MB u8, and every step streams ~6 GB of
@@ -297,7 +299,7 @@ def main():
             "metric": "640x640 tiles/s end-to-end (preproc+YOLOv8m+NMS+georef)",
             "value": total_tiles / (ms * 1e-3), "unit": "tiles/s", "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": BATCH, "conf": CONF, "iou": IOU, "max_det": MAX_DET,
                        "georef": "bounds form (simple_detector.py:487-494)", "parallelism": f"tile-index data parallel x{world}",
                        "l2": f"{NPOOL} distinct input batches rotated (315 MB uint8) and ~6 GB of activations per step stream through the 126 MB L2",

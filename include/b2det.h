@@ -60,7 +60,7 @@ enum {
     B2D_RESIZE_PIL_BICUBIC = 2,  /* PIL Image.resize((640,640))    -- simple_detector.py:463, :655 */
     B2D_RESIZE_LETTERBOX = 3     /* Ultralytics LetterBox, pad 114 -- x_arch/02_analyze_images:1 (cell 6) */
 };
-enum { B2D_OUT_BF16_NHWC4 = 0, B2D_OUT_F32_NCHW = 1, B2D_OUT_U8_NHWC = 2 };
+enum { B2D_OUT_BF16_NHWC4 = 0, B2D_OUT_F32_NCHW = 1, B2D_OUT_U8_NHWC = 2, B2D_OUT_F16_NHWC4 = 3 };
 enum { B2D_HEAD_V8_DFL = 0, B2D_HEAD_V7_ANCHOR = 1 };
 /* georeferencing forms */
 enum {
@@ -79,6 +79,13 @@ void b2d_destroy(b2d_engine* e);
 const char* b2d_last_error(void);
 int b2d_version(void);
 int b2d_device_sm_count(b2d_engine* e);
+/* Storage format of activations and weights (accumulation is fp32 either way; head maps stay fp32).
+ * B2D_PREC_BF16 is the default and the configuration BASELINE.json is quoted on; B2D_PREC_FP16 keeps three
+ * more mantissa bits per stored activation (same tensor-core rate) for callers that want to sit closer to
+ * the reference's fp32 onnxruntime results.  Call right after b2d_create, before any b2d_plan_*.           */
+enum { B2D_PREC_BF16 = 0, B2D_PREC_FP16 = 1 };
+int b2d_set_precision(b2d_engine* e, int precision);
+int b2d_get_precision(b2d_engine* e);
 
 /* ---- plan building: the graph onnxruntime would have read from the .onnx file ---------- */
 /* Buffers are NHWC; id 0 must be the network input [max_batch, H, W, 4] bf16.            */

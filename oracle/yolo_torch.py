@@ -40,6 +40,9 @@ class _Net:
         self.emu = emulate_bf16
 
     def rnd(self, x):
+        # emulate_bf16: True / "bf16" rounds stored activations to bf16, "fp16" to fp16 (the engine's B2D_PREC_FP16 mode)
+        if self.emu == "fp16":
+            return x.to(torch.float16).to(torch.float32)
         return _bf16(x) if self.emu else x
 
     def conv(self, name, x, k=1, s=1, act=True, res=None, groups=1, out_f32=False):

@@ -105,14 +105,15 @@ def test_every_planned_op_large_batch_kernel_variants(arch, imgsz, n, monkeypatc
     assert any("halo-pair" in d for d in seen) and any(" x2 " in d for d in seen) and any(" x4 " in d for d in seen), seen[:8]
 
 
-def _check_every_op(arch, imgsz, n):
+def _check_every_op(arch, imgsz, n, precision="bf16"):
     from _ir_cpu import run_graph_cpu  # noqa: F401  (same arithmetic, per-op form below)
     import torch.nn.functional as F
     seen = []
     g = G.build(arch, imgsz=imgsz)
     w = W.make_synthetic_weights(g, 2)
-    eng = _engine(arch, weights=w, max_batch=n, imgsz=imgsz, graph=g)
+    eng = _engine(arch, weights=w, max_batch=n, imgsz=imgsz, graph=g, precision=precision)
     eng.preprocess(torch.from_numpy(synth.make_tiles(n, imgsz, 9)).cuda(), "identity")
+    rel16 = 4e-3 if precision == "bf16" else 5e-4          # one ulp of the storage format: 2^-8 (bf16), 2^-11 (fp16)
     for i, op in enumerate(g.ops):
         eng.run_op(i, n)
         torch.cuda.synchronize()
@@ -134,7 +135,7 @@ def _check_every_op(arch, imgsz, n):
         got = eng.buffer(op.dst.buf, n).float().cpu()[..., op.dst.c0:op.dst.c0 + op.dst.c].permute(0, 3, 1, 2)
         err = (got - y).abs().max().item()
         # bf16 output rounding is 2^-9 relative; fp32 head outputs and pools/upsamples are far tighter
-        tol = (4e-3 if not g.bufs[op.dst.buf].f32 else 2e-4) * y.abs().max().item() + 1e-5
+        tol = (rel16 if not g.bufs[op.dst.buf].f32 else 2e-4) * y.abs().max().item() + 1e-5
         if op.kind in ("maxpool", "upsample2x"):
             tol = 0.0
         assert err <= tol, (i, eng.describe_op(i), err, tol)
@@ -625,3 +626,41 @@ def test_full_batch_is_permutation_equivariant_and_matches_small_batches():
         for f in fields:
             assert np.array_equal(a[k][f], c[k][f]), (k, f)
     small.close()
+
+
+# ---- B2D_PREC_FP16: activations and weights stored as fp16 ------------------------------------------------------------
+@pytest.mark.parametrize("arch,imgsz,n", [("yolov8m", 320, 2), ("yolov7", 128, 2)])
+def test_every_planned_op_matches_torch_fp16(arch, imgsz, n):
+    _check_every_op(arch, imgsz, n, precision="fp16")
+
+
+def test_fp16_forward_is_closer_to_the_fp32_oracle(tiles4):
+    """The fp16 storage mode (same kernels, same tensor-core rate) against the fp32 oracle -- the stand-in for the
+    reference's onnxruntime CPU results.  north_star's bounds: scores within 1e-3, boxes within 0.5 px, identical keep
+    set away from ties.  With fp16 the typical anchor is an order of magnitude inside the score bound and the keep set
+    differs only at the threshold; the worst anchor of a *random-weight* network still is not."""
+    g = G.build("yolov8m")
+    w = W.make_synthetic_weights(g, 0)
+    n = 2
+    x = torch.from_numpy(tiles4[:n].astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+    f32 = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", w, False).forward(x)])
+    emu = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", w, "fp16").forward(x)])
+    err = {}
+    for prec in ("bf16", "fp16"):
+        eng = _engine("yolov8m", weights=w, max_batch=n, graph=g, precision=prec)
+        eng.preprocess(torch.from_numpy(tiles4[:n]).cuda(), "identity")
+        eng.forward(n)
+        rows = eng.decode_rows(n).cpu().numpy()
+        eng.close()
+        err[prec] = np.abs(rows[..., 4] - f32[..., 4])
+        if prec == "fp16":
+            sel = f32[..., 4] >= 0.3
+            db = np.abs(rows[..., :4] - f32[..., :4])[sel]
+            agree = np.mean((rows[..., 4] >= 0.3) == sel)
+            d_emu = np.abs(emu[..., 4] - f32[..., 4])
+            print("fp16 vs fp32 oracle: median %.2e mean %.2e p99 %.2e max %.2e | boxes median %.3f px p99 %.3f px | keep-set agreement %.5f" % (
+                np.median(err[prec]), err[prec].mean(), np.quantile(err[prec], 0.99), err[prec].max(), np.median(db), np.quantile(db, 0.99), agree))
+            assert np.median(err[prec]) < 1e-4 and err[prec].mean() < 1e-3 and np.quantile(err[prec], 0.99) < 5e-3
+            assert np.median(db) < 0.05 and np.quantile(db, 0.95) < 0.5 and agree > 0.999     # DFL boxes of random weights: broad bin distributions
+            assert err[prec].mean() < 1.25 * d_emu.mean() + 1e-5           # as good as fp16 storage allows
+    assert err["fp16"].mean() < 0.25 * err["bf16"].mean() and np.quantile(err["fp16"], 0.99) < 0.25 * np.quantile(err["bf16"], 0.99)
