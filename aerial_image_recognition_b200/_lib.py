@@ -52,6 +52,11 @@ SIGNATURES = {
     "b2d_utm_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2d_cut_windows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b2d_resize_table": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, P(c_int)]),
+    "b2d_tta_clahe": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p]),
+    "b2d_tta_lut": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_void_p, c_int, c_void_p, c_void_p]),
+    "b2d_tta_contrast": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "b2d_colour_convert": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
+    "b2d_set_conf_scale": (c_int, [c_void_p, c_float]),
     "b2d_run_op": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "b2d_num_ops": (c_int, [c_void_p]),
     "b2d_describe_op": (c_int, [c_void_p, c_int, c_char_p, c_int]),

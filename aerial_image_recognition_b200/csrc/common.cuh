@@ -162,9 +162,9 @@ struct HeadLevel { const float* buf; int hw, c, stride, nc, kind; float anchors[
 struct HeadDesc { HeadLevel lv[3]; int nlevels; int kind; int nc; int rows_total; };
 
 int decode_rows_launch(const HeadDesc* h, int n, float* rows, cudaStream_t stream);
-int candidates_from_head_launch(const HeadDesc* h, int n, float thr, int inclusive, b2d_det* cand, int* cand_count,
+int candidates_from_head_launch(const HeadDesc* h, int n, float thr, int inclusive, float scale, b2d_det* cand, int* cand_count,
                                 int cand_cap, cudaStream_t stream);
-int candidates_from_rows_launch(const float* rows, int n, int num_rows, int ncol, float thr, int inclusive,
+int candidates_from_rows_launch(const float* rows, int n, int num_rows, int ncol, float thr, int inclusive, float scale,
                                 b2d_det* cand, int* cand_count, int cand_cap, cudaStream_t stream);
 int select_launch(const b2d_det* cand, const int* cand_count, int cand_cap, int n, unsigned long long* keys_scratch,
                   float iou_thr, int top_k, int max_det, b2d_det* out, int* out_count, int cap, cudaStream_t stream);
@@ -177,5 +177,12 @@ int closure_launch(const double* x, const double* y, int count, double thr, int 
 size_t dedup_scratch_bytes(int count);
 int utm_forward_launch(const double* lon, const double* lat, int count, int zone, int north, double* x, double* y,
                        cudaStream_t stream);
+// test-time-augmentation variants (tta.cu)
+int tta_colour_launch(const uint8_t* src, long long npix, int code, uint8_t* dst, cudaStream_t stream);
+int tta_clahe_launch(const uint8_t* src, int n, int h, int w, double clip_limit, int tiles_x, int tiles_y, uint8_t* luts, uint8_t* dst,
+                     cudaStream_t stream);
+int tta_lut_launch(const uint8_t* src, int n, long long img_bytes, const uint8_t* lut, int per_image, uint8_t* dst, cudaStream_t stream);
+int tta_contrast_launch(const uint8_t* src, int n, int h, int w, float factor, unsigned long long* sums, uint8_t* luts, uint8_t* dst,
+                        cudaStream_t stream);
 int cut_windows_launch(const uint8_t* mosaic, int mh, int mw, long long pitch, const int32_t* origins, int n, int win,
                        int fill, uint8_t* dst, cudaStream_t stream);

@@ -76,6 +76,12 @@ struct b2d_engine {
     int cand_tiles = 0;
     void* dedup_scratch = nullptr;
     size_t dedup_scratch_bytes = 0;
+    float conf_scale = 1.0f;                // b2d_set_conf_scale: the TTA confidence adjustment (gpu_handler.py:236)
+    // test-time-augmentation scratch: CLAHE tile tables / per-image byte tables, per-image grey sums
+    uint8_t* tta_luts = nullptr;
+    size_t tta_luts_bytes = 0;
+    unsigned long long* tta_sums = nullptr;
+    int tta_sums_n = 0;
     // forward() as a CUDA graph per batch size: the ~94 launches of a step replay without per-launch driver work
     std::map<int, cudaGraphExec_t> fwd_graphs;
     std::map<int, int> fwd_calls;
@@ -310,6 +316,8 @@ void b2d_destroy(b2d_engine* e) {
     }
     if (e->cand) { cudaFree(e->cand); cudaFree(e->cand_count); cudaFree(e->keys); }
     if (e->dedup_scratch) cudaFree(e->dedup_scratch);
+    if (e->tta_luts) cudaFree(e->tta_luts);
+    if (e->tta_sums) cudaFree(e->tta_sums);
     for (auto& kv : e->fwd_graphs) cudaGraphExecDestroy(kv.second);
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     for (auto st : e->side_streams) cudaStreamDestroy(st);
@@ -622,7 +630,7 @@ int b2d_postprocess(b2d_engine* e, int n, float conf_thr, int inclusive, float i
     B2D_CHECK(n > 0 && n <= e->max_batch && dets_dev && counts_dev && cap > 0, "postprocess: bad arguments");
     if (ensure_cand(e, n, e->head.rows_total)) return -2;
     cudaStream_t s = (cudaStream_t)stream;
-    if (candidates_from_head_launch(&e->head, n, conf_thr, inclusive, e->cand, e->cand_count, e->cand_cap, s)) return -2;
+    if (candidates_from_head_launch(&e->head, n, conf_thr, inclusive, e->conf_scale, e->cand, e->cand_count, e->cand_cap, s)) return -2;
     return select_launch(e->cand, e->cand_count, e->cand_cap, n, e->keys, iou_thr, top_k, max_det, dets_dev, counts_dev, cap, s);
 }
 
@@ -631,14 +639,14 @@ int b2d_postprocess_rows(b2d_engine* e, const float* rows_dev, int n, int num_ro
     B2D_CHECK(e && rows_dev && n > 0 && num_rows > 0 && ncol >= 5 && dets_dev && counts_dev && cap > 0, "postprocess_rows: bad arguments");
     if (ensure_cand(e, n, num_rows)) return -2;
     cudaStream_t s = (cudaStream_t)stream;
-    if (candidates_from_rows_launch(rows_dev, n, num_rows, ncol, conf_thr, inclusive, e->cand, e->cand_count, e->cand_cap, s)) return -2;
+    if (candidates_from_rows_launch(rows_dev, n, num_rows, ncol, conf_thr, inclusive, e->conf_scale, e->cand, e->cand_count, e->cand_cap, s)) return -2;
     return select_launch(e->cand, e->cand_count, e->cand_cap, n, e->keys, iou_thr, top_k, max_det, dets_dev, counts_dev, cap, s);
 }
 
 int b2d_georef(b2d_engine* e, const b2d_det* dets_dev, const int32_t* counts_dev, int n, int cap, int mode, const double* params_dev,
                b2d_geodet* out_dev, void* stream) {
     B2D_CHECK(e && dets_dev && counts_dev && params_dev && out_dev, "georef: bad arguments");
-    B2D_CHECK(mode >= 0 && mode <= 2, "georef: unknown mode %d", mode);
+    B2D_CHECK(mode >= 0 && mode <= 3, "georef: unknown mode %d", mode);
     return georef_launch(dets_dev, counts_dev, n, cap, mode, params_dev, out_dev, (cudaStream_t)stream);
 }
 
@@ -680,6 +688,57 @@ int b2d_cut_windows(b2d_engine* e, const uint8_t* mosaic_dev, int mh, int mw, lo
                     int win, int fill, uint8_t* dst_dev, void* stream) {
     B2D_CHECK(e && mosaic_dev && origins_dev && dst_dev && n > 0, "cut_windows: bad arguments");
     return cut_windows_launch(mosaic_dev, mh, mw, pitch, origins_dev, n, win, fill, dst_dev, (cudaStream_t)stream);
+}
+
+int b2d_set_conf_scale(b2d_engine* e, float scale) {
+    B2D_CHECK(e && scale > 0.f, "set_conf_scale: bad arguments");
+    e->conf_scale = scale;
+    return 0;
+}
+
+static int ensure_tta(b2d_engine* e, size_t lut_bytes, int n) {
+    if (lut_bytes > e->tta_luts_bytes) {
+        if (e->tta_luts) cudaFree(e->tta_luts);
+        e->tta_luts = nullptr; e->tta_luts_bytes = 0;
+        B2D_CUDA(cudaMalloc(&e->tta_luts, lut_bytes));
+        e->tta_luts_bytes = lut_bytes;
+    }
+    if (n > e->tta_sums_n) {
+        if (e->tta_sums) cudaFree(e->tta_sums);
+        e->tta_sums = nullptr; e->tta_sums_n = 0;
+        B2D_CUDA(cudaMalloc(&e->tta_sums, (size_t)n * sizeof(unsigned long long)));
+        e->tta_sums_n = n;
+    }
+    return 0;
+}
+
+static bool aligned4(const void* a, const void* b) { return (((uintptr_t)a | (uintptr_t)b) & 3) == 0; }
+
+int b2d_colour_convert(b2d_engine* e, const uint8_t* src_dev, long long npix, int code, uint8_t* dst_dev, void* stream) {
+    B2D_CHECK(e && src_dev && dst_dev && npix >= 0 && (code == B2D_COLOUR_RGB2LAB || code == B2D_COLOUR_LAB2RGB), "colour_convert: bad arguments");
+    B2D_CHECK(aligned4(src_dev, dst_dev), "colour_convert: pointers must be 4-byte aligned");
+    return tta_colour_launch(src_dev, npix, code, dst_dev, (cudaStream_t)stream);
+}
+
+int b2d_tta_clahe(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, double clip_limit, int tiles_x, int tiles_y,
+                  uint8_t* dst_dev, void* stream) {
+    B2D_CHECK(e && src_dev && dst_dev && n > 0 && h > 0 && w > 0 && tiles_x > 0 && tiles_y > 0, "tta_clahe: bad arguments");
+    B2D_CHECK(aligned4(src_dev, dst_dev), "tta_clahe: pointers must be 4-byte aligned");
+    if (ensure_tta(e, (size_t)n * tiles_x * tiles_y * 256, 0)) return -2;
+    return tta_clahe_launch(src_dev, n, h, w, clip_limit, tiles_x, tiles_y, e->tta_luts, dst_dev, (cudaStream_t)stream);
+}
+
+int b2d_tta_lut(b2d_engine* e, const uint8_t* src_dev, int n, long long img_bytes, const uint8_t* lut_dev, int per_image,
+                uint8_t* dst_dev, void* stream) {
+    B2D_CHECK(e && src_dev && dst_dev && lut_dev && n > 0 && img_bytes > 0, "tta_lut: bad arguments");
+    return tta_lut_launch(src_dev, n, img_bytes, lut_dev, per_image, dst_dev, (cudaStream_t)stream);
+}
+
+int b2d_tta_contrast(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, float factor, uint8_t* dst_dev, void* stream) {
+    B2D_CHECK(e && src_dev && dst_dev && n > 0 && h > 0 && w > 0, "tta_contrast: bad arguments");
+    B2D_CHECK(aligned4(src_dev, dst_dev), "tta_contrast: pointers must be 4-byte aligned");
+    if (ensure_tta(e, (size_t)n * 256, n)) return -2;
+    return tta_contrast_launch(src_dev, n, h, w, factor, e->tta_sums, e->tta_luts, dst_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -97,7 +97,7 @@ __device__ __forceinline__ bool passes(float conf, float thr, int inclusive) { r
 
 // Shared body: MODE 0 = dense rows, MODE 1 = thresholded candidates.
 template <int MODE>
-__global__ void __launch_bounds__(256) head_kernel(HeadDesc h, int n, float thr, int inclusive, float* rows, b2d_det* cand,
+__global__ void __launch_bounds__(256) head_kernel(HeadDesc h, int n, float thr, int inclusive, float scale, float* rows, b2d_det* cand,
                                                    int* cand_count, int cand_cap) {
     const int tile = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadDesc h, int n, float thr,
         bool want = in_range;
         if (in_range) {
             v8_scores(pix, h.nc, &conf, &cls);
-            if (MODE == 1) want = passes(conf, thr, inclusive);
+            if (MODE == 1) { conf = __fmul_rn(conf, scale); want = passes(conf, thr, inclusive); }   // scale: gpu_handler.py:236-238
         }
         // the 4 lanes of an anchor agree on `want`; decode only where some anchor of the warp needs it
         const unsigned any = __ballot_sync(0xffffffffu, want);
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadDesc h, int n, float thr,
         if (in_range) {
             const float* p = L.buf + ((size_t)tile * cells + cell) * L.c + ai * no;
             r = v7_row(p, h.nc, gx, gy, (float)L.stride, L.anchors[2 * ai], L.anchors[2 * ai + 1]);
+            if (MODE == 1) r.conf = __fmul_rn(r.conf, scale);
         }
         if (MODE == 0) {
             if (in_range) {
@@ -192,13 +193,13 @@ __global__ void __launch_bounds__(256) head_kernel(HeadDesc h, int n, float thr,
 
 // candidates from already-decoded rows [n][num_rows][ncol]
 __global__ void __launch_bounds__(256) rows_filter_kernel(const float* __restrict__ rows, int num_rows, int ncol, float thr,
-                                                           int inclusive, b2d_det* cand, int* cand_count, int cand_cap) {
+                                                           int inclusive, float scale, b2d_det* cand, int* cand_count, int cand_cap) {
     const int tile = blockIdx.y;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool in_range = a < num_rows;
     const float* p = rows + ((size_t)tile * num_rows + (in_range ? a : 0)) * ncol;
-    const float conf = in_range ? __ldg(p + 4) : -1.f;
+    const float conf = in_range ? __fmul_rn(__ldg(p + 4), scale) : -1.f;
     const bool emit = in_range && passes(conf, thr, inclusive);
     const unsigned em = __ballot_sync(0xffffffffu, emit);
     if (!em) return;
@@ -424,6 +425,15 @@ __global__ void __launch_bounds__(256) georef_kernel(const b2d_det* __restrict__
         g.x_img = (float)x864; g.y_img = (float)y864;
         g.x = __dadd_rn(P[0], __dmul_rn(__ddiv_rn(x864, 864.0), __dsub_rn(P[2], P[0])));
         g.y = __dsub_rn(P[3], __dmul_rn(__ddiv_rn(y864, 864.0), __dsub_rn(P[3], P[1])));
+    } else if (mode == B2D_GEO_TENSOR_F32) {
+        // gpu_handler.py:243-253 (_process_tensors): float32 CUDA-tensor arithmetic.  `boxes[:, :2] / 640` on a CUDA tensor is a
+        // multiplication by the float reciprocal of the scalar; the Python scalars are cast to float32.  P = lon_min, lat_min,
+        // lon_max, lat_max.
+        const float inv = __fdiv_rn(1.0f, 640.0f);
+        const float cxn = __fmul_rn(d.cx, inv), cyn = __fmul_rn(d.cy, inv);
+        const float lon_off = (float)__dsub_rn(P[2], P[0]), lat_off = (float)__dsub_rn(P[3], P[1]);
+        g.x = (double)__fadd_rn((float)P[0], __fmul_rn(cxn, lon_off));
+        g.y = (double)__fsub_rn((float)P[3], __fmul_rn(cyn, lat_off));
     } else {
         // Ultralytics scale_boxes (fp32) then the notebook's centroid + pixel_to_geo (fp64)
         // P = gt[0..5], win_x, win_y, pad_x, pad_y, gain, w0, h0
@@ -450,28 +460,28 @@ int decode_rows_launch(const HeadDesc* h, int n, float* rows, cudaStream_t strea
     if (n <= 0) return 0;
     const int per = (h->kind == B2D_HEAD_V8_DFL) ? 4 : 1;
     dim3 grid(ceil_div(h->rows_total * per, 256), n);
-    head_kernel<0><<<grid, 256, 0, stream>>>(*h, n, 0.f, 1, rows, nullptr, nullptr, 0);
+    head_kernel<0><<<grid, 256, 0, stream>>>(*h, n, 0.f, 1, 1.f, rows, nullptr, nullptr, 0);
     B2D_LAUNCH_CHECK();
     return 0;
 }
 
-int candidates_from_head_launch(const HeadDesc* h, int n, float thr, int inclusive, b2d_det* cand, int* cand_count, int cand_cap,
-                                cudaStream_t stream) {
+int candidates_from_head_launch(const HeadDesc* h, int n, float thr, int inclusive, float scale, b2d_det* cand, int* cand_count,
+                                int cand_cap, cudaStream_t stream) {
     if (n <= 0) return 0;
     B2D_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * n, stream));
     const int per = (h->kind == B2D_HEAD_V8_DFL) ? 4 : 1;
     dim3 grid(ceil_div(h->rows_total * per, 256), n);
-    head_kernel<1><<<grid, 256, 0, stream>>>(*h, n, thr, inclusive, nullptr, cand, cand_count, cand_cap);
+    head_kernel<1><<<grid, 256, 0, stream>>>(*h, n, thr, inclusive, scale, nullptr, cand, cand_count, cand_cap);
     B2D_LAUNCH_CHECK();
     return 0;
 }
 
-int candidates_from_rows_launch(const float* rows, int n, int num_rows, int ncol, float thr, int inclusive, b2d_det* cand,
+int candidates_from_rows_launch(const float* rows, int n, int num_rows, int ncol, float thr, int inclusive, float scale, b2d_det* cand,
                                 int* cand_count, int cand_cap, cudaStream_t stream) {
     if (n <= 0) return 0;
     B2D_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * n, stream));
     dim3 grid(ceil_div(num_rows, 256), n);
-    rows_filter_kernel<<<grid, 256, 0, stream>>>(rows, num_rows, ncol, thr, inclusive, cand, cand_count, cand_cap);
+    rows_filter_kernel<<<grid, 256, 0, stream>>>(rows, num_rows, ncol, thr, inclusive, scale, cand, cand_count, cand_cap);
     B2D_LAUNCH_CHECK();
     return 0;
 }

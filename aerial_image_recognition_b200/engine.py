@@ -15,11 +15,12 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import tta as _tta
 from .graph import ACT_SILU, Graph, build, op_weights
 from .weights import make_synthetic_weights
 
 RESIZE = {"identity": 0, "cv2_linear": 1, "pil_bicubic": 2, "letterbox": 3}
-GEO = {"bounds": 0, "gpuhandler": 1, "affine": 2}
+GEO = {"bounds": 0, "gpuhandler": 1, "affine": 2, "tensor_f32": 3}
 CONV_IMPL = {"auto": 0, "tcgen05": 1, "simt": 2}
 PRECISION = {"bf16": 0, "fp16": 1}
 DET_WORDS = 8          # b2d_det = 8 x 4 bytes
@@ -245,15 +246,91 @@ class Engine:
                                             _ptr(origins.contiguous()), n, win, fill, _ptr(out), self.stream), "cut_windows")
         return out
 
+    # ---- test-time-augmentation views (gpu_handler.py:94-140, gpu_handler_archive.py:67-122) ---------
+    def _u8(self, images: torch.Tensor) -> torch.Tensor:
+        assert images.dtype == torch.uint8 and images.is_cuda and images.dim() == 4 and images.shape[3] == 3
+        return images.contiguous()
+
+    def tta_clahe(self, images: torch.Tensor, clip_limit: float, grid: int) -> torch.Tensor:
+        """RGB2LAB -> CLAHE(clip_limit, (grid, grid)) on L -> LAB2RGB, uint8 [n,h,w,3] -> same (bit-exact with cv2)."""
+        images = self._u8(images)
+        n, h, w, _ = images.shape
+        out = torch.empty_like(images)
+        _lib.check(self.lib.b2d_tta_clahe(self.h, _ptr(images), n, h, w, float(clip_limit), grid, grid, _ptr(out), self.stream),
+                   "tta_clahe")
+        return out
+
+    def tta_lut(self, images: torch.Tensor, lut: np.ndarray) -> torch.Tensor:
+        """Per-byte curve (brightness / gamma): out = lut[images]."""
+        images = self._u8(images)
+        key = bytes(np.asarray(lut, dtype=np.uint8))
+        assert len(key) == 256
+        cache = self.__dict__.setdefault("_lut_cache", {})
+        if key not in cache:
+            cache[key] = torch.from_numpy(np.frombuffer(key, dtype=np.uint8).copy()).to(self.device)
+        out = torch.empty_like(images)
+        n = images.shape[0]
+        _lib.check(self.lib.b2d_tta_lut(self.h, _ptr(images), n, images[0].numel(), _ptr(cache[key]), 0, _ptr(out), self.stream),
+                   "tta_lut")
+        return out
+
+    def tta_contrast(self, images: torch.Tensor, factor: float) -> torch.Tensor:
+        """PIL ImageEnhance.Contrast(img).enhance(factor) per image."""
+        images = self._u8(images)
+        n, h, w, _ = images.shape
+        out = torch.empty_like(images)
+        _lib.check(self.lib.b2d_tta_contrast(self.h, _ptr(images), n, h, w, float(factor), _ptr(out), self.stream), "tta_contrast")
+        return out
+
+    def colour_convert(self, pixels: torch.Tensor, code: str) -> torch.Tensor:
+        """cv2.cvtColor on uint8 [..., 3]: code 'rgb2lab' or 'lab2rgb'."""
+        assert pixels.dtype == torch.uint8 and pixels.is_cuda and pixels.shape[-1] == 3
+        pixels = pixels.contiguous()
+        out = torch.empty_like(pixels)
+        _lib.check(self.lib.b2d_colour_convert(self.h, _ptr(pixels), pixels.numel() // 3, {"rgb2lab": 0, "lab2rgb": 1}[code],
+                                               _ptr(out), self.stream), "colour_convert")
+        return out
+
+    def tta_views(self, images: torch.Tensor, views: Sequence[Tuple[str, tuple]]) -> list:
+        """The uint8 views of a batch of tiles, in the reference's order (``tta.LIGHTING_VIEWS + tta.OCCLUSION_VIEWS``
+        for gpu_handler.py:94-140; ``tta.ARCHIVE_VIEWS`` for the archived handler)."""
+        images = self._u8(images)
+        out, chain = [], images
+        for kind, args in views:
+            if kind == "original":
+                out.append(images)
+            elif kind == "clahe":
+                out.append(self.tta_clahe(images, args[0], args[1]))
+            elif kind == "brightness":
+                out.append(self.tta_lut(images, _tta.brightness_lut(args[0])))
+            elif kind == "gamma":
+                out.append(self.tta_lut(images, _tta.gamma_lut(args[0])))
+            elif kind == "chain":       # cumulative brightness -> contrast (gpu_handler_archive.py:79-84)
+                chain = self.tta_contrast(self.tta_lut(chain, _tta.brightness_lut(args[0])), args[1])
+                out.append(chain)
+            else:
+                raise ValueError(kind)
+        return out
+
+    def set_conf_scale(self, scale: float) -> None:
+        _lib.check(self.lib.b2d_set_conf_scale(self.h, float(scale)), "set_conf_scale")
+
     # ---- whole path ----------------------------------------------------------------------
     def infer(self, images: torch.Tensor, resize: str = "identity", bgr: bool = False, conf_thr: float = 0.3,
-              inclusive: bool = True, iou_thr: float = 0.0, top_k: int = 0, max_det: int = 300, cap: Optional[int] = None):
+              inclusive: bool = True, iou_thr: float = 0.0, top_k: int = 0, max_det: int = 300, cap: Optional[int] = None,
+              conf_scale: float = 1.0):
         """uint8 CUDA tiles -> (dets, counts) on device: preprocess + network + decode/filter(/NMS)."""
         n = images.shape[0]
         assert n <= self.max_batch
         self.preprocess(images, resize, bgr)
         self.forward(n)
-        return self.postprocess(n, conf_thr, inclusive, iou_thr, top_k, max_det, cap)
+        if conf_scale == 1.0:
+            return self.postprocess(n, conf_thr, inclusive, iou_thr, top_k, max_det, cap)
+        self.set_conf_scale(conf_scale)
+        try:
+            return self.postprocess(n, conf_thr, inclusive, iou_thr, top_k, max_det, cap)
+        finally:
+            self.set_conf_scale(1.0)
 
 
 def dets_to_numpy(dets: torch.Tensor, counts: torch.Tensor):

@@ -21,6 +21,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
+from . import tta as _tta
 from .engine import GEO_PARAMS, Engine, geodets_to_numpy
 from .session import InferenceSession, arch_from_model_path, load_weights
 
@@ -107,6 +108,105 @@ class GPUHandler:
                 for r in g:
                     out.append({"lon": float(r["x"]), "lat": float(r["y"]), "confidence": float(r["conf"])})
             i = j
+        return out
+
+    # -- test-time augmentation: gpu_handler.py:94-149, :220-285 ------------------------------
+    def _views_u8(self, img, views):
+        t = torch.from_numpy(_as_u8_hwc(img))[None].to(self.engine.device)
+        return self.engine.tta_views(t, views)
+
+    def _prepare_tensor(self, img):
+        """gpu_handler.py:142-149: uint8 RGB -> float32 CHW **BGR** / 255 on the device (no resize).  ``img`` may be a
+        PIL image, a uint8 HWC array, or a uint8 device tensor [1,h,w,3] produced by the view kernels."""
+        t = img if isinstance(img, torch.Tensor) else torch.from_numpy(_as_u8_hwc(img))[None].to(self.engine.device)
+        # RGB -> BGR is a channel flip of the CHW tensor; x / 255 is torch's own float32 division, as in the reference
+        return t[0].flip(-1).to(dtype=torch.float32).permute(2, 0, 1) / 255.0
+
+    def _get_lighting_variations(self, img):
+        """gpu_handler.py:94-123: original, CLAHE(3.0, 8x8) on L of LAB, brightness x2.0, gamma 2.0."""
+        return [self._prepare_tensor(v) for v in self._views_u8(img, _tta.LIGHTING_VIEWS)]
+
+    def _get_occlusion_variations(self, img):
+        """gpu_handler.py:125-140: CLAHE(4.0, 4x4)."""
+        return [self._prepare_tensor(v) for v in self._views_u8(img, _tta.OCCLUSION_VIEWS)]
+
+    def preprocess_variations(self, img):
+        """The archived handler's ``preprocess_image`` (gpu_handler_archive.py:57-67): lighting + occlusion views."""
+        return self._get_lighting_variations(img) + self._get_occlusion_variations(img)
+
+    def _get_confidence_adjustment(self, variation_index, total_variations):
+        return _tta.confidence_adjustment(variation_index, total_variations)
+
+    def _process_tensors(self, tensor_batch):
+        """gpu_handler.py:220-270: ``tensor_batch`` = [(tensor_variations, bbox), ...] with float32 [3,S,S] device tensors.
+        Per view: network, ``conf *= adjustment`` (float32), ``conf > threshold`` (strict); the kept rows of a tile are
+        concatenated in view order and georeferenced in float32 (the reference's CUDA-tensor arithmetic).  The views of
+        all tiles run as device batches; the output order is the reference's (tile, then view, then row)."""
+        eng = self.engine
+        tiles = [(list(v), tuple(float(b) for b in bbox)) for v, bbox in tensor_batch]
+        nviews = max((len(v) for v, _ in tiles), default=0)
+        per = {}                                   # (tile, view) -> structured geodet array
+        for i in range(nviews):
+            idx = [t for t, (v, _) in enumerate(tiles) if i < len(v)]
+            for c0 in range(0, len(idx), eng.max_batch):
+                chunk = idx[c0:c0 + eng.max_batch]
+                eng.set_input_f32(torch.stack([tiles[t][0][i] for t in chunk]).to(eng.device))
+                eng.forward(len(chunk))
+                eng.set_conf_scale(self._get_confidence_adjustment(i, nviews))
+                try:
+                    dets, counts = eng.postprocess(len(chunk), self.confidence_threshold, False)
+                finally:
+                    eng.set_conf_scale(1.0)
+                params = np.zeros((len(chunk), GEO_PARAMS), dtype=np.float64)
+                for k, t in enumerate(chunk):
+                    params[k, :4] = tiles[t][1]
+                geo = eng.georef(dets, counts, torch.from_numpy(params).to(eng.device), "tensor_f32")
+                for k, g in enumerate(geodets_to_numpy(geo, counts)):
+                    per[(chunk[k], i)] = g
+        out: List[dict] = []
+        for t, (v, _) in enumerate(tiles):
+            for i in range(len(v)):
+                for r in per[(t, i)]:
+                    out.append({"lon": float(np.float32(r["x"])), "lat": float(np.float32(r["y"])), "confidence": float(r["conf"])})
+        return out
+
+    def process_batch_tta(self, images, views=None):
+        """``process_batch`` with the five views per tile, entirely on uint8 device batches: same input contract as
+        ``process_batch`` (gpu_handler.py:156-161), the views of gpu_handler.py:94-140, ``_prepare_tensor``'s BGR order,
+        then ``_process_tensors``' filter and float32 georeferencing.  Equivalent to
+        ``_process_tensors([(preprocess_variations(img), bbox), ...])`` for model-sized tiles, without the float32
+        round trip of the views."""
+        eng = self.engine
+        views = views or (_tta.LIGHTING_VIEWS + _tta.OCCLUSION_VIEWS)
+        items = []
+        for img_set in images:
+            if not img_set or not isinstance(img_set, list) or not img_set[0]:
+                continue
+            img, bbox, _ = img_set[0]
+            items.append((_as_u8_hwc(img), tuple(float(v) for v in bbox)))
+        S = eng.imgsz
+        per = {}
+        for c0 in range(0, len(items), eng.max_batch):
+            chunk = items[c0:c0 + eng.max_batch]
+            for a, _ in chunk:
+                if a.shape[:2] != (S, S):
+                    raise ValueError(f"test-time augmentation needs {S}x{S} tiles (the reference does not resize here), got {a.shape}")
+            tiles = torch.from_numpy(np.stack([a for a, _ in chunk])).pin_memory().to(eng.device, non_blocking=True)
+            params = np.zeros((len(chunk), GEO_PARAMS), dtype=np.float64)
+            for k, (_, bbox) in enumerate(chunk):
+                params[k, :4] = bbox
+            params_dev = torch.from_numpy(params).to(eng.device)
+            for i, view in enumerate(eng.tta_views(tiles, views)):
+                dets, counts = eng.infer(view, "identity", True, self.confidence_threshold, False,
+                                         conf_scale=self._get_confidence_adjustment(i, len(views)))
+                geo = eng.georef(dets, counts, params_dev, "tensor_f32")
+                for k, g in enumerate(geodets_to_numpy(geo, counts)):
+                    per[(c0 + k, i)] = g
+        out: List[dict] = []
+        for t in range(len(items)):
+            for i in range(len(views)):
+                for r in per[(t, i)]:
+                    out.append({"lon": float(np.float32(r["x"])), "lat": float(np.float32(r["y"])), "confidence": float(r["conf"])})
         return out
 
     def cleanup(self):

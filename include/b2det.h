@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B2D_VERSION 100
+#define B2D_VERSION 101
 
 typedef struct b2d_engine b2d_engine;
 
@@ -66,9 +66,12 @@ enum { B2D_HEAD_V8_DFL = 0, B2D_HEAD_V7_ANCHOR = 1 };
 enum {
     B2D_GEO_BOUNDS = 0,      /* simple_detector.py:487-494 : params = west,east,south,north,crop_size   */
     B2D_GEO_GPUHANDLER = 1,  /* _script/gpu_handler.py:182-190 : params = lon_min,lat_min,lon_max,lat_max */
-    B2D_GEO_AFFINE = 2       /* x_arch/02_analyze_images:1 (cell 6) pixel_to_geo: params = gt[6], win_x, win_y,
+    B2D_GEO_AFFINE = 2,      /* x_arch/02_analyze_images:1 (cell 6) pixel_to_geo: params = gt[6], win_x, win_y,
                                 pad_x, pad_y, gain, w0, h0 (letterbox undo = Ultralytics scale_boxes) */
+    B2D_GEO_TENSOR_F32 = 3   /* _script/gpu_handler.py:243-253 (_process_tensors): the float32 CUDA-tensor form of the
+                                test-time-augmentation path; params = lon_min,lat_min,lon_max,lat_max           */
 };
+enum { B2D_COLOUR_RGB2LAB = 0, B2D_COLOUR_LAB2RGB = 1 };
 #define B2D_GEO_PARAMS 16    /* doubles per tile in every form */
 
 /* ---- engine lifetime ------------------------------------------------------------------- */
@@ -176,6 +179,31 @@ int b2d_cut_windows(b2d_engine* e, const uint8_t* mosaic_dev, int mh, int mw, lo
 /* Host-only: the integer coefficient table one axis of b2d_preprocess uses (mode PIL_BICUBIC or
  * CV2_LINEAR).  bounds_out int32 [out][2], coef_out int32 [out][ksize]; pass NULLs to query ksize. */
 int b2d_resize_table(int mode, int in_size, int out_size, int32_t* bounds_out, int32_t* coef_out, int* ksize_out);
+
+/* ---- test-time-augmentation variants -------------------------------
+ * The reference builds five views of every tile (_script/gpu_handler.py:94-140; the archived set at
+ * gpu_handler_archive.py:67-122 has eight), runs the network on each, scales the confidences per view
+ * (:274-283) and keeps `conf > thr` (:238).  The views are uint8 RGB images [n][h][w][3], contiguous, on the
+ * device; each result is bit-identical to the OpenCV / Pillow call it replaces.  dst may equal src.      */
+
+/* cv2.cvtColor(img, COLOR_RGB2LAB) -> cv2.createCLAHE(clip_limit, (tiles_x, tiles_y)).apply(L) -> cv2.merge ->
+ * cv2.cvtColor(COLOR_LAB2RGB): gpu_handler.py:104-110 (3.0, 8x8), :128-136 (4.0, 4x4),
+ * gpu_handler_archive.py:100-117.                                                                           */
+int b2d_tta_clahe(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, double clip_limit, int tiles_x, int tiles_y,
+                  uint8_t* dst_dev, void* stream);
+/* dst[i] = lut[src[i]] over n images of img_bytes bytes; lut_dev: uint8 [256], or [n][256] when per_image.  PIL
+ * ImageEnhance.Brightness(img).enhance(f) (gpu_handler.py:113-115) and the gamma curve
+ * (np.power(img / 255.0, 1 / gamma) * 255).astype(uint8) (:118-121) are such tables (host side: tta.py).   */
+int b2d_tta_lut(b2d_engine* e, const uint8_t* src_dev, int n, long long img_bytes, const uint8_t* lut_dev, int per_image,
+                uint8_t* dst_dev, void* stream);
+/* PIL ImageEnhance.Contrast(img).enhance(factor) (gpu_handler_archive.py:82): grey mean of each image
+ * (ITU-R 601-2 luma, rounded), then Image.blend(mean, image, factor).                                       */
+int b2d_tta_contrast(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, float factor, uint8_t* dst_dev, void* stream);
+/* The 8-bit colour conversions on their own (cv2.cvtColor COLOR_RGB2LAB / COLOR_LAB2RGB), npix pixels.      */
+int b2d_colour_convert(b2d_engine* e, const uint8_t* src_dev, long long npix, int code, uint8_t* dst_dev, void* stream);
+/* `boxes[:, 4] *= conf_adjustment` before the threshold (gpu_handler.py:236-238): every later b2d_postprocess /
+ * b2d_postprocess_rows multiplies the confidence by `scale` (float32) first.  1.0 (the default) is exact.    */
+int b2d_set_conf_scale(b2d_engine* e, float scale);
 
 /* Debug / test hooks ---------------------------------------------------------------------- */
 /* Run a single planned op (index in plan order) -- used by the per-layer parity tests.      */

@@ -94,7 +94,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in b2det.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.b2d_version() == 100
+    assert lib.b2d_version() == 101
 
 
 def test_create_fails_loudly_without_gpu(lib):

@@ -1,0 +1,133 @@
+"""CPU tests (-m "not gpu") of the test-time-augmentation oracle (oracle/tta.py) against the libraries whose arithmetic
+the reference calls: OpenCV (RGB<->Lab, CLAHE) and Pillow (ImageEnhance), SURVEY.md section 8f-4.  These pin the oracle;
+tests/test_gpu_tta.py then holds the CUDA kernels to the oracle and to the libraries again."""
+import os
+import subprocess
+import sys
+
+import cv2
+import numpy as np
+import pytest
+from PIL import Image, ImageEnhance
+
+from oracle import tta as OT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tile():
+    return np.array(Image.open(os.path.join(ROOT, "tests", "golden", "test_tile_864.png")).convert("RGB"))
+
+
+def _cube(first: int) -> np.ndarray:
+    g = np.arange(256, dtype=np.uint8)
+    c = np.zeros((256, 256, 3), np.uint8)
+    c[..., 0] = first
+    c[..., 1] = g[:, None]
+    c[..., 2] = g[None, :]
+    return c
+
+
+def test_rgb2lab_equals_cv2_over_all_inputs():
+    bad = 0
+    for r in range(256):
+        c = _cube(r)
+        bad += int((cv2.cvtColor(c, cv2.COLOR_RGB2LAB) != OT.rgb2lab_u8(c)).sum())
+    assert bad == 0
+
+
+def test_lab2rgb_equals_cv2_over_all_inputs():
+    bad = 0
+    for L in range(256):
+        c = _cube(L)
+        bad += int((cv2.cvtColor(c, cv2.COLOR_LAB2RGB) != OT.lab2rgb_u8(c)).sum())
+    assert bad == 0
+
+
+def test_lab_table_header_is_current():
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_lab_tables.py"), "--check"]) == 0
+
+
+def test_lab2rgb_fits_int32():
+    # the kernels evaluate the 3x3 matrix in int32, as the library does; show the intermediate sums fit
+    t = OT.lab_tables()
+    C = np.array(t["inv"], np.int64)
+    xmax = int(OT._ab_to_xz(np.array([16384 + 255 * 33])).max())      # beyond any reachable fY + a/500
+    bound = (np.abs(C).reshape(3, 3) * np.array([xmax, 16384, xmax])).sum(1).max()
+    assert bound < 2 ** 31
+
+
+@pytest.mark.parametrize("clip,grid", [(3.0, 8), (4.0, 4), (2.0, 8), (3.0, 16), (40.0, 8), (0.0, 8)])
+def test_clahe_equals_cv2(clip, grid):
+    img = _tile()
+    rng = np.random.default_rng(0)
+    cases = [img[..., 1], img[:640, :640, 0], rng.integers(0, 256, (640, 640), dtype=np.uint8), img[:500, :701, 2],
+             (rng.integers(0, 40, (333, 257)) + 100).astype(np.uint8), np.full((64, 64), 7, np.uint8)]
+    for c in cases:
+        c = np.ascontiguousarray(c)
+        ref = cv2.createCLAHE(clipLimit=clip, tileGridSize=(grid, grid)).apply(c)
+        assert np.array_equal(ref, OT.clahe_apply(c, clip, grid, grid)), (c.shape, clip, grid)
+
+
+def test_clahe_variant_equals_reference_expression():
+    # the literal lines of gpu_handler.py:104-110 on the reference's test tile
+    img = _tile()
+    for clip, grid in ((3.0, 8), (4.0, 4)):
+        lab = cv2.cvtColor(img, cv2.COLOR_RGB2LAB)
+        l, a, b = cv2.split(lab)
+        le = cv2.createCLAHE(clipLimit=clip, tileGridSize=(grid, grid)).apply(l)
+        ref = cv2.cvtColor(cv2.merge([le, a, b]), cv2.COLOR_LAB2RGB)
+        assert np.array_equal(ref, OT.clahe_rgb(img, clip, grid, grid))
+
+
+@pytest.mark.parametrize("factor", [2.0, 1.8, 1.4, 1.6, 1.3, 1.0, 0.5, 0.0, 0.37, 3.3])
+def test_brightness_and_contrast_equal_pillow(factor):
+    ramp = np.arange(256, dtype=np.uint8)[None, :, None].repeat(4, 0).repeat(3, 2)
+    for arr in (ramp, _tile()[:300, :300]):
+        im = Image.fromarray(arr)
+        assert np.array_equal(np.array(ImageEnhance.Brightness(im).enhance(factor)), OT.brightness(arr, factor))
+        assert np.array_equal(np.array(ImageEnhance.Contrast(im).enhance(factor)), OT.contrast(arr, factor))
+
+
+def test_gamma_lut_equals_reference_expression():
+    img = _tile()
+    for gamma in (2.0, 1.5):
+        ref = (np.power(img / 255.0, 1.0 / gamma) * 255.0).astype(np.uint8)      # gpu_handler.py:119-120
+        assert np.array_equal(ref, OT.gamma_lut(gamma)[img])
+
+
+def test_archive_chain_equals_pillow():
+    img = _tile()[:256, :320]
+    pil = Image.fromarray(img)
+    refs = []
+    s = pil
+    for b in (1.4, 1.6):                                                       # gpu_handler_archive.py:80-84
+        s = ImageEnhance.Brightness(s).enhance(b)
+        s = ImageEnhance.Contrast(s).enhance(1.3)
+        refs.append(np.array(s))
+    mine = OT.archive_variations(img)
+    assert np.array_equal(mine[2], refs[0]) and np.array_equal(mine[3], refs[1])
+    assert len(mine) == 8
+
+
+def test_process_tensors_restatement_against_torch():
+    import torch
+    rng = np.random.default_rng(3)
+    rows = [rng.random((50, 6), dtype=np.float32) * np.float32(640) for _ in range(5)]
+    for r in rows:
+        r[:, 4] = rng.random(50, dtype=np.float32)
+    bbox = (20.9871234, 52.2291234, 20.9880567, 52.2296891)
+    got = OT.process_tensors_rows(rows, bbox, 0.3)
+    # the reference's own lines (gpu_handler.py:232-253) with torch CPU tensors; torch-CPU divides, torch-CUDA multiplies
+    # by the reciprocal, so the comparison is on the confidence column and to 1 ulp on the coordinates
+    kept = []
+    for i, r in enumerate(rows):
+        b = r.copy()
+        b[:, 4] *= OT.confidence_adjustment(i)
+        kept.append(b[b[:, 4] > 0.3])
+    comb = torch.from_numpy(np.concatenate(kept, 0))
+    centers = comb[:, :2] / 640
+    lons = bbox[0] + centers[:, 0] * (bbox[2] - bbox[0])
+    lats = bbox[3] - centers[:, 1] * (bbox[3] - bbox[1])
+    assert np.array_equal(got[:, 2], comb[:, 4].numpy())
+    assert np.allclose(got[:, 0], lons.numpy(), rtol=0, atol=4e-6) and np.allclose(got[:, 1], lats.numpy(), rtol=0, atol=4e-6)
