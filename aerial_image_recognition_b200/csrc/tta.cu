@@ -109,19 +109,28 @@ struct ClaheGeom {
 enum { OP_RGB2LAB = 0, OP_LAB2RGB = 1, OP_CLAHE = 2 };
 
 // cv2's CLAHE_Interpolation_Body for one pixel: bilinear blend of the four surrounding tiles' tables (fp32, no contraction)
-__device__ __forceinline__ int clahe_interp(const ClaheGeom& g, long long pix, int L) {
-    const int hw = g.h * g.w;
-    const int img = (int)(pix / hw);
-    const int rem = (int)(pix - (long long)img * hw);
-    const int y = rem / g.w, x = rem - y * g.w;
-    const float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
-    const float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
+struct PixPos { int img, y, x; };
+__device__ __forceinline__ PixPos pix_pos(const ClaheGeom& g, unsigned int pix) {      // 32-bit: npix < 2^31 is checked on the host
+    const unsigned int hw = (unsigned int)(g.h * g.w);
+    PixPos p;
+    p.img = (int)(pix / hw);
+    const unsigned int rem = pix - (unsigned int)p.img * hw;
+    p.y = (int)(rem / (unsigned int)g.w);
+    p.x = (int)(rem - (unsigned int)p.y * (unsigned int)g.w);
+    return p;
+}
+__device__ __forceinline__ void pix_next(const ClaheGeom& g, PixPos& p) {
+    if (++p.x == g.w) { p.x = 0; if (++p.y == g.h) { p.y = 0; ++p.img; } }
+}
+__device__ __forceinline__ int clahe_interp(const ClaheGeom& g, const PixPos& p, int L) {
+    const float txf = __fsub_rn(__fmul_rn((float)p.x, g.inv_tw), 0.5f);
+    const float tyf = __fsub_rn(__fmul_rn((float)p.y, g.inv_th), 0.5f);
     int tx1 = __float2int_rd(txf), ty1 = __float2int_rd(tyf);
     const float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
     const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
     const int tx2 = min(tx1 + 1, g.tiles_x - 1), ty2 = min(ty1 + 1, g.tiles_y - 1);
     tx1 = max(tx1, 0); ty1 = max(ty1, 0);
-    const uint8_t* lp = g.luts + (size_t)img * g.tiles_x * g.tiles_y * 256 + L;
+    const uint8_t* lp = g.luts + (size_t)(p.img * g.tiles_y * g.tiles_x) * 256 + L;
     const float l11 = (float)__ldg(lp + (ty1 * g.tiles_x + tx1) * 256), l12 = (float)__ldg(lp + (ty1 * g.tiles_x + tx2) * 256);
     const float l21 = (float)__ldg(lp + (ty2 * g.tiles_x + tx1) * 256), l22 = (float)__ldg(lp + (ty2 * g.tiles_x + tx2) * 256);
     const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
@@ -130,7 +139,7 @@ __device__ __forceinline__ int clahe_interp(const ClaheGeom& g, long long pix, i
 }
 
 template <int OP>
-__device__ __forceinline__ void map_px(const LabTabs* T, const LabCoef& C, const ClaheGeom& g, long long pix, int c0, int c1, int c2,
+__device__ __forceinline__ void map_px(const LabTabs* T, const LabCoef& C, const ClaheGeom& g, const PixPos& pos, int c0, int c1, int c2,
                                        int& o0, int& o1, int& o2) {
     if (OP == OP_RGB2LAB) {
         rgb2lab_px(T, C, c0, c1, c2, o0, o1, o2);
@@ -139,7 +148,7 @@ __device__ __forceinline__ void map_px(const LabTabs* T, const LabCoef& C, const
     } else {
         int L, a, b;
         rgb2lab_px(T, C, c0, c1, c2, L, a, b);
-        lab2rgb_px(T, C, clahe_interp(g, pix, L), a, b, o0, o1, o2);
+        lab2rgb_px(T, C, clahe_interp(g, pos, L), a, b, o0, o1, o2);
     }
 }
 
@@ -156,11 +165,14 @@ __global__ void __launch_bounds__(256) pixel_kernel(const uint8_t* __restrict__ 
         Quad in, out;
         in.w[0] = __ldg(s32 + q * 3); in.w[1] = __ldg(s32 + q * 3 + 1); in.w[2] = __ldg(s32 + q * 3 + 2);
         out.w[0] = out.w[1] = out.w[2] = 0;
+        PixPos pos{0, 0, 0};
+        if (OP == OP_CLAHE) pos = pix_pos(g, (unsigned int)(q * 4));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             int o0, o1, o2;
-            map_px<OP>(&T, C, g, q * 4 + k, quad_byte(in, 3 * k), quad_byte(in, 3 * k + 1), quad_byte(in, 3 * k + 2), o0, o1, o2);
+            map_px<OP>(&T, C, g, pos, quad_byte(in, 3 * k), quad_byte(in, 3 * k + 1), quad_byte(in, 3 * k + 2), o0, o1, o2);
             quad_set(out, 3 * k, o0); quad_set(out, 3 * k + 1, o1); quad_set(out, 3 * k + 2, o2);
+            if (OP == OP_CLAHE) pix_next(g, pos);
         }
         d32[q * 3] = out.w[0]; d32[q * 3 + 1] = out.w[1]; d32[q * 3 + 2] = out.w[2];
     }
@@ -168,7 +180,9 @@ __global__ void __launch_bounds__(256) pixel_kernel(const uint8_t* __restrict__ 
     if (blockIdx.x == 0 && threadIdx.x < (int)(npix & 3)) {
         const long long p = (quads << 2) + threadIdx.x;
         int o0, o1, o2;
-        map_px<OP>(&T, C, g, p, src[p * 3], src[p * 3 + 1], src[p * 3 + 2], o0, o1, o2);
+        PixPos pos{0, 0, 0};
+        if (OP == OP_CLAHE) pos = pix_pos(g, (unsigned int)p);
+        map_px<OP>(&T, C, g, pos, src[p * 3], src[p * 3 + 1], src[p * 3 + 2], o0, o1, o2);
         dst[p * 3] = (uint8_t)o0; dst[p * 3 + 1] = (uint8_t)o1; dst[p * 3 + 2] = (uint8_t)o2;
     }
 }
@@ -190,8 +204,10 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
     const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
     const uint8_t* base = src + (size_t)img * h * w * 3;
     const int area = tw * th;
-    for (int idx = tid; idx < area; idx += 256) {
-        const int yy = idx / tw, xx = idx - yy * tw;
+    const int dq = 256 / tw, dr = 256 - dq * tw;       // idx += 256 as (row, column) increments: no division per pixel
+    int yy = tid / tw, xx = tid - yy * tw;
+    for (int idx = tid; idx < area; idx += 256, yy += dq, xx += dr) {
+        if (xx >= tw) { xx -= tw; ++yy; }
         int Y = tyi * th + yy, X = txi * tw + xx;
         if (Y >= h) Y = 2 * (h - 1) - Y;            // BORDER_REFLECT_101 of the ragged bottom / right edge
         if (X >= w) X = 2 * (w - 1) - X;
@@ -334,6 +350,7 @@ int tta_clahe_launch(const uint8_t* src, int n, int h, int w, double clip_limit,
     B2D_LAUNCH_CHECK();
     ClaheGeom g{h, w, tw, th, tiles_x, tiles_y, 1.0f / (float)tw, 1.0f / (float)th, luts};
     const long long npix = (long long)n * h * w;
+    B2D_CHECK(npix < (1ll << 31), "clahe: %lld pixels in one call (limit 2^31)", npix);
     pixel_kernel<OP_CLAHE><<<grid_for(npix >> 2, 256), 256, 0, stream>>>(src, dst, npix, C, g);
     B2D_LAUNCH_CHECK();
     return 0;

@@ -24,7 +24,7 @@ import numpy as np
 from . import geo
 
 __all__ = ['TileGenerator', 'CheckpointManager', 'ResultsManager', 'create_geodataframe', 'write_geojson', 'read_geojson',
-           'shapefile_bounds']
+           'shapefile_bounds', 'write_shapefile', 'read_shapefile']
 
 CRS84 = {"type": "name", "properties": {"name": "urn:ogc:def:crs:OGC:1.3:CRS84"}}
 
@@ -39,6 +39,78 @@ def shapefile_bounds(path: str) -> Tuple[float, float, float, float]:
     if len(head) < 100 or struct.unpack(">i", head[:4])[0] != 9994:
         raise ValueError(f"{path}: not an ESRI shapefile (bad file code)")
     return struct.unpack("<4d", head[36:68])
+
+
+# ---- ESRI shapefile output -----------------------------------------------------------------------------
+# The reference's frames and earlier results are shapefiles with .cpg "UTF-8" sidecars (gis/frames/*.cpg,
+# gis/shp/x_arch/centroidy/); ``gdf.to_file(path)`` without a driver writes this format.  Point layer, one
+# ``confidence`` field, WGS84 -- the file set GDAL's "ESRI Shapefile" driver produces for such a frame: .shp / .shx
+# (ESRI Shapefile Technical Description, 1998), .dbf (dBASE III, Real fields as N(24,15)), .prj, .cpg.
+WGS84_PRJ = ('GEOGCS["GCS_WGS_1984",DATUM["D_WGS_1984",SPHEROID["WGS_1984",6378137.0,298.257223563]],'
+             'PRIMEM["Greenwich",0.0],UNIT["Degree",0.0174532925199433]]')
+
+
+def _shp_header(file_words: int, bbox) -> bytes:
+    return (struct.pack(">7i", 9994, 0, 0, 0, 0, 0, file_words) + struct.pack("<2i", 1000, 1)
+            + struct.pack("<8d", bbox[0], bbox[1], bbox[2], bbox[3], 0.0, 0.0, 0.0, 0.0))
+
+
+def write_shapefile(detections, path: str) -> None:
+    """Point shapefile of ``[{'lon', 'lat', 'confidence'}, ...]`` (or of a FeatureCollection from
+    ``create_geodataframe``).  ``path`` may end in ``.shp``; the four sidecars are written next to it."""
+    if isinstance(detections, dict):
+        detections = [{"lon": f["geometry"]["coordinates"][0], "lat": f["geometry"]["coordinates"][1],
+                       "confidence": f["properties"]["confidence"]} for f in detections.get("features", [])]
+    base = path[:-4] if path.lower().endswith(".shp") else path
+    pts = [(float(d["lon"]), float(d["lat"]), float(d["confidence"])) for d in detections]
+    n = len(pts)
+    bbox = (min(p[0] for p in pts), min(p[1] for p in pts), max(p[0] for p in pts), max(p[1] for p in pts)) if n else (0.0,) * 4
+    with open(base + ".shp", "wb") as shp, open(base + ".shx", "wb") as shx:
+        shp.write(_shp_header(50 + 14 * n, bbox))
+        shx.write(_shp_header(50 + 4 * n, bbox))
+        for i, (x, y, _) in enumerate(pts):
+            shx.write(struct.pack(">2i", 50 + 14 * i, 10))                     # offset and content length in 16-bit words
+            shp.write(struct.pack(">2i", i + 1, 10) + struct.pack("<i2d", 1, x, y))
+    now = datetime.now()
+    with open(base + ".dbf", "wb") as dbf:
+        dbf.write(struct.pack("<4BIHH20x", 3, now.year - 1900, now.month, now.day, n, 32 + 32 + 1, 1 + 24))
+        dbf.write(b"confidence".ljust(11, b"\0") + b"N" + b"\0" * 4 + bytes([24, 15]) + b"\0" * 14)
+        dbf.write(b"\r")
+        for _, _, c in pts:
+            dbf.write(b" " + f"{c:24.15f}".encode("ascii")[-24:])
+        dbf.write(b"\x1a")
+    with open(base + ".prj", "w") as f:
+        f.write(WGS84_PRJ)
+    with open(base + ".cpg", "w") as f:
+        f.write("UTF-8")
+
+
+def read_shapefile(path: str) -> List[Dict]:
+    """Reads a Point shapefile with a ``confidence`` field back into detection dicts (tests, resume)."""
+    base = path[:-4] if path.lower().endswith(".shp") else path
+    with open(base + ".shp", "rb") as f:
+        data = f.read()
+    if struct.unpack(">i", data[:4])[0] != 9994 or struct.unpack("<i", data[32:36])[0] != 1:
+        raise ValueError(f"{path}: not a Point shapefile")
+    pts, off = [], 100
+    while off < len(data):
+        _, words = struct.unpack(">2i", data[off:off + 8])
+        stype, x, y = struct.unpack("<i2d", data[off + 8:off + 28])
+        if stype == 1:
+            pts.append((x, y))
+        off += 8 + 2 * words
+    with open(base + ".dbf", "rb") as f:
+        d = f.read()
+    nrec, hlen, rlen = struct.unpack("<IHH", d[4:12])
+    fields, o, pos = [], 32, 1
+    while d[o] != 0x0D:
+        name = d[o:o + 11].split(b"\0")[0].decode()
+        fields.append((name, pos, d[o + 16]))
+        pos += d[o + 16]
+        o += 32
+    fpos = {name: (p, ln) for name, p, ln in fields}["confidence"]
+    conf = [float(d[hlen + i * rlen + fpos[0]: hlen + i * rlen + fpos[0] + fpos[1]]) for i in range(nrec)]
+    return [{"lon": x, "lat": y, "confidence": c} for (x, y), c in zip(pts, conf)]
 
 
 # ---- _script/utils.py:15-65 --------------------------------------------------------------------------------
@@ -154,8 +226,9 @@ class CheckpointManager:
 
 # ---- _script/utils.py:181-292 ------------------------------------------------------------------------------
 class ResultsManager:
-    def __init__(self, output_dir, prefix="detections", duplicate_distance=0, engine=None):
+    def __init__(self, output_dir, prefix="detections", duplicate_distance=0, engine=None, shapefile=False):
         self.duplicate_distance = duplicate_distance      # metres
+        self.shapefile = shapefile
         self.output_dir = output_dir
         self.output_file = os.path.join(output_dir, f"{prefix}_results.geojson")
         self.engine = engine                              # the B200 engine that runs the projection + dedup kernels
@@ -169,6 +242,8 @@ class ResultsManager:
         fc = create_geodataframe(unique)
         if fc["features"]:
             write_geojson(fc, self.output_file)
+            if self.shapefile:           # opt-in second copy of the results as an ESRI shapefile (north_star: "shapefile output")
+                write_shapefile(fc, os.path.splitext(self.output_file)[0] + ".shp")
         return unique
 
     def remove_duplicates(self, detections):

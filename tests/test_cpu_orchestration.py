@@ -116,3 +116,31 @@ def test_reference_tile_fixture_and_its_reference_resizes():
     assert list(a.shape) == st["size"] == [864, 864, 3] and zlib.crc32(a.tobytes()) == st["crc32"]
     assert zlib.crc32(RS.emulate_pil_bicubic(a, 640, 640).tobytes()) == st["pil_bicubic_640_crc32"]
     assert zlib.crc32(RS.emulate_cv2_linear(a, 640, 640).tobytes()) == st["cv2_linear_640_crc32"]
+
+
+def test_shapefile_round_trip_and_header_bounds(tmp_path):
+    import struct
+    from aerial_image_recognition_b200 import utils as U
+    rng = np.random.default_rng(2)
+    dets = [{"lon": 21.0 + float(rng.random()) * 1e-2, "lat": 52.2 + float(rng.random()) * 1e-2, "confidence": float(np.float32(rng.random()))}
+            for _ in range(37)]
+    base = str(tmp_path / "cars")
+    U.write_shapefile(dets, base + ".shp")
+    for ext in (".shp", ".shx", ".dbf", ".prj", ".cpg"):
+        assert os.path.exists(base + ext)
+    assert open(base + ".cpg").read() == "UTF-8"                       # as the reference's frames (gis/frames/*.cpg)
+    back = U.read_shapefile(base + ".shp")
+    assert [(d["lon"], d["lat"]) for d in back] == [(d["lon"], d["lat"]) for d in dets]      # doubles, bit for bit
+    assert all(abs(a["confidence"] - b["confidence"]) < 1e-15 for a, b in zip(back, dets))
+    # file lengths in the headers (16-bit words), record offsets in the index, bounds in both headers
+    shp, shx = open(base + ".shp", "rb").read(), open(base + ".shx", "rb").read()
+    assert struct.unpack(">i", shp[24:28])[0] * 2 == len(shp) == 100 + 28 * 37
+    assert struct.unpack(">i", shx[24:28])[0] * 2 == len(shx) == 100 + 8 * 37
+    assert struct.unpack(">2i", shx[100 + 8 * 5:108 + 8 * 5]) == ((100 + 28 * 5) // 2, 10)
+    b = U.shapefile_bounds(base + ".shp")
+    assert b == (min(d["lon"] for d in dets), min(d["lat"] for d in dets), max(d["lon"] for d in dets), max(d["lat"] for d in dets))
+    # the FeatureCollection form and the empty layer
+    U.write_shapefile(U.create_geodataframe(dets), str(tmp_path / "fc"))
+    assert U.read_shapefile(str(tmp_path / "fc")) == back
+    U.write_shapefile([], str(tmp_path / "empty"))
+    assert U.read_shapefile(str(tmp_path / "empty")) == []
