@@ -34,10 +34,33 @@ def timed(fn, iters, warm=3):
     return a.elapsed_time(b) / iters
 
 
+def cpu_views(ntiles):
+    """The reference's own view code (gpu_handler.py:94-140: cv2 + Pillow + NumPy on the host) timed on `ntiles` tiles."""
+    import time
+    import cv2
+    from PIL import Image, ImageEnhance
+    tiles = synth.make_tiles(ntiles, 640, 300)
+    cv2.setNumThreads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    for a in tiles:
+        img = Image.fromarray(a)
+        for clip, grid in ((3.0, 8), (4.0, 4)):
+            lab = cv2.cvtColor(a, cv2.COLOR_RGB2LAB)
+            l, aa, bb = cv2.split(lab)
+            le = cv2.createCLAHE(clipLimit=clip, tileGridSize=(grid, grid)).apply(l)
+            cv2.cvtColor(cv2.merge([le, aa, bb]), cv2.COLOR_LAB2RGB)
+        np.array(ImageEnhance.Brightness(img).enhance(2.0))
+        (np.power(a / 255.0, 1.0 / 2.0) * 255.0).astype(np.uint8)
+    dt = time.perf_counter() - t0
+    return {"value": round(ntiles / dt, 1), "unit": "tiles/s (four derived views per tile, no network)", "cores": os.cpu_count(),
+            "kind": "reference", "sample": f"{ntiles} synthetic 640x640 tiles through the reference's cv2 / Pillow / NumPy lines"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--cpu-tiles", type=int, default=128)
     args = ap.parse_args()
     n = args.batch
     peak = 6532.2
@@ -72,9 +95,12 @@ def main():
             eng.georef(dets, counts, params, "tensor_f32")
     ms = timed(step, max(5, args.iters // 2))
     plain = timed(lambda k: eng.georef(*eng.infer(pool[k % 4], "identity", False, 0.3, True), params, "gpuhandler"), args.iters)
+    vms = timed(lambda k: eng.tta_views(pool[k % 4], views), args.iters)
+    out["views_only"] = {"ms_per_batch": round(vms, 4), "tiles_per_s": round(n / vms * 1e3, 1), "note": "the four derived views of every tile"}
     out["five_view_step"] = {"ms_per_batch": round(ms, 3), "tiles_per_s": round(n / ms * 1e3, 1), "views": len(views),
                              "network_passes_per_s": round(len(views) * n / ms * 1e3, 1)}
     out["single_view_step"] = {"ms_per_batch": round(plain, 3), "tiles_per_s": round(n / plain * 1e3, 1)}
+    out["cpu_baseline"] = cpu_views(args.cpu_tiles)
     print(json.dumps(out))
 
 
