@@ -46,6 +46,10 @@ SIGNATURES = {
     "b2d_postprocess": (c_int, [c_void_p, c_int, c_float, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "b2d_postprocess_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_int, c_int,
                                      c_void_p, c_void_p, c_int, c_void_p]),
+    "b2d_infer_tiles": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_int, c_int, c_float, c_int, c_float, c_int, c_int,
+                                c_void_p, c_void_p, c_int, c_void_p]),
+    "b2d_detect_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "b2d_georef": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2d_dedup": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
     "b2d_seam_closure": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),

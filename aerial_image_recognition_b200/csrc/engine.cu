@@ -82,6 +82,13 @@ struct b2d_engine {
     size_t tta_luts_bytes = 0;
     unsigned long long* tta_sums = nullptr;
     int tta_sums_n = 0;
+    // b2d_detect_host: two staging slots (tiles, params, records, counts), a copy stream and the events that order them
+    struct HostSlot {
+        uint8_t* tiles = nullptr; size_t tiles_bytes = 0;
+        double* params = nullptr; b2d_det* dets = nullptr; b2d_geodet* geo = nullptr; int32_t* counts = nullptr; int cap = 0;
+        cudaEvent_t loaded = nullptr, drained = nullptr;
+    } host_slot[2];
+    cudaStream_t copy_stream = nullptr;
     // forward() as a CUDA graph per batch size: the ~94 launches of a step replay without per-launch driver work
     std::map<int, cudaGraphExec_t> fwd_graphs;
     std::map<int, int> fwd_calls;
@@ -318,6 +325,12 @@ void b2d_destroy(b2d_engine* e) {
     if (e->dedup_scratch) cudaFree(e->dedup_scratch);
     if (e->tta_luts) cudaFree(e->tta_luts);
     if (e->tta_sums) cudaFree(e->tta_sums);
+    for (auto& hs : e->host_slot) {
+        if (hs.tiles) cudaFree(hs.tiles);
+        if (hs.params) { cudaFree(hs.params); cudaFree(hs.dets); cudaFree(hs.geo); cudaFree(hs.counts); }
+        if (hs.loaded) { cudaEventDestroy(hs.loaded); cudaEventDestroy(hs.drained); }
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (auto& kv : e->fwd_graphs) cudaGraphExecDestroy(kv.second);
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     for (auto st : e->side_streams) cudaStreamDestroy(st);
@@ -739,6 +752,77 @@ int b2d_tta_contrast(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w,
     B2D_CHECK(aligned4(src_dev, dst_dev), "tta_contrast: pointers must be 4-byte aligned");
     if (ensure_tta(e, (size_t)n * 256, n)) return -2;
     return tta_contrast_launch(src_dev, n, h, w, factor, e->tta_sums, e->tta_luts, dst_dev, (cudaStream_t)stream);
+}
+
+int b2d_infer_tiles(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, int pitch, long long img_stride, int mode, int bgr,
+                    float conf_thr, int inclusive, float iou_thr, int top_k, int max_det, b2d_det* dets_dev, int32_t* counts_dev, int cap,
+                    void* stream) {
+    int rc = b2d_preprocess(e, src_dev, n, h, w, pitch, img_stride, mode, bgr, B2D_OUT_BF16_NHWC4, nullptr, stream);
+    if (rc) return rc;
+    if ((rc = b2d_forward(e, n, stream)) != 0) return rc;
+    return b2d_postprocess(e, n, conf_thr, inclusive, iou_thr, top_k, max_det, dets_dev, counts_dev, cap, stream);
+}
+
+static int ensure_host_slot(b2d_engine* e, int slot, size_t tiles_bytes, int cap) {
+    auto& hs = e->host_slot[slot];
+    if (!hs.loaded) {
+        B2D_CUDA(cudaEventCreateWithFlags(&hs.loaded, cudaEventDisableTiming));
+        B2D_CUDA(cudaEventCreateWithFlags(&hs.drained, cudaEventDisableTiming));
+    }
+    if (tiles_bytes > hs.tiles_bytes) {
+        if (hs.tiles) cudaFree(hs.tiles);
+        hs.tiles = nullptr; hs.tiles_bytes = 0;
+        B2D_CUDA(cudaMalloc(&hs.tiles, tiles_bytes));
+        hs.tiles_bytes = tiles_bytes;
+    }
+    if (cap > hs.cap) {
+        if (hs.params) { cudaFree(hs.params); cudaFree(hs.dets); cudaFree(hs.geo); cudaFree(hs.counts); }
+        hs.params = nullptr; hs.cap = 0;
+        const size_t nb = (size_t)e->max_batch;
+        B2D_CUDA(cudaMalloc(&hs.params, nb * B2D_GEO_PARAMS * sizeof(double)));
+        B2D_CUDA(cudaMalloc(&hs.dets, nb * cap * sizeof(b2d_det)));
+        B2D_CUDA(cudaMalloc(&hs.geo, nb * cap * sizeof(b2d_geodet)));
+        B2D_CUDA(cudaMalloc(&hs.counts, nb * sizeof(int32_t)));
+        hs.cap = cap;
+    }
+    return 0;
+}
+
+int b2d_detect_host(b2d_engine* e, const uint8_t* tiles_host, int n, int h, int w, int mode, int bgr, float conf_thr, int inclusive,
+                    float iou_thr, int top_k, int max_det, int geo_mode, const double* params_host, b2d_geodet* out_host,
+                    int32_t* counts_host, int cap, void* stream) {
+    B2D_CHECK(e && e->finalized && tiles_host && params_host && out_host && counts_host && n > 0 && h > 0 && w > 0 && cap > 0,
+              "detect_host: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!e->copy_stream) B2D_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    const size_t img_bytes = (size_t)h * w * 3;
+    const int mb = e->max_batch;
+    for (int slot = 0; slot < 2; ++slot)
+        if (ensure_host_slot(e, slot, (size_t)(n < mb ? n : mb) * img_bytes, cap)) return -2;
+    int rc = 0, k = 0;
+    for (int i0 = 0; i0 < n && rc == 0; i0 += mb, ++k) {
+        const int nb = n - i0 < mb ? n - i0 : mb;
+        auto& hs = e->host_slot[k & 1];
+        // copy stream: wait until the chunk that used this slot two iterations ago has been consumed, then load
+        if (k >= 2) B2D_CUDA(cudaStreamWaitEvent(e->copy_stream, hs.drained, 0));
+        B2D_CUDA(cudaMemcpyAsync(hs.tiles, tiles_host + (size_t)i0 * img_bytes, (size_t)nb * img_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        B2D_CUDA(cudaMemcpyAsync(hs.params, params_host + (size_t)i0 * B2D_GEO_PARAMS, (size_t)nb * B2D_GEO_PARAMS * sizeof(double),
+                                 cudaMemcpyHostToDevice, e->copy_stream));
+        B2D_CUDA(cudaEventRecord(hs.loaded, e->copy_stream));
+        B2D_CUDA(cudaStreamWaitEvent(s, hs.loaded, 0));
+        rc = b2d_infer_tiles(e, hs.tiles, nb, h, w, w * 3, (long long)img_bytes, mode, bgr, conf_thr, inclusive, iou_thr, top_k, max_det,
+                             hs.dets, hs.counts, cap, s);
+        if (rc == 0) rc = b2d_georef(e, hs.dets, hs.counts, nb, cap, geo_mode, hs.params, hs.geo, s);
+        if (rc) break;
+        B2D_CUDA(cudaMemcpyAsync(out_host + (size_t)i0 * cap, hs.geo, (size_t)nb * cap * sizeof(b2d_geodet), cudaMemcpyDeviceToHost, s));
+        B2D_CUDA(cudaMemcpyAsync(counts_host + i0, hs.counts, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        B2D_CUDA(cudaEventRecord(hs.drained, s));
+    }
+    cudaError_t err = cudaStreamSynchronize(s);
+    cudaStreamSynchronize(e->copy_stream);
+    if (rc) return rc;
+    B2D_CUDA(err);
+    return 0;
 }
 
 }  // extern "C"

@@ -316,6 +316,24 @@ class Engine:
         _lib.check(self.lib.b2d_set_conf_scale(self.h, float(scale)), "set_conf_scale")
 
     # ---- whole path ----------------------------------------------------------------------
+    def detect_host(self, tiles, params, resize: str = "identity", bgr: bool = False, conf_thr: float = 0.3, inclusive: bool = True,
+                    iou_thr: float = 0.0, top_k: int = 0, max_det: int = 300, cap: Optional[int] = None, geo: str = "bounds"):
+        """Host tiles in, host records out, in ONE C call (``b2d_detect_host``): ``tiles`` uint8 [n,h,w,3] (NumPy array or CPU
+        tensor; any n, pinned memory overlaps the copies), ``params`` float64 [n,16].  Returns one ``GEODET_DTYPE`` array per tile."""
+        t = _host_array(tiles, np.uint8)
+        p = _host_array(params, np.float64)
+        n, h, w, _ = t.shape
+        assert p.shape == (n, GEO_PARAMS)
+        if cap is None:
+            cap = max_det if iou_thr > 0 else (top_k if top_k > 0 else min(self.num_rows, 32768))
+        out = np.zeros((n, cap), dtype=GEODET_DTYPE)
+        counts = np.zeros((n,), dtype=np.int32)
+        _lib.check(self.lib.b2d_detect_host(self.h, C.c_void_p(t.ctypes.data), n, h, w, RESIZE[resize], int(bgr), conf_thr,
+                                            int(inclusive), iou_thr, top_k, max_det, GEO[geo], C.c_void_p(p.ctypes.data),
+                                            C.c_void_p(out.ctypes.data), C.c_void_p(counts.ctypes.data), cap, self.stream),
+                   "detect_host")
+        return [out[i, :counts[i]].copy() for i in range(n)]
+
     def infer(self, images: torch.Tensor, resize: str = "identity", bgr: bool = False, conf_thr: float = 0.3,
               inclusive: bool = True, iou_thr: float = 0.0, top_k: int = 0, max_det: int = 300, cap: Optional[int] = None,
               conf_scale: float = 1.0):
@@ -331,6 +349,12 @@ class Engine:
             return self.postprocess(n, conf_thr, inclusive, iou_thr, top_k, max_det, cap)
         finally:
             self.set_conf_scale(1.0)
+
+
+def _host_array(x, dtype) -> np.ndarray:
+    a = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+    assert a.dtype == dtype
+    return np.ascontiguousarray(a)
 
 
 def dets_to_numpy(dets: torch.Tensor, counts: torch.Tensor):

@@ -249,6 +249,19 @@ def main():
     barrier()
     ms_e2e = t0.elapsed_time(t1)
 
+    # The same through ONE C-ABI call with host buffers (b2d_detect_host): CH chunks of BATCH pinned tiles in, records out;
+    # the library double-buffers the host->device copies itself.  Wall clock around the (synchronous) call.
+    import time as _time
+    CH = min(max(K, 2), 8)
+    big = torch.cat([host_pool[i % NPOOL] for i in range(CH)]).pin_memory()
+    big_params = np.tile(_geo_params(BATCH), (CH, 1))
+    eng.detect_host(big[:BATCH], big_params[:BATCH], conf_thr=CONF, inclusive=False, iou_thr=IOU, max_det=MAX_DET)   # staging buffers
+    barrier()
+    tw0 = _time.perf_counter()
+    eng.detect_host(big, big_params, conf_thr=CONF, inclusive=False, iou_thr=IOU, max_det=MAX_DET)
+    ms_cabi = (_time.perf_counter() - tw0) * 1e3
+    del big
+
     # ---------------- roofline of the dominant kernel family ----------------
     # Duration of the conv_tc_* launches of one step = forward() timed as one back-to-back launch sequence (CUDA events
     # on the launching stream) minus the few non-conv ops (pools, upsamples), which are timed one by one.  Timing every
@@ -279,10 +292,25 @@ def main():
     tc_ms = fwd_ms - other_ms
     n_tc = sum(is_tc)
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    # the HBM-bound stages either side of the network, each timed alone (CUDA events, inputs rotated / larger than L2)
+    def _timed(fn, n=10):
+        fn(0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(n):
+            fn(k + 1)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    pre_ms = _timed(lambda k: eng.preprocess(dev_pool[k % NPOOL], "identity"))
+    post_ms = _timed(lambda k: eng.postprocess(BATCH, CONF, False, IOU, 0, MAX_DET))
+    head_bytes = sum(g_.h * g_.w * g_.c * 4 for g_ in (eng.graph.bufs[lv["buf"]] for lv in eng.graph.head["levels"]))
+
+    t = torch.tensor([ms, ms_e2e, ms_cabi], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, ms_cabi = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         peak_tf, peak_hbm, which = _peaks()
@@ -305,7 +333,9 @@ def main():
                        "l2": f"{NPOOL} distinct input batches rotated (315 MB uint8) and ~6 GB of activations per step stream through the 126 MB L2",
                        "detections_last_step": n_det},
             "e2e": {"value": total_tiles / (ms_e2e * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": BATCH * SIZE * SIZE * 3,
-                    "d2h_bytes_per_step": BATCH * MAX_DET * 40 + BATCH * 4, "ms_per_step": ms_e2e / K},
+                    "d2h_bytes_per_step": BATCH * MAX_DET * 40 + BATCH * 4, "ms_per_step": ms_e2e / K,
+                    "c_abi_one_call": {"value": world * CH * BATCH / (ms_cabi * 1e-3), "unit": "tiles/s", "tiles_per_call": CH * BATCH,
+                                       "call": "b2d_detect_host: pinned host tiles in, host records out, wall clock around the call"}},
             "gpu_launches": K * (eng.num_kernels + 5),     # graph kernels + preprocess, decode/compact, key sort, select/NMS, georef
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "conv_tc_* family (tcgen05 implicit-GEMM conv+bias+SiLU: generic, halo, halo-pair, stem, depthwise)",
@@ -316,6 +346,17 @@ def main():
                          "timing": "CUDA events around forward() (all graph launches back to back) minus the non-conv ops timed singly",
                          "algorithmic_gflop_per_tile": tc_flops / BATCH / 1e9},
         }
+        pre_bytes = SIZE * SIZE * (3 + 8)          # uint8 RGB in, 16-bit NHWC4 out
+        line["roofline_aux"] = {
+            "peak": peak_hbm, "unit": "GB/s", "peak_source": f"{which} hbm_gbs (copy bandwidth)",
+            "preprocess": {"kernel": "prep_identity_vec_kernel (u8 -> 16-bit NHWC4, /255)", "ms_per_step": pre_ms,
+                           "algorithmic_bytes_per_tile": pre_bytes, "achieved": BATCH * pre_bytes / (pre_ms * 1e-3) / 1e9,
+                           "frac": BATCH * pre_bytes / (pre_ms * 1e-3) / 1e9 / peak_hbm},
+            "postprocess": {"kernel": "head_kernel<1> (DFL decode + threshold + compaction) + sort_keys_kernel + select_kernel (NMS)",
+                            "ms_per_step": post_ms, "algorithmic_bytes_per_tile": head_bytes,
+                            "achieved": BATCH * head_bytes / (post_ms * 1e-3) / 1e9,
+                            "frac": BATCH * head_bytes / (post_ms * 1e-3) / 1e9 / peak_hbm,
+                            "note": "bytes = the fp32 head maps read once; the sort / NMS kernels after the compaction are latency-bound (one CTA per tile)"}}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
         print(json.dumps(line))

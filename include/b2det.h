@@ -145,6 +145,22 @@ int b2d_postprocess_rows(b2d_engine* e, const float* rows_dev, int n, int num_ro
                          float conf_thr, int inclusive, float iou_thr, int top_k, int max_det,
                          b2d_det* dets_dev, int32_t* counts_dev, int cap, void* stream);
 
+/* The whole device-resident path in one call (SURVEY.md section 8b "b2d_infer_tiles"): b2d_preprocess into the engine's
+ * input buffer, b2d_forward, b2d_postprocess.  Arguments as in those three.                                    */
+int b2d_infer_tiles(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, int pitch, long long img_stride, int mode, int bgr,
+                    float conf_thr, int inclusive, float iou_thr, int top_k, int max_det, b2d_det* dets_dev,
+                    int32_t* counts_dev, int cap, void* stream);
+
+/* The same from HOST buffers to HOST buffers -- what GPUHandler.process_batch / SimpleDetector.detect_batch do with the
+ * images they are handed (gpu_handler.py:151-213, simple_detector.py:648-677): n tiles uint8 [n][h][w][3] (any n; pinned
+ * memory lets the copies overlap), params_host double [n][B2D_GEO_PARAMS] for b2d_georef in `geo_mode`; results
+ * out_host [n][cap] records and counts_host [n].  Chunks of max_batch tiles are double-buffered: the next chunk's
+ * host->device copy runs on the engine's copy stream while the current chunk computes.  Returns after the results
+ * have landed in host memory.                                                                                    */
+int b2d_detect_host(b2d_engine* e, const uint8_t* tiles_host, int n, int h, int w, int mode, int bgr, float conf_thr,
+                    int inclusive, float iou_thr, int top_k, int max_det, int geo_mode, const double* params_host,
+                    b2d_geodet* out_host, int32_t* counts_host, int cap, void* stream);
+
 /* Pixel -> CRS.  params_dev: double [n][B2D_GEO_PARAMS] per tile.  fp64, no FMA contraction.
  * Replaces simple_detector.py:484-502, gpu_handler.py:178-190, pixel_to_geo.                 */
 int b2d_georef(b2d_engine* e, const b2d_det* dets_dev, const int32_t* counts_dev, int n, int cap,

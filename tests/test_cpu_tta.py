@@ -131,3 +131,23 @@ def test_process_tensors_restatement_against_torch():
     lats = bbox[3] - centers[:, 1] * (bbox[3] - bbox[1])
     assert np.array_equal(got[:, 2], comb[:, 4].numpy())
     assert np.allclose(got[:, 0], lons.numpy(), rtol=0, atol=4e-6) and np.allclose(got[:, 1], lats.numpy(), rtol=0, atol=4e-6)
+
+
+def test_oracle_views_match_golden_crcs():
+    # tests/golden/tta_views.json: the reference's library calls on its own test tile (make_golden.py)
+    import json
+    import zlib
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "tta_views.json")))
+    img = _tile()
+    cur = OT.lighting_variations(img) + OT.occlusion_variations(img)
+    assert [zlib.crc32(np.ascontiguousarray(v).tobytes()) for v in cur] == gold["current_views_crc32"]
+    assert [zlib.crc32(np.ascontiguousarray(v).tobytes()) for v in OT.archive_variations(img)] == gold["archive_views_crc32"]
+
+
+def test_blend_table_equals_pillow_for_every_constant_and_value():
+    v = np.arange(256, dtype=np.uint8)[None, :]
+    img = Image.fromarray(v)
+    for c in range(256):
+        deg = Image.new("L", (256, 1), c)
+        for f in (2.0, 1.8, 1.3, 0.3, -0.5):
+            assert np.array_equal(np.array(Image.blend(deg, img, f))[0], OT.blend_lut(c, f)), (c, f)

@@ -468,6 +468,28 @@ def test_gpu_handler_process_batch_matches_reference_restatement():
     h.engine.close()
 
 
+def test_detect_host_one_call_equals_the_staged_path(eng640):
+    # b2d_detect_host (host buffers in and out, chunks of max_batch double-buffered) against preprocess / forward /
+    # postprocess / georef called one by one on device tensors; 10 tiles through a max_batch-4 engine = 2.5 chunks
+    from aerial_image_recognition_b200.engine import GEO_PARAMS, geodets_to_numpy
+    tiles = synth.make_tiles(10, 640, 61)
+    params = np.zeros((10, GEO_PARAMS))
+    for k in range(10):
+        params[k, :6] = (21.0 + 0.001 * k, 21.0006 + 0.001 * k, 52.0, 52.0004, 864, 640)
+    for kw in (dict(conf_thr=0.3, inclusive=True), dict(conf_thr=0.25, inclusive=False, iou_thr=0.7, max_det=300)):
+        got = eng640.detect_host(torch.from_numpy(tiles).pin_memory(), params, **kw)
+        got2 = eng640.detect_host(tiles, params, **kw)            # pageable memory
+        ref = []
+        for c0 in range(0, 10, 4):
+            d = torch.from_numpy(tiles[c0:c0 + 4]).cuda()
+            dets, counts = eng640.infer(d, "identity", False, kw["conf_thr"], kw["inclusive"], kw.get("iou_thr", 0.0), 0, 300)
+            geo = eng640.georef(dets, counts, torch.from_numpy(params[c0:c0 + 4]).cuda(), "bounds")
+            ref += geodets_to_numpy(geo, counts)
+        assert len(got) == len(ref) == 10 and sum(len(r) for r in ref) > 0
+        for a, b, c in zip(got, got2, ref):
+            assert a.tobytes() == c.tobytes() and b.tobytes() == c.tobytes()
+
+
 # ---- size-independent properties at BASELINE batch size ----------------------------------------------------------------
 def test_full_batch_determinism_and_batch_invariance():
     eng = _engine("yolov8m", max_batch=64)

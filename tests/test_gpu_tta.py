@@ -112,6 +112,17 @@ def test_view_sets_equal_oracle_and_libraries(eng):
             assert np.array_equal(arc[i][k].cpu().numpy(), ref[i]), (k, i)
 
 
+def test_views_of_the_reference_tile_match_golden_crcs(eng):
+    # tests/golden/tta_views.json was made with the reference's library calls on test_tile.jpg (864 x 864, no resize)
+    import json
+    import zlib
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "tta_views.json")))
+    d = _dev(_tile()[None])
+    crc = lambda t: zlib.crc32(t[0].cpu().numpy().tobytes())
+    assert [crc(v) for v in eng.tta_views(d, T.LIGHTING_VIEWS + T.OCCLUSION_VIEWS)] == gold["current_views_crc32"]
+    assert [crc(v) for v in eng.tta_views(d, T.ARCHIVE_VIEWS)] == gold["archive_views_crc32"]
+
+
 def test_conf_scale_strict_filter_and_float32_georef(eng):
     rng = np.random.default_rng(11)
     A = 500
