@@ -349,7 +349,7 @@ def main():
         pre_bytes = SIZE * SIZE * (3 + 8)          # uint8 RGB in, 16-bit NHWC4 out
         line["roofline_aux"] = {
             "peak": peak_hbm, "unit": "GB/s", "peak_source": f"{which} hbm_gbs (copy bandwidth)",
-            "preprocess": {"kernel": "prep_identity_vec_kernel (u8 -> 16-bit NHWC4, /255)", "ms_per_step": pre_ms,
+            "preprocess": {"kernel": "prep_identity_run_kernel (u8 -> 16-bit NHWC4, /255; coalesced 16-byte loads and stores through a per-warp shared slab)", "ms_per_step": pre_ms,
                            "algorithmic_bytes_per_tile": pre_bytes, "achieved": BATCH * pre_bytes / (pre_ms * 1e-3) / 1e9,
                            "frac": BATCH * pre_bytes / (pre_ms * 1e-3) / 1e9 / peak_hbm},
             "postprocess": {"kernel": "head_kernel<1> (DFL decode + threshold + compaction) + sort_keys_kernel + select_kernel (NMS)",
