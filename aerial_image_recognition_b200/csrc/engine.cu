@@ -86,6 +86,7 @@ struct b2d_engine {
     struct HostSlot {
         uint8_t* tiles = nullptr; size_t tiles_bytes = 0;
         double* params = nullptr; b2d_det* dets = nullptr; b2d_geodet* geo = nullptr; int32_t* counts = nullptr; int cap = 0;
+        double* params_pin = nullptr; b2d_geodet* geo_pin = nullptr; int32_t* counts_pin = nullptr;   // pinned host staging
         cudaEvent_t loaded = nullptr, drained = nullptr;
     } host_slot[2];
     cudaStream_t copy_stream = nullptr;
@@ -327,7 +328,10 @@ void b2d_destroy(b2d_engine* e) {
     if (e->tta_sums) cudaFree(e->tta_sums);
     for (auto& hs : e->host_slot) {
         if (hs.tiles) cudaFree(hs.tiles);
-        if (hs.params) { cudaFree(hs.params); cudaFree(hs.dets); cudaFree(hs.geo); cudaFree(hs.counts); }
+        if (hs.params) {
+            cudaFree(hs.params); cudaFree(hs.dets); cudaFree(hs.geo); cudaFree(hs.counts);
+            cudaFreeHost(hs.params_pin); cudaFreeHost(hs.geo_pin); cudaFreeHost(hs.counts_pin);
+        }
         if (hs.loaded) { cudaEventDestroy(hs.loaded); cudaEventDestroy(hs.drained); }
     }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -776,13 +780,19 @@ static int ensure_host_slot(b2d_engine* e, int slot, size_t tiles_bytes, int cap
         hs.tiles_bytes = tiles_bytes;
     }
     if (cap > hs.cap) {
-        if (hs.params) { cudaFree(hs.params); cudaFree(hs.dets); cudaFree(hs.geo); cudaFree(hs.counts); }
+        if (hs.params) {
+            cudaFree(hs.params); cudaFree(hs.dets); cudaFree(hs.geo); cudaFree(hs.counts);
+            cudaFreeHost(hs.params_pin); cudaFreeHost(hs.geo_pin); cudaFreeHost(hs.counts_pin);
+        }
         hs.params = nullptr; hs.cap = 0;
         const size_t nb = (size_t)e->max_batch;
         B2D_CUDA(cudaMalloc(&hs.params, nb * B2D_GEO_PARAMS * sizeof(double)));
         B2D_CUDA(cudaMalloc(&hs.dets, nb * cap * sizeof(b2d_det)));
         B2D_CUDA(cudaMalloc(&hs.geo, nb * cap * sizeof(b2d_geodet)));
         B2D_CUDA(cudaMalloc(&hs.counts, nb * sizeof(int32_t)));
+        B2D_CUDA(cudaMallocHost(&hs.params_pin, nb * B2D_GEO_PARAMS * sizeof(double)));
+        B2D_CUDA(cudaMallocHost(&hs.geo_pin, nb * cap * sizeof(b2d_geodet)));
+        B2D_CUDA(cudaMallocHost(&hs.counts_pin, nb * sizeof(int32_t)));
         hs.cap = cap;
     }
     return 0;
@@ -799,25 +809,39 @@ int b2d_detect_host(b2d_engine* e, const uint8_t* tiles_host, int n, int h, int 
     const int mb = e->max_batch;
     for (int slot = 0; slot < 2; ++slot)
         if (ensure_host_slot(e, slot, (size_t)(n < mb ? n : mb) * img_bytes, cap)) return -2;
-    int rc = 0, k = 0;
+    // The user's result arrays may be pageable (a device->host copy into pageable memory blocks the calling thread until the
+    // stream has drained, which would serialise the chunks), so results land in the slot's pinned buffers and are moved to the
+    // user's arrays one chunk behind, while the next chunk computes.
+    int rc = 0, k = 0, prev_i0 = -1, prev_nb = 0;
+    auto flush = [&](int slot, int i0, int nb) -> int {
+        auto& hs = e->host_slot[slot];
+        B2D_CUDA(cudaEventSynchronize(hs.drained));
+        memcpy(out_host + (size_t)i0 * cap, hs.geo_pin, (size_t)nb * cap * sizeof(b2d_geodet));
+        memcpy(counts_host + i0, hs.counts_pin, (size_t)nb * sizeof(int32_t));
+        return 0;
+    };
     for (int i0 = 0; i0 < n && rc == 0; i0 += mb, ++k) {
         const int nb = n - i0 < mb ? n - i0 : mb;
         auto& hs = e->host_slot[k & 1];
         // copy stream: wait until the chunk that used this slot two iterations ago has been consumed, then load
         if (k >= 2) B2D_CUDA(cudaStreamWaitEvent(e->copy_stream, hs.drained, 0));
+        memcpy(hs.params_pin, params_host + (size_t)i0 * B2D_GEO_PARAMS, (size_t)nb * B2D_GEO_PARAMS * sizeof(double));
         B2D_CUDA(cudaMemcpyAsync(hs.tiles, tiles_host + (size_t)i0 * img_bytes, (size_t)nb * img_bytes, cudaMemcpyHostToDevice, e->copy_stream));
-        B2D_CUDA(cudaMemcpyAsync(hs.params, params_host + (size_t)i0 * B2D_GEO_PARAMS, (size_t)nb * B2D_GEO_PARAMS * sizeof(double),
-                                 cudaMemcpyHostToDevice, e->copy_stream));
+        B2D_CUDA(cudaMemcpyAsync(hs.params, hs.params_pin, (size_t)nb * B2D_GEO_PARAMS * sizeof(double), cudaMemcpyHostToDevice,
+                                 e->copy_stream));
         B2D_CUDA(cudaEventRecord(hs.loaded, e->copy_stream));
         B2D_CUDA(cudaStreamWaitEvent(s, hs.loaded, 0));
         rc = b2d_infer_tiles(e, hs.tiles, nb, h, w, w * 3, (long long)img_bytes, mode, bgr, conf_thr, inclusive, iou_thr, top_k, max_det,
                              hs.dets, hs.counts, cap, s);
         if (rc == 0) rc = b2d_georef(e, hs.dets, hs.counts, nb, cap, geo_mode, hs.params, hs.geo, s);
         if (rc) break;
-        B2D_CUDA(cudaMemcpyAsync(out_host + (size_t)i0 * cap, hs.geo, (size_t)nb * cap * sizeof(b2d_geodet), cudaMemcpyDeviceToHost, s));
-        B2D_CUDA(cudaMemcpyAsync(counts_host + i0, hs.counts, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        B2D_CUDA(cudaMemcpyAsync(hs.geo_pin, hs.geo, (size_t)nb * cap * sizeof(b2d_geodet), cudaMemcpyDeviceToHost, s));
+        B2D_CUDA(cudaMemcpyAsync(hs.counts_pin, hs.counts, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         B2D_CUDA(cudaEventRecord(hs.drained, s));
+        if (prev_i0 >= 0 && flush((k & 1) ^ 1, prev_i0, prev_nb)) return -2;
+        prev_i0 = i0; prev_nb = nb;
     }
+    if (rc == 0 && prev_i0 >= 0 && flush((k - 1) & 1, prev_i0, prev_nb)) return -2;
     cudaError_t err = cudaStreamSynchronize(s);
     cudaStreamSynchronize(e->copy_stream);
     if (rc) return rc;
