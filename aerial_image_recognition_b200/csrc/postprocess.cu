@@ -220,7 +220,10 @@ __global__ void __launch_bounds__(256) rows_filter_kernel(const float* __restric
 }
 
 // ---- select: per-tile sort (+ NMS) ----------------------------------------------------------------
-constexpr int kSelThreads = 256;
+constexpr int kSelCand = 256;                     // candidates per NMS chunk
+constexpr int kSelParts = 4;                      // thread groups sharing a chunk's work (= 64-bit words of a suppression mask)
+constexpr int kSelThreads = kSelCand * kSelParts;
+static_assert(kSelParts == kSelCand / 64, "one part per mask word");
 constexpr int kSmemKeys = 2048;
 constexpr int kMaxDet = 512;
 
@@ -241,10 +244,12 @@ __device__ void bitonic_sort(unsigned long long* keys, int n2) {
 }
 
 __device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& b, float ab, float thr) {
-    // torchvision nms arithmetic: inter / (area_a + area_b - inter) > thr, fp32, no contraction
-    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
-    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    // torchvision nms arithmetic: inter / (area_a + area_b - inter) > thr, fp32, no contraction.  Disjoint boxes (the common
+    // case) leave before the division: there torchvision computes 0 / union = 0 (or 0 / 0 = NaN), never > thr for thr > 0.
+    const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    if (!(w > 0.f)) return false;
+    const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    if (!(h > 0.f)) return false;
     const float inter = __fmul_rn(w, h);
     const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
     return ovr > thr;
@@ -289,11 +294,12 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __re
                                                               int cap) {
     __shared__ float4 kbox[kMaxDet];
     __shared__ float karea[kMaxDet];
-    __shared__ float4 cbox[kSelThreads];
-    __shared__ float carea[kSelThreads];
-    __shared__ unsigned long long cmask[kSelThreads][kSelThreads / 64];
-    __shared__ unsigned int alive_w[kSelThreads / 32];
-    __shared__ int keep_slot[kSelThreads];
+    __shared__ float4 cbox[kSelCand];
+    __shared__ float carea[kSelCand];
+    __shared__ unsigned long long cmask[kSelCand][kSelCand / 64];
+    __shared__ unsigned int alive_w[kSelCand / 32];
+    __shared__ int keep_slot[kSelCand];
+    __shared__ int dead[kSelCand];
     __shared__ int s_nk;
 
     const int tile = blockIdx.x;
@@ -318,15 +324,17 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __re
     }
 
     // ---- greedy NMS over the sorted list, 256 candidates at a time ----
+    // One tile has one CTA, so the work of a chunk is spread over four thread groups ("parts") of 256: part p tests candidate c
+    // against the kept boxes k = p, p + 4, ... and builds word p of c's suppression mask.
     if (max_det > kMaxDet) max_det = kMaxDet;
     if (max_det > cap) max_det = cap;
+    const int c = tid & (kSelCand - 1), part = tid / kSelCand;
     if (tid == 0) s_nk = 0;
     __syncthreads();
-    for (int base = 0; base < cnt; base += kSelThreads) {
+    for (int base = 0; base < cnt; base += kSelCand) {
         const int nk = s_nk;
         if (nk >= max_det) break;
-        const int i = base + tid;
-        const int chunk_n = min(kSelThreads, cnt - base);
+        const int i = base + c;
         const bool valid = i < cnt;
         b2d_det d;
         float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -342,23 +350,32 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __re
             bx.w = __fadd_rn(__fadd_rn(d.cy, hh), off);
             ar = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
         }
-        cbox[tid] = bx;
-        carea[tid] = ar;
-        bool alive = valid;
-        for (int k = 0; k < nk && alive; ++k)
-            if (iou_gt(kbox[k], karea[k], bx, ar, iou_thr)) alive = false;
-        const unsigned al = __ballot_sync(0xffffffffu, alive);
-        if ((tid & 31) == 0) alive_w[tid >> 5] = al;
-        keep_slot[tid] = -1;
+        if (part == 0) {
+            cbox[c] = bx;
+            carea[c] = ar;
+            dead[c] = valid ? 0 : 1;
+            keep_slot[c] = -1;
+        }
         __syncthreads();
-        // which later, still alive candidates of this chunk does `tid` suppress?  (dead rows and dead columns are skipped:
+        if (valid) {
+            for (int k = part; k < nk; k += kSelParts)
+                if (iou_gt(kbox[k], karea[k], bx, ar, iou_thr)) { dead[c] = 1; break; }
+        }
+        __syncthreads();
+        const bool alive = dead[c] == 0;
+        if (part == 0) {
+            const unsigned al = __ballot_sync(0xffffffffu, alive);
+            if ((c & 31) == 0) alive_w[c >> 5] = al;
+        }
+        __syncthreads();
+        // which later, still alive candidates of this chunk does `c` suppress?  (dead rows and dead columns are skipped:
         // after the test against the kept boxes most of a chunk is already gone)
-#pragma unroll
-        for (int w = 0; w < kSelThreads / 64; ++w) {
+        {
+            const int w = part;
             unsigned long long m = 0;
             if (alive) {
                 unsigned long long am = ((unsigned long long)alive_w[2 * w + 1] << 32) | (unsigned long long)alive_w[2 * w];
-                if (w * 64 <= tid) am &= (tid - w * 64 >= 63) ? 0ull : (~0ull << (tid - w * 64 + 1));      // only j > tid
+                if (w * 64 <= c) am &= (c - w * 64 >= 63) ? 0ull : (~0ull << (c - w * 64 + 1));      // only j > c
                 while (am) {
                     const int jj = __ffsll((long long)am) - 1;
                     am &= am - 1;
@@ -366,14 +383,14 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __re
                     if (iou_gt(bx, ar, cbox[j], carea[j], iou_thr)) m |= (1ull << jj);
                 }
             }
-            cmask[tid][w] = m;
+            cmask[c][w] = m;
         }
         __syncthreads();
         if (tid == 0) {
-            unsigned long long removed[kSelThreads / 64] = {0, 0, 0, 0};
+            unsigned long long removed[kSelCand / 64] = {0, 0, 0, 0};
             int k = nk;
 #pragma unroll
-            for (int w = 0; w < kSelThreads / 64; ++w) {
+            for (int w = 0; w < kSelCand / 64; ++w) {
                 unsigned long long am = ((unsigned long long)alive_w[2 * w + 1] << 32) | (unsigned long long)alive_w[2 * w];
                 while (k < max_det) {
                     am &= ~removed[w];
@@ -383,17 +400,19 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __re
                     const int j = w * 64 + jj;
                     keep_slot[j] = k++;
 #pragma unroll
-                    for (int v = 0; v < kSelThreads / 64; ++v) removed[v] |= cmask[j][v];
+                    for (int v = 0; v < kSelCand / 64; ++v) removed[v] |= cmask[j][v];
                 }
             }
             s_nk = k;
         }
         __syncthreads();
-        const int slot = keep_slot[tid];
-        if (slot >= 0) {
-            kbox[slot] = bx;
-            karea[slot] = ar;
-            to[slot] = d;
+        if (part == 0) {
+            const int slot = keep_slot[c];
+            if (slot >= 0) {
+                kbox[slot] = bx;
+                karea[slot] = ar;
+                to[slot] = d;
+            }
         }
         __syncthreads();
     }
