@@ -37,8 +37,8 @@ CONF, IOU, MAX_DET = 0.25, 0.7, 300
 WORKLOAD = "C2: YOLOv8m-tokyo (nc=2, seeded synthetic weights), synthetic 640x640 uint8 tiles, batch 64 per step"
 CONV_GFLOP_PER_TILE = 67.43      # 2 x 33.713 GMAC
 # DRAM bytes moved by the conv_tc_* kernel family in ONE step (its 89 launches summed), from the ncu pass in
-# profiles/r1_final2_kernel_shares.txt (dram__bytes_read.sum + dram__bytes_write.sum): 10.460 GB + 4.070 GB
-CONV_DRAM_BYTES_PER_STEP = 14.530e9
+# profiles/r1_final3_kernel_shares.txt (dram__bytes_read.sum + dram__bytes_write.sum): 10.460 GB + 4.076 GB
+CONV_DRAM_BYTES_PER_STEP = 14.536e9
 
 
 def _peaks():
@@ -340,7 +340,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "conv_tc_* family (tcgen05 implicit-GEMM conv+bias+SiLU: generic, halo, halo-pair, stem, depthwise)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": CONV_DRAM_BYTES_PER_STEP, "traffic_note": "DRAM bytes per step summed over the family's launches (ncu, profiles/r1_final2_kernel_shares.txt); achieved/peak are per step too",
+                         "traffic": CONV_DRAM_BYTES_PER_STEP, "traffic_note": "DRAM bytes per step summed over the family's launches (ncu, profiles/r1_final3_kernel_shares.txt); achieved/peak are per step too",
                          "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_per_step": n_tc, "ms_per_step_in_kernel": tc_ms, "forward_ms": fwd_ms, "non_conv_ms": other_ms,
                          "timing": "CUDA events around forward() (all graph launches back to back) minus the non-conv ops timed singly",
