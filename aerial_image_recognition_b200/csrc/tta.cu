@@ -204,17 +204,39 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
     const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
     const uint8_t* base = src + (size_t)img * h * w * 3;
     const int area = tw * th;
-    const int dq = 256 / tw, dr = 256 - dq * tw;       // idx += 256 as (row, column) increments: no division per pixel
-    int yy = tid / tw, xx = tid - yy * tw;
-    for (int idx = tid; idx < area; idx += 256, yy += dq, xx += dr) {
-        if (xx >= tw) { xx -= tw; ++yy; }
-        int Y = tyi * th + yy, X = txi * tw + xx;
-        if (Y >= h) Y = 2 * (h - 1) - Y;            // BORDER_REFLECT_101 of the ragged bottom / right edge
-        if (X >= w) X = 2 * (w - 1) - X;
-        const uint8_t* p = base + ((size_t)Y * w + X) * 3;
-        const int R = s_gamma[__ldg(p)], G = s_gamma[__ldg(p + 1)], B = s_gamma[__ldg(p + 2)];
-        const int L = lab_l_from_fy(s_cbrt[(R * C.f[3] + G * C.f[4] + B * C.f[5] + (1 << 11)) >> 12]);
-        atomicAdd(&hist[warp][L], 1u);
+    if (((w | tw) & 3) == 0 && (txi + 1) * tw <= w) {
+        // quad path: tile rows start on a 4-pixel boundary and lie inside the image in x, so four pixels are three aligned
+        // 32-bit words (the rows below the image are reflected as whole rows)
+        const int tq = tw >> 2, quads = tq * th;
+        const int dq = 256 / tq, dr = 256 - dq * tq;
+        int yy = tid / tq, xq = tid - yy * tq;
+        for (int q = tid; q < quads; q += 256, yy += dq, xq += dr) {
+            if (xq >= tq) { xq -= tq; ++yy; }
+            int Y = tyi * th + yy;
+            if (Y >= h) Y = 2 * (h - 1) - Y;
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(base + ((size_t)Y * w + txi * tw + 4 * xq) * 3);
+            Quad in;
+            in.w[0] = __ldg(p); in.w[1] = __ldg(p + 1); in.w[2] = __ldg(p + 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int R = s_gamma[quad_byte(in, 3 * k)], G = s_gamma[quad_byte(in, 3 * k + 1)], B = s_gamma[quad_byte(in, 3 * k + 2)];
+                const int L = lab_l_from_fy(s_cbrt[(R * C.f[3] + G * C.f[4] + B * C.f[5] + (1 << 11)) >> 12]);
+                atomicAdd(&hist[warp][L], 1u);
+            }
+        }
+    } else {
+        const int dq = 256 / tw, dr = 256 - dq * tw;       // idx += 256 as (row, column) increments: no division per pixel
+        int yy = tid / tw, xx = tid - yy * tw;
+        for (int idx = tid; idx < area; idx += 256, yy += dq, xx += dr) {
+            if (xx >= tw) { xx -= tw; ++yy; }
+            int Y = tyi * th + yy, X = txi * tw + xx;
+            if (Y >= h) Y = 2 * (h - 1) - Y;            // BORDER_REFLECT_101 of the ragged bottom / right edge
+            if (X >= w) X = 2 * (w - 1) - X;
+            const uint8_t* p = base + ((size_t)Y * w + X) * 3;
+            const int R = s_gamma[__ldg(p)], G = s_gamma[__ldg(p + 1)], B = s_gamma[__ldg(p + 2)];
+            const int L = lab_l_from_fy(s_cbrt[(R * C.f[3] + G * C.f[4] + B * C.f[5] + (1 << 11)) >> 12]);
+            atomicAdd(&hist[warp][L], 1u);
+        }
     }
     __syncthreads();
     int hv = 0;
