@@ -151,3 +151,21 @@ def test_blend_table_equals_pillow_for_every_constant_and_value():
         deg = Image.new("L", (256, 1), c)
         for f in (2.0, 1.8, 1.3, 0.3, -0.5):
             assert np.array_equal(np.array(Image.blend(deg, img, f))[0], OT.blend_lut(c, f)), (c, f)
+
+
+def test_product_host_tables_equal_pillow_and_numpy():
+    # aerial_image_recognition_b200/tta.py builds the byte curves the device applies (b2d_tta_lut); same checks as the oracle's
+    from aerial_image_recognition_b200 import tta as T
+    ramp = np.arange(256, dtype=np.uint8)[None, :, None].repeat(2, 0).repeat(3, 2)
+    im = Image.fromarray(ramp)
+    for f in (2.0, 1.8, 1.4, 1.6, 1.3, 1.0, 0.5, 0.0, 3.3):
+        assert np.array_equal(np.array(ImageEnhance.Brightness(im).enhance(f))[0, :, 0], T.brightness_lut(f)), f
+        assert np.array_equal(T.brightness_lut(f), OT.blend_lut(0, f))
+    img = _tile()
+    for gamma in (2.0, 1.5):
+        assert np.array_equal((np.power(img / 255.0, 1.0 / gamma) * 255.0).astype(np.uint8), T.gamma_lut(gamma)[img])
+    # view order and weights of gpu_handler.py:94-140, :274-283 and of the archived handler
+    assert [k for k, _ in T.LIGHTING_VIEWS + T.OCCLUSION_VIEWS] == ["original", "clahe", "brightness", "gamma", "clahe"]
+    assert [T.confidence_adjustment(i) for i in range(6)] == [1.0, 0.95, 0.90, 0.92, 0.88, 0.85]
+    assert [T.confidence_adjustment(i, 12, archive=True) for i in (0, 4, 5, 7, 8, 11, 12)] == [1.0, 1.0, 0.98, 0.98, 0.95, 0.95, 0.85]
+    assert len(T.ARCHIVE_VIEWS) == 8
