@@ -110,6 +110,29 @@ class GPUHandler:
             i = j
         return out
 
+    def process_tiles(self, tiles: torch.Tensor, bboxes) -> List[dict]:
+        """``process_batch`` for tiles that are already one uint8 tensor [B, H, W, 3] (device-resident or CPU) with
+        ``bboxes`` float64 [B, 4] = (lon_min, lat_min, lon_max, lat_max): same filter, top-k and georeferencing, same
+        records, without the per-image host staging (SURVEY.md section 8b input contract)."""
+        eng = self.engine
+        assert tiles.dtype == torch.uint8 and tiles.dim() == 4 and tiles.shape[3] == 3
+        bb = np.asarray(bboxes, dtype=np.float64).reshape(tiles.shape[0], 4)
+        tiles = tiles.to(eng.device, non_blocking=True)
+        S = eng.imgsz
+        mode = "identity" if tuple(tiles.shape[1:3]) == (S, S) else "cv2_linear"
+        out: List[dict] = []
+        for i in range(0, tiles.shape[0], eng.max_batch):
+            chunk = tiles[i:i + eng.max_batch]
+            n = chunk.shape[0]
+            dets, counts = eng.infer(chunk, mode, self.bgr, self.confidence_threshold, True, 0.0, self.top_k)
+            params = np.zeros((n, GEO_PARAMS), dtype=np.float64)
+            params[:, :4] = bb[i:i + n]
+            geo = eng.georef(dets, counts, torch.from_numpy(params).to(eng.device), "gpuhandler")
+            for g in geodets_to_numpy(geo, counts):
+                for r in g:
+                    out.append({"lon": float(r["x"]), "lat": float(r["y"]), "confidence": float(r["conf"])})
+        return out
+
     # -- test-time augmentation: gpu_handler.py:94-149, :220-285 ------------------------------
     def _views_u8(self, img, views):
         t = torch.from_numpy(_as_u8_hwc(img))[None].to(self.engine.device)

@@ -63,6 +63,8 @@ class SimpleDetector:
         (``:649-652``); the result is the concatenation in input order, which a device batch
         reproduces."""
         eng = self.engine
+        if isinstance(images, torch.Tensor):
+            return self._detect_device_tiles(images, preview_infos)
         arrs = [_as_u8_hwc(im) for im in images]
         out: List[dict] = []
         i = 0
@@ -85,6 +87,28 @@ class SimpleDetector:
             for g in geodets_to_numpy(geo, counts):
                 out.extend(self._records(g))
             i = j
+        return out
+
+    def _detect_device_tiles(self, tiles: torch.Tensor, preview_infos) -> List[dict]:
+        """``images`` given as one uint8 tensor [B, H, W, 3] (device-resident tiles skip the host staging; a CPU tensor is
+        copied once): same records as the list form (SURVEY.md section 8b input contract)."""
+        eng = self.engine
+        assert tiles.dtype == torch.uint8 and tiles.dim() == 4 and tiles.shape[3] == 3 and len(preview_infos) == tiles.shape[0]
+        tiles = tiles.to(eng.device, non_blocking=True)
+        mode = "identity" if tuple(tiles.shape[1:3]) == (self.model_size, self.model_size) else "pil_bicubic"
+        out: List[dict] = []
+        for i in range(0, tiles.shape[0], eng.max_batch):
+            chunk = tiles[i:i + eng.max_batch]
+            n = chunk.shape[0]
+            dets, counts = eng.infer(chunk, mode, False, self.confidence_threshold, True)
+            params = np.zeros((n, GEO_PARAMS), dtype=np.float64)
+            for k in range(n):
+                b = preview_infos[i + k]["spatial_info"]["bounds"]
+                params[k, :6] = (b["west"], b["east"], b["south"], b["north"],
+                                 preview_infos[i + k]["image_info"]["crop_size"], self.model_size)
+            geo = eng.georef(dets, counts, torch.from_numpy(params).to(eng.device), "bounds")
+            for g in geodets_to_numpy(geo, counts):
+                out.extend(self._records(g))
         return out
 
     @staticmethod

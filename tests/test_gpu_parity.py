@@ -425,6 +425,11 @@ def test_simple_detector_matches_reference_restatement():
     assert det._process_detections(rows, info) == out
     two = det.detect_batch([img, img], [info, _preview(-118.24, 34.05)])
     assert two[:len(out)] == out and len(two) == 2 * len(out)
+    # the tensor input forms of SURVEY 8b: one uint8 tensor [B,H,W,3], on the device or on the host (3 tiles > max_batch 2)
+    t3 = torch.from_numpy(np.stack([np.array(img)] * 3))
+    infos = [info, _preview(-118.24, 34.05), info]
+    ref3 = det.detect_batch([img, img, img], infos)
+    assert det.detect_batch(t3.cuda(), infos) == ref3 and det.detect_batch(t3, infos) == ref3
     # network tolerance against the independent CPU oracle on the same preprocessed tensor
     ref_rows = OP.v8_rows_adapter(make_oracle("yolov8m", w, True).forward(torch.from_numpy(arr))[0].numpy())
     assert np.median(np.abs(rows[:, 4] - ref_rows[:, 4])) < 1e-3
@@ -464,6 +469,9 @@ def test_gpu_handler_process_batch_matches_reference_restatement():
             ref.append({"lon": lon, "lat": lat, "confidence": float(r[4])})
     assert len(out) == len(ref) > 0
     assert out == ref
+    # tensor input form: uint8 [B,H,W,3] + float64 [B,4]
+    same = [np.array(im) for im in imgs[:3]]
+    assert h.process_tiles(torch.from_numpy(np.stack(same)).cuda(), bboxes[:3]) == h.process_batch([[(im, bb, None)] for im, bb in zip(imgs[:3], bboxes[:3])])
     h.cleanup()
     h.engine.close()
 
