@@ -32,7 +32,8 @@ def _as_u8_hwc(img) -> np.ndarray:
         a = np.repeat(a[..., None], 3, 2)
     if a.shape[2] == 4:
         a = a[..., :3]
-    return np.ascontiguousarray(a, dtype=np.uint8)
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a if a.flags.writeable else a.copy()      # np.asarray(PIL image) is read-only; torch.from_numpy wants a writable array
 
 
 class SimpleDetector:
