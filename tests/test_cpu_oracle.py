@@ -109,6 +109,24 @@ def test_create_fails_loudly_without_gpu(lib):
         Engine("yolov8m", max_batch=1)
 
 
+def test_entry_points_reject_bad_arguments_with_a_message(lib):
+    # status < 0 and a text in b2d_last_error(), never a crash: no engine handle is needed to see the argument checks
+    null = C.c_void_p(0)
+    calls = [
+        ("b2d_tta_clahe", (null, null, 1, 640, 640, 3.0, 8, 8, null, null), b"tta_clahe"),
+        ("b2d_tta_lut", (null, null, 1, 100, null, 0, null, null), b"tta_lut"),
+        ("b2d_tta_contrast", (null, null, 1, 640, 640, 1.3, null, null), b"tta_contrast"),
+        ("b2d_colour_convert", (null, null, 16, 0, null, null), b"colour_convert"),
+        ("b2d_set_conf_scale", (null, 0.95), b"set_conf_scale"),
+        ("b2d_detect_host", (null, null, 1, 640, 640, 0, 0, 0.3, 1, 0.0, 0, 300, 0, null, null, null, 300, null), b"detect_host"),
+        ("b2d_preprocess", (null, null, 1, 640, 640, 1920, 1228800, 0, 0, 0, null, null), b"preprocess"),
+        ("b2d_georef", (null, null, null, 1, 1, 0, null, null, null), b"georef"),
+    ]
+    for name, args, word in calls:
+        assert getattr(lib, name)(*args) < 0, name
+        assert word in lib.b2d_last_error(), (name, lib.b2d_last_error())
+
+
 @pytest.mark.parametrize("mode,fn", [(2, "pil"), (1, "cv2")])
 @pytest.mark.parametrize("sizes", [(864, 640), (1280, 640), (1300, 640), (300, 640), (640, 640)])
 def test_c_resize_tables_equal_python_tables(lib, mode, fn, sizes):
