@@ -255,10 +255,75 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& 
     return ovr > thr;
 }
 
-// Sort kernel: one CTA of 1024 threads per tile builds the 64-bit keys (conf desc, anchor asc | row order) in shared
-// memory (up to 16384 keys; beyond that in the global scratch), sorts them and leaves the sorted list in the scratch.
+// Sort kernel: one CTA of 1024 threads per tile builds the 64-bit keys (conf desc, anchor asc | row order), sorts them and
+// leaves the sorted list in the scratch.  2048 .. 16384 keys (the usual case: 8400 anchors) are sorted with the keys in
+// registers -- element i = m * 1024 + tid lives in r[m]; exchange distances >= 1024 stay inside a thread, distances < 32 are
+// warp shuffles, only 32 <= j < 1024 goes through shared memory (35 block-wide steps instead of 105 at 16384 keys).  Smaller
+// lists are sorted in shared memory, larger ones in the global scratch.
 constexpr int kSortThreads = 1024;
 constexpr int kSortSmemKeys = 16384;
+
+__device__ __forceinline__ unsigned long long sort_key(const b2d_det* tc, int i, int cnt, int by_conf) {
+    if (i >= cnt) return ~0ull;
+    const unsigned a = (unsigned)tc[i].anchor & 0x1FFFFu;
+    const unsigned long long lo = ((unsigned long long)a << 15) | (unsigned long long)(i & 0x7FFF);
+    return by_conf ? (((unsigned long long)(~__float_as_uint(tc[i].conf)) << 32) | lo)     // conf desc, anchor asc
+                   : lo;                                                                    // row order
+}
+
+template <int KPT>
+__device__ void bitonic_sort_regs(const b2d_det* tc, int cnt, int by_conf, unsigned long long* smem, unsigned long long* out) {
+    constexpr int N2 = KPT * kSortThreads;
+    const int tid = threadIdx.x;
+    unsigned long long r[KPT];
+#pragma unroll
+    for (int m = 0; m < KPT; ++m) r[m] = sort_key(tc, m * kSortThreads + tid, cnt, by_conf);
+    for (int k = 2; k <= N2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= kSortThreads) {
+#pragma unroll
+                for (int d = KPT / 2; d >= 1; d >>= 1) {
+                    if (j == d * kSortThreads) {
+#pragma unroll
+                        for (int m = 0; m < KPT; ++m) {
+                            if ((m & d) == 0) {
+                                const bool up = (((m * kSortThreads + tid) & k) == 0);
+                                const unsigned long long a = r[m], b = r[m | d];
+                                if ((a > b) == up) { r[m] = b; r[m | d] = a; }
+                            }
+                        }
+                    }
+                }
+            } else if (j >= 32) {
+#pragma unroll
+                for (int m = 0; m < KPT; ++m) smem[m * kSortThreads + tid] = r[m];
+                __syncthreads();
+#pragma unroll
+                for (int m = 0; m < KPT; ++m) {
+                    const int i = m * kSortThreads + tid;
+                    const unsigned long long o = smem[i ^ j];
+                    const bool take_min = (((i & k) == 0) == ((i & j) == 0));     // ascending run: the lower index keeps the minimum
+                    r[m] = take_min ? (r[m] < o ? r[m] : o) : (r[m] > o ? r[m] : o);
+                }
+                __syncthreads();
+            } else {
+#pragma unroll
+                for (int m = 0; m < KPT; ++m) {
+                    const int i = m * kSortThreads + tid;
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, r[m], j);
+                    const bool take_min = (((i & k) == 0) == ((i & j) == 0));
+                    r[m] = take_min ? (r[m] < o ? r[m] : o) : (r[m] > o ? r[m] : o);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < KPT; ++m) {
+        const int i = m * kSortThreads + tid;
+        if (i < cnt) out[i] = r[m];
+    }
+}
+
 __global__ void __launch_bounds__(kSortThreads) sort_keys_kernel(const b2d_det* __restrict__ cand, const int* __restrict__ cand_count,
                                                                   int cand_cap, unsigned long long* keys_scratch, int keys_stride,
                                                                   int by_conf) {
@@ -271,17 +336,15 @@ __global__ void __launch_bounds__(kSortThreads) sort_keys_kernel(const b2d_det* 
     int n2 = 1;
     while (n2 < cnt) n2 <<= 1;
     unsigned long long* out = keys_scratch + (size_t)tile * keys_stride;
-    unsigned long long* keys = (n2 <= kSortSmemKeys) ? dkeys : out;
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-        unsigned long long k = ~0ull;
-        if (i < cnt) {
-            const unsigned a = (unsigned)tc[i].anchor & 0x1FFFFu;
-            const unsigned long long lo = ((unsigned long long)a << 15) | (unsigned long long)(i & 0x7FFF);
-            if (by_conf) k = ((unsigned long long)(~__float_as_uint(tc[i].conf)) << 32) | lo;   // conf desc, anchor asc
-            else k = lo;                                                                     // row order
-        }
-        keys[i] = k;
+    switch (n2) {
+        case 2048: bitonic_sort_regs<2>(tc, cnt, by_conf, dkeys, out); return;
+        case 4096: bitonic_sort_regs<4>(tc, cnt, by_conf, dkeys, out); return;
+        case 8192: bitonic_sort_regs<8>(tc, cnt, by_conf, dkeys, out); return;
+        case 16384: bitonic_sort_regs<16>(tc, cnt, by_conf, dkeys, out); return;
+        default: break;
     }
+    unsigned long long* keys = (n2 <= kSortSmemKeys) ? dkeys : out;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) keys[i] = sort_key(tc, i, cnt, by_conf);
     __syncthreads();
     bitonic_sort(keys, n2);
     if (keys != out)
