@@ -251,12 +251,14 @@ class Engine:
         assert images.dtype == torch.uint8 and images.is_cuda and images.dim() == 4 and images.shape[3] == 3
         return images.contiguous()
 
-    def tta_clahe(self, images: torch.Tensor, clip_limit: float, grid: int) -> torch.Tensor:
-        """RGB2LAB -> CLAHE(clip_limit, (grid, grid)) on L -> LAB2RGB, uint8 [n,h,w,3] -> same (bit-exact with cv2)."""
+    def tta_clahe(self, images: torch.Tensor, clip_limit: float, grid) -> torch.Tensor:
+        """RGB2LAB -> CLAHE(clip_limit, tileGridSize) on L -> LAB2RGB, uint8 [n,h,w,3] -> same (bit-exact with cv2).
+        ``grid``: an int (square grid) or cv2's ``(tiles_x, tiles_y)``."""
         images = self._u8(images)
         n, h, w, _ = images.shape
+        tx, ty = (grid, grid) if isinstance(grid, int) else (int(grid[0]), int(grid[1]))
         out = torch.empty_like(images)
-        _lib.check(self.lib.b2d_tta_clahe(self.h, _ptr(images), n, h, w, float(clip_limit), grid, grid, _ptr(out), self.stream),
+        _lib.check(self.lib.b2d_tta_clahe(self.h, _ptr(images), n, h, w, float(clip_limit), tx, ty, _ptr(out), self.stream),
                    "tta_clahe")
         return out
 

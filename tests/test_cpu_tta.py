@@ -169,3 +169,22 @@ def test_product_host_tables_equal_pillow_and_numpy():
     assert [T.confidence_adjustment(i) for i in range(6)] == [1.0, 0.95, 0.90, 0.92, 0.88, 0.85]
     assert [T.confidence_adjustment(i, 12, archive=True) for i in (0, 4, 5, 7, 8, 11, 12)] == [1.0, 1.0, 0.98, 0.98, 0.95, 0.95, 0.85]
     assert len(T.ARCHIVE_VIEWS) == 8
+
+
+def test_clahe_equals_cv2_on_random_shapes_grids_and_limits():
+    rng = np.random.default_rng(123)
+    for it in range(80):
+        h, w = int(rng.integers(17, 300)), int(rng.integers(17, 300))
+        tx, ty = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16])), int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16]))
+        clip = float(rng.choice([0.0, 0.5, 1.0, 2.0, 3.0, 4.0, 7.3, 40.0, 1000.0]))
+        kind = it % 4
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        elif kind == 1:
+            img = (rng.integers(0, 30, (h, w)) + rng.integers(0, 220)).astype(np.uint8)
+        elif kind == 2:
+            img = np.clip(np.add.outer(np.arange(h), np.arange(w)) * 255 // (h + w) + rng.integers(-5, 5, (h, w)), 0, 255).astype(np.uint8)
+        else:
+            img = np.full((h, w), int(rng.integers(0, 256)), np.uint8)
+        ref = cv2.createCLAHE(clipLimit=clip, tileGridSize=(tx, ty)).apply(img)
+        assert np.array_equal(ref, OT.clahe_apply(img, clip, tx, ty)), (h, w, tx, ty, clip, kind)

@@ -77,6 +77,29 @@ def test_clahe_views_equal_cv2(eng, clip, grid):
         assert np.array_equal(got, OT.clahe_rgb(a, clip, grid, grid))
 
 
+def test_clahe_views_equal_cv2_on_random_shapes_grids_and_limits(eng):
+    import cv2
+    rng = np.random.default_rng(321)
+    for it in range(48):
+        h, w = int(rng.integers(17, 300)), int(rng.integers(17, 300))
+        if it % 3 == 0:
+            h, w = 4 * (h // 4 + 1), 8 * (w // 8 + 1)           # shapes that take the aligned 4-pixel histogram path
+        tx, ty = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16])), int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16]))
+        clip = float(rng.choice([0.0, 0.5, 1.0, 2.0, 3.0, 4.0, 7.3, 40.0, 1000.0]))
+        n = 1 + it % 3
+        if it % 4 == 3:
+            a = (rng.integers(0, 30, (n, h, w, 3)) + rng.integers(0, 220)).astype(np.uint8)
+        else:
+            a = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        got = eng.tta_clahe(_dev(a), clip, (tx, ty)).cpu().numpy()
+        for k in range(n):
+            lab = cv2.cvtColor(a[k], cv2.COLOR_RGB2LAB)
+            l, aa, bb = cv2.split(lab)
+            le = cv2.createCLAHE(clipLimit=clip, tileGridSize=(tx, ty)).apply(l)
+            ref = cv2.cvtColor(cv2.merge([le, aa, bb]), cv2.COLOR_LAB2RGB)
+            assert np.array_equal(got[k], ref), (h, w, tx, ty, clip, n, k, int((got[k] != ref).sum()))
+
+
 def test_brightness_gamma_contrast_equal_pillow_and_numpy(eng):
     from PIL import Image, ImageEnhance
     img = _tile()
