@@ -217,3 +217,20 @@ def test_generate_tiles_metric_accumulates_by_addition():
     step = 64.0 * (1 - 0.2)
     assert t[0] == (0.0, 0.0, 64.0, 64.0) and t[1][0] == step and t[2][0] == step + step
     assert len(t) == 3 * 2
+
+
+def test_utm_forward_against_published_meridian_arcs():
+    # On the central meridian the northing is k0 x the meridian arc.  WGS84 arcs from the geodesy literature: quarter meridian
+    # 10 001 965.729 m, equator -> 45 deg 4 984 944.378 m, equator -> 30 deg 3 320 113.398 m.  Pins the Krueger series of the
+    # oracle and of the product's host projection (geo.py) where pyproj itself cannot be run.
+    from aerial_image_recognition_b200 import geo
+    k0 = 0.9996
+    for fwd in (OP.utm_forward, geo.utm_forward):
+        e, n = fwd(3.0, 0.0, 31, True)
+        assert float(e) == 500000.0 and float(n) == 0.0
+        e, n = fwd(3.0, 45.0, 31, True)
+        assert abs(float(e) - 500000.0) < 1e-6 and abs(float(n) - k0 * 4984944.378) < 1e-3
+        e, n = fwd(3.0, 89.999999, 31, True)
+        assert abs(float(n) - k0 * 10001965.729) < 0.2
+        e, n = fwd(9.0, -30.0, 32, False)
+        assert abs(float(n) - (10000000.0 - k0 * 3320113.398)) < 1e-3
