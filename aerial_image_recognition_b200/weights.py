@@ -5,22 +5,39 @@ Every model blob the reference loads is absent (``.MISSING_LARGE_BLOBS:2-5``;
 so throughput and parity are measured with random-init weights of the right
 architecture.  The generator is deterministic in ``(arch, nc, seed)``.
 
-* conv weights are He-style for SiLU (pre-activation variance ~1), then rounded
-  to bf16-representable fp32 so the bf16 engine and the fp32 oracle see *the
-  same* weights (what is compared is the arithmetic, not a quantiser);
-* BatchNorm is already folded: each conv has ``.weight`` and ``.bias``;
-* the last cls / objectness bias is shifted so that a few percent of anchors
-  clear the reference's 0.3 threshold (``simple_detector.py:30``), and the DFL
-  logits are tilted towards small bins so boxes are car-sized rather than
-  tile-sized.
+* conv weights are He-style, rounded to bf16-representable fp32 so the 16-bit
+  engine and the fp32 oracle see *the same* weights (what is compared is the
+  arithmetic, not a quantiser); BatchNorm is already folded (``.weight`` / ``.bias``);
+* every conv is rescaled, layer by layer in graph order, so that its
+  pre-activation has standard deviation ``PREACT_STD`` = 4 on two seeded 640x640
+  tiles.  4, not 1: the map "input std -> output std" of a SiLU layer has
+  elasticity 1.10 at std 1 (a tile with 6 % more contrast ends 60 layers later
+  with 8x the logit spread -- measured) and 0.99 at std 4, so the statistics of
+  the head stay put from tile to tile, as a trained network's do;
+* the detect head is calibrated like a trained one:
+  DFL logits are peaked -- bin k of a box side gets ``2 k d - k^2`` where the
+  distance ``d`` (in cells, mean 1.5, std 1) is one linear feature of the branch,
+  i.e. a discrete Gaussian around ``d`` with std 0.7, plus a small random part --
+  and the last cls / objectness bias is placed so that about 6 % of the v8
+  anchors (~500 of 8400 per tile) clear conf 0.25 (2 % of the 25200 v7 rows
+  clear the reference's 0.3, ``simple_detector.py:30``).
 """
 from __future__ import annotations
 
-from typing import Dict
+from typing import Dict, Tuple
 
 import numpy as np
 
 from .graph import Graph, op_weights
+
+PREACT_STD = 4.0          # LSUV target of every SiLU conv (see the module docstring)
+CAL_SIZE, CAL_TILES = 640, 2
+DFL_SIGMA_D, DFL_D0, DFL_NOISE = 1.0, 1.5, 0.25
+CLS_STD, V8_PASS_FRACTION, V7_PASS_FRACTION = 2.0, 0.06, 0.02
+GENERATOR_VERSION = 2
+
+_CACHE: Dict[Tuple, Dict[str, np.ndarray]] = {}
+
 
 def round_to_bf16(x: np.ndarray) -> np.ndarray:
     """Round-to-nearest-even fp32 -> bf16 -> fp32 (NaN-free inputs)."""
@@ -43,73 +60,102 @@ def _quantised_scale(s: float) -> float:
     return float(2.0 ** (np.round(np.log2(max(s, 1e-12)) * 8.0) / 8.0))
 
 
-def make_synthetic_weights(graph: Graph, seed: int = 0, calibrate: bool = True) -> Dict[str, np.ndarray]:
-    """Deterministic deploy-form weights for ``graph``.
-
-    With ``calibrate`` (default) each conv is rescaled layer by layer, in graph
-    order, so that its pre-activation has unit standard deviation on one seeded
-    synthetic 320x320 tile (LSUV-style).  A fixed analytic gain does not work for
-    SiLU: the per-layer gain depends on the signal scale, so depth-60 stacks
-    either collapse onto the bias noise or overflow.
-    """
-    rng = np.random.default_rng([seed, 0xB200])
-    w: Dict[str, np.ndarray] = {}
-    final = set()
+def _final_layers(graph: Graph):
     if graph.head["kind"] == "v8_dfl":
-        for i in range(3):
-            final.add(f"model.22.cv2.{i}.2")
-            final.add(f"model.22.cv3.{i}.2")
-    else:
-        for i in range(3):
-            final.add(f"model.105.m.{i}")
+        return {f"model.22.cv2.{i}.2" for i in range(3)}, {f"model.22.cv3.{i}.2" for i in range(3)}
+    return set(), {f"model.105.m.{i}" for i in range(3)}
+
+
+def make_synthetic_weights(graph: Graph, seed: int = 0, calibrate: bool = True) -> Dict[str, np.ndarray]:
+    """Deterministic deploy-form weights for ``graph`` (independent of ``graph.imgsz``).
+
+    ``calibrate=False`` skips the layer-sequential rescale and the head calibration (shape-only
+    uses: the ONNX reader tests)."""
+    key = (graph.arch, graph.nc, seed, calibrate)
+    if key in _CACHE:
+        return {k: v.copy() for k, v in _CACHE[key].items()}
+    rng = np.random.default_rng([seed, 0xB200, GENERATOR_VERSION])
+    w: Dict[str, np.ndarray] = {}
+    box_final, _ = _final_layers(graph)
     for name, (cout, cing, k, groups) in graph.wshapes.items():
         fan_in = cing * k * k
         std = (2.0 / fan_in) ** 0.5
         wt = rng.standard_normal((cout, cing, k, k), dtype=np.float32) * np.float32(std)
         b = rng.standard_normal(cout, dtype=np.float32) * np.float32(0.1)
-        if name in final:
-            if "cv2" in name and graph.head["kind"] == "v8_dfl":
-                # DFL logits: tilt towards small bins -> boxes of a few cells
-                b = b + np.tile(-0.6 * np.arange(16, dtype=np.float32), 4)
-            elif graph.head["kind"] == "v8_dfl":
-                b = b - np.float32(3.0)
-            else:
-                no = graph.nc + 5
-                bb = b.reshape(3, no)
-                bb[:, 4] -= np.float32(3.0)
-                b = bb.reshape(-1)
+        if name in box_final:
+            # DFL rows of one box side share a direction v (the "distance" feature): row k = k * v + noise
+            for side in range(4):
+                v = rng.standard_normal(cing).astype(np.float32) / np.float32(np.sqrt(cing))
+                for kk in range(16):
+                    r = wt[side * 16 + kk, :, 0, 0]
+                    wt[side * 16 + kk, :, 0, 0] = kk * v + DFL_NOISE * r / np.linalg.norm(r) * np.linalg.norm(v)
         w[name + ".weight"] = round_to_bf16(wt)
         w[name + ".bias"] = b.astype(np.float32)
     if calibrate:
-        _lsuv(graph, w, seed)
+        _calibrate(graph, w, seed)
+    _CACHE[key] = {k: v.copy() for k, v in w.items()}
     return w
 
 
-def _lsuv(graph: Graph, w: Dict[str, np.ndarray], seed: int) -> None:
-    """Layer-sequential unit-variance rescale on a small calibration tile (CPU torch;
-    this is weight *generation*, not the inference path)."""
+def _calibrate(graph: Graph, w: Dict[str, np.ndarray], seed: int) -> None:
+    """Layer-sequential rescale on two calibration tiles (CPU torch; this is weight *generation*,
+    not the inference path)."""
     import torch
     import torch.nn.functional as F
     from .graph import build
     from .synth import make_tiles
 
-    hw = 320
-    g = build(graph.arch, graph.nc, hw)
-    x = torch.from_numpy(make_tiles(1, hw, seed=seed + 7919)[0].astype(np.float32) / 255.0).permute(2, 0, 1)[None]
-    bufs = {n: torch.zeros(1, b.c, b.h, b.w) for n, b in g.bufs.items()}
+    g = build(graph.arch, graph.nc, CAL_SIZE)
+    box_final, cls_final = _final_layers(g)
+    v8 = g.head["kind"] == "v8_dfl"
+    x = torch.from_numpy(make_tiles(CAL_TILES, CAL_SIZE, seed=seed + 7919).astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+    bufs = {n: torch.zeros(CAL_TILES, b.c, b.h, b.w) for n, b in g.bufs.items()}
     bufs["input"][:, :3] = x
+    inv = lambda op, a: a if op.out_perm is None else a[np.argsort(np.asarray(op.out_perm))]    # buffer order -> model order
     with torch.no_grad():
         for op in g.ops:
             src = bufs[op.src.buf][:, op.src.c0:op.src.c0 + op.src.c]
             if op.kind in ("conv", "dwconv"):
                 if op.src.buf == "input":
                     src = src[:, :3]
-                wt, b = (torch.from_numpy(np.ascontiguousarray(a)) for a in op_weights(op, w))    # buffer channel order
-                groups = g.wshapes[op.weight][3]
-                y = F.conv2d(src, wt, None, stride=op.s, padding=op.k // 2, groups=groups)
-                sc = _quantised_scale(1.0 / float(y.std()))
-                wt = torch.from_numpy(round_to_bf16((wt * sc).numpy()))
-                w[op.weight + ".weight"] = round_to_bf16((torch.from_numpy(w[op.weight + ".weight"]) * sc).numpy())   # model order
+                name = op.weight
+                groups = g.wshapes[name][3]
+                wt, b = (np.ascontiguousarray(a) for a in op_weights(op, w))          # buffer channel order
+                y = F.conv2d(src, torch.from_numpy(wt), None, stride=op.s, padding=op.k // 2, groups=groups)
+                cout = wt.shape[0]
+                sc = np.ones(cout, dtype=np.float32)
+                if name in box_final:
+                    # logit of bin k = 2 k d - k^2 (+ noise), d = D0 + SIGMA_D * (feature - mean) / std per side
+                    ks = np.arange(16, dtype=np.float32)
+                    for side in range(4):
+                        rows = slice(side * 16, side * 16 + 16)
+                        f1 = y[:, side * 16 + 1]                                       # row 1 = v . x (+ its noise)
+                        s1 = _quantised_scale(2.0 * DFL_SIGMA_D / float(f1.std()))
+                        sc[rows] = s1
+                        mean = y[:, rows].mean(dim=(0, 2, 3)).numpy()
+                        b[rows] = b[rows] - mean * s1 + 2.0 * ks * DFL_D0 - ks * ks
+                elif name in cls_final:
+                    s1 = _quantised_scale(CLS_STD / float(y.std()))
+                    sc[:] = s1
+                    z = y * s1
+                    if v8:
+                        score = z.amax(1)                                               # conf = max class logit
+                        thr, frac = float(np.log(0.25 / 0.75)), V8_PASS_FRACTION
+                        shift = thr - float(np.quantile(score.numpy().ravel(), 1.0 - frac))
+                        b[:] = b + shift
+                    else:
+                        no = g.nc + 5
+                        obj = z.view(z.shape[0], 3, no, z.shape[2], z.shape[3])[:, :, 4]
+                        thr, frac = float(np.log(0.3 / 0.7)), V7_PASS_FRACTION
+                        shift = thr - float(np.quantile(obj.numpy().ravel(), 1.0 - frac))
+                        bb = b.reshape(3, no)
+                        bb[:, 4] += shift
+                        b = bb.reshape(-1)
+                else:
+                    sc[:] = _quantised_scale(PREACT_STD / float(y.std()))
+                w[name + ".weight"] = round_to_bf16(w[name + ".weight"] * inv(op, sc)[:, None, None, None])   # model order
+                w[name + ".bias"] = inv(op, b).astype(np.float32)
+                wt, b = (torch.from_numpy(np.ascontiguousarray(a)) for a in op_weights(op, w))
                 y = F.conv2d(src, wt, b, stride=op.s, padding=op.k // 2, groups=groups)
                 if op.act:
                     y = y * torch.sigmoid(y)
