@@ -78,7 +78,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("B2DET_LIB", str(LIB_PATH))
+    path = str(LIB_PATH)
     if not os.path.exists(path):
         raise B2DError(
             f"{path} not found: build it with `python __graft_entry__.py` (or `make -C "
@@ -92,8 +92,10 @@ def load() -> C.CDLL:
     return lib
 
 
-def check(rc: int, what: str = "") -> int:
-    if rc < 0:
+def check(rc: int, what: str = "", index: bool = False) -> int:
+    """Every entry point returns 0 or a negative status; the ``b2d_plan_*`` calls return the index of what they added
+    (``index=True``).  Anything else is an error."""
+    if rc < 0 or (rc != 0 and not index):
         msg = load().b2d_last_error().decode("utf-8", "replace")
         raise B2DError(f"{what}: {msg}" if what else msg)
     return rc

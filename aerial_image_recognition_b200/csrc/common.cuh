@@ -32,6 +32,11 @@ void b2d_set_error(const char* fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory on the CURRENT device, once per (device, kernel): the
+// attribute is per device, so a process-global "done" flag would leave the second GPU of a process without it
+// (engine.cu; thread-safe).
+int b2d_func_smem_optin(const void* func, int bytes);
+
 // ---------------------------------------------------------------------------------------
 // tcgen05 implicit-GEMM convolution (conv_tc.cu)
 // ---------------------------------------------------------------------------------------
@@ -106,40 +111,14 @@ void conv_tc_free(ConvTcPlan* plan);
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen);
 
 // ---------------------------------------------------------------------------------------
-// CUDA-core kernels (conv_simt.cu): stem conv, depthwise conv, pools, upsample
+// pools and upsample (pool.cu)
 // ---------------------------------------------------------------------------------------
-struct ConvSimtPlan {
-    const __nv_bfloat16* src; int src_h, src_w, src_cs, src_c0, cin;
-    void* dst; int dst_h, dst_w, dst_cs, dst_c0, cout, dst_f32;
-    int ksz, stride, act;
-    const __nv_bfloat16* res; int res_cs, res_c0;
-    float* w_dev;      // [taps][cin][cout_pad16] fp32 (bf16-rounded values)
-    float* bias_dev;   // [cout_pad16]
-    int cout_pad;
-};
-int conv_simt_plan(ConvSimtPlan* plan, const __nv_bfloat16* src, int src_h, int src_w, int src_cs, int src_c0, int cin,
-                   int cin_w, void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32,
-                   int ksz, int stride, int act, const float* w_host, const float* b_host,
-                   const __nv_bfloat16* res, int res_cs, int res_c0);
-int conv_simt_launch(const ConvSimtPlan* plan, int n, cudaStream_t stream);
-void conv_simt_free(ConvSimtPlan* plan);
-
-struct DwConvPlan {
-    const __nv_bfloat16* src; int h, w, src_cs, src_c0;
-    __nv_bfloat16* dst; int dst_cs, dst_c0, c, act;
-    float* w_dev;      // [9][c]
-    float* bias_dev;   // [c]
-};
-int dwconv_plan(DwConvPlan* plan, const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
-                __nv_bfloat16* dst, int dst_cs, int dst_c0, int c, int act, const float* w_host, const float* b_host);
-int dwconv_launch(const DwConvPlan* plan, int n, cudaStream_t stream);
-void dwconv_free(DwConvPlan* plan);
-
 int maxpool_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                    __nv_bfloat16* dst, int oh, int ow, int dst_cs, int dst_c0, int c, int k, int stride,
                    int n, cudaStream_t stream, int f16 = 0);
 int poolchain_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* const* dst, const int* dst_c0,
                      int dst_cs, int c, int stages, int n, cudaStream_t stream, int f16 = 0);
+int poolchain_fits(int h, int w);
 int upsample2x_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                       __nv_bfloat16* dst, int dst_cs, int dst_c0, int c, int n, cudaStream_t stream);
 

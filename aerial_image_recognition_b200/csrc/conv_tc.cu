@@ -1798,12 +1798,7 @@ int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
         grid = 2 * (prs < plan->sm_count / 2 ? prs : plan->sm_count / 2);
     }
     ConvKernel k = pick_kernel(p.kind, p.pair, p.act, p.has_res, p.out_f32);
-    static bool attr_done[5][2][2][2];
-    bool& done = attr_done[p.pair ? 4 : p.kind][p.act ? 1 : 0][p.has_res ? 1 : 0][p.out_f32 ? 1 : 0];
-    if (!done) {
-        B2D_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        done = true;
-    }
+    if (b2d_func_smem_optin((const void*)k, 227 * 1024)) return -2;
     if (p.trace) B2D_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * kTraceRoles * kTraceTiles * kTraceEvents, stream));
     {
         cudaLaunchConfig_t cfg{};

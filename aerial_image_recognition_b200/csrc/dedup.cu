@@ -19,16 +19,22 @@
 namespace {
 
 struct DedupTable {
-    long long* cell_key;   // [cap] hashed cell id, -1 = empty  (stored as (cx<<32)|(cy & 0xffffffff))
+    long long* cell_key;   // [cap] cell id ((cx + 2^31) << 32) | (cy + 2^31), -1 = empty (not a key: cells are range-checked to |c| < 2^31 - 2)
     int* cell_head;        // [cap] head of the linked list of points in the cell
     int* next;             // [n]
     uint8_t* state;        // [n] 0 undecided, 1 kept, 2 removed
-    int* flag;             // [1] number of points still undecided after a round
+    int* flag;             // [0] number of points still undecided after a round, [1] != 0: a point's cell index is out of range
     unsigned cap_mask;
 };
 
+// Cell indices are biased by 2^31 so that no in-range cell packs to the empty-slot sentinel 0xFFFF...F (cell (-1, -1) did
+// with plain two's-complement packing: points there were inserted but never found, so their duplicates survived).
+constexpr long long kCellBias = 1ll << 31, kCellMax = (1ll << 31) - 2;
 __device__ __forceinline__ unsigned long long pack_cell(long long cx, long long cy) {
-    return ((unsigned long long)(unsigned)(int)cx << 32) | (unsigned long long)(unsigned)(int)cy;
+    return ((unsigned long long)(cx + kCellBias) << 32) | (unsigned long long)(cy + kCellBias);
+}
+__device__ __forceinline__ bool cell_in_range(long long cx, long long cy) {
+    return cx > -kCellMax && cx < kCellMax && cy > -kCellMax && cy < kCellMax;
 }
 __device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
@@ -39,13 +45,18 @@ __global__ void dedup_init_kernel(DedupTable t, int n, unsigned cap) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap) { t.cell_key[i] = -1; t.cell_head[i] = -1; }
     if (i < (unsigned)n) { t.state[i] = 0; t.next[i] = -1; }
-    if (i == 0) *t.flag = 0;
+    if (i == 0) { t.flag[0] = 0; t.flag[1] = 0; }
 }
 
 __global__ void dedup_build_kernel(DedupTable t, const double* __restrict__ x, const double* __restrict__ y, int n, double inv_cell) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned long long key = pack_cell((long long)floor(x[i] * inv_cell), (long long)floor(y[i] * inv_cell));
+    const double fx = floor(x[i] * inv_cell), fy = floor(y[i] * inv_cell);
+    if (!(fabs(fx) < (double)kCellMax && fabs(fy) < (double)kCellMax)) {      // also catches NaN / inf coordinates
+        t.flag[1] = 1;
+        return;                                                               // the host reports the error; the point stays unlinked
+    }
+    const unsigned long long key = pack_cell((long long)fx, (long long)fy);
     unsigned slot = hash_cell(key) & t.cap_mask;
     while (true) {
         const long long prev = atomicCAS((unsigned long long*)&t.cell_key[slot], (unsigned long long)-1LL, key);
@@ -201,13 +212,14 @@ int closure_launch(const double* x, const double* y, int count, double thr, int 
     DedupTable t;
     double inv_cell;
     if (build_table(t, x, y, count, thr, scratch, scratch_bytes, stream, &inv_cell)) return -1;
-    int h_flag = 1;
-    for (int round = 0; h_flag != 0; ++round) {
+    int h_flag[2] = {1, 0};
+    for (int round = 0; h_flag[0] != 0; ++round) {
         B2D_CUDA(cudaMemsetAsync(t.flag, 0, sizeof(int), stream));
         closure_round_kernel<<<(count + 255) / 256, 256, 0, stream>>>(t, x, y, count, inv_cell, thr * thr, inclusive, flag);
         B2D_LAUNCH_CHECK();
-        B2D_CUDA(cudaMemcpyAsync(&h_flag, t.flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        B2D_CUDA(cudaMemcpyAsync(h_flag, t.flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         B2D_CUDA(cudaStreamSynchronize(stream));
+        B2D_CHECK(h_flag[1] == 0, "closure: a coordinate / thr is outside the grid's +-2^31 cells (or not finite)");
         B2D_CHECK(round <= count + 8, "closure: did not converge");
     }
     return 0;
@@ -223,14 +235,15 @@ int dedup_launch(const double* x, const double* y, const float* conf, const long
     const int threads = 256;
     // Rounds: every round decides at least the highest-priority undecided point, so the loop ends;
     // real data needs a handful of rounds.  The host reads the undecided count back every 4 rounds.
-    int h_flag = 1;
-    for (int round = 0; h_flag != 0; ++round) {
+    int h_flag[2] = {1, 0};
+    for (int round = 0; h_flag[0] != 0; ++round) {
         B2D_CUDA(cudaMemsetAsync(t.flag, 0, sizeof(int), stream));
         dedup_round_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, x, y, conf, tiebreak, count, inv_cell, thr2, inclusive);
         B2D_LAUNCH_CHECK();
         if ((round & 3) == 3 || count < 4096) {
-            B2D_CUDA(cudaMemcpyAsync(&h_flag, t.flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            B2D_CUDA(cudaMemcpyAsync(h_flag, t.flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             B2D_CUDA(cudaStreamSynchronize(stream));
+            B2D_CHECK(h_flag[1] == 0, "dedup: a coordinate / thr is outside the grid's +-2^31 cells (or not finite)");
         }
         B2D_CHECK(round <= count + 8, "dedup: did not converge");
     }

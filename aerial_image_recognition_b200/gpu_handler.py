@@ -22,8 +22,8 @@ import numpy as np
 import torch
 
 from . import tta as _tta
-from .engine import GEO_PARAMS, Engine, geodets_to_numpy
-from .session import InferenceSession, arch_from_model_path, load_weights
+from .engine import GEO_PARAMS, GEODET_BYTES, GEODET_DTYPE, Engine, geodets_to_numpy
+from .session import InferenceSession, arch_from_model_path, resolve_weights
 
 
 def _as_u8_hwc(img) -> np.ndarray:
@@ -36,9 +36,17 @@ def _as_u8_hwc(img) -> np.ndarray:
     return a if a.flags.writeable else a.copy()      # np.asarray(PIL image) is read-only; torch.from_numpy wants a writable array
 
 
+def _shape_of(img):
+    """(h, w, 3) of a PIL image / array without converting it."""
+    if hasattr(img, "size") and hasattr(img, "mode") and not isinstance(img, np.ndarray):
+        return (img.size[1], img.size[0], 3)
+    a = np.asarray(img)
+    return (a.shape[0], a.shape[1], 3)
+
+
 class GPUHandler:
     def __init__(self, model_path, max_gpu_memory=5.0, confidence_threshold=0.3, output_dir=None, *,
-                 arch: Optional[str] = None, weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 64,
+                 arch: Optional[str] = None, weights=None, max_batch: int = 64,
                  top_k: int = 10, bgr: bool = False, device: int = 0, seed: int = 0, swallow_errors: bool = False,
                  precision: str = "bf16"):
         self.model_path = model_path
@@ -51,10 +59,28 @@ class GPUHandler:
         self.session = None
         self._setup_gpu()
         arch = arch or arch_from_model_path(model_path)
-        if weights is None and model_path:
-            weights = load_weights(model_path, arch)
+        weights = resolve_weights(model_path, arch, weights)     # FileNotFoundError unless weights="synthetic" (session.py)
         self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, precision=precision)
         self.session = InferenceSession(engine=self.engine)
+        self._stage = {}                    # (h, w) -> two pinned uint8 [max_batch, h, w, 3] staging buffers, reused across calls
+        self._stage_free = {}
+
+    def _staging(self, shape, k):
+        """Pinned host buffer ``k % 2`` for tiles of ``shape`` plus the event after which it may be overwritten: images are
+        copied straight into page-locked memory (no ``np.stack`` + ``pin_memory`` per batch), and two buffers let the host
+        fill batch i+1 while batch i is still in flight."""
+        key = tuple(shape[:2])
+        if key not in self._stage:
+            self._stage[key] = [torch.empty((self.engine.max_batch, shape[0], shape[1], 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._stage_free[key] = [None, None]
+        return self._stage[key][k % 2], self._stage_free[key], k % 2
+
+    def _result_staging(self, cap, k):
+        key = ("out", cap)
+        if key not in self._stage:
+            self._stage[key] = [(torch.empty((self.engine.max_batch, cap, GEODET_BYTES), dtype=torch.uint8).pin_memory(),
+                                 torch.empty((self.engine.max_batch,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+        return self._stage[key][k % 2]
 
     def _setup_gpu(self):
         if not torch.cuda.is_available():
@@ -86,29 +112,54 @@ class GPUHandler:
             if not img_set or not isinstance(img_set, list) or not img_set[0]:
                 continue
             img, bbox, _ = img_set[0]
-            items.append((_as_u8_hwc(img), tuple(float(v) for v in bbox)))
+            items.append((img, tuple(float(v) for v in bbox)))
+        shapes = [_shape_of(it[0]) for it in items]
+        pending = []                                   # (pinned records, pinned counts, n, event) of the batches in flight
         out: List[dict] = []
-        i = 0
+
+        def drain(upto):                               # results are read one batch behind, while the next batch computes
+            while len(pending) > upto:
+                geo_h, cnt_h, n, ev = pending.pop(0)
+                ev.synchronize()
+                recs = geo_h.numpy().view(GEODET_DTYPE)[..., 0]
+                for t, c in enumerate(cnt_h.numpy()[:n].tolist()):
+                    g = recs[t, :c]
+                    x, y, cf = g["x"].tolist(), g["y"].tolist(), g["conf"].tolist()
+                    out.extend({"lon": x[r], "lat": y[r], "confidence": cf[r]} for r in range(c))
+
+        i = b = 0
         while i < len(items):
             # consecutive tiles of one shape form a device batch
-            shape = items[i][0].shape
+            shape = shapes[i]
             j = i
-            while j < len(items) and j - i < eng.max_batch and items[j][0].shape == shape:
+            while j < len(items) and j - i < eng.max_batch and shapes[j] == shape:
                 j += 1
             n = j - i
-            host = torch.from_numpy(np.stack([it[0] for it in items[i:j]])).pin_memory()
-            tiles = host.to(eng.device, non_blocking=True)
+            host, free, slot = self._staging(shape, b)
+            if free[slot] is not None:
+                free[slot].synchronize()                # the copy that last read this buffer has finished
+            hv = host.numpy()
+            for k in range(n):
+                hv[k] = _as_u8_hwc(items[i + k][0])
+            tiles = host[:n].to(eng.device, non_blocking=True)
+            free[slot] = torch.cuda.Event()
+            free[slot].record()
             S = eng.imgsz
             mode = "identity" if shape[:2] == (S, S) else "cv2_linear"
             dets, counts = eng.infer(tiles, mode, self.bgr, self.confidence_threshold, True, 0.0, self.top_k)
             params = np.zeros((n, GEO_PARAMS), dtype=np.float64)
-            for k in range(n):
-                params[k, :4] = items[i + k][1]
+            params[:, :4] = [it[1] for it in items[i:j]]
             geo = eng.georef(dets, counts, torch.from_numpy(params).to(eng.device), "gpuhandler")
-            for g in geodets_to_numpy(geo, counts):
-                for r in g:
-                    out.append({"lon": float(r["x"]), "lat": float(r["y"]), "confidence": float(r["conf"])})
+            geo_h, cnt_h = self._result_staging(geo.shape[1], b)
+            geo_h[:n].copy_(geo, non_blocking=True)
+            cnt_h[:n].copy_(counts, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((geo_h, cnt_h, n, ev))
+            drain(1)
             i = j
+            b += 1
+        drain(0)
         return out
 
     def process_tiles(self, tiles: torch.Tensor, bboxes) -> List[dict]:

@@ -71,6 +71,17 @@ def seam_flags(py: np.ndarray, rank: int, covers: Sequence[Tuple[int, int]], mar
     return flag
 
 
+def seam_flags_device(py, rank: int, covers: Sequence[Tuple[int, int]], margin_px: float):
+    """``seam_flags`` on the device: ``py`` is a CUDA float tensor, the result a CUDA uint8 tensor (no host round trip)."""
+    import torch
+    flag = torch.zeros(py.shape, dtype=torch.bool, device=py.device)
+    for r, (lo, hi) in enumerate(covers):
+        if r == rank or hi <= lo:
+            continue
+        flag |= (py >= lo - margin_px) & (py < hi + margin_px)
+    return flag.to(torch.uint8)
+
+
 def affine_params(windows: np.ndarray, geotransform: Sequence[float], win: int = 640) -> np.ndarray:
     """float64 [n,16] georef parameters for B2D_GEO_AFFINE: gt[6], win_x, win_y, pad_x, pad_y, gain,
     w0, h0 (the letterbox undo of Ultralytics ``scale_boxes``; gain is 1 for model-sized windows)."""
@@ -90,12 +101,33 @@ def affine_params(windows: np.ndarray, geotransform: Sequence[float], win: int =
 # -------------------------------------------------------------------------------------------------
 # seam exchange: host-side protocol, independent of the device (tested on CPU with gloo)
 # -------------------------------------------------------------------------------------------------
-RECORD_WORDS = 6   # float64 words per exchanged record: x, y, conf, global window id, slot in window, class
+# One exchanged seam record = 4 x 8 bytes: x (f64), y (f64), [conf (f32) | class (i32)], order key (i64 = window * 65536 +
+# slot).  SURVEY 8e sketches 24 bytes {x, y, conf, tile id}; the slot inside the window is needed too -- it is the last
+# component of the total order every rank must agree on -- so the id word is 64-bit and the record 32 bytes.
+RECORD_WORDS = 4
+
+
+def pack_records(x, y, conf, cls, key):
+    """Device tensors -> int64 [k, RECORD_WORDS] (bit patterns; see RECORD_WORDS)."""
+    import torch
+    w2 = (conf.contiguous().view(torch.int32).long() & 0xFFFFFFFF) | (cls.long() << 32)
+    return torch.stack([x.contiguous().view(torch.int64), y.contiguous().view(torch.int64), w2, key.long()], 1)
+
+
+def unpack_records(rec):
+    """int64 [k, RECORD_WORDS] -> (x f64, y f64, conf f32, cls i32, key i64)."""
+    import torch
+    x = rec[:, 0].contiguous().view(torch.float64)
+    y = rec[:, 1].contiguous().view(torch.float64)
+    bits = rec[:, 2] & 0xFFFFFFFF                                                  # the float's bit pattern as 0 .. 2^32 - 1
+    conf = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32).view(torch.float32)
+    cls = (rec[:, 2] >> 32).to(torch.int32)
+    return x, y, conf, cls, rec[:, 3].contiguous()
 
 
 def exchange_seam(records, world: int, all_gather_counts: Callable, all_gather_padded: Callable):
-    """records: [k, RECORD_WORDS] float64 array/tensor of this rank's flagged detections.
-    Returns the concatenation over ranks in rank order (same on every rank) and the rank of origin
+    """records: [k, RECORD_WORDS] int64 array/tensor of this rank's flagged detections.
+    Returns the per-rank parts in rank order (same on every rank) and the rank of origin
     of each row.  Two collectives: counts (world x int64), then a padded payload."""
     k = int(records.shape[0])
     counts = all_gather_counts(k)                       # list[int], length world
@@ -132,7 +164,10 @@ class MosaicDetector:
         eng = self.eng
         dev = eng.device
         outs = []
-        B = eng.max_batch
+        # equal batches: 780 windows at max_batch 64 are 13 launches either way, but 13 x 60 keeps every step full
+        # where 12 x 64 + 12 ends a band on a step that is four fifths empty
+        nb = -(-len(windows) // eng.max_batch) if len(windows) else 1
+        B = -(-len(windows) // nb) if len(windows) else eng.max_batch
         local = windows.copy()
         local[:, 1] -= y_offset
         # every per-window table goes to the device once; the batch loop below queues kernels only (no host
@@ -177,30 +212,27 @@ class MosaicDetector:
         eng = self.eng
         key = self.order_key(wid, slot)
         margin_px = self.dedup_thr / min(abs(self.gt[1]), abs(self.gt[5])) + 1.0
-        flag = torch.from_numpy(seam_flags(py.cpu().numpy(), rank, covers, margin_px)).to(eng.device)
+        flag = seam_flags_device(py, rank, covers, margin_px)
         eng.seam_closure(x, y, flag, self.dedup_thr, True)
         seam = flag.bool()
         lx, ly, lc, lk = x[~seam], y[~seam], conf[~seam], key[~seam]
         lkeep = eng.dedup(lx, ly, lc, self.dedup_thr, True, tiebreak=lk).bool()
         local = self._pack(lx[lkeep], ly[lkeep], lc[lkeep], cls[~seam][lkeep], wid[~seam][lkeep], slot[~seam][lkeep])
-        rec = torch.stack([x[seam], y[seam], conf[seam].double(), wid[seam].double(), slot[seam].double(), cls[seam].double()], 1)
-        return local, rec
+        return local, pack_records(x[seam], y[seam], conf[seam], cls[seam], key[seam])
 
     def seam_merge(self, parts, origin: np.ndarray, rank: int) -> np.ndarray:
         """The identical greedy pass every rank runs on the gathered seam records; returns the
         survivors that originated on ``rank``."""
         import torch
         eng = self.eng
-        allrec = torch.cat([p.to(eng.device) for p in parts]) if parts else torch.zeros((0, RECORD_WORDS), dtype=torch.float64, device=eng.device)
+        allrec = torch.cat([torch.as_tensor(p).to(eng.device) for p in parts]) if parts else torch.zeros((0, RECORD_WORDS), dtype=torch.int64, device=eng.device)
         self.last_seam_records = int(allrec.shape[0])
         if not allrec.shape[0]:
             return np.zeros(0, self.OUT_DTYPE)
-        gk = self.order_key(allrec[:, 3].long(), allrec[:, 4].long())
-        gkeep = eng.dedup(allrec[:, 0].contiguous(), allrec[:, 1].contiguous(), allrec[:, 2].float().contiguous(),
-                          self.dedup_thr, True, tiebreak=gk).bool()
+        gx, gy, gc, gcls, gk = unpack_records(allrec)
+        gkeep = eng.dedup(gx, gy, gc, self.dedup_thr, True, tiebreak=gk).bool()
         mine = gkeep & torch.from_numpy(origin == rank).to(eng.device)
-        m = allrec[mine]
-        return self._pack(m[:, 0], m[:, 1], m[:, 2].float(), m[:, 5].int(), m[:, 3].long(), m[:, 4].int())
+        return self._pack(gx[mine], gy[mine], gc[mine], gcls[mine], gk[mine] >> 16, (gk[mine] & 0xFFFF).int())
 
     def dedup(self, x, y, conf, cls, wid, slot, py, rank: int, world: int, covers, group=None):
         import torch
@@ -211,27 +243,44 @@ class MosaicDetector:
             return self._pack(x[keep], y[keep], conf[keep], cls[keep], wid[keep], slot[keep])
         local, rec = self.seam_split(x, y, conf, cls, wid, slot, py, rank, covers)
 
-        # seam part: NCCL all-gather over NVLink (counts, then padded payload)
+        # seam part: NCCL all-gather over NVLink -- the counts as one [world] tensor read back once, then the padded payload
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
         def gather_counts(k):
-            t = torch.tensor([k], dtype=torch.int64, device=eng.device)
-            out = [torch.zeros_like(t) for _ in range(world)]
-            dist.all_gather(out, t, group=group)
-            return [int(o.item()) for o in out]
+            out = torch.empty((world,), dtype=torch.int64, device=eng.device)
+            dist.all_gather_into_tensor(out, torch.full((1,), k, dtype=torch.int64, device=eng.device), group=group)
+            return out.tolist()
 
         def gather_padded(r, cap):
-            pad = torch.zeros((cap, RECORD_WORDS), dtype=torch.float64, device=eng.device)
+            pad = torch.zeros((cap, RECORD_WORDS), dtype=torch.int64, device=eng.device)
             pad[:r.shape[0]] = r
-            out = [torch.empty_like(pad) for _ in range(world)]
-            dist.all_gather(out, pad, group=group)
-            return out
+            out = torch.empty((world, cap, RECORD_WORDS), dtype=torch.int64, device=eng.device)
+            ev[0].record()
+            dist.all_gather_into_tensor(out, pad, group=group)
+            ev[1].record()
+            return list(out.unbind(0))
 
         parts, origin = exchange_seam(rec, world, gather_counts, gather_padded)
-        return np.concatenate([local, self.seam_merge(parts, origin, rank)])
+        merged = self.seam_merge(parts, origin, rank)
+        self.last_allgather_us = ev[0].elapsed_time(ev[1]) * 1e3      # both events have completed: seam_merge read its result back
+        return np.concatenate([local, merged])
 
     def _pack(self, x, y, conf, cls, wid, slot) -> np.ndarray:
-        out = np.zeros(int(x.numel()), dtype=self.OUT_DTYPE)
-        out["x"] = x.cpu().numpy(); out["y"] = y.cpu().numpy(); out["conf"] = conf.cpu().numpy()
-        out["cls"] = cls.cpu().numpy(); out["window"] = wid.cpu().numpy(); out["slot"] = slot.cpu().numpy()
+        """Device columns -> one structured host array, through ONE device->host copy of 32-byte records."""
+        import torch
+        n = int(x.numel())
+        rec = torch.empty((n, 4), dtype=torch.int64, device=x.device)
+        rec[:, 0] = x.contiguous().view(torch.int64)
+        rec[:, 1] = y.contiguous().view(torch.int64)
+        rec[:, 2] = (conf.contiguous().view(torch.int32).long() & 0xFFFFFFFF) | (cls.long() << 32)
+        rec[:, 3] = wid.long()
+        host = rec.cpu().numpy()
+        out = np.zeros(n, dtype=self.OUT_DTYPE)
+        out["x"] = host[:, 0].view(np.float64); out["y"] = host[:, 1].view(np.float64)
+        out["conf"] = (host[:, 2] & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+        out["cls"] = (host[:, 2] >> 32).astype(np.int32)
+        out["window"] = host[:, 3]
+        out["slot"] = slot.cpu().numpy() if n else np.zeros(0, np.int32)
         return out
 
     def run(self, mosaic, height: int, width: int, rank: int = 0, world: int = 1, y_offset: int = 0, group=None) -> np.ndarray:

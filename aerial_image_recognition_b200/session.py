@@ -12,8 +12,7 @@ their meaning (``simple_detector.py:479-480``).
 from __future__ import annotations
 
 import os
-import warnings
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Union
 
 import numpy as np
 import torch
@@ -39,7 +38,23 @@ def arch_from_model_path(model_path: Optional[str]) -> str:
     return "yolov8m"
 
 
-def load_weights(model_path: Optional[str], arch: Optional[str] = None) -> Optional[Dict[str, np.ndarray]]:
+SYNTHETIC = "synthetic"      # explicit opt-in for seeded random weights (bench, tests): ``weights="synthetic"``
+
+
+def resolve_weights(model_path: Optional[str], arch: str, weights: Union[None, str, Dict[str, np.ndarray]]
+                    ) -> Optional[Dict[str, np.ndarray]]:
+    """What ``GPUHandler`` / ``SimpleDetector`` / ``InferenceSession`` hand to the engine: the caller's tensors, the
+    tensors of ``model_path``, or ``None`` (= the engine's seeded synthetic weights) only for ``weights="synthetic"``."""
+    if isinstance(weights, str):
+        if weights != SYNTHETIC:
+            raise ValueError(f"weights={weights!r}: expected a dict of tensors or {SYNTHETIC!r}")
+        return None
+    if weights is not None:
+        return weights
+    return load_weights(model_path, arch)
+
+
+def load_weights(model_path: Optional[str], arch: Optional[str] = None) -> Dict[str, np.ndarray]:
     """Deploy-form tensors (``model.N....weight`` / ``.bias``) from ``model_path``:
 
     * ``.onnx`` -- what the reference loads (``_script/config.py:25``, ``simple_detector.py:710``): the
@@ -47,8 +62,10 @@ def load_weights(model_path: Optional[str], arch: Optional[str] = None) -> Optio
       and checked against the engine's graph for ``arch``;
     * ``.npz`` -- the same tensors saved with ``numpy.savez``.
 
-    The reference's own blobs are absent (``.MISSING_LARGE_BLOBS:2-5``): when the path does not exist the
-    engine runs seeded synthetic weights of the right architecture and says so."""
+    A missing file raises ``FileNotFoundError``, as ``ort.InferenceSession(model_path)`` does in the reference
+    (``_script/gpu_handler.py:61-65``): a mistyped path must not silently produce detections from random weights.
+    The reference's own blobs are absent (``.MISSING_LARGE_BLOBS:2-5``), so benchmarks and tests opt in to seeded
+    synthetic weights explicitly with ``weights="synthetic"`` (``resolve_weights``)."""
     if model_path and os.path.exists(model_path):
         if model_path.endswith(".npz"):
             with np.load(model_path) as z:
@@ -58,18 +75,17 @@ def load_weights(model_path: Optional[str], arch: Optional[str] = None) -> Optio
             from .onnx_reader import load_onnx_weights
             return load_onnx_weights(model_path, build(arch or arch_from_model_path(model_path)))
         raise ValueError(f"{model_path}: unknown model file type (expected .onnx or .npz)")
-    warnings.warn(f"model file {model_path!r} not found; using seeded synthetic weights", stacklevel=3)
-    return None
+    raise FileNotFoundError(f"model file {model_path!r} not found (pass weights=\"synthetic\" to run seeded synthetic "
+                            f"weights of the architecture instead)")
 
 
 class InferenceSession:
     def __init__(self, model_path: Optional[str] = None, sess_options=None, providers=None, *, arch: Optional[str] = None,
-                 weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 8, device: int = 0, seed: int = 0,
+                 weights: Union[None, str, Dict[str, np.ndarray]] = None, max_batch: int = 8, device: int = 0, seed: int = 0,
                  engine: Optional[Engine] = None, precision: str = "bf16"):
         if engine is None:
             arch = arch or arch_from_model_path(model_path)
-            if weights is None:
-                weights = load_weights(model_path, arch) if model_path else None
+            weights = resolve_weights(model_path, arch, weights)
             engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, precision=precision)
         self.engine = engine
         self._inputs = [_Input("images", [None, 3, engine.imgsz, engine.imgsz])]

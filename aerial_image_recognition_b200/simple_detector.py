@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from .engine import GEO_PARAMS, Engine, geodets_to_numpy
-from .session import InferenceSession, arch_from_model_path, load_weights
+from .session import InferenceSession, arch_from_model_path, resolve_weights
 
 
 def _as_u8_hwc(img) -> np.ndarray:
@@ -38,7 +38,7 @@ def _as_u8_hwc(img) -> np.ndarray:
 
 class SimpleDetector:
     def __init__(self, model_path, output_dir, *, arch: Optional[str] = None,
-                 weights: Optional[Dict[str, np.ndarray]] = None, max_batch: int = 8, device: int = 0, seed: int = 0, precision: str = "bf16"):
+                 weights=None, max_batch: int = 8, device: int = 0, seed: int = 0, precision: str = "bf16"):
         self.zoom = 21
         self.model_size = 640
         self.confidence_threshold = 0.3
@@ -48,8 +48,7 @@ class SimpleDetector:
         earth_circumference = 40075016.686
         self.meters_per_pixel = earth_circumference / (2 ** self.zoom) / 256
         arch = arch or arch_from_model_path(model_path)
-        if weights is None and model_path:
-            weights = load_weights(model_path, arch)
+        weights = resolve_weights(model_path, arch, weights)     # FileNotFoundError unless weights="synthetic" (session.py)
         self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, imgsz=self.model_size,
                              precision=precision)
         self.model = InferenceSession(engine=self.engine)
@@ -144,15 +143,17 @@ class SimpleDetector:
         eng = self.engine
         lon = np.array([d["lon"] for d in detections], dtype=np.float64)
         lat = np.array([d["lat"] for d in detections], dtype=np.float64)
-        # priority = position in the reference's stable descending sort (:565); passing -rank as the
-        # fp32 "confidence" makes the kernel's (conf desc, index asc) order exactly that sort
+        # priority = position in the reference's stable descending sort (:565), handed to the kernel as its int64
+        # tie-break with a constant confidence: the kernel's (conf desc, tiebreak asc) order is then exactly that sort
         ranked = sorted(range(len(detections)), key=lambda i: detections[i]["confidence"], reverse=True)
-        conf = np.empty(len(detections), dtype=np.float32)
-        conf[ranked] = -np.arange(len(detections), dtype=np.float32)
+        rank = np.empty(len(detections), dtype=np.int64)
+        rank[ranked] = np.arange(len(detections), dtype=np.int64)
+        conf = np.zeros(len(detections), dtype=np.float32)
         utm_zone = int((detections[0]["lon"] + 180) / 6) + 1      # :546
         north = detections[0]["lat"] > 0                           # :547
         x, y = eng.utm_forward(torch.from_numpy(lon).to(eng.device), torch.from_numpy(lat).to(eng.device), utm_zone, north)
-        keep = eng.dedup(x, y, torch.from_numpy(conf).to(eng.device), float(distance_threshold), inclusive=True).cpu().numpy()
+        keep = eng.dedup(x, y, torch.from_numpy(conf).to(eng.device), float(distance_threshold), inclusive=True,
+                         tiebreak=torch.from_numpy(rank).to(eng.device)).cpu().numpy()
         idx = np.nonzero(keep)[0]
         # kept detections come back in descending-confidence order, input order among ties (:565, :590)
         order = sorted(idx.tolist(), key=lambda i: detections[i]["confidence"], reverse=True)

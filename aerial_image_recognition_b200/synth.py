@@ -66,3 +66,34 @@ def make_mosaic(height: int, width: int, seed: int = 0, y0: int = 0, y1: int | N
             blk = make_block(seed, by, bx)
             out[ys - y0:ye - y0, xs:xe] = blk[ys - by * BLOCK:ye - by * BLOCK, :xe - xs]
     return out
+
+
+MOSAIC_POOL = 32   # distinct procedural blocks a device-side mosaic is assembled from
+
+
+def mosaic_block_pool(seed: int = 77) -> np.ndarray:
+    """uint8 [MOSAIC_POOL, 512, 512, 3]: the blocks ``mosaic_band_device`` tiles a mosaic with."""
+    return np.stack([make_block(seed, 0, i) for i in range(MOSAIC_POOL)])
+
+
+def mosaic_band_device(pool, height: int, width: int, y_lo: int, y_hi: int, seed: int = 5):
+    """uint8 CUDA tensor [y_hi - y_lo, width, 3]: pixel rows [y_lo, y_hi) of the ``height x width`` mosaic whose 512-px
+    block (by, bx) is ``pool[hash(seed, by, bx)]`` (``pool`` = ``mosaic_block_pool`` on the device).  The content depends on the
+    *global* block coordinates only, so every rank of a tile-sharded run (BASELINE config C4) materialises its own band on
+    its own device with no host traffic, and the mosaic is the same for every world size."""
+    import torch
+    by0, by1 = y_lo // BLOCK, (y_hi + BLOCK - 1) // BLOCK
+    nbx = (width + BLOCK - 1) // BLOCK
+    by = np.arange(by0, by1, dtype=np.uint64)[:, None]
+    bx = np.arange(nbx, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        h = (by * np.uint64(0x9E3779B97F4A7C15) + bx * np.uint64(0xC2B2AE3D27D4EB4F) + np.uint64(seed) * np.uint64(0x165667B19E3779F9))
+    h ^= h >> np.uint64(29)
+    idx = torch.from_numpy((h % np.uint64(pool.shape[0])).astype(np.int64)).to(pool.device)
+    rows = []
+    for r in range(by1 - by0):                                  # one block row at a time keeps the temporary small
+        strip = pool[idx[r]].permute(1, 0, 2, 3).reshape(BLOCK, nbx * BLOCK, 3)[:, :width]
+        lo = max(y_lo, (by0 + r) * BLOCK) - (by0 + r) * BLOCK
+        hi = min(y_hi, (by0 + r + 1) * BLOCK) - (by0 + r) * BLOCK
+        rows.append(strip[lo:hi])
+    return torch.cat(rows).contiguous()

@@ -200,10 +200,13 @@ class CheckpointManager:
         """``processing_state.json`` (``processed_count``, ``total_tiles``, ``timestamp``, indent 2) and, when there
         are detections, ``latest_detections.geojson`` (``_script/utils.py:77-95``)."""
         state = {'processed_count': int(processed_count), 'total_tiles': int(total_tiles), 'timestamp': datetime.now().isoformat()}
-        with open(self.state_file, 'w') as f:
-            json.dump(state, f, indent=2)
+        # detections first, then the state, each through a temporary file + os.replace: an interrupted save leaves the
+        # previous (consistent) checkpoint in place instead of a truncated JSON that would silently restart from zero
         if detections:
             write_geojson(self._create_geodataframe(detections), self.data_file)
+        with open(self.temp_state_file, 'w') as f:
+            json.dump(state, f, indent=2)
+        os.replace(self.temp_state_file, self.state_file)
 
     def load_checkpoint(self):
         """(processed_count, detections); a missing or unreadable checkpoint is ``(0, [])`` as in the reference
@@ -268,11 +271,12 @@ class ResultsManager:
                                "there is no CPU fallback")
         import torch
         eng = self.engine
-        rank = np.empty(len(dets), dtype=np.float32)
-        rank[order] = -np.arange(len(dets), dtype=np.float32)     # priority = position in the descending sort
+        rank = np.empty(len(dets), dtype=np.int64)
+        rank[order] = np.arange(len(dets), dtype=np.int64)        # priority = position in the descending sort (int64 tie-break, constant conf)
         x, y = eng.utm_forward(torch.from_numpy(lon).to(eng.device), torch.from_numpy(lat).to(eng.device), zone, True)
         if self.duplicate_distance > 0:
-            keep = eng.dedup(x, y, torch.from_numpy(rank).to(eng.device), float(self.duplicate_distance), inclusive=False).cpu().numpy()
+            keep = eng.dedup(x, y, torch.zeros(len(dets), dtype=torch.float32, device=eng.device), float(self.duplicate_distance),
+                             inclusive=False, tiebreak=torch.from_numpy(rank).to(eng.device)).cpu().numpy()
         else:
             keep = np.ones(len(dets), dtype=np.uint8)         # `distance < 0` is never true (:255): nothing is removed
         xs, ys = x.cpu().numpy(), y.cpu().numpy()

@@ -52,7 +52,7 @@ typedef struct b2d_geodet {
 
 /* ---- enums ----------------------------------------------------------------------------- */
 enum { B2D_ACT_NONE = 0, B2D_ACT_SILU = 1 };
-enum { B2D_CONV_AUTO = 0, B2D_CONV_TCGEN05 = 1, B2D_CONV_SIMT = 2 };
+enum { B2D_CONV_AUTO = 0, B2D_CONV_TCGEN05 = 1 };   /* one backend: a shape the tensor-core kernels cannot run fails b2d_plan_finalize */
 /* resize modes of b2d_preprocess */
 enum {
     B2D_RESIZE_IDENTITY = 0,     /* input already model-sized (BASELINE configs C2/C3)            */

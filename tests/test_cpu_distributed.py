@@ -68,22 +68,22 @@ def _worker(rank, world, port, H, W, res, thr, q):
     flag = _closure_np(gx, gy, flag, thr)
     lk = _greedy_with_key(gx[~flag], gy[~flag], conf[~flag], key[~flag], thr)
     local_keys = key[~flag][lk]
-    rec = torch.from_numpy(np.stack([gx[flag], gy[flag], conf[flag].astype(np.float64), mine[flag, 3], mine[flag, 4],
-                                     np.zeros(flag.sum())], 1).reshape(-1, M.RECORD_WORDS))
+    rec = M.pack_records(torch.from_numpy(gx[flag]), torch.from_numpy(gy[flag]), torch.from_numpy(conf[flag]),
+                         torch.zeros(int(flag.sum()), dtype=torch.int32), torch.from_numpy(key[flag]))      # the product's 32-byte records
+    assert rec.dtype == torch.int64 and tuple(rec.shape) == (int(flag.sum()), M.RECORD_WORDS)
 
     def gather_counts(k):
         t = torch.tensor([k], dtype=torch.int64); out = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(out, t); return [int(o) for o in out]
 
     def gather_padded(r, cap):
-        pad = torch.zeros((cap, M.RECORD_WORDS), dtype=torch.float64); pad[:r.shape[0]] = r
+        pad = torch.zeros((cap, M.RECORD_WORDS), dtype=torch.int64); pad[:r.shape[0]] = r
         out = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(out, pad); return out
 
     parts, origin = M.exchange_seam(rec, world, gather_counts, gather_padded)
-    allrec = torch.cat(parts).numpy()
-    gkey = allrec[:, 3].astype(np.int64) * 65536 + allrec[:, 4].astype(np.int64)
-    gk = _greedy_with_key(allrec[:, 0], allrec[:, 1], allrec[:, 2].astype(np.float32), gkey, thr)
+    ax, ay, ac, _, gkey = (t.numpy() for t in M.unpack_records(torch.cat(parts)))
+    gk = _greedy_with_key(ax, ay, ac, gkey, thr)
     seam_keys = gkey[gk][origin[gk] == rank]
     q.put((rank, np.concatenate([local_keys, seam_keys]), int(flag.sum()), len(mine)))
     dist.barrier()
@@ -122,6 +122,20 @@ def test_band_sharding_covers_every_window_once():
     assert tuple(w[78]) == (39936, 0, 64, 640) and tuple(w[-1]) == (39936, 39936, 64, 64)
     ref = OP.sliding_windows(40000, 40000, 640, 512)
     assert all((x1 - x0, y1 - y0) == (int(a[2]), int(a[3])) and (x0, y0) == (int(a[0]), int(a[1])) for (x0, y0, x1, y1), a in zip(ref[:200], w[:200]))
+
+
+def test_seam_records_round_trip_bit_exact():
+    rng = np.random.default_rng(3)
+    x, y = rng.normal(2.3e6, 1e3, 257), rng.normal(6.8e6, 1e3, 257)
+    conf = rng.random(257).astype(np.float32); conf[:3] = (-0.0, 1.0, np.float32(0.4) + np.float32(1e-7))
+    cls = rng.integers(0, 80, 257).astype(np.int32)
+    key = rng.integers(0, 2 ** 40, 257)
+    rec = M.pack_records(*(torch.from_numpy(a) for a in (x, y, conf, cls, key)))
+    bx, by, bc, bcls, bkey = (t.numpy() for t in M.unpack_records(rec))
+    assert np.array_equal(bx, x) and np.array_equal(by, y) and np.array_equal(bc.view(np.uint32), conf.view(np.uint32))
+    assert np.array_equal(bcls, cls) and np.array_equal(bkey, key)
+    dev = M.seam_flags_device(torch.tensor([100.0, 5100.0, 5115.0, 5200.0, 5260.0, 9000.0]), 0, [(0, 5248), (5120, 10368)], 11.0)
+    assert dev.dtype == torch.uint8 and dev.tolist() == [0, 0, 1, 1, 1, 1]
 
 
 def test_seam_flags_only_near_other_ranks():

@@ -60,8 +60,12 @@ def test_session_load_weights_dispatches_on_extension(tmp_path, v8):
     assert np.array_equal(got["model.21.cv2.weight"], w["model.21.cv2.weight"])
     np.savez(str(tmp_path / "m.npz"), **w)
     assert np.array_equal(S.load_weights(str(tmp_path / "m.npz"))["model.0.bias"], w["model.0.bias"])
-    with pytest.warns(UserWarning, match="synthetic"):
-        assert S.load_weights(str(tmp_path / "absent.onnx")) is None
+    with pytest.raises(FileNotFoundError, match="synthetic"):          # as ort.InferenceSession(model_path) does; no silent random weights
+        S.load_weights(str(tmp_path / "absent.onnx"))
+    with pytest.raises(FileNotFoundError):
+        S.resolve_weights(str(tmp_path / "absent.onnx"), "yolov8m", None)
+    assert S.resolve_weights(str(tmp_path / "absent.onnx"), "yolov8m", "synthetic") is None      # the explicit opt-in
+    assert S.resolve_weights(None, "yolov8m", w) is w
     (tmp_path / "m.bin").write_bytes(b"x")
     with pytest.raises(ValueError):
         S.load_weights(str(tmp_path / "m.bin"))

@@ -3,7 +3,7 @@
 Not a test and not the bench: a development tool run under gpurun, one section per
 process so that a hung kernel in one section cannot hide the others:
 
-    python tools/diag.py pre | simt | tcops | forward | post | time [--arch yolov8m] [--batch N]
+    python tools/diag.py pre | tcops | forward | post | time [--arch yolov8m] [--batch N]
 """
 import argparse
 import json
@@ -38,7 +38,7 @@ def stats(name, got, ref):
 def sec_pre(args):
     import cv2
     from PIL import Image
-    eng = Engine(args.arch, max_batch=2, imgsz=640, conv_impl="simt")
+    eng = Engine(args.arch, max_batch=2, imgsz=640, conv_impl="auto")
     rng = np.random.default_rng(0)
     cases = [rng.integers(0, 256, (864, 864, 3), dtype=np.uint8), rng.integers(0, 256, (1280, 1280, 3), dtype=np.uint8),
              rng.integers(0, 256, (1000, 1300, 3), dtype=np.uint8), synth.make_tiles(1, 640, 1)[0]]
@@ -322,6 +322,6 @@ if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     log(f"=== diag {a.section} arch={a.arch} batch={a.batch} imgsz={a.imgsz} dev={torch.cuda.get_device_name(0)}")
     t0 = time.time()
-    {"pre": sec_pre, "simt": lambda x: sec_ops(x, "simt"), "tcops": lambda x: sec_ops(x, "auto"), "forward": sec_forward,
+    {"pre": sec_pre, "tcops": lambda x: sec_ops(x, "auto"), "forward": sec_forward,
      "post": sec_post, "time": sec_time}[a.section](a)
     log(f"=== done {a.section} in {time.time()-t0:.1f}s")

@@ -26,28 +26,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 GT = (2335637.62, 0.1, 0.0, 6845688.78, 0.0, -0.1)     # 10 cm/px, EPSG:3857-style metres
-NPOOL = 32
-
-
-def band_on_device(pool, height, width, y_lo, y_hi, seed):
-    """uint8 CUDA [y_hi - y_lo, width, 3]: rows [y_lo, y_hi) of the mosaic whose 512-px block (by, bx) is
-    pool[hash(seed, by, bx)]."""
-    import torch
-    from aerial_image_recognition_b200.synth import BLOCK
-    by0, by1 = y_lo // BLOCK, (y_hi + BLOCK - 1) // BLOCK
-    nbx = (width + BLOCK - 1) // BLOCK
-    by = np.arange(by0, by1, dtype=np.uint64)[:, None]
-    bx = np.arange(nbx, dtype=np.uint64)[None, :]
-    h = (by * np.uint64(0x9E3779B97F4A7C15) + bx * np.uint64(0xC2B2AE3D27D4EB4F) + np.uint64(seed) * np.uint64(0x165667B19E3779F9))
-    h ^= h >> np.uint64(29)
-    idx = torch.from_numpy((h % np.uint64(NPOOL)).astype(np.int64)).to(pool.device)
-    rows = []
-    for r in range(by1 - by0):                                  # one block row at a time keeps the temporary small
-        strip = pool[idx[r]].permute(1, 0, 2, 3).reshape(BLOCK, nbx * BLOCK, 3)[:, :width]
-        lo = max(y_lo, (by0 + r) * BLOCK) - (by0 + r) * BLOCK
-        hi = min(y_hi, (by0 + r + 1) * BLOCK) - (by0 + r) * BLOCK
-        rows.append(strip[lo:hi])
-    return torch.cat(rows).contiguous()
 
 
 def main():
@@ -69,9 +47,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     H = W = args.size
     eng = Engine("yolov8m", max_batch=args.batch, device=local, seed=0)
-    pool = torch.from_numpy(np.stack([synth.make_block(77, 0, i) for i in range(NPOOL)])).to(eng.device)
+    pool = torch.from_numpy(synth.mosaic_block_pool(77)).to(eng.device)
     windows, ids, cover = M.shard_windows(H, W, rank, world)
-    band = band_on_device(pool, H, W, cover[0], cover[1], 5)
+    band = synth.mosaic_band_device(pool, H, W, cover[0], cover[1], 5)
     det = M.MosaicDetector(eng, GT, conf=0.4, dedup_thr=1.0)
 
     def barrier():

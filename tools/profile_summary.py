@@ -1,6 +1,8 @@
 """Aggregate an `ncu --metrics ... --csv` launch list of bench.py into per-kernel shares of ONE step.
-usage: python tools/profile_summary.py gpurun_out/launches_r1_metrics.csv > profiles/<name>.txt"""
-import collections, csv, sys
+usage: python tools/profile_summary.py gpurun_out/launches_metrics.csv [profiles/conv_dram_traffic.json] > profiles/<name>.txt
+With a second argument the conv_tc_* family's DRAM bytes per step are also written as JSON, together with the commit the
+pass was taken at -- bench.py reports that figure as roofline.traffic instead of a constant in its source."""
+import collections, csv, json, subprocess, sys
 rows = list(csv.reader(open(sys.argv[1])))
 h = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 hdr = rows[h]
@@ -34,3 +36,13 @@ for n, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
 conv = [a for n, a in agg.items() if n.startswith('conv_tc')]
 print(f"conv_tc_* family: {sum(a[0] for a in conv):.1f} us ({100 * sum(a[0] for a in conv) / tot:.1f}% of the step), {sum(a[1] for a in conv)} launches, "
       f"dram read {sum(a[2] for a in conv) / 1e9:.3f} GB + write {sum(a[3] for a in conv) / 1e9:.3f} GB = {sum(a[2] + a[3] for a in conv) / 1e9:.3f} GB per step")
+if len(sys.argv) > 2:
+    try:
+        commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], stdout=subprocess.PIPE, text=True).stdout.strip()
+        dirty = bool(subprocess.run(["git", "status", "--porcelain", "--", "aerial_image_recognition_b200/csrc"], stdout=subprocess.PIPE, text=True).stdout.strip())
+    except Exception:
+        commit, dirty = "unknown", True
+    json.dump({"dram_bytes_per_step": sum(a[2] + a[3] for a in conv), "dram_read_bytes": sum(a[2] for a in conv), "dram_write_bytes": sum(a[3] for a in conv),
+               "launches": sum(a[1] for a in conv), "commit": commit + ("+uncommitted csrc changes" if dirty else ""),
+               "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active... --clock-control none over `python bench.py --steps 2 --warmup 1 --legs ''`, one step (between two preprocess launches); " + sys.argv[1]},
+              open(sys.argv[2], "w"), indent=1)
