@@ -81,7 +81,9 @@ struct __align__(64) ConvTcParams {
     int in_h, in_w;       // input spatial size (stem)
     const void* src_raw;  // stem: NHWC4 bf16 input
     const void* w_raw;    // stem: packed weights [n_tile][64] bf16
-    int f16;              // 16-bit activation / weight format: 0 bf16, 1 fp16 (B2D_PREC_FP16)
+    int f16;              // 16-bit activation / weight format: 0 bf16, 1 fp16 (B2D_PREC_FP16, B2D_PREC_FP16X2)
+    int x2;               // 1: split-fp16 storage (B2D_PREC_FP16X2): inputs are [hi x 8 | lo x 8] groups, 16-bit outputs are written that way
+    float acc_scale;      // the accumulator is multiplied by this before the bias (1/255 in the stem: its input is the raw pixel value)
     int b_res;            // halo kernel: 1 = all 9 * chunks weight boxes stay resident in the stage slots (loaded once per CTA)
     int rev;              // 1: this op walks its M tiles in descending order (set per op by the engine)
     int rev_last;         // per launch: index of the last M tile when walking backwards, else -1
@@ -104,7 +106,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch,
                  const __nv_bfloat16* src, int src_h, int src_w, int src_cs, int src_c0, int cin,
                  void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32,
                  int ksz, int stride, int act, const float* w_host, const float* b_host,
-                 const __nv_bfloat16* res, int res_cs, int res_c0, int depthwise = 0, int f16 = 0);
+                 const __nv_bfloat16* res, int res_cs, int res_c0, int depthwise = 0, int f16 = 0, int x2 = 0, float acc_scale = 1.f);
 int conv_tc_dw_supported(int cin, int cout, int ksz, int stride, int dst_f32, int has_res);
 int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream);
 void conv_tc_free(ConvTcPlan* plan);
@@ -115,7 +117,7 @@ int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen);
 // ---------------------------------------------------------------------------------------
 int maxpool_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                    __nv_bfloat16* dst, int oh, int ow, int dst_cs, int dst_c0, int c, int k, int stride,
-                   int n, cudaStream_t stream, int f16 = 0);
+                   int n, cudaStream_t stream, int f16 = 0, int x2 = 0);
 int poolchain_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* const* dst, const int* dst_c0,
                      int dst_cs, int c, int stages, int n, cudaStream_t stream, int f16 = 0);
 int poolchain_fits(int h, int w);

@@ -335,21 +335,34 @@ __device__ __forceinline__ void sts_b64x2(uint32_t a, uint64_t x, uint64_t y) {
 // caller can run two 16-column units side by side (sixteen independent SiLU chains in flight per thread instead of
 // eight: with only two epilogue warps per scheduler the dependent FFMA2 / MUFU latencies are otherwise exposed).
 // `base` is the swizzled address of the unit's first 16-byte piece; the others are base ^ (j << 4).
+// `scale2` = the accumulator scale of the layer in both lanes: 0.5 for SiLU layers (the halving of silu2_h), 1 otherwise,
+// times ConvTcParams::acc_scale (1/255 in the stem, whose input is the raw 0..255 pixel value; 1 elsewhere).  fma(acc, 1, b)
+// rounds exactly like acc + b.
 template <int ACT, int NC>
-__device__ __forceinline__ void epi_bias(const uint32_t (&r)[16], uint32_t bias_addr, uint64_t (&v)[8]) {
-    const uint64_t half2 = pk2(0.5f, 0.5f);
+__device__ __forceinline__ void epi_bias(const uint32_t (&r)[16], uint32_t bias_addr, uint64_t (&v)[8], uint64_t scale2) {
 #pragma unroll
     for (int j = 0; j < NC / 4; ++j) {
         uint64_t b0, b1;
         lds_b64x2(bias_addr + 16 * j, b0, b1);          // ACT layers keep 0.5 * bias in shared memory (prologue)
-        if (ACT) {
-            v[2 * j] = fma2(pk2u(r[4 * j], r[4 * j + 1]), half2, b0);
-            v[2 * j + 1] = fma2(pk2u(r[4 * j + 2], r[4 * j + 3]), half2, b1);
-        } else {
-            v[2 * j] = add2(pk2u(r[4 * j], r[4 * j + 1]), b0);
-            v[2 * j + 1] = add2(pk2u(r[4 * j + 2], r[4 * j + 3]), b1);
-        }
+        v[2 * j] = fma2(pk2u(r[4 * j], r[4 * j + 1]), scale2, b0);
+        v[2 * j + 1] = fma2(pk2u(r[4 * j + 2], r[4 * j + 3]), scale2, b1);
     }
+}
+// Split-fp16 storage (B2D_PREC_FP16X2): a value v is kept as hi = fp16(v) and lo = fp16(v - hi), ~22 mantissa bits.  Eight
+// channels form one 32-byte group [hi x 8 | lo x 8]; a convolution reads the pair as 16 K positions against the same
+// weight twice, so the tensor core computes w * hi + w * lo with exact products and fp32 accumulation.
+__device__ __forceinline__ void split2(uint64_t v, uint32_t& hi, uint32_t& lo) {      // two values -> packed hi pair, packed lo pair
+    float a, b;
+    upk2(v, a, b);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(__fsub_rn(a, hf.x), __fsub_rn(b, hf.y));
+    hi = *(const uint32_t*)&h;
+    lo = *(const uint32_t*)&l;
+}
+__device__ __forceinline__ uint64_t join2(uint32_t hi, uint32_t lo) {                  // packed hi pair + packed lo pair -> two fp32 values
+    const float2 a = __half22float2(*(const __half2*)&hi), b = __half22float2(*(const __half2*)&lo);
+    return pk2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
 }
 template <int RES, int F32, int NC>
 __device__ __forceinline__ void epi_store(uint64_t (&v)[8], uint32_t base, int exp, int f16) {
@@ -360,7 +373,24 @@ __device__ __forceinline__ void epi_store(uint64_t (&v)[8], uint32_t base, int e
         if (acc == 0x123456789ull) sts_b64x2(base, acc, acc);
         return;
     }
-    if (F32) {
+    if (F32 == 2) {             // split fp16: per 8 columns one 16-byte piece of high parts, then one of low parts
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+            const uint32_t a_hi = base ^ (uint32_t)((2 * j) << 4), a_lo = base ^ (uint32_t)((2 * j + 1) << 4);
+            if (RES) {
+                const uint4 xh = lds128(a_hi), xl = lds128(a_lo);
+                v[4 * j] = add2(v[4 * j], join2(xh.x, xl.x));
+                v[4 * j + 1] = add2(v[4 * j + 1], join2(xh.y, xl.y));
+                v[4 * j + 2] = add2(v[4 * j + 2], join2(xh.z, xl.z));
+                v[4 * j + 3] = add2(v[4 * j + 3], join2(xh.w, xl.w));
+            }
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split2(v[4 * j + i], h[i], l[i]);
+            sts128(a_hi, make_uint4(h[0], h[1], h[2], h[3]));
+            sts128(a_lo, make_uint4(l[0], l[1], l[2], l[3]));
+        }
+    } else if (F32) {
 #pragma unroll
         for (int j = 0; j < NC / 4; ++j) sts_b64x2(base ^ (uint32_t)(j << 4), v[2 * j], v[2 * j + 1]);
     } else {
@@ -398,9 +428,9 @@ __device__ __forceinline__ void epi_store(uint64_t (&v)[8], uint32_t base, int e
     }
 }
 template <int ACT, int RES, int F32, int NC = 16>
-__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base, int exp, int f16) {
+__device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_addr, uint32_t base, int exp, int f16, uint64_t scale2) {
     uint64_t v[8];
-    epi_bias<ACT, NC>(r, bias_addr, v);
+    epi_bias<ACT, NC>(r, bias_addr, v, scale2);
     if (ACT && !(exp & 8)) {
 #pragma unroll
         for (int i = 0; i < NC / 2; ++i) v[i] = silu2_h(v[i]);
@@ -411,7 +441,7 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_
 // Geometry of the staging slabs, shared by the epilogue warps and the store warp.  A tile row of n_tile columns is cut
 // into chunks of 128 / 64 / 32 bytes (one tensor map per width); a quarter's slab of one tile holds 32 rows x chunk for
 // every chunk, full 128-byte chunks first, then one 64-byte, then one 32-byte chunk (mirrors conv_tc_plan).
-template <int F32>
+template <int F32>      // 0: 16-bit outputs, 1: fp32 outputs, 2: split fp16 (hi | lo) -- 4 bytes per output column like fp32
 struct EpiGeom {
     static constexpr int esize = F32 ? 4 : 2;
     uint32_t row_bytes, tile_bytes, slab0, buf_stride, n128, has64, has32;
@@ -468,7 +498,7 @@ __device__ __forceinline__ void store_loop(const ConvTcParams& p, int total_tile
         const uint32_t sa = g.slab0 + (uint32_t)slab * g.tile_bytes;
         if (load) {
             const uint32_t bar = rbar_u32 + (uint32_t)slab * 8u;
-            mbar_expect_tx_u32(bar, 32u * (uint32_t)(n_tile * 2));
+            mbar_expect_tx_u32(bar, 32u * (uint32_t)(n_tile * EpiGeom<F32>::esize));
             g.for_each_chunk([&](int map, uint32_t off, int col0) { tma_load_4d(&p.tmR[map], bar, sa + off, c0 + col0, c1, c2, c3); });
         } else {
             g.for_each_chunk([&](int map, uint32_t off, int col0) { tma_store_4d(&p.tmO[map], sa + off, c0 + col0, c1, c2, c3); });
@@ -548,6 +578,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     const uint32_t tempty_arrive = pair ? mapa_u32(tempty_u32, 0) : tempty_u32;   // the leader's barrier gates the pair's MMAs
     const bool ldt = !B2D_EXP(p, 4);
     const int f16 = p.f16;
+    const float sc = (ACT ? 0.5f : 1.0f) * p.acc_scale;
+    const uint64_t scale2 = pk2(sc, sc);
     const int split_col = (nunits - 1) * 16 + half * 8;
     for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
         const int as = it & 1;
@@ -575,8 +607,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
                 if (RES) mbar_wait_u32(rbar_u32 + (uint32_t)slab * 8u, use & 1u);
             }
             const uint32_t moff = (uint32_t)slab * tile_bytes;
-            if (u < my_units) epi_unit<ACT, RES, F32, 16>(rb, baddr + u * 128, unit_base((uint32_t)(half + 2 * u) * ubytes) + moff, B2D_EXPW(p), f16);
-            else epi_unit<ACT, RES, F32, 8>(rb, bias_base + (uint32_t)(ch_base + split_col) * 4u, unit_base((uint32_t)split_col * esize) + moff, B2D_EXPW(p), f16);
+            if (u < my_units) epi_unit<ACT, RES, F32, 16>(rb, baddr + u * 128, unit_base((uint32_t)(half + 2 * u) * ubytes) + moff, B2D_EXPW(p), f16, scale2);
+            else epi_unit<ACT, RES, F32, 8>(rb, bias_base + (uint32_t)(ch_base + split_col) * 4u, unit_base((uint32_t)split_col * esize) + moff, B2D_EXPW(p), f16, scale2);
             if (u == ipt - 1) {                                                // last item: hand the slab to the store warp (64 arrivals per quarter)
                 fence_proxy_async();                                           // generic-proxy slab writes -> visible to the TMA store
                 mbar_arrive_u32(sfull_u32 + (uint32_t)slab * 8u);
@@ -1170,7 +1202,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
 // holds the four groups' diagonal entries side by side (k = group * 16 + n), so a group's block is the
 // same 16 rows at K offset 32 B x group -- 144 full 128-byte TMA rows instead of 576 32-byte ones.
 // ---------------------------------------------------------------------------------------------
-template <int ACT>
+// Split-fp16 storage (OUT == 2): a 64-channel storage chunk holds 32 real channels as four [hi x 8 | lo x 8] groups; real
+// channels 16 g2 .. 16 g2 + 15 (storage groups 2 g2 and 2 g2 + 1) share one block of 16 accumulator columns, filled by two
+// K = 16 MMAs per tap whose B blocks carry the channel's weight at both its hi and its lo position.
+template <int ACT, int OUT>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1187,7 +1222,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
     const uint32_t smem_a = smem_u32(smem), smem_b = smem_a + 2u * (uint32_t)mt * halo_bytes;
     const uint32_t full_u32 = smem_u32(b.full), empty_u32 = smem_u32(b.empty);
     const uint32_t hfull_u32 = smem_u32(b.hfull), hempty_u32 = smem_u32(b.hempty);
-    const int chunks = p.chunks;                 // 64-channel chunks per n_tile
+    const int chunks = p.chunks;                 // 64-channel (storage) chunks per n_tile
 
     if (warp == 0) {
         int stage = 0, hb = 0;
@@ -1250,7 +1285,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
                 tc_fence_after();
                 if (ch == 0 && isu == 0) trace(p, 1, it, 2);
                 const uint32_t a_base = smem_a + (uint32_t)(hb * mt) * halo_bytes;
-                const int ngroups = min(4, (n_tile - ch * 64) >> 4);      // 16-channel groups in this chunk
+                const int ngroups = min(4, ((OUT == 2 ? 2 * n_tile : n_tile) - ch * 64) >> 4);      // 16-channel (storage) groups in this chunk
                 if (elect_one()) {
                     const uint32_t b_lo = desc_lo(smem_b) + (uint32_t)stage * b_units;
                     for (int m = 0; m < nv; ++m) {
@@ -1258,10 +1293,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
                         for (int tap = 0; tap < 9; ++tap) {
                             const uint32_t a_lo = desc_lo(a_base + (uint32_t)m * halo_bytes + (uint32_t)(tap / 3) * kh_bytes + (uint32_t)(tap % 3) * 128u);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (j < ngroups && (j & 1) == isu)
+                            for (int j = 0; j < 4; ++j) {
+                                if (OUT == 2) {      // storage groups 2 g2, 2 g2 + 1 -> accumulator block g2 (one issuer per block: the two MMAs are ordered)
+                                    if (j < ngroups && ((j >> 1) & 1) == isu)
+                                        umma_bf16(d_tmem + (uint32_t)(m * n_tile + ch * 32 + (j >> 1) * 16), desc64(hi_a, a_lo + 2 * j),
+                                                  desc64(hi_b, b_lo + (uint32_t)(tap * 128 + 2 * j)), idesc, (uint32_t)(tap != 0 || (j & 1) != 0));
+                                } else if (j < ngroups && (j & 1) == isu) {
                                     umma_bf16(d_tmem + (uint32_t)(m * n_tile + ch * 64 + j * 16), desc64(hi_a, a_lo + 2 * j),
                                               desc64(hi_b, b_lo + (uint32_t)(tap * 128 + 2 * j)), idesc, (uint32_t)(tap != 0));
+                                }
+                            }
                         }
                     }
                     umma_commit(empty_u32 + stage * 8);
@@ -1274,9 +1315,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
             if (isu == 0) trace(p, 1, it, 3);
         }
     } else if (warp == 3) {
-        store_loop<0, 0>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
+        store_loop<0, OUT>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
     } else if (warp >= 4) {
-        epilogue_loop<ACT, 0, 0>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
+        epilogue_loop<ACT, 0, OUT>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
     }
     epilogue_exit(p, tmem_base, warp);
 }
@@ -1289,7 +1330,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dw_kernel(const __grid_co
 // pattern (k = tap * 4 + c, zero-padded to 48).  Three K=16 MMAs per tile against the weights, which
 // stay resident in shared memory.  Bound by its output (bias + SiLU + 96 B written per pixel).
 // ---------------------------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, int OUT>
 __global__ void __launch_bounds__(kStemThreads, 1) conv_tc_stem_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1396,9 +1437,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_tc_stem_kernel(const __g
             if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 3) {
-        store_loop<0, 0>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
+        store_loop<0, OUT>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
     } else if (warp >= 4) {
-        epilogue_loop<ACT, 0, 0>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
+        epilogue_loop<ACT, 0, OUT>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
     }
     epilogue_exit(p, tmem_base, warp);
 }
@@ -1507,7 +1548,7 @@ int conv_tc_supported(int cin, int ksz, int stride) {
 
 // depthwise 3x3 stride 1 with 16-channel groups on the tensor cores
 int conv_tc_dw_supported(int cin, int cout, int ksz, int stride, int dst_f32, int has_res) {
-    return cin == cout && cin % 16 == 0 && ksz == 3 && stride == 1 && !dst_f32 && !has_res && env_int("B2D_DW_TC", 1) != 0;
+    return cin == cout && cin % 16 == 0 && ksz == 3 && stride == 1 && !dst_f32 && !has_res;
 }
 
 // the network input: 4-channel NHWC buffer of which the first `cin` (<= 4) carry weights, 3x3 or 1x1, bf16 output
@@ -1518,9 +1559,13 @@ int conv_tc_stem_supported(int src_cs, int cin, int ksz, int stride, int cout, i
 int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloat16* src, int src_h, int src_w, int src_cs,
                  int src_c0, int cin, void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32, int ksz,
                  int stride, int act, const float* w_host, const float* b_host, const __nv_bfloat16* res, int res_cs,
-                 int res_c0, int depthwise, int f16) {
+                 int res_c0, int depthwise, int f16, int x2, float acc_scale) {
+    // Channel arguments are REAL channel counts.  In split-fp16 storage (x2) a 16-bit buffer keeps 2 x 16 bits per channel
+    // ([hi x 8 | lo x 8] groups, see split2): the A operand then has K = 2 * cin storage channels against weights packed twice,
+    // and 16-bit outputs / residuals are 4 bytes per channel like fp32 ones.  The network input (stem) is never split.
     memset(plan, 0, sizeof(*plan));
     const bool dw = depthwise != 0;
+    B2D_CHECK(!x2 || f16, "conv_tc: split storage is fp16");
     if (dw) B2D_CHECK(conv_tc_dw_supported(cin, cout, ksz, stride, dst_f32, res != nullptr), "conv_tc: unsupported depthwise shape");
     const bool stem = !dw && conv_tc_stem_supported(src_cs, cin, ksz, stride, cout, dst_f32, res != nullptr) && src_c0 == 0;
     if (!stem) {
@@ -1530,17 +1575,20 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     }
     ConvTcParams& p = plan->p;
     plan->sm_count = sm_count;
+    const int kmul = (x2 && !stem) ? 2 : 1;        // storage channels per real input channel
+    const int kin = cin * kmul, src_cs_s = src_cs * kmul, src_c0_s = src_c0 * kmul;
     p.in_h = src_h; p.in_w = src_w; p.src_raw = src;
-    p.W = dst_w; p.H = dst_h; p.cin = cin; p.cout = cout;
+    p.W = dst_w; p.H = dst_h; p.cin = kin; p.cout = cout;
     p.ksz = ksz; p.taps = ksz * ksz; p.stride = stride;
     p.act = act; p.out_f32 = dst_f32;
-    p.chunks = stem ? 1 : ceil_div(cin, 64);       // a short last chunk is zero-filled by TMA (A) and zero-padded in the packed weights (B)
+    p.x2 = x2; p.acc_scale = acc_scale;
+    p.chunks = stem ? 1 : ceil_div(kin, 64);       // a short last chunk is zero-filled by TMA (A) and zero-padded in the packed weights (B)
     const int cout_pad = ceil_div(cout, 16) * 16;
     int split = 1;
-    while (cout_pad % split != 0 || (cout_pad / split) % 16 != 0 || cout_pad / split > 256 || (dw && split > 1 && (cout_pad / split) % 64 != 0)) ++split;
+    while (cout_pad % split != 0 || (cout_pad / split) % 16 != 0 || cout_pad / split > 256 || (dw && split > 1 && (kmul * cout_pad / split) % 64 != 0)) ++split;
     p.n_tile = cout_pad / split;
     p.n_tiles_n = split;
-    if (dw) p.chunks = ceil_div(p.n_tile, 64);     // depthwise: chunks of one channel tile
+    if (dw) p.chunks = ceil_div(kmul * p.n_tile, 64);     // depthwise: storage chunks of one channel tile
     pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn, dw);
     p.perm = p.bn > 1 ? 1 : 0;
     p.tiles_x = ceil_div(dst_w, p.bw);
@@ -1554,7 +1602,8 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.a_tx_bytes = p.a_bytes;
     p.b_tx_bytes = dw ? 144 * 128 : p.n_tile * 64 * 2;      // depthwise: [9 taps][16 rows] x 128 B per 64-channel chunk
     p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
-    const int esize = dst_f32 ? 4 : 2;
+    const int esize = (dst_f32 || x2) ? 4 : 2;     // bytes per output column in the destination buffer
+    const int esize_r = x2 ? 4 : 2;                // ... and per residual column
     B2D_CHECK(!(dst_f32 && res), "conv_tc: residual with fp32 output is not supported");
     B2D_CHECK(((size_t)dst_cs * esize) % 16 == 0 && ((size_t)dst_c0 * esize) % 16 == 0,
               "conv_tc: destination slice must be 16-byte aligned (cs=%d c0=%d)", dst_cs, dst_c0);
@@ -1675,7 +1724,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.tmem_cols = cols;
     // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     p.f16 = f16;
-    p.idesc = (1u << 4) | (f16 ? 0u : (1u << 7) | (1u << 10)) |        // D fp32; A / B format: 1 = bf16, 0 = fp16
+    p.idesc = (1u << 4) | (f16 ? 0u : (1u << 7) | (1u << 10)) |        // D fp32; A / B format: 1 = bf16, 0 = fp16 (also the split storage)
               ((uint32_t)((dw ? 16 : p.n_tile) >> 3) << 17) | ((uint32_t)((p.pair ? 2 * kTileM : kTileM) >> 4) << 24);
 
     // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin_pad] (zero padded) ----
@@ -1683,7 +1732,18 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     const size_t ktot = stem ? 64 : (size_t)p.taps * cin_pad;     // stem: k = tap * 4 + c, one 128-byte row per output channel
     const int dw_chunks = p.chunks * split;                       // depthwise: 64-channel chunks over all channels
     std::vector<uint16_t> wp(dw ? (size_t)dw_chunks * 9 * 16 * 64 : (size_t)cout_pad * ktot, 0);
-    if (dw) {
+    if (dw && x2) {
+        // a 64-channel storage chunk = 32 real channels; real channel r of the chunk -> accumulator block g2 = r / 16, column
+        // n = r % 16, storage K group q = 2 g2 + n / 8, K positions j = n % 8 (its hi) and j + 8 (its lo)
+        for (int c = 0; c < cout; ++c)
+            for (int t = 0; t < 9; ++t) {
+                const int chunk = c / 32, r = c % 32, g2 = r / 16, n = r % 16, q = 2 * g2 + n / 8, j = n % 8;
+                const size_t row = ((size_t)chunk * 9 + t) * 16 + n;
+                const uint16_t v = f2h(w_host[(size_t)c * 9 + t]);
+                wp[row * 64 + q * 16 + j] = v;
+                wp[row * 64 + q * 16 + j + 8] = v;
+            }
+    } else if (dw) {
         // row (chunk * 9 + tap) * 16 + n, 64 k each: k = group * 16 + n carries w[chunk * 64 + group * 16 + n][tap]
         for (int c = 0; c < cout; ++c)
             for (int t = 0; t < 9; ++t) {
@@ -1694,8 +1754,18 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     } else {
         for (int o = 0; o < cout; ++o)
             for (int c = 0; c < cin; ++c)
-                for (int t = 0; t < p.taps; ++t)
-                    wp[(size_t)o * ktot + (stem ? (size_t)t * 4 + c : (size_t)t * cin_pad + c)] = f16 ? f2h(w_host[((size_t)o * cin + c) * p.taps + t]) : f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
+                for (int t = 0; t < p.taps; ++t) {
+                    const uint16_t v = f16 ? f2h(w_host[((size_t)o * cin + c) * p.taps + t]) : f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
+                    if (stem) {
+                        wp[(size_t)o * ktot + (size_t)t * 4 + c] = v;
+                    } else if (kmul == 2) {      // the weight sits under the channel's hi and lo position
+                        const size_t k = (size_t)t * cin_pad + 16 * (c / 8) + (c % 8);
+                        wp[(size_t)o * ktot + k] = v;
+                        wp[(size_t)o * ktot + k + 8] = v;
+                    } else {
+                        wp[(size_t)o * ktot + (size_t)t * cin_pad + c] = v;
+                    }
+                }
     }
     std::vector<float> bp(cout_pad, 0.f);
     for (int o = 0; o < cout; ++o) bp[o] = b_host ? b_host[o] : 0.f;
@@ -1720,20 +1790,20 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
             uint32_t box[2] = {64u, (uint32_t)(p.pair ? p.n_tile / 2 : p.n_tile)};
             if (encode_map(&p.tmB, plan->w_dev, 2, dims, str, box, 128)) return -1;
         }
-        const uint64_t pix = (uint64_t)src_cs * 2, rowb = (uint64_t)src_w * pix, imgb = (uint64_t)src_h * rowb;
+        const uint64_t pix = (uint64_t)src_cs_s * 2, rowb = (uint64_t)src_w * pix, imgb = (uint64_t)src_h * rowb;
         if (p.kind == 1 || p.kind == 3) {
-            if (encode_act_map(&p.tmA[0], (void*)(src + src_c0), cin, src_w, src_h, max_batch, pix, rowb, imgb, 64u, (uint32_t)p.halo_w,
+            if (encode_act_map(&p.tmA[0], (void*)(src + src_c0_s), kin, src_w, src_h, max_batch, pix, rowb, imgb, 64u, (uint32_t)p.halo_w,
                                (uint32_t)(p.bh + 2), (uint32_t)p.bn, perm, 128))
                 return -1;
         } else if (stride == 1) {
-            if (encode_act_map(&p.tmA[0], (void*)(src + src_c0), cin, src_w, src_h, max_batch, pix, rowb, imgb, 64u, (uint32_t)p.bw, (uint32_t)p.bh,
+            if (encode_act_map(&p.tmA[0], (void*)(src + src_c0_s), kin, src_w, src_h, max_batch, pix, rowb, imgb, 64u, (uint32_t)p.bw, (uint32_t)p.bh,
                                (uint32_t)p.bn, perm, 128))
                 return -1;
         } else {
             for (int py = 0; py < 2; ++py)
                 for (int px = 0; px < 2; ++px) {
-                    const __nv_bfloat16* base = src + ((size_t)py * src_w + px) * src_cs + src_c0;
-                    if (encode_act_map(&p.tmA[py * 2 + px], (void*)base, cin, src_w / 2, src_h / 2, max_batch, 2 * pix, 2 * rowb, imgb, 64u,
+                    const __nv_bfloat16* base = src + ((size_t)py * src_w + px) * src_cs_s + src_c0_s;
+                    if (encode_act_map(&p.tmA[py * 2 + px], (void*)base, kin, src_w / 2, src_h / 2, max_batch, 2 * pix, 2 * rowb, imgb, 64u,
                                        (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, perm, 128))
                         return -1;
                 }
@@ -1750,12 +1820,12 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         for (int si = 0; si < 3; ++si) {
             if (!used[si]) continue;
             if (encode_act_map(&p.tmO[si], (uint8_t*)dst + (size_t)dst_c0 * esize, cout, dst_w, dst_h, max_batch, pix, rowb, imgb,
-                               spans[si] / (uint32_t)esize, (uint32_t)p.bw, sbh, sbn, perm, spans[si], dst_f32 != 0))
+                               spans[si] / (uint32_t)esize, (uint32_t)p.bw, sbh, sbn, perm, spans[si], esize == 4))
                 return -1;
             if (res) {
-                const uint64_t rpix = (uint64_t)res_cs * 2, rrow = (uint64_t)dst_w * rpix, rimg = (uint64_t)dst_h * rrow;
-                if (encode_act_map(&p.tmR[si], (void*)(res + res_c0), cout, dst_w, dst_h, max_batch, rpix, rrow, rimg, spans[si] / 2u,
-                                   (uint32_t)p.bw, sbh, sbn, perm, spans[si], false))
+                const uint64_t rpix = (uint64_t)res_cs * esize_r, rrow = (uint64_t)dst_w * rpix, rimg = (uint64_t)dst_h * rrow;
+                if (encode_act_map(&p.tmR[si], (void*)((const uint8_t*)res + (size_t)res_c0 * esize_r), cout, dst_w, dst_h, max_batch, rpix, rrow, rimg,
+                                   spans[si] / (uint32_t)esize_r, (uint32_t)p.bw, sbh, sbn, perm, spans[si], esize_r == 4))
                     return -1;
             }
         }
@@ -1765,14 +1835,16 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
 
 namespace {
 typedef void (*ConvKernel)(const ConvTcParams, int);
-// (kind, act, res, f32) -> instantiation; fp32 outputs never carry a residual
-ConvKernel pick_kernel(int kind, int pair, int act, int res, int f32) {
+// (kind, act, res, out) -> instantiation; out: 0 16-bit, 1 fp32 (never with a residual), 2 split fp16
+ConvKernel pick_kernel(int kind, int pair, int act, int res, int out) {
 #define B2D_PICK(K)                                                        \
-    if (f32) return act ? K<1, 0, 1> : K<0, 0, 1>;                         \
+    if (out == 1) return act ? K<1, 0, 1> : K<0, 0, 1>;                    \
+    if (out == 2 && res) return act ? K<1, 1, 2> : K<0, 1, 2>;             \
+    if (out == 2) return act ? K<1, 0, 2> : K<0, 0, 2>;                    \
     if (res) return act ? K<1, 1, 0> : K<0, 1, 0>;                         \
     return act ? K<1, 0, 0> : K<0, 0, 0>;
-    if (kind == 2) return act ? conv_tc_stem_kernel<1> : conv_tc_stem_kernel<0>;
-    if (kind == 3) return act ? conv_tc_dw_kernel<1> : conv_tc_dw_kernel<0>;
+    if (kind == 2) return out == 2 ? (act ? conv_tc_stem_kernel<1, 2> : conv_tc_stem_kernel<0, 2>) : (act ? conv_tc_stem_kernel<1, 0> : conv_tc_stem_kernel<0, 0>);
+    if (kind == 3) return out == 2 ? (act ? conv_tc_dw_kernel<1, 2> : conv_tc_dw_kernel<0, 2>) : (act ? conv_tc_dw_kernel<1, 0> : conv_tc_dw_kernel<0, 0>);
     if (kind == 1 && pair) { B2D_PICK(conv_tc_halo2_kernel) }
     if (kind == 1) { B2D_PICK(conv_tc_halo_kernel) }
     B2D_PICK(conv_tc_kernel)
@@ -1797,7 +1869,7 @@ int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
         const int prs = ceil_div(tiles, 2);
         grid = 2 * (prs < plan->sm_count / 2 ? prs : plan->sm_count / 2);
     }
-    ConvKernel k = pick_kernel(p.kind, p.pair, p.act, p.has_res, p.out_f32);
+    ConvKernel k = pick_kernel(p.kind, p.pair, p.act, p.has_res, p.out_f32 ? 1 : p.x2 ? 2 : 0);
     if (b2d_func_smem_optin((const void*)k, 227 * 1024)) return -2;
     if (p.trace) B2D_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * kTraceRoles * kTraceTiles * kTraceEvents, stream));
     {
@@ -1859,6 +1931,6 @@ int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
     static const char* kinds[5] = {"", "-halo", "-stem", "-depthwise", "-halo-pair"};
     return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d%s stg %d tmem %u smem %zu",
-                    kinds[p.pair ? 4 : p.kind], p.ksz, p.stride, p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
+                    kinds[p.pair ? 4 : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
                     p.b_res ? " (resident)" : "", p.stg_bufs, p.tmem_cols, plan->smem_bytes);
 }

@@ -91,6 +91,7 @@ struct b2d_engine {
     int sm_count = 0;
     bool finalized = false;
     int f16 = 0;                            // 16-bit activation / weight format: 0 bf16 (default), 1 fp16 (b2d_set_precision)
+    int x2 = 0;                             // 1: split-fp16 storage (B2D_PREC_FP16X2): every 16-bit activation is an fp16 hi + an fp16 lo part
     std::vector<Buffer> bufs;
     std::vector<OpDesc> descs;
     std::vector<Op> ops;
@@ -205,8 +206,11 @@ int launch_op(b2d_engine* e, const Op& op, int n, cudaStream_t s) {
         case OP_CONV_TC: return conv_tc_launch(&op.tc, n, s);
         case OP_MAXPOOL:
             return maxpool_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.dst, op.oh, op.ow, op.dst_cs, op.dst_c0, op.c, op.k,
-                                  op.stride, n, s, e->f16);
-        case OP_UPSAMPLE: return upsample2x_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.dst, op.dst_cs, op.dst_c0, op.c, n, s);
+                                  op.stride, n, s, e->f16, e->x2);
+        case OP_UPSAMPLE: {       // a copy: in split storage a channel is simply 4 bytes instead of 2
+            const int m = e->x2 ? 2 : 1;
+            return upsample2x_launch(op.src, op.h, op.w, op.src_cs * m, op.src_c0 * m, op.dst, op.dst_cs * m, op.dst_c0 * m, op.c * m, n, s);
+        }
         case OP_POOLCHAIN:
             return poolchain_launch(op.src, op.h, op.w, op.src_cs, op.src_c0, op.chain_dst, op.chain_c0, op.dst_cs, op.c, op.chain_stages, n, s, e->f16);
         case OP_NOP: return 0;
@@ -371,18 +375,23 @@ int b2d_device_sm_count(b2d_engine* e) { return e ? e->sm_count : -1; }
 
 int b2d_set_precision(b2d_engine* e, int precision) {
     B2D_CHECK(e && !e->finalized && e->descs.empty(), "set_precision: call right after b2d_create, before planning");
-    B2D_CHECK(precision == B2D_PREC_BF16 || precision == B2D_PREC_FP16, "set_precision: unknown precision %d", precision);
-    e->f16 = precision == B2D_PREC_FP16;
+    B2D_CHECK(precision == B2D_PREC_BF16 || precision == B2D_PREC_FP16 || precision == B2D_PREC_FP16X2, "set_precision: unknown precision %d", precision);
+    B2D_CHECK(e->bufs.empty(), "set_precision: call before b2d_plan_buffer (the storage width of every buffer depends on it)");
+    e->f16 = precision != B2D_PREC_BF16;
+    e->x2 = precision == B2D_PREC_FP16X2;
     return 0;
 }
-int b2d_get_precision(b2d_engine* e) { return e ? (e->f16 ? B2D_PREC_FP16 : B2D_PREC_BF16) : -1; }
+int b2d_get_precision(b2d_engine* e) { return e ? (e->x2 ? B2D_PREC_FP16X2 : e->f16 ? B2D_PREC_FP16 : B2D_PREC_BF16) : -1; }
 
 int b2d_plan_buffer(b2d_engine* e, int h, int w, int c, int is_f32) {
     B2D_CHECK(e && !e->finalized, "plan_buffer: engine finalized or null");
     B2D_CHECK(h > 0 && w > 0 && c > 0, "plan_buffer: bad shape");
     B2D_ENTER(e);
     Buffer b{h, w, c, is_f32, nullptr, 0};
-    b.bytes = (size_t)e->max_batch * h * w * c * (is_f32 ? 4 : 2);
+    // bytes per channel: 4 (fp32 head maps), 2 (bf16 / fp16), or 2 + 2 in split storage -- except buffer 0, the network
+    // input, which holds raw pixel values (exact in 16 bits) in every mode
+    const bool split = e->x2 && !is_f32 && !e->bufs.empty();
+    b.bytes = (size_t)e->max_batch * h * w * c * ((is_f32 || split) ? 4 : 2);
     B2D_CUDA(cudaMalloc(&b.ptr, b.bytes));
     B2D_CUDA(cudaMemset(b.ptr, 0, b.bytes));
     e->bufs.push_back(b);
@@ -495,16 +504,18 @@ int b2d_plan_finalize(b2d_engine* e) {
             B2D_CHECK(tc, "plan_finalize: op %zu (conv k%d s%d cin %d, source slice %d of %d channels) has no tcgen05 kernel", i, d.k, d.stride,
                       d.cin, d.src_c0, sb.c);
             op.kind = OP_CONV_TC;
+            // the network input holds raw 0..255 pixel values: the reference's `/ 255.0` is the stem's accumulator scale
+            const float acc_scale = d.src == 0 ? 1.0f / 255.0f : 1.0f;
             if (conv_tc_plan(&op.tc, e->sm_count, e->max_batch, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin,
                              db.ptr, db.h, db.w, db.c, d.dst_c0, d.cout, db.f32, d.k, d.stride, d.act, d.w.data(), d.b.data(), res,
-                             res_cs, d.res_c0, 0, e->f16))
+                             res_cs, d.res_c0, 0, e->f16, e->x2, acc_scale))
                 return -1;
         } else if (d.kind_req == 1) {
             B2D_CHECK(conv_tc_dw_supported(d.cin, d.cout, 3, 1, db.f32, 0) && sb.c % 8 == 0 && d.src_c0 % 8 == 0,
                       "plan_finalize: op %zu (depthwise, %d channels) has no tcgen05 kernel", i, d.cin);
             op.kind = OP_CONV_TC;
             if (conv_tc_plan(&op.tc, e->sm_count, e->max_batch, (const __nv_bfloat16*)sb.ptr, sb.h, sb.w, sb.c, d.src_c0, d.cin, db.ptr, db.h,
-                             db.w, db.c, d.dst_c0, d.cout, 0, 3, 1, d.act, d.w.data(), d.b.data(), nullptr, 0, 0, 1, e->f16))
+                             db.w, db.c, d.dst_c0, d.cout, 0, 3, 1, d.act, d.w.data(), d.b.data(), nullptr, 0, 0, 1, e->f16, e->x2))
                 return -1;
         } else {
             op.kind = d.kind_req == 2 ? OP_MAXPOOL : OP_UPSAMPLE;
@@ -522,6 +533,7 @@ int b2d_plan_finalize(b2d_engine* e) {
     // source, which are the same three tensors because max-pooling with -inf padding composes).
     for (size_t i = 0; i + 1 < e->ops.size(); ++i) {
         Op& a = e->ops[i];
+        if (e->x2) break;                        // split storage: the pools run one by one (maxpool_x2_kernel)
         if (a.kind != OP_MAXPOOL || a.stride != 1 || a.k != 5) continue;
         if (!poolchain_fits(a.h, a.w)) continue;
         int stages = 1;

@@ -81,6 +81,53 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* src, 
     *(uint4*)(dst + pix * dst_cs + dst_c0 + g * 8) = f16 ? pack8h(m) : pack8(m);
 }
 
+// Split-fp16 storage (B2D_PREC_FP16X2): 8 channels = 32 bytes [hi x 8 | lo x 8]; the value is hi + lo (exact in fp32), the
+// winner's pair is copied unchanged.  thread = (output pixel, 8-channel group).
+__global__ void __launch_bounds__(256) maxpool_x2_kernel(const __half* src, int h, int w, int src_cs, int src_c0, __half* dst, int oh, int ow,
+                                                          int dst_cs, int dst_c0, int c, int k, int stride, int n) {
+    const int groups = c / 8;
+    const long long total = (long long)n * oh * ow * groups;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int x = (int)(pix % ow);
+    const int y = (int)((pix / ow) % oh);
+    const int img = (int)(pix / ((long long)ow * oh));
+    const int pad = (stride == 1) ? (k >> 1) : 0;
+    float m[8];
+    uint32_t bh[4] = {0, 0, 0, 0}, bl[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int kh = 0; kh < k; ++kh) {
+        const int iy = y * stride + kh - pad;
+        if (iy < 0 || iy >= h) continue;
+        for (int kw = 0; kw < k; ++kw) {
+            const int ix = x * stride + kw - pad;
+            if (ix < 0 || ix >= w) continue;
+            const uint4* sp = (const uint4*)(src + ((((long long)img * h + iy) * w + ix) * src_cs + src_c0) * 2 + g * 16);
+            const uint4 uh = __ldg(sp), ul = __ldg(sp + 1);
+            float a[8], b[8];
+            unpack8h(uh, a);
+            unpack8h(ul, b);
+            const uint32_t wh[4] = {uh.x, uh.y, uh.z, uh.w}, wl[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = a[j] + b[j];
+                if (v > m[j]) {
+                    m[j] = v;
+                    const uint32_t mask = (j & 1) ? 0xFFFF0000u : 0x0000FFFFu;
+                    bh[j >> 1] = (bh[j >> 1] & ~mask) | (wh[j >> 1] & mask);
+                    bl[j >> 1] = (bl[j >> 1] & ~mask) | (wl[j >> 1] & mask);
+                }
+            }
+        }
+    }
+    uint4* dp = (uint4*)(dst + (pix * dst_cs + dst_c0) * 2 + g * 16);
+    dp[0] = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+    dp[1] = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+}
+
 // thread = (source pixel, 8-channel group): one 16-byte load, four 16-byte stores
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0,
                                                           __nv_bfloat16* dst, int dst_cs, int dst_c0, int c, int n) {
@@ -165,10 +212,16 @@ __global__ void __launch_bounds__(256) poolchain_kernel(const __nv_bfloat16* src
 }  // namespace
 
 int maxpool_launch(const __nv_bfloat16* src, int h, int w, int src_cs, int src_c0, __nv_bfloat16* dst, int oh, int ow,
-                   int dst_cs, int dst_c0, int c, int k, int stride, int n, cudaStream_t stream, int f16) {
+                   int dst_cs, int dst_c0, int c, int k, int stride, int n, cudaStream_t stream, int f16, int x2) {
     B2D_CHECK(c % 8 == 0 && src_cs % 8 == 0 && src_c0 % 8 == 0 && dst_cs % 8 == 0 && dst_c0 % 8 == 0,
               "maxpool: channel counts/offsets must be multiples of 8");
     const long long total = (long long)n * oh * ow * (c / 8);
+    if (x2) {       // channel arguments are real channels; the buffers hold 2 x 16 bits per channel
+        maxpool_x2_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>((const __half*)src, h, w, src_cs, src_c0, (__half*)dst, oh, ow, dst_cs,
+                                                                          dst_c0, c, k, stride, n);
+        B2D_LAUNCH_CHECK();
+        return 0;
+    }
     maxpool_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, h, w, src_cs, src_c0, dst, oh, ow, dst_cs, dst_c0, c, k,
                                                                    stride, n, f16);
     B2D_LAUNCH_CHECK();

@@ -28,9 +28,11 @@ constexpr int PIL_BITS = 22;
 
 __device__ __forceinline__ uint8_t clip8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
-// two pixels values / 255 in the engine's 16-bit activation format (bf16, or fp16 when the engine runs in B2D_PREC_FP16)
+// Two pixel values in the engine's network-input format: the RAW 0..255 value as bf16 / fp16 (exact in both).  The
+// reference's `/ 255.0` (simple_detector.py:465, gpu_handler.py:79) is applied to the fp32 accumulator of the first
+// convolution (ConvTcParams::acc_scale), so the input carries no 16-bit rounding of pixel / 255 at all.
 __device__ __forceinline__ uint32_t bf16x2_of(uint8_t a, uint8_t b, int f16 = 0) {
-    const float x = __fdiv_rn((float)a, 255.0f), y = __fdiv_rn((float)b, 255.0f);
+    const float x = (float)a, y = (float)b;
     if (f16) {
         __half2 h = __floats2half2_rn(x, y);
         return *(uint32_t*)&h;
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(256) prep_identity_vec_kernel(const uint8_t* _
 __global__ void __launch_bounds__(256) prep_identity_run_kernel(const uint4* __restrict__ src, long long in_chunks, uint4* __restrict__ dst,
                                                                  int bgr, int f16) {
     __shared__ __align__(16) uint8_t slab[8][1536];
-    __shared__ uint16_t q[256];          // byte -> 16-bit (v / 255): the IEEE division done once per value, not once per sample
+    __shared__ uint16_t q[256];          // byte -> its value in the 16-bit input format (see bf16x2_of)
     q[threadIdx.x] = (uint16_t)(bf16x2_of((uint8_t)threadIdx.x, 0, f16) & 0xffffu);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(256) cut_windows_kernel(const uint8_t* __restr
 }
 
 
-// ---- f32 NCHW in [0,1] (the tensor the reference hands to session.run) -> bf16 NHWC4 ---------
+// ---- f32 NCHW in [0,1] (the tensor the reference hands to session.run) -> 16-bit NHWC4 network input ---------
 __global__ void __launch_bounds__(256) input_from_f32_kernel(const float* __restrict__ src, int n, int h, int w, uint2* __restrict__ dst,
                                                               int f16) {
     const long long total = (long long)n * h * w;
@@ -248,15 +250,19 @@ __global__ void __launch_bounds__(256) input_from_f32_kernel(const float* __rest
     const int img = (int)(idx / plane);
     const long long p = idx - (long long)img * plane;
     const float* s = src + (long long)img * 3 * plane + p;
+    // The network input is 8-bit: the reference only ever feeds pixel / 255 (simple_detector.py:465, gpu_handler.py:79-85),
+    // so the tensor is mapped back to the pixel value it came from (exact for every u8 / 255.0f) and stored raw.
+    auto px = [](float v) { return fminf(fmaxf(rintf(__fmul_rn(v, 255.0f)), 0.f), 255.f); };
+    const float r = px(__ldg(s)), g = px(__ldg(s + plane)), b = px(__ldg(s + 2 * plane));
     if (f16) {
-        __half2 a = __floats2half2_rn(__ldg(s), __ldg(s + plane));
-        __half2 b = __floats2half2_rn(__ldg(s + 2 * plane), 0.f);
-        dst[idx] = make_uint2(*(uint32_t*)&a, *(uint32_t*)&b);
+        __half2 a = __floats2half2_rn(r, g);
+        __half2 c = __floats2half2_rn(b, 0.f);
+        dst[idx] = make_uint2(*(uint32_t*)&a, *(uint32_t*)&c);
         return;
     }
-    __nv_bfloat162 a = __floats2bfloat162_rn(__ldg(s), __ldg(s + plane));
-    __nv_bfloat162 b = __floats2bfloat162_rn(__ldg(s + 2 * plane), 0.f);
-    dst[idx] = make_uint2(*(uint32_t*)&a, *(uint32_t*)&b);
+    __nv_bfloat162 a = __floats2bfloat162_rn(r, g);
+    __nv_bfloat162 c = __floats2bfloat162_rn(b, 0.f);
+    dst[idx] = make_uint2(*(uint32_t*)&a, *(uint32_t*)&c);
 }
 
 }  // namespace

@@ -92,7 +92,8 @@ class CarDetector:
             else:
                 processed_count, previous = self.checkpoint_manager.load_checkpoint()
             all_detections = list(previous) if previous else []
-            interval = 2000                       # checkpoint and duplicate removal share one interval (:183)
+            # checkpoint and duplicate removal share one interval (:183-185 hard-codes 2000 = DEFAULT_CONFIG['checkpoint_interval'])
+            interval = int(self.config.get('checkpoint_interval', 2000))
             last_save = processed_count
             self.stats = {'total_tiles': total_tiles, 'start': processed_count, 'checkpoints': 0, 'seconds': 0.0}
             t0 = time.time()

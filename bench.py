@@ -445,8 +445,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (`value`) ----------------
-    for i in range(W_):
+    # warm-up: at least W steps AND at least 1.5 s of back-to-back steps -- the GPU sat idle while the CPU baseline ran, and
+    # its clocks need several hundred milliseconds of load to settle (20 steps timed right after 5 cold ones came out 15 %
+    # slower than the same steps a second later)
+    t_w, i = time.perf_counter(), 0
+    while i < W_ or time.perf_counter() - t_w < 1.5:
         device_step(i)
+        i += 1
+        if i % 8 == 0:
+            torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -85,13 +85,18 @@ int b2d_device_sm_count(b2d_engine* e);
 /* Storage format of activations and weights (accumulation is fp32 either way; head maps stay fp32).
  * B2D_PREC_BF16 is the default and the configuration BASELINE.json is quoted on; B2D_PREC_FP16 keeps three
  * more mantissa bits per stored activation (same tensor-core rate) for callers that want to sit closer to
- * the reference's fp32 onnxruntime results.  Call right after b2d_create, before any b2d_plan_*.           */
-enum { B2D_PREC_BF16 = 0, B2D_PREC_FP16 = 1 };
+ * the reference's fp32 onnxruntime results.  B2D_PREC_FP16X2 stores every activation as an fp16 high part plus an
+ * fp16 low part (~22 mantissa bits; weights as fp16, exact for bf16-representable weights): the same kernels with
+ * K doubled, about half the throughput, results within 1e-3 on scores / 0.5 px on boxes of an fp32 runtime
+ * (tests/test_gpu_parity.py).  Call right after b2d_create, before any b2d_plan_*.                         */
+enum { B2D_PREC_BF16 = 0, B2D_PREC_FP16 = 1, B2D_PREC_FP16X2 = 2 };
 int b2d_set_precision(b2d_engine* e, int precision);
 int b2d_get_precision(b2d_engine* e);
 
 /* ---- plan building: the graph onnxruntime would have read from the .onnx file ---------- */
-/* Buffers are NHWC; id 0 must be the network input [max_batch, H, W, 4] bf16.            */
+/* Buffers are NHWC; id 0 must be the network input [max_batch, H, W, 4], 16-bit, holding RAW pixel values 0..255
+ * (exact in bf16 and fp16): the reference's `/ 255.0` is applied to the fp32 accumulator of the convolutions that
+ * read buffer 0.                                                                          */
 int b2d_plan_buffer(b2d_engine* e, int h, int w, int c, int is_f32);
 /* weight_host: fp32 [cout][cin][k][k] (deploy form, BN folded); bias_host: fp32 [cout].  */
 int b2d_plan_conv(b2d_engine* e, int src, int src_c0, int cin, int dst, int dst_c0, int cout,
@@ -110,15 +115,18 @@ int b2d_num_anchors(b2d_engine* e);
 int b2d_num_kernels_per_forward(b2d_engine* e);
 
 /* ---- stages ---------------------------------------------------------------------------- */
-/* Resize + normalise (/255, IEEE division) + layout.  Replaces simple_detector.py:463-467,
- * :655-659 and _script/gpu_handler.py:67-92 (and the BGR variant :142-149 via `bgr`).
+/* Resize + normalise + layout.  Replaces simple_detector.py:463-467, :655-659 and
+ * _script/gpu_handler.py:67-92 (and the BGR variant :142-149 via `bgr`).
  * src_dev: n images uint8 HWC RGB, row pitch `pitch` bytes, image stride `img_stride`.
- * dst_dev == NULL writes the engine's own input buffer (B2D_OUT_BF16_NHWC4 only).          */
+ * out_kind B2D_OUT_F32_NCHW is the tensor the reference builds (pixel / 255.0f, IEEE division, CHW);
+ * B2D_OUT_U8_NHWC the resized image; B2D_OUT_BF16_NHWC4 / B2D_OUT_F16_NHWC4 the engine's network-input format (raw
+ * pixel values, see b2d_plan_buffer).  dst_dev == NULL writes the engine's own input buffer.  */
 int b2d_preprocess(b2d_engine* e, const uint8_t* src_dev, int n, int h, int w, int pitch,
                    long long img_stride, int mode, int bgr, int out_kind, void* dst_dev, void* stream);
 
 /* Load the tensor the reference hands to session.run -- float32 [n,3,H,W] in [0,1], RGB
- * (simple_detector.py:466-467, :474) -- into the engine's bf16 NHWC4 input buffer.              */
+ * (simple_detector.py:466-467, :474) -- into the engine's input buffer.  The network input is 8-bit: every value is
+ * mapped back to the pixel it came from (rint(x * 255), exact for every u8 / 255.0f the reference produces).   */
 int b2d_set_input_f32(b2d_engine* e, const float* src_dev, int n, void* stream);
 
 /* The network: replaces session.run at simple_detector.py:474, :666 and

@@ -17,8 +17,8 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg
 may import this module.
 
 ``emulate_bf16=True`` rounds every stored activation to bf16 exactly where the
-engine stores bf16 (after bias+SiLU(+residual) of each conv, and the network
-input); accumulation stays fp32.  That mode checks the kernels' arithmetic;
+engine stores bf16 (after bias+SiLU(+residual) of each conv; not the network
+input, which the engine keeps as the exact 8-bit pixel value); accumulation stays fp32.  That mode checks the kernels' arithmetic;
 ``emulate_bf16=False`` is the fp32 stand-in for the onnxruntime CPU path.
 """
 from __future__ import annotations
@@ -75,7 +75,6 @@ class YoloV8mOracle(_Net):
     @torch.no_grad()
     def raw_head(self, x: torch.Tensor) -> List[torch.Tensor]:
         """x: [B,3,H,W] fp32 in [0,1].  Returns per level [B, 64+nc, h, w] fp32 raw."""
-        x = self.rnd(x)
         x0 = self.conv("model.0", x, 3, 2)
         x1 = self.conv("model.1", x0, 3, 2)
         x2 = self.c2f("model.2", x1, 2, True)
@@ -175,7 +174,6 @@ class YoloV7Oracle(_Net):
 
     @torch.no_grad()
     def raw_head(self, x):
-        x = self.rnd(x)
         x = self.c(0, x, 3, 1); x = self.c(1, x, 3, 2); x = self.c(2, x, 3, 1); x = self.c(3, x, 3, 2)
         x11 = self.elan(4, x)
         p3 = self.elan(17, self.mp(12, x11))

@@ -66,18 +66,27 @@ def test_preprocess_identity_and_engine_input(eng640, tiles4):
     assert np.array_equal(eng640.preprocess(t, "identity", out="u8").cpu().numpy(), tiles4)
     eng640.preprocess(t, "identity")
     got = eng640.buffer("input", 4).float().cpu().numpy()
-    ref = torch.from_numpy(tiles4.astype(np.float32) / 255.0).to(torch.bfloat16).float().numpy()
-    assert np.array_equal(got[..., :3], ref) and (got[..., 3] == 0).all()
+    # the network input is the raw pixel value (exact in bf16); `/ 255.0` is the stem's accumulator scale
+    assert np.array_equal(got[..., :3], tiles4.astype(np.float32)) and (got[..., 3] == 0).all()
 
 
-def test_letterbox_matches_cv2_resize_plus_114_pad(eng640):
+@pytest.mark.parametrize("h,w", [(600, 1200), (601, 1203), (333, 640), (1200, 601), (640, 333), (777, 500), (64, 640), (640, 64)])
+def test_letterbox_matches_ultralytics_letterbox(eng640, h, w):
+    """Ultralytics LetterBox(auto=False, scaleup=True, center=True) restated with cv2 itself: r = min(640/h, 640/w), resize to
+    (round(w r), round(h r)) with INTER_LINEAR, then ``top, bottom = round(dh - 0.1), round(dh + 0.1)`` (same for left / right)
+    rows of 114 -- odd paddings (601x1203 -> 320 rows + 1 odd, 333x640, 777x500 ...) put the extra row / column at the bottom / right."""
     import cv2
-    rng = np.random.default_rng(4)
-    img = rng.integers(0, 256, (600, 1200, 3), dtype=np.uint8)
+    rng = np.random.default_rng(h * 10007 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
     got = eng640.preprocess(torch.from_numpy(img)[None].cuda(), "letterbox", out="u8").cpu().numpy()[0]
-    ref = np.full((640, 640, 3), 114, np.uint8)
-    ref[160:480] = cv2.resize(img, (640, 320))
-    assert np.array_equal(got, ref)
+    r = min(640 / h, 640 / w)
+    nw, nh = int(round(w * r)), int(round(h * r))
+    dw, dh = (640 - nw) / 2, (640 - nh) / 2
+    res = cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR) if (w, h) != (nw, nh) else img
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    ref = cv2.copyMakeBorder(res, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))
+    assert ref.shape == (640, 640, 3) and np.array_equal(got, ref)
 
 
 def test_session_input_path_equals_preprocess_path(eng640, tiles4):
@@ -105,6 +114,12 @@ def test_every_planned_op_large_batch_kernel_variants(arch, imgsz, n, monkeypatc
     assert any("halo-pair" in d for d in seen) and any(" x2 " in d for d in seen) and any(" x4 " in d for d in seen), seen[:8]
 
 
+def test_every_planned_op_matches_torch_split_fp16():
+    """B2D_PREC_FP16X2: every op on its own inputs (hi + lo read back as fp32) to ~fp32 accuracy."""
+    _check_every_op("yolov8m", 320, 2, precision="fp16x2")
+    _check_every_op("yolov7", 128, 2, precision="fp16x2")
+
+
 def _check_every_op(arch, imgsz, n, precision="bf16"):
     from _ir_cpu import run_graph_cpu  # noqa: F401  (same arithmetic, per-op form below)
     import torch.nn.functional as F
@@ -113,14 +128,15 @@ def _check_every_op(arch, imgsz, n, precision="bf16"):
     w = W.make_synthetic_weights(g, 2)
     eng = _engine(arch, weights=w, max_batch=n, imgsz=imgsz, graph=g, precision=precision)
     eng.preprocess(torch.from_numpy(synth.make_tiles(n, imgsz, 9)).cuda(), "identity")
-    rel16 = 4e-3 if precision == "bf16" else 5e-4          # one ulp of the storage format: 2^-8 (bf16), 2^-11 (fp16)
+    # one ulp of the storage format: 2^-8 (bf16), 2^-11 (fp16); split fp16 keeps ~22 bits, the bound is fp32 summation order
+    rel16 = {"bf16": 4e-3, "fp16": 5e-4, "fp16x2": 2e-5}[precision]
     for i, op in enumerate(g.ops):
         eng.run_op(i, n)
         torch.cuda.synchronize()
         src = eng.buffer(op.src.buf, n).float().cpu()[..., op.src.c0:op.src.c0 + op.src.c].permute(0, 3, 1, 2)
         if op.kind in ("conv", "dwconv"):
             if op.src.buf == "input":
-                src = src[:, :3]
+                src = src[:, :3] / 255.0                 # the input buffer holds raw pixel values; this is the reference's tensor
             wt, bs = (torch.from_numpy(np.ascontiguousarray(a)) for a in G.op_weights(op, w))
             y = F.conv2d(src, wt, bs,
                          stride=op.s, padding=op.k // 2, groups=g.wshapes[op.weight][3])
@@ -135,7 +151,7 @@ def _check_every_op(arch, imgsz, n, precision="bf16"):
         got = eng.buffer(op.dst.buf, n).float().cpu()[..., op.dst.c0:op.dst.c0 + op.dst.c].permute(0, 3, 1, 2)
         err = (got - y).abs().max().item()
         # bf16 output rounding is 2^-9 relative; fp32 head outputs and pools/upsamples are far tighter
-        tol = (rel16 if not g.bufs[op.dst.buf].f32 else 2e-4) * y.abs().max().item() + 1e-5
+        tol = (rel16 if not g.bufs[op.dst.buf].f32 else min(2e-4, 10 * rel16)) * y.abs().max().item() + 1e-5
         if op.kind in ("maxpool", "upsample2x"):
             tol = 0.0
         assert err <= tol, (i, eng.describe_op(i), err, tol)
@@ -145,32 +161,102 @@ def _check_every_op(arch, imgsz, n, precision="bf16"):
 
 
 # ---- whole network vs the oracle -------------------------------------------------------------------
-def test_forward_against_bf16_emulating_and_fp32_oracle(eng640, tiles4):
-    """Scores/boxes vs the oracle.  north_star asks 1e-3 on scores and 0.5 px on boxes; with bf16
-    activations through ~60 layers and *random* weights (broad DFL distributions) that bound holds
-    for the typical anchor, not for the worst one -- the test pins median and 99th percentile and
-    DESIGN.md reports the full distribution."""
-    n = 2
-    eng640.preprocess(torch.from_numpy(tiles4[:n]).cuda(), "identity")
-    eng640.forward(n)
-    rows = eng640.decode_rows(n).cpu().numpy()
-    x = torch.from_numpy(tiles4[:n].astype(np.float32) / 255.0).permute(0, 3, 1, 2)
-    for emu, med_tol, p99_tol in ((True, 1e-3, 2e-2), (False, 2e-3, 4e-2)):
-        ref = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", eng640._weights, emu).forward(x)])
-        dc = np.abs(rows[..., 4] - ref[..., 4])
-        assert np.median(dc) < med_tol and np.quantile(dc, 0.99) < p99_tol, (emu, np.median(dc), np.quantile(dc, 0.99))
-        sel = ref[..., 4] >= 0.3
-        db = np.abs(rows[..., :4] - ref[..., :4])[sel]
-        assert np.median(db) < 0.5, (emu, np.median(db))
-        agree = np.mean((rows[..., 4] >= 0.3) == sel)
-        assert agree > 0.99, agree
-    # The deviation from the fp32 reference is the bf16 storage format's, not the kernels': a CPU model that only
-    # rounds its activations to bf16 (same places, torch's own arithmetic) is just as far from fp32 as the engine is.
-    f32 = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", eng640._weights, False).forward(x)])
-    emu = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", eng640._weights, True).forward(x)])
-    d_eng, d_emu = np.abs(rows[..., 4] - f32[..., 4]), np.abs(emu[..., 4] - f32[..., 4])
-    assert d_eng.mean() < 1.25 * d_emu.mean() + 1e-5 and np.quantile(d_eng, 0.99) < 1.25 * np.quantile(d_emu, 0.99) + 1e-4, (
-        d_eng.mean(), d_emu.mean(), np.quantile(d_eng, 0.99), np.quantile(d_emu, 0.99))
+# Contract (BASELINE.json north_star; the reference's fp32 `session.run`, simple_detector.py:474-481): scores within 1e-3
+# absolute, boxes within 0.5 px, identical keep set away from score ties.  Asserted at 640x640 on C2 tiles (the bench's
+# generator) against the fp32 oracle, over every anchor with score >= 0.05, and the keep set (`score >= thr`, thr = the
+# reference's 0.3 and the bench's 0.25) must be identical outside the band |score - thr| < 2e-3.
+SCORE_TOL, BOX_TOL_PX, TIE_BAND, SCORE_FLOOR = 1e-3, 0.5, 2e-3, 0.05
+
+
+@pytest.fixture(scope="module")
+def c2_reference():
+    """Four C2 tiles and the fp32 oracle's rows for them (cx, cy, w, h, conf, cls)."""
+    g = G.build("yolov8m")
+    w = W.make_synthetic_weights(g, 0)
+    tiles = synth.make_tiles(4, 640, 1000)
+    x = torch.from_numpy(tiles.astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+    ref = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", w, False).forward(x)])
+    return g, w, tiles, x, ref
+
+
+def _rows_of(precision, g, w, tiles):
+    eng = _engine("yolov8m", weights=w, max_batch=len(tiles), graph=g, precision=precision)
+    eng.preprocess(torch.from_numpy(tiles).cuda(), "identity")
+    eng.forward(len(tiles))
+    rows = eng.decode_rows(len(tiles)).cpu().numpy()
+    eng.close()
+    return rows
+
+
+def _deviation(rows, ref, tag):
+    sel = ref[..., 4] >= SCORE_FLOOR
+    ds = np.abs(rows[..., 4] - ref[..., 4])[sel]
+    db = np.abs(rows[..., :4] - ref[..., :4]).max(-1)[sel]
+    q = lambda a: tuple(float(np.quantile(a, p)) for p in (0.5, 0.99, 0.999, 1.0))
+    worst = {}
+    for thr in (0.3, 0.25):
+        dis = (rows[..., 4] >= thr) != (ref[..., 4] >= thr)
+        worst[thr] = (int(dis.sum()), int((ref[..., 4] >= thr).sum()), float(np.abs(ref[..., 4] - thr)[dis].max()) if dis.any() else 0.0)
+    print(f"\n[{tag}] {int(sel.sum())} anchors with score >= {SCORE_FLOOR}: |d score| median / p99 / p99.9 / max = %.2e %.2e %.2e %.2e ; "
+          "|d box| px = %.3f %.3f %.3f %.3f ; keep set: " % (q(ds) + q(db)) +
+          ", ".join(f"thr {t}: {n} of {m} differ, farthest from thr {d:.1e}" for t, (n, m, d) in worst.items()))
+    return q(ds), q(db), worst
+
+
+def test_contract_scores_boxes_keep_set_split_fp16_vs_fp32_oracle(c2_reference):
+    """The configuration that meets the contract: B2D_PREC_FP16X2 (activations as fp16 hi + lo, fp32 accumulate)."""
+    g, w, tiles, x, ref = c2_reference
+    ds, db, worst = _deviation(_rows_of("fp16x2", g, w, tiles), ref, "fp16x2 vs fp32 oracle")
+    assert ds[3] <= SCORE_TOL, ds
+    assert db[3] <= BOX_TOL_PX, db
+    for thr, (n, m, far) in worst.items():
+        assert far < TIE_BAND, (thr, n, m, far)          # every disagreement is a tie with the threshold
+
+
+def test_fast_storage_modes_stated_deviation_from_fp32_oracle(c2_reference):
+    """bf16 (the BASELINE configuration) and fp16 store one 16-bit value per activation: 2^-9 / 2^-12 relative rounding at
+    each of ~60 layers.  That is NOT within the 1e-3 contract at the tail; the bounds the test pins are the measured ones
+    (DESIGN.md section 2 has the table), and the deviation is shown to be the storage format's, not the kernels': a CPU model
+    that only rounds its stored activations the same way is as far from fp32 as the engine is."""
+    g, w, tiles, x, ref = c2_reference
+    bounds = {"fp16": dict(p99=6e-3, smax=1.5e-2, bmax=1.5, band=1.5e-2), "bf16": dict(p99=5e-2, smax=0.15, bmax=12.0, band=0.15)}
+    for prec, emu in (("fp16", "fp16"), ("bf16", True)):
+        rows = _rows_of(prec, g, w, tiles)
+        ds, db, worst = _deviation(rows, ref, f"{prec} vs fp32 oracle")
+        b = bounds[prec]
+        assert ds[1] <= b["p99"] and ds[3] <= b["smax"] and db[3] <= b["bmax"], (prec, ds, db)
+        for thr, (n, m, far) in worst.items():
+            assert far < b["band"] and n <= 0.03 * m, (prec, thr, n, m, far)
+        emu_rows = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", w, emu).forward(x)])
+        d_eng, d_emu = np.abs(rows[..., 4] - ref[..., 4]), np.abs(emu_rows[..., 4] - ref[..., 4])
+        assert d_eng.mean() < 1.25 * d_emu.mean() + 1e-5 and np.quantile(d_eng, 0.99) < 1.25 * np.quantile(d_emu, 0.99) + 1e-4, (
+            prec, d_eng.mean(), d_emu.mean(), np.quantile(d_eng, 0.99), np.quantile(d_emu, 0.99))
+
+
+def test_split_fp16_whole_pipeline_matches_oracle_detections(c2_reference):
+    """Decode + Ultralytics NMS on the precise rows: the detections of every tile are the oracle's (same anchors kept, in the
+    same order) unless a competing pair sits within the tie band."""
+    g, w, tiles, x, ref = c2_reference
+    n = len(tiles)
+    eng = _engine("yolov8m", weights=w, max_batch=n, graph=g, precision="fp16x2")
+    dets, counts = eng.infer(torch.from_numpy(tiles).cuda(), "identity", False, 0.25, False, 0.7, 0, 300)
+    from aerial_image_recognition_b200.engine import dets_to_numpy
+    got = dets_to_numpy(dets, counts)
+    pred = make_oracle("yolov8m", w, False).forward(x).numpy()
+    agree = total = 0
+    for i in range(n):
+        ref_det = OP.ultralytics_nms(pred[i:i + 1], 0.25, 0.7, 300)[0]
+        ga = set(int(a) for a in got[i]["anchor"])
+        # map the oracle's kept boxes back to anchors through their (unique) scores + centres
+        rs = ref[i]
+        ra = set()
+        for d in ref_det:
+            cx, cy = (d[0] + d[2]) / 2, (d[1] + d[3]) / 2
+            k = np.argmin(np.abs(rs[:, 0] - cx) + np.abs(rs[:, 1] - cy) + 1e3 * np.abs(rs[:, 4] - d[4]))
+            ra.add(int(k))
+        agree += len(ga & ra); total += len(ga | ra)
+    eng.close()
+    assert agree / total > 0.995, (agree, total)
 
 
 def test_decode_kernel_matches_oracle_decode_on_identical_head_maps(eng640, tiles4):
@@ -328,6 +414,22 @@ def test_dedup_identical_to_sequential_greedy(eng640, m):
         k = keep.astype(bool)
         again = eng640.dedup(torch.from_numpy(x[k]).cuda(), torch.from_numpy(y[k]).cuda(), torch.from_numpy(conf[k]).cuda(), 1.0, False)
         assert again.all()
+
+
+def test_dedup_negative_and_origin_cells(eng640):
+    """Points in grid cell (-1, -1) and around the origin (negative-coordinate CRS, raw lon/lat near 0): with plain
+    two's-complement packing that cell's key was the hash table's empty-slot sentinel and its points were invisible."""
+    rng = np.random.default_rng(12)
+    x = rng.uniform(-3.0, 3.0, 4000); y = rng.uniform(-3.0, 3.0, 4000)
+    conf = rng.random(4000).astype(np.float32)
+    for incl in (True, False):
+        keep = eng640.dedup(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(conf).cuda(), 1.0, incl).cpu().numpy()
+        ref = np.zeros(4000, bool); ref[OP.dedup_greedy(x, y, conf, 1.0, incl)] = True
+        assert np.array_equal(ref, keep.astype(bool))
+    from aerial_image_recognition_b200._lib import B2DError
+    far = torch.tensor([0.0, 1e13], dtype=torch.float64).cuda()       # |x / thr| >= 2^31: refused, not truncated
+    with pytest.raises(B2DError, match="outside the grid"):
+        eng640.dedup(far, far.clone(), torch.ones(2).cuda(), 1.0, True)
 
 
 def test_dedup_chain_and_exact_threshold(eng640):
@@ -533,6 +635,10 @@ def test_detector_built_from_onnx_file_equals_detector_built_from_tensors(tmp_pa
     x = (synth.make_tiles(2, 640, 8).astype(np.float32) / 255.0).transpose(0, 3, 1, 2)
     a = SimpleDetector(path, None, max_batch=2)
     b = SimpleDetector("absent.onnx", None, weights=w, max_batch=2)
+    with pytest.raises(FileNotFoundError):                     # a mistyped path fails like ort.InferenceSession does: no silent random weights
+        SimpleDetector(str(tmp_path / "absent.onnx"), None, max_batch=2)
+    with pytest.raises(FileNotFoundError):
+        GPUHandler(str(tmp_path / "absent.onnx"), max_batch=2)
     ra = a.model.run(None, {"images": x})[0]
     rb = b.model.run(None, {"images": x})[0]
     assert ra.shape == (2, 8400, 6) and np.array_equal(ra, rb)
@@ -621,6 +727,29 @@ def test_car_detector_production_loop(tmp_path):
     out2 = det2.detect(interactive=False, force_restart=False)
     assert det2.stats['start'] == 16 and len(out2) == len(out)
     assert [d['confidence'] for d in out2] == [d['confidence'] for d in out]
+    # the loop's own checkpoints: the saved cursor is the END of the last batch whose detections are in the file, so a
+    # resume neither re-runs that batch nor duplicates its detections (duplicate_distance 0: nothing would remove them)
+    cfg0 = dict(cfg, duplicate_distance=0, output_prefix="nodup", checkpoint_interval=8)
+    full = CarDetector(str(tmp_path), cfg0).detect(interactive=False, force_restart=True)
+
+    class _Stop(Exception):
+        pass
+    det4 = CarDetector(str(tmp_path), cfg0)
+    orig, calls = det4._process_batch, []
+
+    def interrupted(batch_tiles, processed_count, total_tiles):
+        if len(calls) == 3:
+            raise _Stop()
+        calls.append(processed_count)
+        return orig(batch_tiles, processed_count, total_tiles)
+    det4._process_batch = interrupted
+    with pytest.raises(_Stop):
+        det4.detect(interactive=False, force_restart=True)
+    assert det4.stats['checkpoints'] >= 2 and json.load(open(det4.checkpoint_manager.state_file))['processed_count'] == 24
+    det5 = CarDetector(str(tmp_path), cfg0)
+    resumed = det5.detect(interactive=False, force_restart=False)
+    assert det5.stats['start'] == 24
+    assert sorted(d['confidence'] for d in resumed) == sorted(d['confidence'] for d in full)     # no batch counted twice
 
 
 # ---- BASELINE size (C2: batch 64 at 640x640): size-independent properties ---------------------------------------------
@@ -662,35 +791,3 @@ def test_full_batch_is_permutation_equivariant_and_matches_small_batches():
 @pytest.mark.parametrize("arch,imgsz,n", [("yolov8m", 320, 2), ("yolov7", 128, 2)])
 def test_every_planned_op_matches_torch_fp16(arch, imgsz, n):
     _check_every_op(arch, imgsz, n, precision="fp16")
-
-
-def test_fp16_forward_is_closer_to_the_fp32_oracle(tiles4):
-    """The fp16 storage mode (same kernels, same tensor-core rate) against the fp32 oracle -- the stand-in for the
-    reference's onnxruntime CPU results.  north_star's bounds: scores within 1e-3, boxes within 0.5 px, identical keep
-    set away from ties.  With fp16 the typical anchor is an order of magnitude inside the score bound and the keep set
-    differs only at the threshold; the worst anchor of a *random-weight* network still is not."""
-    g = G.build("yolov8m")
-    w = W.make_synthetic_weights(g, 0)
-    n = 2
-    x = torch.from_numpy(tiles4[:n].astype(np.float32) / 255.0).permute(0, 3, 1, 2)
-    f32 = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", w, False).forward(x)])
-    emu = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", w, "fp16").forward(x)])
-    err = {}
-    for prec in ("bf16", "fp16"):
-        eng = _engine("yolov8m", weights=w, max_batch=n, graph=g, precision=prec)
-        eng.preprocess(torch.from_numpy(tiles4[:n]).cuda(), "identity")
-        eng.forward(n)
-        rows = eng.decode_rows(n).cpu().numpy()
-        eng.close()
-        err[prec] = np.abs(rows[..., 4] - f32[..., 4])
-        if prec == "fp16":
-            sel = f32[..., 4] >= 0.3
-            db = np.abs(rows[..., :4] - f32[..., :4])[sel]
-            agree = np.mean((rows[..., 4] >= 0.3) == sel)
-            d_emu = np.abs(emu[..., 4] - f32[..., 4])
-            print("fp16 vs fp32 oracle: median %.2e mean %.2e p99 %.2e max %.2e | boxes median %.3f px p99 %.3f px | keep-set agreement %.5f" % (
-                np.median(err[prec]), err[prec].mean(), np.quantile(err[prec], 0.99), err[prec].max(), np.median(db), np.quantile(db, 0.99), agree))
-            assert np.median(err[prec]) < 1e-4 and err[prec].mean() < 1e-3 and np.quantile(err[prec], 0.99) < 5e-3
-            assert np.median(db) < 0.05 and np.quantile(db, 0.95) < 0.5 and agree > 0.999     # DFL boxes of random weights: broad bin distributions
-            assert err[prec].mean() < 1.25 * d_emu.mean() + 1e-5           # as good as fp16 storage allows
-    assert err["fp16"].mean() < 0.25 * err["bf16"].mean() and np.quantile(err["fp16"], 0.99) < 0.25 * np.quantile(err["bf16"], 0.99)
