@@ -1585,7 +1585,8 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.chunks = stem ? 1 : ceil_div(kin, 64);       // a short last chunk is zero-filled by TMA (A) and zero-padded in the packed weights (B)
     const int cout_pad = ceil_div(cout, 16) * 16;
     int split = 1;
-    while (cout_pad % split != 0 || (cout_pad / split) % 16 != 0 || cout_pad / split > 256 || (dw && split > 1 && (kmul * cout_pad / split) % 64 != 0)) ++split;
+    const int n_max = x2 && !dst_f32 ? 128 : 256;      // split outputs are 4 bytes per column: a 256-column staging tile alone would be 128 KB
+    while (cout_pad % split != 0 || (cout_pad / split) % 16 != 0 || cout_pad / split > n_max || (dw && split > 1 && (kmul * cout_pad / split) % 64 != 0)) ++split;
     p.n_tile = cout_pad / split;
     p.n_tiles_n = split;
     if (dw) p.chunks = ceil_div(kmul * p.n_tile, 64);     // depthwise: storage chunks of one channel tile

@@ -179,12 +179,33 @@ def _expected_shape(g: Graph, name: str) -> Tuple[int, int, int, int]:
     return (cout, cing, k, k)
 
 
-def load_onnx_weights(path: str, g: Graph) -> Dict[str, np.ndarray]:
+def _check_conv_node(path: str, g: Graph, name: str, nd: "OnnxNode") -> None:
+    """The file's Conv node for ``name`` must be the convolution the engine's graph runs: kernel, stride, groups."""
+    op = next(o for o in g.ops if o.kind in ("conv", "dwconv") and o.weight == name)
+    _cout, _cing, k, groups = g.wshapes[name]
+    ks, st, gr = nd.attrs.get("kernel_shape"), nd.attrs.get("strides"), nd.attrs.get("group")
+    if ks is not None and list(ks) != [k, k]:
+        raise ValueError(f"{path}: Conv node {nd.name!r} has kernel_shape {list(ks)}, the {g.arch} graph runs {name} with {k}x{k}")
+    if st is not None and list(st) != [op.s, op.s]:
+        raise ValueError(f"{path}: Conv node {nd.name!r} has strides {list(st)}, the {g.arch} graph runs {name} with stride {op.s}")
+    if (gr or 1) != groups:
+        raise ValueError(f"{path}: Conv node {nd.name!r} has group {gr or 1}, the {g.arch} graph runs {name} with {groups} groups")
+
+
+def load_onnx_weights(path: str, g: Graph, by_name: bool = True) -> Dict[str, np.ndarray]:
     """Deploy-form weights ``{name + '.weight', name + '.bias'}`` (float32, the model's own channel
-    order) for every conv of ``g`` from the ONNX file at ``path``."""
+    order) for every conv of ``g`` from the ONNX file at ``path``.  ``by_name=False`` skips the name
+    mapping and goes by graph order (what happens anyway when an exporter has renamed the weights)."""
     nodes, inits = read_onnx(path)
     names = _conv_names(g)
     out: Dict[str, np.ndarray] = {}
+    # The engine runs deploy-form convolutions (BatchNorm folded into weight + bias, as Ultralytics / YOLOv7 exports are):
+    # a file that still carries BatchNormalization nodes would silently lose its scale and shift.
+    bn = [nd.name or nd.outputs[0] for nd in nodes if nd.op_type == "BatchNormalization"]
+    if bn:
+        raise ValueError(f"{path}: {len(bn)} BatchNormalization nodes (e.g. {bn[0]!r}); export the fused (eval-mode) model -- the engine "
+                         f"runs convolutions with BatchNorm folded in")
+    consumer = {nd.inputs[1]: nd for nd in nodes if nd.op_type == "Conv" and len(nd.inputs) > 1}
 
     def put(name: str, wt: np.ndarray, bs: Optional[np.ndarray], where: str) -> None:
         exp = _expected_shape(g, name)
@@ -194,13 +215,16 @@ def load_onnx_weights(path: str, g: Graph) -> Dict[str, np.ndarray]:
         out[name + ".bias"] = (np.zeros(exp[0], np.float32) if bs is None else np.ascontiguousarray(bs, dtype=np.float32).reshape(exp[0]))
 
     # 1. by initializer name (Ultralytics keeps the module path; Conv modules add '.conv')
-    by_name = 0
-    for name in names:
+    found = 0
+    for name in names if by_name else []:
         for stem in (name + ".conv", name):
             if stem + ".weight" in inits:
                 put(name, inits[stem + ".weight"], inits.get(stem + ".bias"), f"initializer {stem}.weight")
-                by_name += 1
+                if stem + ".weight" in consumer:
+                    _check_conv_node(path, g, name, consumer[stem + ".weight"])
+                found += 1
                 break
+    by_name = found
     if by_name == len(names):
         return out
     if by_name:
@@ -221,6 +245,7 @@ def load_onnx_weights(path: str, g: Graph) -> Dict[str, np.ndarray]:
         raise ValueError(f"{path}: {len(convs)} Conv nodes with weights in the file, the {g.arch} graph has {len(names)} convolutions")
     for name, (nd, wt, bs) in zip(names, convs):
         put(name, wt, bs, f"Conv node {nd.name or nd.outputs[0]!r}")
+        _check_conv_node(path, g, name, nd)
     return out
 
 
@@ -249,6 +274,15 @@ def _enc_tensor(name: str, a: np.ndarray) -> bytes:
     return body
 
 
+def _enc_attr_int(name: str, v: int) -> bytes:       # AttributeProto: name 1, i 3, type 20 (INT = 2)
+    return _enc_field(5, _enc_field(1, name.encode()) + _enc_varint((3 << 3) | 0) + _enc_varint(v) + _enc_varint((20 << 3) | 0) + _enc_varint(2))
+
+
+def _enc_attr_ints(name: str, vs) -> bytes:          # ints 8 (unpacked), type INTS = 7
+    body = _enc_field(1, name.encode()) + b"".join(_enc_varint((8 << 3) | 0) + _enc_varint(int(v)) for v in vs)
+    return _enc_field(5, body + _enc_varint((20 << 3) | 0) + _enc_varint(7))
+
+
 def write_conv_onnx(path: str, g: Graph, w: Dict[str, np.ndarray], named: bool = True, half: bool = False) -> None:
     """Writes an ONNX file holding one ``Conv`` node (+ weight / bias initializers) per convolution of
     ``g`` in execution order, plus the DFL arange conv for ``yolov8m`` -- the part of an Ultralytics
@@ -258,6 +292,7 @@ def write_conv_onnx(path: str, g: Graph, w: Dict[str, np.ndarray], named: bool =
     dt = np.float16 if half else np.float32
     k = 0
     prev = "images"
+    ops = {op.weight: op for op in g.ops if op.kind in ("conv", "dwconv")}
     for name in _conv_names(g):
         wn, bn = (f"{name}.conv.weight", f"{name}.conv.bias") if named else (f"onnx::Conv_{700 + 2 * k}", f"onnx::Conv_{701 + 2 * k}")
         if named and name.startswith("model.22.") and name.endswith(".2"):
@@ -265,6 +300,9 @@ def write_conv_onnx(path: str, g: Graph, w: Dict[str, np.ndarray], named: bool =
         outn = f"/{name.replace('.', '/')}/Conv_output_0"
         node = _enc_field(1, prev.encode()) + _enc_field(1, wn.encode()) + _enc_field(1, bn.encode()) + _enc_field(2, outn.encode())
         node += _enc_field(3, f"/{name.replace('.', '/')}/conv/Conv".encode()) + _enc_field(4, b"Conv")
+        kk, st, groups = g.wshapes[name][2], ops[name].s, g.wshapes[name][3]
+        node += _enc_attr_int("group", groups) + _enc_attr_ints("kernel_shape", (kk, kk)) + _enc_attr_ints("strides", (st, st))
+        node += _enc_attr_ints("pads", (kk // 2,) * 4) + _enc_attr_ints("dilations", (1, 1))
         parts.append(_enc_field(1, node))
         parts.append(_enc_field(5, _enc_tensor(wn, w[name + ".weight"].astype(dt))))
         parts.append(_enc_field(5, _enc_tensor(bn, w[name + ".bias"].astype(dt))))

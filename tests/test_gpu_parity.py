@@ -226,7 +226,7 @@ def test_fast_storage_modes_stated_deviation_from_fp32_oracle(c2_reference):
         b = bounds[prec]
         assert ds[1] <= b["p99"] and ds[3] <= b["smax"] and db[3] <= b["bmax"], (prec, ds, db)
         for thr, (n, m, far) in worst.items():
-            assert far < b["band"] and n <= 0.03 * m, (prec, thr, n, m, far)
+            assert far < b["band"] and n <= 0.05 * m, (prec, thr, n, m, far)
         emu_rows = np.stack([OP.v8_rows_adapter(r.numpy()) for r in make_oracle("yolov8m", w, emu).forward(x)])
         d_eng, d_emu = np.abs(rows[..., 4] - ref[..., 4]), np.abs(emu_rows[..., 4] - ref[..., 4])
         assert d_eng.mean() < 1.25 * d_emu.mean() + 1e-5 and np.quantile(d_eng, 0.99) < 1.25 * np.quantile(d_emu, 0.99) + 1e-4, (
