@@ -120,6 +120,13 @@ def test_every_planned_op_matches_torch_split_fp16():
     _check_every_op("yolov7", 128, 2, precision="fp16x2")
 
 
+def test_every_planned_op_at_full_size_with_tiles_spanning_images():
+    """At 640x640 the 20x20 layers run 4x4-pixel x 8-image M tiles and the 40x40 ones 8x8 x 2: n = 8 fills such tiles with
+    eight different images (n = 2 leaves six of the eight image slots of a tile empty)."""
+    seen = _check_every_op("yolov8m", 640, 8)
+    assert any("tile 4x4x8" in d for d in seen) and any("tile 8x8x2" in d for d in seen), [d for d in seen if "20x20" in d][:3]
+
+
 def _check_every_op(arch, imgsz, n, precision="bf16"):
     from _ir_cpu import run_graph_cpu  # noqa: F401  (same arithmetic, per-op form below)
     import torch.nn.functional as F
@@ -738,17 +745,17 @@ def test_car_detector_production_loop(tmp_path):
     orig, calls = det4._process_batch, []
 
     def interrupted(batch_tiles, processed_count, total_tiles):
-        if len(calls) == 3:
+        if len(calls) == 2:                       # 20 tiles = three batches of 8: stop before the last one
             raise _Stop()
         calls.append(processed_count)
         return orig(batch_tiles, processed_count, total_tiles)
     det4._process_batch = interrupted
     with pytest.raises(_Stop):
         det4.detect(interactive=False, force_restart=True)
-    assert det4.stats['checkpoints'] >= 2 and json.load(open(det4.checkpoint_manager.state_file))['processed_count'] == 24
+    assert det4.stats['checkpoints'] == 2 and json.load(open(det4.checkpoint_manager.state_file))['processed_count'] == 16
     det5 = CarDetector(str(tmp_path), cfg0)
     resumed = det5.detect(interactive=False, force_restart=False)
-    assert det5.stats['start'] == 24
+    assert det5.stats['start'] == 16
     assert sorted(d['confidence'] for d in resumed) == sorted(d['confidence'] for d in full)     # no batch counted twice
 
 
