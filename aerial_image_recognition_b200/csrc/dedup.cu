@@ -148,19 +148,32 @@ unsigned table_cap(int n) {
 
 size_t dedup_scratch_bytes(int count) {
     const unsigned cap = table_cap(count);
-    return (size_t)cap * 8 + (size_t)cap * 4 + (size_t)count * 4 + (size_t)((count + 15) & ~15) + 64;
+    // cell keys + cell heads + next links + flags (16 B) + state bytes, then the closure's labels and component marks
+    return (size_t)cap * 8 + (size_t)cap * 4 + (size_t)count * 4 + 16 + (size_t)((count + 15) & ~15) + (size_t)count * 4 + (size_t)((count + 15) & ~15) + 64;
 }
 
-// Seam closure: flag[i] != 0 marks detections that may interact with another shard; the closure
-// propagates the flag along the "within thr" relation until it is stable, so that every
-// connected component of the suppression graph is either entirely flagged or entirely local.
-__global__ void closure_round_kernel(DedupTable t, const double* __restrict__ x, const double* __restrict__ y, int n, double inv_cell,
-                                     double thr2, int inclusive, uint8_t* flag) {
+// Seam closure: flag[i] != 0 marks detections that may interact with another shard; the closure extends the flag to every
+// detection connected to a flagged one through the "within thr" relation, so that every connected component of the
+// suppression graph is either entirely flagged or entirely local.
+//
+// Connected components by label propagation with pointer jumping: label[i] starts as i; a hook round gives every point
+// (and its current representative) the smallest label among its neighbours, a jump round replaces every label by its
+// root.  Labels only ever point to a smaller index in the same component, and the rounds stop when no edge joins two
+// different roots -- a number of rounds logarithmic in the longest chain, where flooding the flag one hop per round took
+// one round per metre of chain (detections line up along image edges for kilometres; 8 800 rounds on config C4).
+__global__ void closure_init_kernel(int* __restrict__ label, uint8_t* __restrict__ comp, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { label[i] = i; comp[i] = 0; }
+}
+
+__global__ void closure_hook_kernel(DedupTable t, const double* __restrict__ x, const double* __restrict__ y, int n, double inv_cell,
+                                    double thr2, int inclusive, int* label) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (((volatile uint8_t*)flag)[i]) return;
     const double xi = x[i], yi = y[i];
     const long long cx = (long long)floor(xi * inv_cell), cy = (long long)floor(yi * inv_cell);
+    const int li = ((volatile int*)label)[i];
+    int m = li;
     for (int dx = -1; dx <= 1; ++dx)
         for (int dy = -1; dy <= 1; ++dy) {
             const unsigned long long key = pack_cell(cx + dx, cy + dy);
@@ -173,16 +186,42 @@ __global__ void closure_round_kernel(DedupTable t, const double* __restrict__ x,
                 slot = (slot + 1) & t.cap_mask;
             }
             for (int j = head; j >= 0; j = t.next[j]) {
-                if (j == i || !((volatile uint8_t*)flag)[j]) continue;
+                if (j == i) continue;
                 const double ddx = __dsub_rn(xi, x[j]), ddy = __dsub_rn(yi, y[j]);
                 const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
                 if (inclusive ? (d2 <= thr2) : (d2 < thr2)) {
-                    flag[i] = 1;
-                    atomicAdd(t.flag, 1);
-                    return;
+                    const int lj = ((volatile int*)label)[j];
+                    if (lj < m) m = lj;
                 }
             }
         }
+    if (m < li) {
+        atomicMin(&label[i], m);
+        atomicMin(&label[li], m);          // the old representative joins too: whole trees merge, not single points
+        t.flag[0] = 1;
+    }
+}
+
+__global__ void closure_jump_kernel(int* label, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int l = ((volatile int*)label)[i];
+    while (true) {
+        const int ll = ((volatile int*)label)[l];
+        if (ll >= l) break;
+        l = ll;
+    }
+    label[i] = l;
+}
+
+__global__ void closure_mark_kernel(const int* __restrict__ label, const uint8_t* __restrict__ flag, uint8_t* comp, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) comp[label[i]] = 1;
+}
+
+__global__ void closure_apply_kernel(const int* __restrict__ label, const uint8_t* __restrict__ comp, uint8_t* flag, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = comp[label[i]];
 }
 
 static int build_table(DedupTable& t, const double* x, const double* y, int count, double thr, void* scratch, size_t scratch_bytes,
@@ -212,16 +251,24 @@ int closure_launch(const double* x, const double* y, int count, double thr, int 
     DedupTable t;
     double inv_cell;
     if (build_table(t, x, y, count, thr, scratch, scratch_bytes, stream, &inv_cell)) return -1;
+    int* label = (int*)(t.state + (((size_t)count + 15) & ~(size_t)15));
+    uint8_t* comp = (uint8_t*)(label + count);
+    const int blocks = (count + 255) / 256;
+    closure_init_kernel<<<blocks, 256, 0, stream>>>(label, comp, count);
     int h_flag[2] = {1, 0};
     for (int round = 0; h_flag[0] != 0; ++round) {
         B2D_CUDA(cudaMemsetAsync(t.flag, 0, sizeof(int), stream));
-        closure_round_kernel<<<(count + 255) / 256, 256, 0, stream>>>(t, x, y, count, inv_cell, thr * thr, inclusive, flag);
+        closure_hook_kernel<<<blocks, 256, 0, stream>>>(t, x, y, count, inv_cell, thr * thr, inclusive, label);
+        closure_jump_kernel<<<blocks, 256, 0, stream>>>(label, count);
         B2D_LAUNCH_CHECK();
         B2D_CUDA(cudaMemcpyAsync(h_flag, t.flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         B2D_CUDA(cudaStreamSynchronize(stream));
         B2D_CHECK(h_flag[1] == 0, "closure: a coordinate / thr is outside the grid's +-2^31 cells (or not finite)");
         B2D_CHECK(round <= count + 8, "closure: did not converge");
     }
+    closure_mark_kernel<<<blocks, 256, 0, stream>>>(label, flag, comp, count);
+    closure_apply_kernel<<<blocks, 256, 0, stream>>>(label, comp, flag, count);
+    B2D_LAUNCH_CHECK();
     return 0;
 }
 

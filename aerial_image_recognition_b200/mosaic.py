@@ -154,6 +154,8 @@ class MosaicDetector:
         self.conf, self.nms_conf, self.iou, self.max_det = conf, nms_conf, iou, max_det
         self.dedup_thr = dedup_thr
         self.fill = fill
+        self.profile = False            # True: synchronise around the phases of `dedup` and keep their wall times in `self.timings` (ms)
+        self.timings = {}
         assert self.gt[2] == 0.0 and self.gt[4] == 0.0, "seam margins assume an axis-aligned geotransform"
 
     # ---- per-rank detection over its windows --------------------------------------------------
@@ -205,20 +207,37 @@ class MosaicDetector:
         """Global total order among equal confidences: window order, then rank inside the window."""
         return wid * 65536 + slot.long()
 
+    def _tick(self, name, t0):
+        if self.profile:
+            import time
+            import torch
+            torch.cuda.synchronize()
+            self.timings[name] = self.timings.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+            return time.perf_counter()
+        return t0
+
     def seam_split(self, x, y, conf, cls, wid, slot, py, rank: int, covers):
         """Dedup everything that cannot interact with another shard; return (local survivors,
         records [k, RECORD_WORDS] float64 on device that must be exchanged)."""
         import torch
         eng = self.eng
+        import time
+        t0 = time.perf_counter()
         key = self.order_key(wid, slot)
         margin_px = self.dedup_thr / min(abs(self.gt[1]), abs(self.gt[5])) + 1.0
         flag = seam_flags_device(py, rank, covers, margin_px)
+        t0 = self._tick("flags", t0)
         eng.seam_closure(x, y, flag, self.dedup_thr, True)
+        t0 = self._tick("closure", t0)
         seam = flag.bool()
         lx, ly, lc, lk = x[~seam], y[~seam], conf[~seam], key[~seam]
+        t0 = self._tick("split", t0)
         lkeep = eng.dedup(lx, ly, lc, self.dedup_thr, True, tiebreak=lk).bool()
+        t0 = self._tick("local_dedup", t0)
         local = self._pack(lx[lkeep], ly[lkeep], lc[lkeep], cls[~seam][lkeep], wid[~seam][lkeep], slot[~seam][lkeep])
-        return local, pack_records(x[seam], y[seam], conf[seam], cls[seam], key[seam])
+        rec = pack_records(x[seam], y[seam], conf[seam], cls[seam], key[seam])
+        self._tick("pack", t0)
+        return local, rec
 
     def seam_merge(self, parts, origin: np.ndarray, rank: int) -> np.ndarray:
         """The identical greedy pass every rank runs on the gathered seam records; returns the
@@ -260,8 +279,12 @@ class MosaicDetector:
             ev[1].record()
             return list(out.unbind(0))
 
+        import time
+        t0 = time.perf_counter()
         parts, origin = exchange_seam(rec, world, gather_counts, gather_padded)
+        t0 = self._tick("exchange", t0)
         merged = self.seam_merge(parts, origin, rank)
+        self._tick("merge", t0)
         self.last_allgather_us = ev[0].elapsed_time(ev[1]) * 1e3      # both events have completed: seam_merge read its result back
         return np.concatenate([local, merged])
 

@@ -24,6 +24,8 @@ architecture.  The generator is deterministic in ``(arch, nc, seed)``.
 """
 from __future__ import annotations
 
+import os
+import sys
 from typing import Dict, Tuple
 
 import numpy as np
@@ -34,7 +36,7 @@ PREACT_STD = 4.0          # LSUV target of every SiLU conv (see the module docst
 CAL_SIZE, CAL_TILES = 640, 2
 DFL_SIGMA_D, DFL_D0, DFL_NOISE = 1.0, 1.5, 0.25
 CLS_STD, V8_PASS_FRACTION, V7_PASS_FRACTION = 2.0, 0.06, 0.02
-GENERATOR_VERSION = 2
+GENERATOR_VERSION = 2          # part of the seed: bump when the recipe changes
 
 _CACHE: Dict[Tuple, Dict[str, np.ndarray]] = {}
 
@@ -60,6 +62,13 @@ def _quantised_scale(s: float) -> float:
     return float(2.0 ** (np.round(np.log2(max(s, 1e-12)) * 8.0) / 8.0))
 
 
+def _snap(v, bits: int = 12):
+    """Round calibration-derived biases to multiples of 2**-bits.  They come out of CPU reductions whose last bits depend on
+    the thread count (torchrun sets OMP_NUM_THREADS=1): un-snapped, two ranks of one job would run weights that differ in
+    the last ulp.  The statistics themselves are taken in float64 with NumPy's (single-threaded) reductions."""
+    return np.round(np.asarray(v, dtype=np.float64) * (1 << bits)) / (1 << bits)
+
+
 def _final_layers(graph: Graph):
     if graph.head["kind"] == "v8_dfl":
         return {f"model.22.cv2.{i}.2" for i in range(3)}, {f"model.22.cv3.{i}.2" for i in range(3)}
@@ -74,6 +83,15 @@ def make_synthetic_weights(graph: Graph, seed: int = 0, calibrate: bool = True) 
     key = (graph.arch, graph.nc, seed, calibrate)
     if key in _CACHE:
         return {k: v.copy() for k, v in _CACHE[key].items()}
+    disk = _disk_cache_path(key) if calibrate else None
+    if disk and os.path.exists(disk):
+        try:
+            with np.load(disk) as z:
+                w = {k: z[k] for k in z.files}
+            _CACHE[key] = {k: v.copy() for k, v in w.items()}
+            return w
+        except Exception:
+            pass                      # unreadable cache file: regenerate
     rng = np.random.default_rng([seed, 0xB200, GENERATOR_VERSION])
     w: Dict[str, np.ndarray] = {}
     box_final, _ = _final_layers(graph)
@@ -94,12 +112,51 @@ def make_synthetic_weights(graph: Graph, seed: int = 0, calibrate: bool = True) 
     if calibrate:
         _calibrate(graph, w, seed)
     _CACHE[key] = {k: v.copy() for k, v in w.items()}
+    if disk:
+        try:                          # the calibration takes ~10 s on one thread; every process of a job wants the same tensors
+            os.makedirs(os.path.dirname(disk), exist_ok=True)
+            tmp = f"{disk}.{os.getpid()}.tmp.npz"
+            np.savez(tmp, **w)
+            os.replace(tmp, disk)
+        except OSError:
+            pass
     return w
+
+
+def _disk_cache_path(key) -> str:
+    """Generated weights are cached on disk, keyed by the arguments and by a hash of this generator's own source (and of the
+    graph / tile generators it calibrates on), so an edit to any of them invalidates the cache."""
+    import hashlib
+    import tempfile
+    from . import graph as _g, synth as _s
+    h = hashlib.sha256()
+    for mod in (sys.modules[__name__], _g, _s):
+        with open(mod.__file__, "rb") as f:
+            h.update(f.read())
+    root = os.environ.get("B2D_WEIGHT_CACHE", os.path.join(tempfile.gettempdir(), "b2det_weights"))
+    return os.path.join(root, f"{key[0]}_nc{key[1]}_seed{key[2]}_{h.hexdigest()[:16]}.npz")
 
 
 def _calibrate(graph: Graph, w: Dict[str, np.ndarray], seed: int) -> None:
     """Layer-sequential rescale on two calibration tiles (CPU torch; this is weight *generation*,
     not the inference path)."""
+    import torch
+    import torch.nn.functional as F
+    from .graph import build
+    from .synth import make_tiles
+
+    # One CPU thread: the blocking (hence the summation order) of the CPU convolutions depends on the thread count, and the
+    # head biases below are derived from their outputs -- every process of a job (torchrun sets OMP_NUM_THREADS=1, a plain
+    # `python bench.py` does not) must generate bit-identical weights, or shards of one mosaic disagree in the last ulp.
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        _calibrate_single_thread(graph, w, seed)
+    finally:
+        torch.set_num_threads(threads)
+
+
+def _calibrate_single_thread(graph: Graph, w: Dict[str, np.ndarray], seed: int) -> None:
     import torch
     import torch.nn.functional as F
     from .graph import build
@@ -132,8 +189,8 @@ def _calibrate(graph: Graph, w: Dict[str, np.ndarray], seed: int) -> None:
                         f1 = y[:, side * 16 + 1]                                       # row 1 = v . x (+ its noise)
                         s1 = _quantised_scale(2.0 * DFL_SIGMA_D / float(f1.std()))
                         sc[rows] = s1
-                        mean = y[:, rows].mean(dim=(0, 2, 3)).numpy()
-                        b[rows] = b[rows] - mean * s1 + 2.0 * ks * DFL_D0 - ks * ks
+                        mean = y[:, rows].numpy().astype(np.float64).mean(axis=(0, 2, 3))
+                        b[rows] = _snap(b[rows] - mean * s1 + 2.0 * ks * DFL_D0 - ks * ks)
                 elif name in cls_final:
                     s1 = _quantised_scale(CLS_STD / float(y.std()))
                     sc[:] = s1
@@ -141,15 +198,15 @@ def _calibrate(graph: Graph, w: Dict[str, np.ndarray], seed: int) -> None:
                     if v8:
                         score = z.amax(1)                                               # conf = max class logit
                         thr, frac = float(np.log(0.25 / 0.75)), V8_PASS_FRACTION
-                        shift = thr - float(np.quantile(score.numpy().ravel(), 1.0 - frac))
-                        b[:] = b + shift
+                        shift = thr - float(np.quantile(score.numpy().ravel().astype(np.float64), 1.0 - frac))
+                        b[:] = _snap(b + shift)
                     else:
                         no = g.nc + 5
                         obj = z.view(z.shape[0], 3, no, z.shape[2], z.shape[3])[:, :, 4]
                         thr, frac = float(np.log(0.3 / 0.7)), V7_PASS_FRACTION
-                        shift = thr - float(np.quantile(obj.numpy().ravel(), 1.0 - frac))
+                        shift = thr - float(np.quantile(obj.numpy().ravel().astype(np.float64), 1.0 - frac))
                         bb = b.reshape(3, no)
-                        bb[:, 4] += shift
+                        bb[:, 4] = _snap(bb[:, 4] + shift)
                         b = bb.reshape(-1)
                 else:
                     sc[:] = _quantised_scale(PREACT_STD / float(y.std()))

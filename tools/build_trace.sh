@@ -2,7 +2,7 @@
 set -e
 cd "$(dirname "$0")/../aerial_image_recognition_b200/csrc"
 mkdir -p ../../tools/ubench/build/tr
-for f in engine conv_tc conv_simt preprocess postprocess dedup; do
+for f in engine conv_tc pool preprocess postprocess dedup tta; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -gencode arch=compute_100a,code=sm_100a -DB2D_ENABLE_TRACE -c $f.cu -o ../../tools/ubench/build/tr/$f.o &
 done
 wait

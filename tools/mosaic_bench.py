@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--dump", default="")
+    ap.add_argument("--dump-raw", default="", help="debug: save every rank's raw (pre-dedup) detections to <prefix>.rank<r>.npz")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -51,6 +52,7 @@ def main():
     windows, ids, cover = M.shard_windows(H, W, rank, world)
     band = synth.mosaic_band_device(pool, H, W, cover[0], cover[1], 5)
     det = M.MosaicDetector(eng, GT, conf=0.4, dedup_thr=1.0)
+    det.profile = bool(os.environ.get("B2D_MOSAIC_PROFILE"))
 
     def barrier():
         if world > 1:
@@ -75,6 +77,12 @@ def main():
     if world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    if det.profile:
+        print(f"rank {rank} dedup phases (ms, summed over {args.repeat + 1} runs): " + ", ".join(f"{k} {v:.1f}" for k, v in det.timings.items()), file=sys.stderr)
+    if args.dump_raw:
+        x, y, conf, cls, wid, slot, py = det.detect_windows(band, windows, ids, cover[0])
+        np.savez(f"{args.dump_raw}.rank{rank}.npz", x=x.cpu().numpy(), y=y.cpu().numpy(), conf=conf.cpu().numpy(), wid=wid.cpu().numpy(),
+                 slot=slot.cpu().numpy(), py=py.cpu().numpy())
     if args.dump:
         np.save(f"{args.dump}.rank{rank}.npy", out)
     if rank == 0:
