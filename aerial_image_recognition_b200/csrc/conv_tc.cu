@@ -253,6 +253,19 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
     return c;
 }
 
+// CTA pairs: round `rd` of a pair = two M tiles of one output-channel tile nt, one per CTA (rank 0 / 1); an odd last M tile
+// is computed (and stored, identically) by both.  Tile index t = m * n_tiles_n + nt as everywhere else.
+__device__ __forceinline__ int pair_rounds(const ConvTcParams& p, int total_tiles) {
+    const int nn = p.n_tiles_n, mt = total_tiles / nn;
+    return ((mt + 1) >> 1) * nn;
+}
+__device__ __forceinline__ int pair_tile(const ConvTcParams& p, int rd, int rank, int total_tiles) {
+    const int nn = p.n_tiles_n;
+    if (nn == 1) return min(2 * rd + rank, total_tiles - 1);
+    const int mp = (int)__umulhi((uint32_t)rd, p.rcp_nn), nt = rd - mp * nn;
+    return min(2 * mp + rank, total_tiles / nn - 1) * nn + nt;
+}
+
 // Ablation flags for timing experiments (trace builds only; results are wrong when set): p.exp bit 0 = the MMA warp
 // does not wait for operand barriers, bit 1 = the epilogue skips TMEM loads / math / stores, bit 2 = the producer
 // issues no TMA loads (arrives on the barriers instead).
@@ -485,10 +498,10 @@ __device__ __forceinline__ void store_loop(const ConvTcParams& p, int total_tile
     const uint32_t sfull_u32 = smem_u32(sfull_bar) + (uint32_t)(q * S) * 8u, sempty_u32 = smem_u32(sempty_bar) + (uint32_t)(q * S) * 8u;
     const uint32_t rbar_u32 = smem_u32(res_bar) + (uint32_t)(q * S) * 8u;
     const uint32_t rank = pair ? cluster_ctarank() : 0u;
-    const int rounds = pair ? (total_tiles + 1) / 2 : (total_tiles + mt - 1) / mt;
+    const int rounds = pair ? pair_rounds(p, total_tiles) : (total_tiles + mt - 1) / mt;
     const int rd0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, rd_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const bool no_store = B2D_EXP(p, 1) || B2D_EXP(p, 5);
-    auto first_tile = [&](int rd) { return pair ? min(2 * rd + (int)rank, total_tiles - 1) : rd * mt; };
+    auto first_tile = [&](int rd) { return pair ? pair_tile(p, rd, (int)rank, total_tiles) : rd * mt; };
     auto valid_tiles = [&](int rd) { return pair ? 1 : min(mt, total_tiles - rd * mt); };
     // TMA boxes of this quarter's rows of tile t: residual loads into / stores out of slab `slab`
     auto tile_io = [&](int t, int slab, bool load) {
@@ -573,7 +586,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     // tile walk: a CTA takes rounds blockIdx.x, + gridDim.x, ... of mt tiles; in a CTA pair (mt == 1) the pair takes two
     // consecutive tiles per round, one per CTA, and an odd last tile is computed (and stored, identically) by both
     const uint32_t rank = pair ? cluster_ctarank() : 0u;
-    const int rounds = pair ? (total_tiles + 1) / 2 : (total_tiles + mt - 1) / mt;
+    const int rounds = pair ? pair_rounds(p, total_tiles) : (total_tiles + mt - 1) / mt;
     const int rd0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, rd_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const uint32_t tempty_arrive = pair ? mapa_u32(tempty_u32, 0) : tempty_u32;   // the leader's barrier gates the pair's MMAs
     const bool ldt = !B2D_EXP(p, 4);
@@ -584,7 +597,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        const int t0 = pair ? min(2 * rd + (int)rank, total_tiles - 1) : rd * mt;
+        const int t0 = pair ? pair_tile(p, rd, (int)rank, total_tiles) : rd * mt;
         const int nv = pair ? 1 : min(mt, total_tiles - t0);        // valid tiles of this round
         if (warp == 4 && lane == 0) trace(p, 2, it, 0);
         mbar_wait_u32(tfull_u32 + as * 8, aphase);
@@ -1191,6 +1204,158 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair generic kernel (1x1 and stride-2 layers with n_tile >= 128): the generic kernel's operand feed -- one A box per
+// (tap, chunk) -- with the pair's MMA stream.  Each CTA loads the A box of its own M tile and HALF of every weight box into
+// the same stage slot; the leader issues one cta_group::2 MMA (M = 256) per K = 16 step.  Per SM the weight traffic from L2
+// and the B-operand reads are halved: these layers run N = 192 tiles, where a single SM needs ~105 bytes of operands per
+// clock to keep its tensor pipe busy and L2 delivers about half of that.
+// Barriers as in the halo pair kernel: full / tempty live in the leader (both CTAs arrive), empty / tfull are signalled in
+// both CTAs by the leader's multicast commits.
+// ---------------------------------------------------------------------------------------------
+template <int ACT, int RES, int F32>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_pair_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const Bars b = carve_bars(smem, p);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int total_tiles = p.tiles_x * p.tiles_y * ((nimg + p.bn - 1) / p.bn) * p.n_tiles_n;
+    const int rounds = pair_rounds(p, total_tiles);
+    const int rd0 = (int)(blockIdx.x >> 1), rd_step = (int)(gridDim.x >> 1);
+    const int ksteps = p.taps * p.chunks;
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA[0]);
+        if (p.stride == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
+        tma_prefetch_desc(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&b.full[i], 2);                 // one arrive.expect_tx per CTA (the leader's copy is the one waited on)
+            mbar_init(&b.empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&b.tfull[i], 1);
+            mbar_init(&b.tempty[i], 512);             // epilogue threads of both CTAs
+            mbar_init(&b.hfull[i], 1);
+            mbar_init(&b.hempty[i], 1);
+        }
+        for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
+            if (p.has_res) mbar_init(&b.res[i], 1);
+            mbar_init(&b.sfull[i], 64);
+            mbar_init(&b.sempty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2sm(b.tmem_slot, p.tmem_cols);
+    for (int i = threadIdx.x; i < p.n_tile * p.n_tiles_n; i += blockDim.x) b.bias_s[i] = p.act ? 0.5f * p.bias[i] : p.bias[i];
+    tc_fence_before();
+    cluster_sync_all();                               // barriers of both CTAs initialised before anyone signals them
+    tc_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t tmem_base = *b.tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_u32 = smem_u32(b.full), empty_u32 = smem_u32(b.empty);
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs): own A box + this CTA's half of the weight box =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        const int pad = p.ksz >> 1;
+        const int nstages = p.stages, taps = p.taps, chunks = p.chunks, ksz = p.ksz, n_tile = p.n_tile;
+        const int cin_pad = chunks * 64;
+        const bool s2 = (p.stride == 2), perm = p.perm != 0;
+        const uint32_t lead_full = mapa_u32(full_u32, 0);
+        const uint32_t tx_bytes = p.a_tx_bytes + p.b_tx_bytes;
+        for (int rd = rd0; rd < rounds; rd += rd_step) {
+            const TileCoord tc = decode_tile(p, pair_tile(p, rd, (int)rank, total_tiles));
+            const int b_row0 = tc.nt * n_tile + (int)rank * (n_tile >> 1);
+            int kh = 0, kw = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+                const CUtensorMap* mapA = &p.tmA[0];
+                int ox = kw - pad, oy = kh - pad;
+                if (s2) {
+                    const int dy = kh - 1, dx = kw - 1;
+                    const int py = dy & 1, px = dx & 1;
+                    mapA = &p.tmA[py * 2 + px];
+                    ox = (dx - px) / 2;
+                    oy = (dy - py) / 2;
+                }
+                const int kb = tap * cin_pad;
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes, fb = lead_full + stage * 8;
+                        mbar_expect_tx_cluster(fb, tx_bytes);
+                        const int cy = tc.y0 + oy;
+                        tma_load_4d_2sm(mapA, fb, sa, ch * 64, tc.x0 + ox, perm ? tc.n0 : cy, perm ? cy : tc.n0);
+                        tma_load_2d_2sm(&p.tmB, fb, sa + p.a_bytes, kb + ch * 64, b_row0);
+                    }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+                if (++kw == ksz) { kw = 0; ++kh; }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        int stage = 0, it = 0;
+        uint32_t phase = 0;
+        const bool leader = elect_one();
+        const uint32_t hi = desc_hi(1024);
+        const uint32_t lo_base = desc_lo(smem_base);
+        const uint32_t stage_units = stage_bytes >> 4, a_units = p.a_bytes >> 4;
+        const uint32_t idesc = p.idesc;                                   // M = 256
+        const int nstages = p.stages, n_tile = p.n_tile, chunks = p.chunks, taps = p.taps;
+        const int last_kmmas = (p.cin - (chunks - 1) * 64 + 15) >> 4;
+        const uint32_t tfull_u32 = smem_u32(b.tfull), tempty_u32 = smem_u32(b.tempty);
+        for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait_u32(tempty_u32 + as * 8, aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
+            int ks = 0;
+            auto step = [&](auto KM) {
+                mbar_wait_u32(full_u32 + stage * 8, phase);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t a_lo = lo_base + (uint32_t)stage * stage_units;
+                    const uint32_t b_lo = a_lo + a_units;
+                    const uint32_t acc0 = (uint32_t)(ks != 0);
+#pragma unroll
+                    for (int k = 0; k < decltype(KM)::value; ++k)
+                        umma_bf16_2sm(d_tmem, desc64(hi, a_lo + 2 * k), desc64(hi, b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u);
+                    umma_commit_2sm(empty_u32 + stage * 8);                       // frees the slot in both CTAs
+                    if (ks == ksteps - 1) umma_commit_2sm(tfull_u32 + as * 8);
+                }
+                ++ks;
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+            };
+            for (int tap = 0; tap < taps; ++tap) {
+                for (int ch = 0; ch < chunks - 1; ++ch) step(KConst<4>{});
+                if (last_kmmas == 4) step(KConst<4>{});
+                else if (last_kmmas == 3) step(KConst<3>{});
+                else if (last_kmmas == 2) step(KConst<2>{});
+                else step(KConst<1>{});
+            }
+        }
+    } else if (warp == 3) {
+        store_loop<RES, F32>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane, true);
+    } else if (warp >= 4) {
+        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane, true);
+    }
+    tc_fence_before();
+    cluster_sync_all();                               // the peer may still signal this CTA's barriers / read its smem until here
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // depthwise kernel: 3x3 stride-1 depthwise conv (Ultralytics 8.3.x cls branch) on the tensor cores.
 // Channels are cut into groups of 16; for a group the depthwise filter is a dense 16 -> 16 conv whose
 // weight matrix per tap is diagonal, i.e. one M128 x N16 x K16 MMA per (tap, group): A = the halo
@@ -1684,6 +1849,26 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         int st = (int)(room / p.b_bytes);
         p.stages = st > kMaxStages ? kMaxStages : st;
     }
+    // CTA pairs for generic layers (1x1, stride 2) with wide output tiles and a SHORT reduction: half a weight tile per CTA per
+    // stage.  Measured per op at batch 64 (profiles/r2_pair_generic_per_op.txt): K = cin * taps < 576 gains 5-18 % (the weight
+    // tile is a large share of a short round's operand traffic), K >= 576 loses 1-6 % (the leader's barrier round trip through
+    // the cluster per K step is no longer hidden), so the planner pairs only the short ones.
+    const int k_total = cin * p.taps;
+    const bool pair_short_k = k_total < env_int("B2D_PAIRG_MAX_K", 576) || (stride == 2 && cin <= 96);
+    if (p.kind == 0 && !stem && p.n_tile >= env_int("B2D_PAIRG_MIN_N", 128) && p.n_tile % 32 == 0 && p.mt == 1 &&
+        (pair_short_k || env_int("B2D_PAIR", 1) == 2) &&
+        (total_tiles >= 2 * sm_count || env_int("B2D_PAIR", 1) == 2) && env_int("B2D_PAIR", 1) != 0 && env_int("B2D_PAIRG", 1) != 0) {
+        p.pair = 1;
+        p.b_tx_bytes = (uint32_t)(p.n_tile / 2) * 128u;
+        p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
+        const uint32_t sb = p.a_bytes + p.b_bytes;
+        if (avail > 2u * tile_stg + 4u * sb + slab_bars(1, 2) && env_int("B2D_STG2", 1) != 0) p.stg_bufs = 2;
+        const uint32_t room = avail - (uint32_t)p.stg_bufs * tile_stg - slab_bars(1, p.stg_bufs);
+        int st = (int)(room / sb);
+        const int ksteps = p.taps * p.chunks;
+        if (st > 2 * ksteps) st = 2 * ksteps;
+        p.stages = st > kMaxStages ? kMaxStages : st;
+    }
     if (best_kind == 1) p.a_tx_bytes = halo_rows * 128u;
     const uint32_t stg_bytes = (uint32_t)p.stg_bufs * p.mt * tile_stg;
     uint32_t operand_bytes;
@@ -1847,6 +2032,7 @@ ConvKernel pick_kernel(int kind, int pair, int act, int res, int out) {
     if (kind == 2) return out == 2 ? (act ? conv_tc_stem_kernel<1, 2> : conv_tc_stem_kernel<0, 2>) : (act ? conv_tc_stem_kernel<1, 0> : conv_tc_stem_kernel<0, 0>);
     if (kind == 3) return out == 2 ? (act ? conv_tc_dw_kernel<1, 2> : conv_tc_dw_kernel<0, 2>) : (act ? conv_tc_dw_kernel<1, 0> : conv_tc_dw_kernel<0, 0>);
     if (kind == 1 && pair) { B2D_PICK(conv_tc_halo2_kernel) }
+    if (kind == 0 && pair) { B2D_PICK(conv_tc_pair_kernel) }
     if (kind == 1) { B2D_PICK(conv_tc_halo_kernel) }
     B2D_PICK(conv_tc_kernel)
 #undef B2D_PICK
@@ -1867,7 +2053,7 @@ int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
     }
     if (grid < 1) return 0;
     if (p.pair) {
-        const int prs = ceil_div(tiles, 2);
+        const int prs = ceil_div(tiles / p.n_tiles_n, 2) * p.n_tiles_n;      // rounds of a pair (see pair_rounds)
         grid = 2 * (prs < plan->sm_count / 2 ? prs : plan->sm_count / 2);
     }
     ConvKernel k = pick_kernel(p.kind, p.pair, p.act, p.has_res, p.out_f32 ? 1 : p.x2 ? 2 : 0);
@@ -1930,8 +2116,8 @@ void conv_tc_free(ConvTcPlan* plan) {
 
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
-    static const char* kinds[5] = {"", "-halo", "-stem", "-depthwise", "-halo-pair"};
+    static const char* kinds[6] = {"", "-halo", "-stem", "-depthwise", "-halo-pair", "-pair"};
     return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d%s stg %d tmem %u smem %zu",
-                    kinds[p.pair ? 4 : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
+                    kinds[p.pair ? (p.kind == 0 ? 5 : 4) : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
                     p.b_res ? " (resident)" : "", p.stg_bufs, p.tmem_cols, plan->smem_bytes);
 }
