@@ -82,6 +82,7 @@ struct __align__(64) ConvTcParams {
     const void* src_raw;  // stem: NHWC4 bf16 input
     const void* w_raw;    // stem: packed weights [n_tile][64] bf16
     int f16;              // 16-bit activation / weight format: 0 bf16, 1 fp16 (B2D_PREC_FP16, B2D_PREC_FP16X2)
+    int epi_parts;        // epilogue warps per TMEM lane quarter: 2 (warps 4-11) or 3 (warps 4-15), each taking every epi_parts-th 16-column unit
     int x2;               // 1: split-fp16 storage (B2D_PREC_FP16X2): inputs are [hi x 8 | lo x 8] groups, 16-bit outputs are written that way
     float acc_scale;      // the accumulator is multiplied by this before the bias (1/255 in the stem: its input is the raw pixel value)
     int b_res;            // halo kernel: 1 = all 9 * chunks weight boxes stay resident in the stage slots (loaded once per CTA)

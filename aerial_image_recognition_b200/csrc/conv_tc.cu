@@ -43,8 +43,8 @@
 
 namespace {
 
-constexpr int kThreads = 384;         // 4 control warps + 8 epilogue warps
-constexpr int kStemThreads = 512;     // + 4 gather warps
+constexpr int kThreads = 512;         // 4 control warps + up to 12 epilogue warps (ConvTcParams::epi_parts per TMEM lane quarter)
+constexpr int kStemThreads = 512;     // 4 control warps + 8 epilogue warps + 4 gather warps
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 9;         // 9: a 3x3 layer with one K chunk keeps all nine weight taps resident (b_res)
 constexpr int kMaxMt = 4;
@@ -554,7 +554,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* sfull_bar, uint64_t* sempty_bar,
                                               uint64_t* res_bar, uint8_t* stg_base, int warp, int lane, bool pair = false) {
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - 4) >> 2;                  // this warp's part of the quarter's column units: 0 .. epi_parts - 1
+    const int nparts = p.epi_parts;
+    if (half >= nparts) return;                        // a layer with two parts per quarter leaves warps 12-15 idle
     const EpiGeom<F32> g(p, stg_base, q);
     constexpr int esize = F32 ? 4 : 2;
     const int n_tile = p.n_tile, mt = p.mt;
@@ -566,9 +568,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     const uint32_t tfull_u32 = smem_u32(tfull_bar), tempty_u32 = smem_u32(tempty_bar);
     // 16-column units alternate between the two warps of a quarter; an odd last unit is split 8 + 8 so both warps carry
     // the same load (n_tile = 16, 48, 144 would otherwise leave one warp idle for a unit)
+    // With three parts (n_tile a multiple of 48) every warp takes the units part, part + 3, ... and nothing is split.
     const int nunits = n_tile >> 4;
-    const bool split_last = (nunits & 1) != 0;
-    const int my_units = split_last ? (nunits - 1) >> 1 : (nunits - half + 1) >> 1;     // full units half, half + 2, ...
+    const bool split_last = nparts == 2 && (nunits & 1) != 0;
+    const int my_units = nparts == 3 ? nunits / 3 : split_last ? (nunits - 1) >> 1 : (nunits - half + 1) >> 1;     // full units half, half + nparts, ...
     const int ipt = my_units + (split_last ? 1 : 0);                                    // work items per tile
     // Swizzled slab address of this lane's row for the 16-column unit starting at byte `b` of the row.
     const uint32_t n128 = g.n128, has64 = g.has64;
@@ -605,11 +608,12 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         if (warp == 4 && lane == 0) trace(p, 2, it, 1);
         const int ch_base = p.n_tiles_n > 1 ? (int)((uint32_t)t0 - __umulhi((uint32_t)t0, p.rcp_nn) * (uint32_t)p.n_tiles_n) * n_tile : 0;   // n_tiles_n > 1 implies mt == 1
         const uint32_t baddr = bias_base + (uint32_t)(ch_base + half * 16) * 4u;
+        const uint32_t ustep = (uint32_t)nparts * 16u;                             // columns between this warp's consecutive units
         const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * mt * n_tile);
         const int c_base = it * mt;
         auto item_ld = [&](int m, int u, uint32_t (&rb)[16]) {
             if (!ldt) return;
-            if (u < my_units) tmem_ld16(tq + (uint32_t)(m * n_tile + half * 16 + u * 32), rb);
+            if (u < my_units) tmem_ld16(tq + (uint32_t)(m * n_tile + half * 16) + (uint32_t)u * ustep, rb);
             else tmem_ld8(tq + (uint32_t)(m * n_tile + split_col), rb);
         };
         auto item_do = [&](int m, int u, const uint32_t (&rb)[16]) {
@@ -620,7 +624,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
                 if (RES) mbar_wait_u32(rbar_u32 + (uint32_t)slab * 8u, use & 1u);
             }
             const uint32_t moff = (uint32_t)slab * tile_bytes;
-            if (u < my_units) epi_unit<ACT, RES, F32, 16>(rb, baddr + u * 128, unit_base((uint32_t)(half + 2 * u) * ubytes) + moff, B2D_EXPW(p), f16, scale2);
+            if (u < my_units) epi_unit<ACT, RES, F32, 16>(rb, baddr + (uint32_t)u * ustep * 4u, unit_base((uint32_t)(half + nparts * u) * ubytes) + moff, B2D_EXPW(p), f16, scale2);
             else epi_unit<ACT, RES, F32, 8>(rb, bias_base + (uint32_t)(ch_base + split_col) * 4u, unit_base((uint32_t)split_col * esize) + moff, B2D_EXPW(p), f16, scale2);
             if (u == ipt - 1) {                                                // last item: hand the slab to the store warp (64 arrivals per quarter)
                 fence_proxy_async();                                           // generic-proxy slab writes -> visible to the TMA store
@@ -686,13 +690,13 @@ __device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&b.tfull[i], issuers);
-            mbar_init(&b.tempty[i], 256);
+            mbar_init(&b.tempty[i], 128 * p.epi_parts);       // every thread of the active epilogue warps
             mbar_init(&b.hfull[i], 1);
             mbar_init(&b.hempty[i], issuers);
         }
         for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
-            mbar_init(&b.sfull[i], 64);
+            mbar_init(&b.sfull[i], 32 * p.epi_parts);         // the epilogue warps of one quarter
             mbar_init(&b.sempty[i], 1);
         }
         fence_barrier_init();
@@ -1049,13 +1053,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&b.tfull[i], 1);
-            mbar_init(&b.tempty[i], 512);             // epilogue threads of both CTAs
+            mbar_init(&b.tempty[i], 256 * p.epi_parts);   // epilogue threads of both CTAs
             mbar_init(&b.hfull[i], 2);
             mbar_init(&b.hempty[i], 1);
         }
         for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
-            mbar_init(&b.sfull[i], 64);
+            mbar_init(&b.sfull[i], 32 * p.epi_parts);
             mbar_init(&b.sempty[i], 1);
         }
         fence_barrier_init();
@@ -1238,13 +1242,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_pair_kernel(const __grid_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&b.tfull[i], 1);
-            mbar_init(&b.tempty[i], 512);             // epilogue threads of both CTAs
+            mbar_init(&b.tempty[i], 256 * p.epi_parts);   // epilogue threads of both CTAs
             mbar_init(&b.hfull[i], 1);
             mbar_init(&b.hempty[i], 1);
         }
         for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
-            mbar_init(&b.sfull[i], 64);
+            mbar_init(&b.sfull[i], 32 * p.epi_parts);
             mbar_init(&b.sempty[i], 1);
         }
         fence_barrier_init();
@@ -1899,6 +1903,12 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         p.epi_nchunks = n;
     }
     p.has_res = res ? 1 : 0;
+    // Epilogue warps per TMEM lane quarter.  A warp's epilogue is a chain of dependent instructions (TMEM load -> bias FMA ->
+    // MUFU.TANH -> FMA -> pack -> shared store) that issues about one instruction per six cycles; with two warps per scheduler
+    // the epilogue ran at 3-4.5 outputs per clock per SM against 15 for the same code with eight warps per scheduler
+    // (role traces, profiles/r2_role_traces.txt).  A third warp per quarter takes every third 16-column unit when the tile
+    // width allows an even split (48, 96, 144, 192 ...); the stem's 16 warps are taken (gather warps).
+    p.epi_parts = (!stem && (p.n_tile >> 4) % 3 == 0 && env_int("B2D_EPI3", 1) != 0) ? 3 : 2;
     p.exp = env_int("B2D_EXP", 0);
     p.trace = nullptr;
     if (getenv("B2D_TRACE")) {
