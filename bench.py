@@ -69,42 +69,86 @@ def _conv_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region, through NVML in a thread of this process
+    (`nvidia_ml_py`): one clock read and one event-reason bitmask every 50 ms.  An `nvidia-smi --query-gpu=... -lms 100`
+    child process does the same job but was measured to slow the observed step by 3-15 % on some boxes (its query list is
+    re-evaluated through the driver every period); it remains the fallback when the NVML binding is missing."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.t0 = index, [], None, None
+        self.index, self.rows, self.t0, self.stop_flag, self.thread, self.max_mhz, self.how = index, [], None, False, None, None, None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+        mode = os.environ.get("B2D_BENCH_SAMPLER", "nvml")
+        if mode == "none":
+            return
+        if mode == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+                self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            if self.t0 is not None:                  # only samples taken inside the timed region count
-                self.rows.append([c.strip() for c in line.split(",")])
+                def loop():
+                    while not self.stop_flag:
+                        try:
+                            mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                            why = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                            if self.t0 is not None:
+                                self.rows.append((float(mhz), int(why)))
+                        except Exception:
+                            pass
+                        time.sleep(0.05)
+                self.thread = threading.Thread(target=loop, daemon=True)
+                self.thread.start()
+                self.how = "nvml"
+                return
+            except Exception:
+                pass
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self._physical_index()}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+            def read():
+                for line in self.proc.stdout:
+                    c = [x.strip() for x in line.split(",")]
+                    if self.t0 is not None and len(c) >= 6 and c[0].replace(".", "").isdigit():
+                        self.max_mhz = float(c[1]) if c[1].replace(".", "").isdigit() else self.max_mhz
+                        why = sum(bit for (name, bit), v in zip(self.REASONS, c[2:6]) if v.lower().startswith("active"))
+                        self.rows.append((float(c[0]), why))
+            self.thread = threading.Thread(target=read, daemon=True)
+            self.thread.start()
+            self.how = "nvidia-smi"
+        except Exception:
+            self.how = None
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].strip().isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def mark(self):
-        """Start of the timed region.  The process is started earlier (before the warm-up) so that nvidia-smi's own
-        start-up -- NVML initialisation on a busy GPU -- cannot fall into the region it is meant to observe."""
+        """Start of the timed region (the sampler itself is started earlier, so its start-up cannot fall into it)."""
         self.t0 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        time.sleep(0.06)
+        self.stop_flag = True
+        if getattr(self, "proc", None) is not None:
+            self.proc.terminate()
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sampler available"]}
+        sm = [r[0] for r in self.rows]
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [name for name, bit in self.REASONS if bits & bit], "samples": len(sm), "sampler": self.how}
 
 
 def _geo_params(n: int) -> np.ndarray:
@@ -459,6 +503,9 @@ def main():
     if rank == 0:
         sampler.start()
     burst_ms = None
+    for i0 in range(2):                 # first calls: lazy module loading, function attributes, CUDA-graph capture
+        device_step(i0)
+    torch.cuda.synchronize()
     t_w, i, prev, stable = time.perf_counter(), 0, None, 0
     while True:
         w0, w1 = _events()
@@ -479,15 +526,38 @@ def main():
     warm_steps = i
     barrier()
     sampler.mark()
-    e0, e1 = _events()
-    e0.record()
-    for i in range(K):
-        geo, counts = device_step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    # EXACTLY K steps, bracketed by barrier + synchronize on both sides -- three times over, and the median is reported: about
+    # one run in four carries a one-off ~50 ms stall inside its first timed loop (7.4 instead of 6.3 ms per step; the same loop
+    # repeated immediately afterwards is back at 6.3; not the clock sampler, not the allocator -- B2D_BENCH_DEBUG shows it).
+    runs = []
+    for rep in range(3):
+        barrier()
+        e0, e1 = _events()
+        e0.record()
+        for i in range(K):
+            geo, counts = device_step(i)
+        e1.record()
+        barrier()
+        runs.append(e0.elapsed_time(e1))
+    runs_t = torch.tensor(runs, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(runs_t, op=dist.ReduceOp.MAX)             # per run: the slowest rank
+    runs = [float(v) for v in runs_t]
+    ms = sorted(runs)[1]
     clocks = sampler.stop() if rank == 0 else None
     n_det = int(counts.sum().item())
+
+    def _value_again(tag):              # diagnostic (B2D_BENCH_DEBUG=1): the same K-step loop again, to stderr
+        if os.environ.get("B2D_BENCH_DEBUG"):
+            a0, a1 = _events()
+            a0.record()
+            for i in range(K):
+                device_step(i)
+            a1.record()
+            torch.cuda.synchronize()
+            print(f"debug[{tag}]: {a0.elapsed_time(a1) / K:.3f} ms/step (timed value {ms / K:.3f})", file=sys.stderr)
+    _value_again("after value")
+    _value_again("after value 2")
 
     # ---------------- end to end through the host-buffer API (`e2e`) ----------------
     # double-buffered: the H2D copy of step i+1 overlaps the compute of step i; both streams and the
@@ -520,7 +590,9 @@ def main():
             out_cnt.copy_(cnt, non_blocking=True)
         main_stream.synchronize()
 
+    _value_again("after e2e buffers allocated")
     e2e_run(W_)
+    _value_again("after e2e warm-up")
     barrier()
     t0, t1 = _events()
     t0.record()
@@ -528,6 +600,7 @@ def main():
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
+    _value_again("after e2e")
 
     # The same through ONE C-ABI call with host buffers (b2d_detect_host): CH chunks of BATCH pinned tiles in, records out;
     # the library double-buffers the host->device copies itself.  Wall clock around the (synchronous) call.
@@ -559,10 +632,10 @@ def main():
     post_ms = _timed(lambda k: eng.postprocess(BATCH, CONF, False, IOU, 0, MAX_DET))
     head_bytes = sum(g_.h * g_.w * g_.c * 4 for g_ in (eng.graph.bufs[lv["buf"]] for lv in eng.graph.head["levels"]))
 
-    t = torch.tensor([ms, ms_e2e, ms_cabi], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_e2e, ms_cabi], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_cabi = float(t[0]), float(t[1]), float(t[2])
+    ms_e2e, ms_cabi = float(t[0]), float(t[1])
 
     peak_tf, peak_burst, peak_hbm, which = _peaks()
     extra = {}
@@ -609,7 +682,7 @@ def main():
         line = {
             "metric": "640x640 tiles/s end-to-end (preproc+YOLOv8m+NMS+georef)",
             "value": total_tiles / (ms * 1e-3), "unit": "tiles/s", "n_gpus": world, "steps": K, "warmup": W_,
-            "ms_per_step": ms / K, "warmup_steps_run": warm_steps,
+            "ms_per_step": ms / K, "ms_per_step_runs": [r / K for r in runs], "warmup_steps_run": warm_steps,
             "burst": {"value": BATCH * world / (burst_ms * 1e-3), "ms_per_step": burst_ms,
                       "note": "the first 8 steps after an idle period, at boost clocks (1965 MHz); `value` is the settled, power-capped rate (~1650 MHz at the 1000 W cap) -- round 1's 10 972 tiles/s was a 0.12 s burst measurement"},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -624,7 +697,7 @@ def main():
                     "c_abi_one_call": {"value": world * CH * BATCH / (ms_cabi * 1e-3), "unit": "tiles/s", "tiles_per_call": CH * BATCH,
                                        "call": "b2d_detect_host: pinned host tiles in, host records out, wall clock around the call"},
                     "plugin_api": plugin},
-            "gpu_launches": K * (eng.num_kernels + 5),     # graph kernels + preprocess, decode/compact, key sort, select/NMS, georef
+            "gpu_launches": K * (eng.num_kernels + 5),     # per timed K-step run     # graph kernels + preprocess, decode/compact, key sort, select/NMS, georef
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "conv_tc_* family (tcgen05 implicit-GEMM conv+bias+SiLU: generic, halo, halo-pair, stem, depthwise)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
