@@ -279,7 +279,7 @@ __device__ __forceinline__ int pair_tile(const ConvTcParams& p, int rd, int rank
 
 // Debug trace (build with -DB2D_ENABLE_TRACE, run with B2D_TRACE=1): CTA 0 records clock64() at role
 // events of its first kTraceTiles rounds.  Compiled out of product builds.
-constexpr int kTraceTiles = 24, kTraceEvents = 4, kTraceRoles = 3;   // roles: 0 producer, 1 MMA, 2 epilogue warp 4
+constexpr int kTraceTiles = 24, kTraceEvents = 4, kTraceRoles = 4;   // roles: 0 producer, 1 MMA, 2 epilogue warp 4, 3 = warp 4's cycles per round in: TMEM-load waits, slab / residual waits, epi_unit, fence + hand-off
 __device__ __forceinline__ void trace(const ConvTcParams& p, int role, int it, int ev) {
 #ifdef B2D_ENABLE_TRACE
     if (p.trace && blockIdx.x == 0 && it < kTraceTiles) p.trace[(role * kTraceTiles + it) * kTraceEvents + ev] = clock64();
@@ -336,6 +336,7 @@ __device__ __forceinline__ uint64_t silu2_h(uint64_t h) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
     return fma2(h, pk2(t0, t1), h);
 }
+// (tanh.approx.f16x2 does not help: sm_100a lowers it to two MUFU.TANH.F16, one per half -- same MUFU count, less accuracy.)
 __device__ __forceinline__ void lds_b64x2(uint32_t a, uint64_t& x, uint64_t& y) {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
 }
@@ -616,19 +617,33 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
             if (u < my_units) tmem_ld16(tq + (uint32_t)(m * n_tile + half * 16) + (uint32_t)u * ustep, rb);
             else tmem_ld8(tq + (uint32_t)(m * n_tile + split_col), rb);
         };
+#ifdef B2D_ENABLE_TRACE
+        long long w_ld = 0, w_slab = 0, w_math = 0, w_hand = 0, w0 = 0;
+#define B2D_TICK() (w0 = clock64())
+#define B2D_TOCK(acc) (acc += clock64() - w0)
+#else
+#define B2D_TICK() ((void)0)
+#define B2D_TOCK(acc) ((void)0)
+#endif
         auto item_do = [&](int m, int u, const uint32_t (&rb)[16]) {
             const int c = c_base + m, slab = c & (S - 1);
             const uint32_t use = (uint32_t)(c >> s_shift);
             if (u == 0) {                                                      // first item of a tile: its slab must be free (and the residual in it)
+                B2D_TICK();
                 mbar_wait_u32(sempty_u32 + (uint32_t)slab * 8u, (use & 1u) ^ 1u);
                 if (RES) mbar_wait_u32(rbar_u32 + (uint32_t)slab * 8u, use & 1u);
+                B2D_TOCK(w_slab);
             }
             const uint32_t moff = (uint32_t)slab * tile_bytes;
+            B2D_TICK();
             if (u < my_units) epi_unit<ACT, RES, F32, 16>(rb, baddr + (uint32_t)u * ustep * 4u, unit_base((uint32_t)(half + nparts * u) * ubytes) + moff, B2D_EXPW(p), f16, scale2);
             else epi_unit<ACT, RES, F32, 8>(rb, bias_base + (uint32_t)(ch_base + split_col) * 4u, unit_base((uint32_t)split_col * esize) + moff, B2D_EXPW(p), f16, scale2);
+            B2D_TOCK(w_math);
             if (u == ipt - 1) {                                                // last item: hand the slab to the store warp (64 arrivals per quarter)
+                B2D_TICK();
                 fence_proxy_async();                                           // generic-proxy slab writes -> visible to the TMA store
                 mbar_arrive_u32(sfull_u32 + (uint32_t)slab * 8u);
+                B2D_TOCK(w_hand);
             }
         };
         const int nitems = nv * ipt;
@@ -639,13 +654,17 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         for (int j = 0; j < nitems; j += 2) {
             int m1 = m0, u1 = u0 + 1;
             if (u1 == ipt) { u1 = 0; ++m1; }
+            B2D_TICK();
             tmem_ld_wait();
+            B2D_TOCK(w_ld);
             if (j + 1 < nitems) item_ld(m1, u1, rbuf[1]);
             item_do(m0, u0, rbuf[0]);
             if (j + 1 < nitems) {
                 int m2 = m1, u2 = u1 + 1;
                 if (u2 == ipt) { u2 = 0; ++m2; }
+                B2D_TICK();
                 tmem_ld_wait();
+                B2D_TOCK(w_ld);
                 if (j + 2 < nitems) item_ld(m2, u2, rbuf[0]);
                 item_do(m1, u1, rbuf[1]);
                 m0 = m2; u0 = u2;
@@ -655,7 +674,16 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         if (pair) mbar_arrive_cluster(tempty_arrive + as * 8);
         else mbar_arrive_u32(tempty_u32 + as * 8);       // accumulator stage free: all tcgen05.ld of this round have completed
         if (warp == 4 && lane == 0) trace(p, 2, it, 2);
+#ifdef B2D_ENABLE_TRACE
+        if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < kTraceTiles) {       // durations, stored relative to the first stamp
+            long long* tr = p.trace + (3 * kTraceTiles + it) * kTraceEvents;
+            const long long base = p.trace[0] ? p.trace[0] : p.trace[kTraceTiles * kTraceEvents];
+            tr[0] = base + w_ld; tr[1] = base + w_slab; tr[2] = base + w_math; tr[3] = base + w_hand;
+        }
+#endif
     }
+#undef B2D_TICK
+#undef B2D_TOCK
 }
 
 // barrier block shared by all kernels (offsets in 8-byte units from bar_off)
@@ -2097,7 +2125,7 @@ int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream) {
         B2D_CUDA(cudaStreamSynchronize(stream));
         B2D_CUDA(cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost));
         long long t0 = h[0] ? h[0] : h[kTraceTiles * kTraceEvents];
-        const char* names[kTraceRoles] = {"load", "mma ", "epi "};
+        const char* names[kTraceRoles] = {"load", "mma ", "epi ", "epi: ld-wait slab-wait math hand-off"};
         fprintf(stderr, "trace (cycles from first stamp; load: first issue, last issue | mma: start, tmem free, first operand, last commit | epi: slab free, acc ready, math done, store issued)\n");
         for (int it = 0; it < kTraceTiles; ++it) {
             fprintf(stderr, "round %2d", it);
