@@ -240,6 +240,29 @@ def test_fast_storage_modes_stated_deviation_from_fp32_oracle(c2_reference):
             prec, d_eng.mean(), d_emu.mean(), np.quantile(d_eng, 0.99), np.quantile(d_emu, 0.99))
 
 
+def test_contract_yolov7_split_fp16_vs_fp32_oracle():
+    """The same contract on the canonical YOLOv7 graph (BASELINE config C3; the reference's own filter reads column 4 = objectness,
+    simple_detector.py:479-481): rows (cx, cy, w, h, obj, cls) at 640 x 640 against the fp32 oracle."""
+    g = G.build("yolov7")
+    w = W.make_synthetic_weights(g, 0)
+    tiles = synth.make_tiles(2, 640, 3000)
+    x = torch.from_numpy(tiles.astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+    ref = make_oracle("yolov7", w, False).forward(x).numpy()
+    eng = _engine("yolov7", weights=w, max_batch=2, graph=g, precision="fp16x2")
+    eng.preprocess(torch.from_numpy(tiles).cuda(), "identity")
+    eng.forward(2)
+    rows = eng.decode_rows(2).cpu().numpy()
+    eng.close()
+    sel = ref[..., 4] >= SCORE_FLOOR
+    ds = np.abs(rows[..., 4] - ref[..., 4])[sel]
+    db = np.abs(rows[..., :4] - ref[..., :4]).max(-1)[sel]
+    dis = (rows[..., 4] >= 0.3) != (ref[..., 4] >= 0.3)
+    far = float(np.abs(ref[..., 4] - 0.3)[dis].max()) if dis.any() else 0.0
+    print(f"\n[yolov7 fp16x2 vs fp32 oracle] {int(sel.sum())} rows with obj >= {SCORE_FLOOR}: |d obj| max {ds.max():.2e} p99 {np.quantile(ds, 0.99):.2e}; "
+          f"|d box| px max {db.max():.3f}; keep set (obj >= 0.3): {int(dis.sum())} of {int((ref[..., 4] >= 0.3).sum())} differ, farthest {far:.1e}")
+    assert ds.max() <= SCORE_TOL and db.max() <= BOX_TOL_PX and far < TIE_BAND, (ds.max(), db.max(), far)
+
+
 def test_split_fp16_whole_pipeline_matches_oracle_detections(c2_reference):
     """Decode + Ultralytics NMS on the precise rows: the detections of every tile are the oracle's (same anchors kept, in the
     same order) unless a competing pair sits within the tie band."""
