@@ -226,6 +226,11 @@ __device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+// K-major descriptor WITHOUT swizzle (layout type 0, "interleave"): a core matrix is 8 rows x 16 bytes stored as 128 contiguous
+// bytes; LBO = bytes between the two core matrices of one K = 16 step, SBO = bytes between 8-row groups
+// (canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO)) of cute's UMMA::make_umma_desc).
+__device__ __forceinline__ uint32_t desc_hi_ns(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
+__device__ __forceinline__ uint32_t desc_lo_ns(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
 
 struct TileCoord { int nt, x0, y0, n0; };
 template <int V> struct KConst { static constexpr int value = V; };
@@ -492,6 +497,7 @@ template <int RES, int F32>
 __device__ __forceinline__ void store_loop(const ConvTcParams& p, int total_tiles, uint64_t* sfull_bar, uint64_t* sempty_bar,
                                            uint64_t* res_bar, uint8_t* stg_base, int lane, bool pair = false) {
     if (lane >= 4) return;
+    if (B2D_EXP(p, 7)) return;                 // ablation: no slab hand-off at all
     const int q = lane;
     const EpiGeom<F32> g(p, stg_base, q);
     const int mt = p.mt, n_tile = p.n_tile;
@@ -587,6 +593,75 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     };
     const uint32_t ubytes = 16u * esize;               // bytes of one unit in a row
     int it = 0;
+    if (my_units <= 2 && !split_last && p.n_tiles_n == 1 && !B2D_EXP(p, 10)) {
+        // Narrow tiles (n_tile = 32, 48, 64, 96: the stem, the 160^2 stage, the 96-channel 3x3 layers, the head's box branch): a warp
+        // owns the same one or two 16-column units of every tile, so the staging addresses and the bias pointers are loop
+        // invariants and a tile is one straight-line block -- TMEM loads of the next tile in flight behind the SiLU of this
+        // one -- instead of the general path's per-item bookkeeping (~180 instructions per 16 columns at ~7 cycles each).
+        const bool two = my_units == 2;
+        const uint32_t ub0 = unit_base((uint32_t)half * ubytes), ub1 = two ? unit_base((uint32_t)(half + nparts) * ubytes) : ub0;
+        const uint32_t baddr0 = bias_base + (uint32_t)(half * 16) * 4u, baddr1 = baddr0 + (uint32_t)nparts * 64u;
+        const uint32_t rank = pair ? cluster_ctarank() : 0u;
+        const int rounds = pair ? pair_rounds(p, total_tiles) : (total_tiles + mt - 1) / mt;
+        const int rd0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, rd_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+        const uint32_t tempty_arrive = pair ? mapa_u32(tempty_u32, 0) : tempty_u32;
+        const int f16 = p.f16;
+        const float sc = (ACT ? 0.5f : 1.0f) * p.acc_scale;
+        const uint64_t scale2 = pk2(sc, sc);
+        const uint32_t col0 = (uint32_t)(half * 16), col1 = col0 + (uint32_t)nparts * 16u;
+        for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
+            const int as = it & 1;
+            const int nv = pair ? 1 : min(mt, total_tiles - rd * mt);
+            if (warp == 4 && lane == 0) trace(p, 2, it, 0);
+            mbar_wait_u32(tfull_u32 + as * 8, (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            if (warp == 4 && lane == 0) trace(p, 2, it, 1);
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * mt * n_tile);
+            uint32_t ra[16], rb[16];
+            tmem_ld16(tq + col0, ra);
+            if (two) tmem_ld16(tq + col1, rb);
+#pragma unroll 1
+            for (int m = 0; m < nv; ++m) {
+                const int c = it * mt + m, slab = c & (S - 1);
+                const uint32_t use = (uint32_t)(c >> s_shift);
+                mbar_wait_u32(sempty_u32 + (uint32_t)slab * 8u, (use & 1u) ^ 1u);      // the tile's slab is free ...
+                if (RES) mbar_wait_u32(rbar_u32 + (uint32_t)slab * 8u, use & 1u);     // ... and its residual has landed in it
+                const uint32_t moff = (uint32_t)slab * tile_bytes;
+                uint64_t v0[8], v1[8];
+                tmem_ld_wait();
+                epi_bias<ACT, 16>(ra, baddr0, v0, scale2);
+                if (two) epi_bias<ACT, 16>(rb, baddr1, v1, scale2);
+                if (m + 1 < nv) {                                                      // next tile's accumulators while this one's SiLU runs
+                    tmem_ld16(tq + (uint32_t)((m + 1) * n_tile) + col0, ra);
+                    if (two) tmem_ld16(tq + (uint32_t)((m + 1) * n_tile) + col1, rb);
+                }
+                if (ACT) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v0[i] = silu2_h(v0[i]);
+                }
+                epi_store<RES, F32, 16>(v0, ub0 + moff, 0, f16);
+                if (two) {
+                    if (ACT) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v1[i] = silu2_h(v1[i]);
+                    }
+                    epi_store<RES, F32, 16>(v1, ub1 + moff, 0, f16);
+                }
+                fence_proxy_async();                                                   // generic-proxy slab writes -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0) mbar_arrive_u32(sfull_u32 + (uint32_t)slab * 8u);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (pair) mbar_arrive_cluster(tempty_arrive + as * 8);
+                else mbar_arrive_u32(tempty_u32 + as * 8);
+            }
+            if (warp == 4 && lane == 0) trace(p, 2, it, 2);
+        }
+        (void)rank;
+        return;
+    }
     // tile walk: a CTA takes rounds blockIdx.x, + gridDim.x, ... of mt tiles; in a CTA pair (mt == 1) the pair takes two
     // consecutive tiles per round, one per CTA, and an odd last tile is computed (and stored, identically) by both
     const uint32_t rank = pair ? cluster_ctarank() : 0u;
@@ -628,7 +703,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
         auto item_do = [&](int m, int u, const uint32_t (&rb)[16]) {
             const int c = c_base + m, slab = c & (S - 1);
             const uint32_t use = (uint32_t)(c >> s_shift);
-            if (u == 0) {                                                      // first item of a tile: its slab must be free (and the residual in it)
+            if (u == 0 && !B2D_EXP(p, 7)) {                                    // first item of a tile: its slab must be free (and the residual in it)
                 B2D_TICK();
                 mbar_wait_u32(sempty_u32 + (uint32_t)slab * 8u, (use & 1u) ^ 1u);
                 if (RES) mbar_wait_u32(rbar_u32 + (uint32_t)slab * 8u, use & 1u);
@@ -639,10 +714,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
             if (u < my_units) epi_unit<ACT, RES, F32, 16>(rb, baddr + (uint32_t)u * ustep * 4u, unit_base((uint32_t)(half + nparts * u) * ubytes) + moff, B2D_EXPW(p), f16, scale2);
             else epi_unit<ACT, RES, F32, 8>(rb, bias_base + (uint32_t)(ch_base + split_col) * 4u, unit_base((uint32_t)split_col * esize) + moff, B2D_EXPW(p), f16, scale2);
             B2D_TOCK(w_math);
-            if (u == ipt - 1) {                                                // last item: hand the slab to the store warp (64 arrivals per quarter)
+            if (u == ipt - 1 && !B2D_EXP(p, 7)) {                              // last item: hand the slab to the store warp (one arrival per warp of the quarter)
                 B2D_TICK();
-                fence_proxy_async();                                           // generic-proxy slab writes -> visible to the TMA store
-                mbar_arrive_u32(sfull_u32 + (uint32_t)slab * 8u);
+                if (!B2D_EXP(p, 9)) fence_proxy_async();                       // generic-proxy slab writes -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0) mbar_arrive_u32(sfull_u32 + (uint32_t)slab * 8u);
                 B2D_TOCK(w_hand);
             }
         };
@@ -670,9 +746,16 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
                 m0 = m2; u0 = u2;
             }
         }
+        // accumulator stage free: all tcgen05.ld of this round have completed (tcgen05.wait::ld is warp-wide).  ONE lane per
+        // warp arrives: 32 arrivals of a warp on one mbarrier are 32 serialised shared-memory atomics (~9 cycles each, measured:
+        // with 384 arrivals per round on tempty and 96 per tile and quarter on sfull an empty epilogue still took ~3 500 cycles
+        // per round on every layer, profiles/r2_ablation_handoff.txt)
         tc_fence_before();
-        if (pair) mbar_arrive_cluster(tempty_arrive + as * 8);
-        else mbar_arrive_u32(tempty_u32 + as * 8);       // accumulator stage free: all tcgen05.ld of this round have completed
+        __syncwarp();
+        if (lane == 0) {
+            if (pair) mbar_arrive_cluster(tempty_arrive + as * 8);
+            else mbar_arrive_u32(tempty_u32 + as * 8);
+        }
         if (warp == 4 && lane == 0) trace(p, 2, it, 2);
 #ifdef B2D_ENABLE_TRACE
         if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && it < kTraceTiles) {       // durations, stored relative to the first stamp
@@ -718,13 +801,13 @@ __device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&b.tfull[i], issuers);
-            mbar_init(&b.tempty[i], 128 * p.epi_parts);       // every thread of the active epilogue warps
+            mbar_init(&b.tempty[i], 4 * p.epi_parts);         // one elected lane of every active epilogue warp
             mbar_init(&b.hfull[i], 1);
             mbar_init(&b.hempty[i], issuers);
         }
         for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
-            mbar_init(&b.sfull[i], 32 * p.epi_parts);         // the epilogue warps of one quarter
+            mbar_init(&b.sfull[i], p.epi_parts);              // the epilogue warps of one quarter, one arrival each
             mbar_init(&b.sempty[i], 1);
         }
         fence_barrier_init();
@@ -1081,13 +1164,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&b.tfull[i], 1);
-            mbar_init(&b.tempty[i], 256 * p.epi_parts);   // epilogue threads of both CTAs
+            mbar_init(&b.tempty[i], 8 * p.epi_parts);     // epilogue warps of both CTAs, one arrival each
             mbar_init(&b.hfull[i], 2);
             mbar_init(&b.hempty[i], 1);
         }
         for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
-            mbar_init(&b.sfull[i], 32 * p.epi_parts);
+            mbar_init(&b.sfull[i], p.epi_parts);
             mbar_init(&b.sempty[i], 1);
         }
         fence_barrier_init();
@@ -1270,13 +1353,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_pair_kernel(const __grid_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&b.tfull[i], 1);
-            mbar_init(&b.tempty[i], 256 * p.epi_parts);   // epilogue threads of both CTAs
+            mbar_init(&b.tempty[i], 8 * p.epi_parts);     // epilogue warps of both CTAs, one arrival each
             mbar_init(&b.hfull[i], 1);
             mbar_init(&b.hempty[i], 1);
         }
         for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
-            mbar_init(&b.sfull[i], 32 * p.epi_parts);
+            mbar_init(&b.sfull[i], p.epi_parts);
             mbar_init(&b.sempty[i], 1);
         }
         fence_barrier_init();
@@ -1549,7 +1632,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_tc_stem_kernel(const __g
         }
         fence_proxy_async();
     }
-    const uint32_t tmem_base = prologue(p, b, warp, lane, 128);
+    const uint32_t tmem_base = prologue(p, b, warp, lane, 4);        // one arrival per gather warp
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_u32 = smem_u32(b.full), empty_u32 = smem_u32(b.empty);
 
@@ -1629,8 +1712,116 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_tc_stem_kernel(const __g
                 }
             }
             fence_proxy_async();                                      // generic-proxy writes -> visible to the MMA's smem reads
-            mbar_arrive_u32(full_u32 + stage * 8);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_u32(full_u32 + stage * 8);
             if (r == 0) trace(p, 0, git, 3);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 3) {
+        store_loop<0, OUT>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
+    } else if (warp >= 4) {
+        epilogue_loop<ACT, 0, OUT>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
+    }
+    epilogue_exit(p, tmem_base, warp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stride-2 stem kernel (YOLOv8 model.0: 3x3 stride 2 on the 4-channel network input), fed by TMA.
+// Seen through a 2 x 2 space-to-depth lens the layer is a 2 x 2 stride-1 convolution over blocks of 2 x 2 input pixels
+// with 16 channels each (row phase, column phase, 4 channels): output (i, j) reads input rows 2i-1 .. 2i+1 = block row i-1
+// (phase 1 only) and block row i (both phases), the same for columns.  The NHWC4 input needs no repacking for that view: the
+// two pixels of a block row phase are 16 contiguous bytes, so a 4-D tensor map (8 pixels-pairs of a row | row phase | block
+// row | image) with an UN-swizzled box of (bw+1) x 2 x (bh+1) lands in shared memory as
+//     [block row][row phase][block column][16 B]
+// which IS the no-swizzle K-major operand layout: eight consecutive block columns = one 8-row x 16-byte core matrix, the
+// second core matrix of a K = 16 step (row phase 1) LBO = (bw+1) * 16 bytes further, the next 8-row group (next output row)
+// SBO = 2 * LBO further.  The four taps (di, dj) are four descriptor offsets (di * SBO + dj * 16) into the one box: four
+// K = 16 MMAs per tile against resident weights whose k index is tap * 16 + row phase * 8 + column phase * 4 + channel, with
+// zeros where the 3x3 filter has no entry.  No gather warps: the 128 threads that built im2col rows from 36 scattered
+// 8-byte loads each (~5 600 cycles per four-tile round) are gone, and their warp slots go to a third epilogue warp per
+// TMEM lane quarter.  Out-of-image blocks (the zero padding) are TMA's out-of-bounds fill.
+// ---------------------------------------------------------------------------------------------
+template <int ACT, int OUT>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_stem2_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const Bars b = carve_bars(smem, p);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int mt = p.mt;
+    const int total_tiles = p.tiles_x * p.tiles_y * nimg;                // bn == 1
+    const int rounds = (total_tiles + mt - 1) / mt;
+    const uint32_t tile_bytes = p.a_bytes, stage_bytes = (uint32_t)mt * tile_bytes;
+    uint8_t* wres = smem + (size_t)p.stages * stage_bytes;               // resident weights [n_tile][64] 16-bit, SWIZZLE_128B
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&p.tmA[0]);
+    {
+        const uint4* wg = (const uint4*)p.w_raw;
+        const uint32_t wbase = smem_u32(wres);
+        for (int i = threadIdx.x; i < p.n_tile * 8; i += kThreads) {
+            const int n = i >> 3, j = i & 7;
+            sts128(wbase + (uint32_t)n * 128u + (uint32_t)((j ^ (n & 7)) << 4), __ldg(wg + i));
+        }
+        fence_proxy_async();
+    }
+    const uint32_t tmem_base = prologue(p, b, warp, lane, 1);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_u32 = smem_u32(b.full), empty_u32 = smem_u32(b.empty);
+
+    if (warp == 0) {
+        // ===================== TMA producer: one box per tile =====================
+        int stage = 0, pit = 0;
+        uint32_t phase = 0;
+        const int nstages = p.stages;
+        for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++pit) {
+            const int t0 = rd * mt, nv = min(mt, total_tiles - t0);
+            trace(p, 0, pit, 0);
+            mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+            if (elect_one()) {
+                const uint32_t fb = full_u32 + stage * 8, sa = smem_base + (uint32_t)stage * stage_bytes;
+                mbar_expect_tx_u32(fb, (uint32_t)nv * p.a_tx_bytes);
+                for (int m = 0; m < nv; ++m) {
+                    const TileCoord tc = decode_tile(p, t0 + m);
+                    tma_load_4d(&p.tmA[0], fb, sa + (uint32_t)m * tile_bytes, (tc.x0 - 1) * 8, 0, tc.y0 - 1, tc.n0);
+                }
+            }
+            trace(p, 0, pit, 1);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: four taps per tile =====================
+        int stage = 0, it = 0;
+        uint32_t phase = 0;
+        const bool leader = elect_one();
+        const uint32_t lbo = (uint32_t)p.halo_w * 16u, sbo = 2u * lbo;
+        const uint32_t hi_a = desc_hi_ns(sbo), hi_b = desc_hi(1024);
+        const uint32_t b_lo = desc_lo(smem_u32(wres));
+        const uint32_t idesc = p.idesc;
+        const int nstages = p.stages, n_tile = p.n_tile;
+        const uint32_t tfull_u32 = smem_u32(b.tfull), tempty_u32 = smem_u32(b.tempty);
+        for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x, ++it) {
+            const int as = it & 1;
+            const int nv = min(mt, total_tiles - rd * mt);
+            trace(p, 1, it, 0);
+            mbar_wait_u32(tempty_u32 + as * 8, ((it >> 1) & 1) ^ 1);
+            trace(p, 1, it, 1);
+            mbar_wait_u32(full_u32 + stage * 8, phase);
+            tc_fence_after();
+            trace(p, 1, it, 2);
+            if (leader) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * mt * n_tile);
+                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                for (int m = 0; m < nv; ++m) {
+                    const uint32_t a0 = sa + (uint32_t)m * tile_bytes;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        umma_bf16(d_tmem + (uint32_t)(m * n_tile), desc64(hi_a, desc_lo_ns(a0 + (uint32_t)(t >> 1) * sbo + (uint32_t)(t & 1) * 16u, lbo)),
+                                  desc64(hi_b, b_lo + 2 * t), idesc, (uint32_t)(t != 0));
+                }
+                umma_commit(empty_u32 + stage * 8);
+                umma_commit(tfull_u32 + as * 8);
+            }
+            trace(p, 1, it, 3);
             if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 3) {
@@ -1666,7 +1857,8 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
     for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
     CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+                          : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
     CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                      : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1787,7 +1979,16 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     p.n_tile = cout_pad / split;
     p.n_tiles_n = split;
     if (dw) p.chunks = ceil_div(kmul * p.n_tile, 64);     // depthwise: storage chunks of one channel tile
+    // the stride-2 stem is fed by TMA through a space-to-depth view (conv_tc_stem2_kernel) when an 8-pixel-wide one-image
+    // tile fits; anything else on the 4-channel input (stride 1, 1x1, odd sizes) keeps the gather kernel
+    bool stem2 = stem && ksz == 3 && stride == 2 && src_h % 2 == 0 && src_w % 2 == 0 && env_int("B2D_STEM_S2D", 1) != 0;
     pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn, dw);
+    if (stem2) {
+        int w8, h8, n8;
+        pick_tile(dst_w, dst_h, max_batch, &w8, &h8, &n8, true);
+        if (n8 == 1) { p.bw = w8; p.bh = h8; p.bn = n8; }
+        else stem2 = false;
+    }
     p.perm = p.bn > 1 ? 1 : 0;
     p.tiles_x = ceil_div(dst_w, p.bw);
     p.tiles_y = ceil_div(dst_h, p.bh);
@@ -1798,6 +1999,11 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     const int total_tiles = p.tiles_x * p.tiles_y * ceil_div(max_batch, p.bn) * split;
     p.a_bytes = kTileM * 64 * 2;
     p.a_tx_bytes = p.a_bytes;
+    if (stem2) {        // one tile's box: (bh + 1) block rows x 2 row phases x (bw + 1) block columns x 16 bytes
+        p.halo_w = p.bw + 1;
+        p.a_tx_bytes = (uint32_t)((p.bh + 1) * 2 * (p.bw + 1) * 16);
+        p.a_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+    }
     p.b_tx_bytes = dw ? 144 * 128 : p.n_tile * 64 * 2;      // depthwise: [9 taps][16 rows] x 128 B per 64-channel chunk
     p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
     const int esize = (dst_f32 || x2) ? 4 : 2;     // bytes per output column in the destination buffer
@@ -1819,7 +2025,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // halo: 3x3 stride 1 on 8-pixel-wide tiles (uniform (bw+2)-row stride between 8-row groups)
     const bool halo_ok = !stem && ksz == 3 && stride == 1 && p.bw == 8 && (dw || env_int("B2D_HALO", 1) != 0);
     B2D_CHECK(!dw || halo_ok, "conv_tc: depthwise needs an 8-pixel-wide tile");
-    p.halo_w = p.bw + 2;
+    if (!stem2) p.halo_w = p.bw + 2;
     p.halo_kh_rows = (uint32_t)(p.bn * p.halo_w);
     const uint32_t halo_rows = (uint32_t)(p.halo_w * p.bn * (p.bh + 2));
     p.halo_bytes = (halo_rows * 128u + 1023u) & ~1023u;
@@ -1867,7 +2073,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         }
     }
     B2D_CHECK(best_kind >= 0, "conv_tc: no shared-memory configuration fits (n_tile %d)", p.n_tile);
-    p.kind = dw ? 3 : best_kind; p.mt = best_mt; p.stages = best_stages; p.stg_bufs = best_bufs; p.b_res = best_bres;
+    p.kind = dw ? 3 : stem2 ? 4 : best_kind; p.mt = best_mt; p.stages = best_stages; p.stg_bufs = best_bufs; p.b_res = best_bres;
     // CTA pairs for wide halo layers: weight stages shrink to half a tile per CTA (so the ring gets deeper)
     p.pair = 0;
     if (p.kind == 1 && split == 1 && p.n_tile >= env_int("B2D_PAIR_MIN_N", 128) && p.n_tile % 32 == 0 && (total_tiles >= 2 * sm_count || env_int("B2D_PAIR", 1) == 2) && env_int("B2D_PAIR", 1) != 0) {
@@ -1936,7 +2142,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // the epilogue ran at 3-4.5 outputs per clock per SM against 15 for the same code with eight warps per scheduler
     // (role traces, profiles/r2_role_traces.txt).  A third warp per quarter takes every third 16-column unit when the tile
     // width allows an even split (48, 96, 144, 192 ...); the stem's 16 warps are taken (gather warps).
-    p.epi_parts = (!stem && (p.n_tile >> 4) % 3 == 0 && env_int("B2D_EPI3", 1) != 0) ? 3 : 2;
+    p.epi_parts = ((!stem || stem2) && (p.n_tile >> 4) % 3 == 0 && env_int("B2D_EPI3", 1) != 0) ? 3 : 2;
     p.exp = env_int("B2D_EXP", 0);
     p.trace = nullptr;
     if (getenv("B2D_TRACE")) {
@@ -1980,7 +2186,11 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
             for (int c = 0; c < cin; ++c)
                 for (int t = 0; t < p.taps; ++t) {
                     const uint16_t v = f16 ? f2h(w_host[((size_t)o * cin + c) * p.taps + t]) : f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
-                    if (stem) {
+                    if (stem2) {      // tap (kh, kw) -> block (di, dj), phase (rp, px): k = (di * 2 + dj) * 16 + rp * 8 + px * 4 + c
+                        const int kh = t / 3, kw = t % 3;
+                        const int di = kh == 0 ? 0 : 1, rp = kh == 1 ? 0 : 1, dj = kw == 0 ? 0 : 1, px = kw == 1 ? 0 : 1;
+                        wp[(size_t)o * ktot + (size_t)((di * 2 + dj) * 16 + rp * 8 + px * 4 + c)] = v;
+                    } else if (stem) {
                         wp[(size_t)o * ktot + (size_t)t * 4 + c] = v;
                     } else if (kmul == 2) {      // the weight sits under the channel's hi and lo position
                         const size_t k = (size_t)t * cin_pad + 16 * (c / 8) + (c % 8);
@@ -2033,6 +2243,12 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                 }
         }
     }
+    if (stem2) {        // (8-byte pixels of one input row as 16-bit elements | row phase | block row | image), un-swizzled box
+        uint64_t dims[4] = {(uint64_t)src_w * 4, 2u, (uint64_t)src_h / 2, (uint64_t)max_batch};
+        uint64_t str[3] = {(uint64_t)src_w * 8, (uint64_t)src_w * 16, (uint64_t)src_h * src_w * 8};
+        uint32_t box[4] = {(uint32_t)(p.bw + 1) * 8u, 2u, (uint32_t)(p.bh + 1), 1u};
+        if (encode_map(&p.tmA[0], (void*)src, 4, dims, str, box, 0)) return -1;
+    }
     {   // output / residual sub-box maps: one warp quarter's 32 rows of a tile, one map per chunk width
         const int rows_per_y = p.bw * p.bn;
         const uint32_t sbn = (uint32_t)(rows_per_y >= 32 ? 32 / p.bw : p.bn);
@@ -2068,6 +2284,7 @@ ConvKernel pick_kernel(int kind, int pair, int act, int res, int out) {
     if (res) return act ? K<1, 1, 0> : K<0, 1, 0>;                         \
     return act ? K<1, 0, 0> : K<0, 0, 0>;
     if (kind == 2) return out == 2 ? (act ? conv_tc_stem_kernel<1, 2> : conv_tc_stem_kernel<0, 2>) : (act ? conv_tc_stem_kernel<1, 0> : conv_tc_stem_kernel<0, 0>);
+    if (kind == 4) return out == 2 ? (act ? conv_tc_stem2_kernel<1, 2> : conv_tc_stem2_kernel<0, 2>) : (act ? conv_tc_stem2_kernel<1, 0> : conv_tc_stem2_kernel<0, 0>);
     if (kind == 3) return out == 2 ? (act ? conv_tc_dw_kernel<1, 2> : conv_tc_dw_kernel<0, 2>) : (act ? conv_tc_dw_kernel<1, 0> : conv_tc_dw_kernel<0, 0>);
     if (kind == 1 && pair) { B2D_PICK(conv_tc_halo2_kernel) }
     if (kind == 0 && pair) { B2D_PICK(conv_tc_pair_kernel) }
@@ -2154,8 +2371,8 @@ void conv_tc_free(ConvTcPlan* plan) {
 
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
-    static const char* kinds[6] = {"", "-halo", "-stem", "-depthwise", "-halo-pair", "-pair"};
+    static const char* kinds[7] = {"", "-halo", "-stem", "-depthwise", "-halo-pair", "-pair", "-stem-s2d"};
     return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d%s stg %d tmem %u smem %zu",
-                    kinds[p.pair ? (p.kind == 0 ? 5 : 4) : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
+                    kinds[p.pair ? (p.kind == 0 ? 5 : 4) : p.kind == 4 ? 6 : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
                     p.b_res ? " (resident)" : "", p.stg_bufs, p.tmem_cols, plan->smem_bytes);
 }
