@@ -458,67 +458,66 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[16], uint32_t bias_
 }
 
 // Geometry of the staging slabs, shared by the epilogue warps and the store warp.  A tile row of n_tile columns is cut
-// into chunks of 128 / 64 / 32 bytes (one tensor map per width); a quarter's slab of one tile holds 32 rows x chunk for
-// every chunk, full 128-byte chunks first, then one 64-byte, then one 32-byte chunk (mirrors conv_tc_plan).
+// into chunks of 128 / 64 / 32 bytes (one tensor map per width); a tile's slab holds, chunk after chunk, all 128 rows x chunk
+// width: full 128-byte chunks first, then one 64-byte, then one 32-byte chunk (mirrors conv_tc_plan).  One TMA store (or
+// residual load) moves a whole chunk of a tile: the box of the maps is the M tile itself.
 template <int F32>      // 0: 16-bit outputs, 1: fp32 outputs, 2: split fp16 (hi | lo) -- 4 bytes per output column like fp32
 struct EpiGeom {
     static constexpr int esize = F32 ? 4 : 2;
-    uint32_t row_bytes, tile_bytes, slab0, buf_stride, n128, has64, has32;
-    int dy, dn, nb;
-    __device__ __forceinline__ EpiGeom(const ConvTcParams& p, uint8_t* stg_base, int q) {
+    uint32_t row_bytes, tile_bytes, base, n128, has64, has32;
+    int nb;
+    __device__ __forceinline__ EpiGeom(const ConvTcParams& p, uint8_t* stg_base) {
         row_bytes = (uint32_t)(p.n_tile * esize);
         tile_bytes = 128u * row_bytes;                                          // staging bytes of one M tile
-        slab0 = smem_u32(stg_base) + (uint32_t)q * 32u * row_bytes;             // this quarter's slab of tile 0, buffer 0
+        base = smem_u32(stg_base);                                              // slab 0
         nb = p.stg_bufs;
-        buf_stride = nb == 2 ? (uint32_t)p.mt * tile_bytes : 0u;
         n128 = row_bytes >> 7; has64 = (row_bytes >> 6) & 1u; has32 = (row_bytes >> 5) & 1u;
-        // sub-box of a tile covered by this quarter's 32 rows (row m = (y * bn + n) * bw + x)
-        const int rows_per_y = p.bw * p.bn;
-        dy = rows_per_y >= 32 ? (q * 32) / rows_per_y : q * (32 / rows_per_y);
-        dn = rows_per_y >= 32 ? ((q * 32) % rows_per_y) / p.bw : 0;
     }
-    // TMA boxes of one tile's quarter slab: fn(map index, byte offset in the slab, first column)
+    // TMA boxes of one tile's slab: fn(map index, byte offset in the slab, first column)
     template <typename Fn>
     __device__ __forceinline__ void for_each_chunk(Fn&& fn) const {
         constexpr int cols128 = 128 / esize, cols64 = 64 / esize;
-        for (uint32_t k = 0; k < n128; ++k) fn(0, k * 4096u, (int)k * cols128);
-        if (has64) fn(1, n128 * 4096u, (int)n128 * cols128);
-        if (has32) fn(2, n128 * 4096u + has64 * 2048u, (int)n128 * cols128 + (int)has64 * cols64);
+        for (uint32_t k = 0; k < n128; ++k) fn(0, k * 16384u, (int)k * cols128);
+        if (has64) fn(1, n128 * 16384u, (int)n128 * cols128);
+        if (has32) fn(2, n128 * 16384u + has64 * 8192u, (int)n128 * cols128 + (int)has64 * cols64);
     }
 };
 
-// Store warp (warp 3): lane q < 4 serves TMEM lane quarter q.  The quarter's staging area is a ring of
-// S = stg_bufs * mt one-tile slabs.  For every tile, in the order the epilogue produces them, the lane waits for the slab
-// to be written (sfull), issues the tile's TMA stores, waits until the TMA unit has read the slab, hands it back (sempty)
-// and -- for residual layers -- starts the residual loads of the tile that will use this slab next, so they have S tiles
-// of time to land.  Issuing a TMA instruction costs its thread ~200 cycles; taking that, the slab wait and the residual
-// latency out of the epilogue warps' loop is what the layers with epilogue-bound rounds needed.
+// Store warp (warp 3), one elected lane.  The staging area is a ring of S = stg_bufs * mt one-tile slabs.  For every tile, in
+// the order the epilogue produces them, the lane waits for the slab to be written by all epilogue warps (sfull), issues one
+// TMA store per chunk of the tile, waits until the TMA unit has read the slab, hands it back (sempty) and -- for residual
+// layers -- starts the residual loads of the tile that will use this slab next, so they have S tiles of time to land.
+// Issuing a TMA instruction costs its thread ~200 cycles; taking that, the slab wait and the residual latency out of the
+// epilogue warps' loop is what the layers with epilogue-bound rounds needed.
+// (Until round 2 four lanes served one TMEM lane quarter each with quarter-sized boxes: 4 x the TMA instructions, and UTMASTG
+// takes uniform registers, so the compiler serialised the four lanes in a loop around every one of them -- ncu showed the
+// warp 100 % busy with 62 % of its samples in those loops and the epilogue warps waiting for free slabs on the stem.)
 template <int RES, int F32>
 __device__ __forceinline__ void store_loop(const ConvTcParams& p, int total_tiles, uint64_t* sfull_bar, uint64_t* sempty_bar,
                                            uint64_t* res_bar, uint8_t* stg_base, int lane, bool pair = false) {
-    if (lane >= 4) return;
+    if (!elect_one()) return;
     if (B2D_EXP(p, 7)) return;                 // ablation: no slab hand-off at all
-    const int q = lane;
-    const EpiGeom<F32> g(p, stg_base, q);
+    (void)lane;
+    const EpiGeom<F32> g(p, stg_base);
     const int mt = p.mt, n_tile = p.n_tile;
     const int S = g.nb * mt, s_shift = 31 - __clz(S);                          // S is 1, 2, 4 or 8
-    const uint32_t sfull_u32 = smem_u32(sfull_bar) + (uint32_t)(q * S) * 8u, sempty_u32 = smem_u32(sempty_bar) + (uint32_t)(q * S) * 8u;
-    const uint32_t rbar_u32 = smem_u32(res_bar) + (uint32_t)(q * S) * 8u;
+    const uint32_t sfull_u32 = smem_u32(sfull_bar), sempty_u32 = smem_u32(sempty_bar), rbar_u32 = smem_u32(res_bar);
     const uint32_t rank = pair ? cluster_ctarank() : 0u;
     const int rounds = pair ? pair_rounds(p, total_tiles) : (total_tiles + mt - 1) / mt;
     const int rd0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, rd_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const bool no_store = B2D_EXP(p, 1) || B2D_EXP(p, 5);
+    const bool perm = p.perm != 0;
     auto first_tile = [&](int rd) { return pair ? pair_tile(p, rd, (int)rank, total_tiles) : rd * mt; };
     auto valid_tiles = [&](int rd) { return pair ? 1 : min(mt, total_tiles - rd * mt); };
-    // TMA boxes of this quarter's rows of tile t: residual loads into / stores out of slab `slab`
+    // TMA boxes of tile t: residual loads into / stores out of slab `slab`
     auto tile_io = [&](int t, int slab, bool load) {
         const TileCoord tc = decode_tile(p, t);
         const int c0 = tc.nt * n_tile, c1 = tc.x0;
-        const int c2 = p.perm ? tc.n0 + g.dn : tc.y0 + g.dy, c3 = p.perm ? tc.y0 + g.dy : tc.n0 + g.dn;
-        const uint32_t sa = g.slab0 + (uint32_t)slab * g.tile_bytes;
+        const int c2 = perm ? tc.n0 : tc.y0, c3 = perm ? tc.y0 : tc.n0;
+        const uint32_t sa = g.base + (uint32_t)slab * g.tile_bytes;
         if (load) {
             const uint32_t bar = rbar_u32 + (uint32_t)slab * 8u;
-            mbar_expect_tx_u32(bar, 32u * (uint32_t)(n_tile * EpiGeom<F32>::esize));
+            mbar_expect_tx_u32(bar, g.tile_bytes);
             g.for_each_chunk([&](int map, uint32_t off, int col0) { tma_load_4d(&p.tmR[map], bar, sa + off, c0 + col0, c1, c2, c3); });
         } else {
             g.for_each_chunk([&](int map, uint32_t off, int col0) { tma_store_4d(&p.tmO[map], sa + off, c0 + col0, c1, c2, c3); });
@@ -564,13 +563,12 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     const int half = (warp - 4) >> 2;                  // this warp's part of the quarter's column units: 0 .. epi_parts - 1
     const int nparts = p.epi_parts;
     if (half >= nparts) return;                        // a layer with two parts per quarter leaves warps 12-15 idle
-    const EpiGeom<F32> g(p, stg_base, q);
+    const EpiGeom<F32> g(p, stg_base);
     constexpr int esize = F32 ? 4 : 2;
     const int n_tile = p.n_tile, mt = p.mt;
     const int S = g.nb * mt, s_shift = 31 - __clz(S);
-    const uint32_t tile_bytes = g.tile_bytes, slab0 = g.slab0;
-    const uint32_t sfull_u32 = smem_u32(sfull_bar) + (uint32_t)(q * S) * 8u, sempty_u32 = smem_u32(sempty_bar) + (uint32_t)(q * S) * 8u;
-    const uint32_t rbar_u32 = smem_u32(res_bar) + (uint32_t)(q * S) * 8u;
+    const uint32_t tile_bytes = g.tile_bytes;
+    const uint32_t sfull_u32 = smem_u32(sfull_bar), sempty_u32 = smem_u32(sempty_bar), rbar_u32 = smem_u32(res_bar);
     const uint32_t bias_base = smem_u32(bias_s);
     const uint32_t tfull_u32 = smem_u32(tfull_bar), tempty_u32 = smem_u32(tempty_bar);
     // 16-column units alternate between the two warps of a quarter; an odd last unit is split 8 + 8 so both warps carry
@@ -580,13 +578,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     const bool split_last = nparts == 2 && (nunits & 1) != 0;
     const int my_units = nparts == 3 ? nunits / 3 : split_last ? (nunits - 1) >> 1 : (nunits - half + 1) >> 1;     // full units half, half + nparts, ...
     const int ipt = my_units + (split_last ? 1 : 0);                                    // work items per tile
-    // Swizzled slab address of this lane's row for the 16-column unit starting at byte `b` of the row.
+    // Swizzled slab address of this lane's row (row q * 32 + lane of the tile) for the 16-column unit starting at byte `b` of the row.
     const uint32_t n128 = g.n128, has64 = g.has64;
-    const uint32_t row128 = slab0 + (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
-    const uint32_t row64 = slab0 + n128 * 4096u + (uint32_t)lane * 64u, sw64 = (uint32_t)((lane >> 1) & 3);
-    const uint32_t row32 = slab0 + n128 * 4096u + has64 * 2048u + (uint32_t)lane * 32u, sw32 = (uint32_t)((lane >> 2) & 1);
+    const uint32_t trow = (uint32_t)(q * 32 + lane);
+    const uint32_t row128 = g.base + trow * 128u, sw128 = (uint32_t)(lane & 7);
+    const uint32_t row64 = g.base + n128 * 16384u + trow * 64u, sw64 = (uint32_t)((lane >> 1) & 3);
+    const uint32_t row32 = g.base + n128 * 16384u + has64 * 8192u + trow * 32u, sw32 = (uint32_t)((lane >> 2) & 1);
     auto unit_base = [&](uint32_t b) -> uint32_t {
-        if (b < (n128 << 7)) return row128 + (b >> 7) * 4096u + ((((b & 127u) >> 4) ^ sw128) << 4);
+        if (b < (n128 << 7)) return row128 + (b >> 7) * 16384u + ((((b & 127u) >> 4) ^ sw128) << 4);
         const uint32_t rem = b - (n128 << 7);
         if (has64 && rem < 64u) return row64 + (((rem >> 4) ^ sw64) << 4);
         return row32 + ((((rem >> 4) & 1u) ^ sw32) << 4);
@@ -771,7 +770,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
 
 // barrier block shared by all kernels (offsets in 8-byte units from bar_off)
 struct Bars {
-    uint64_t *full, *empty, *tfull, *tempty, *hfull, *hempty, *res, *sfull, *sempty;   // res / sfull / sempty: [quarter][slab], stg_bufs * mt one-tile slabs per quarter
+    uint64_t *full, *empty, *tfull, *tempty, *hfull, *hempty, *res, *sfull, *sempty;   // res / sfull / sempty: one per slab (stg_bufs * mt one-tile slabs)
     uint32_t* tmem_slot;
     float* bias_s;
 };
@@ -784,10 +783,10 @@ __device__ __forceinline__ Bars carve_bars(uint8_t* smem, const ConvTcParams& p)
     b.hfull = b.tempty + 2;
     b.hempty = b.hfull + 2;
     b.res = b.hempty + 2;
-    const int nslab = 4 * p.stg_bufs * p.mt;            // [quarter][slab]; the residual barriers exist only for residual layers
+    const int nslab = p.stg_bufs * p.mt;                // one per slab; the residual barriers exist only for residual layers
     b.sfull = b.res + (p.has_res ? nslab : 0);
     b.sempty = b.sfull + nslab;
-    b.tmem_slot = (uint32_t*)(b.sempty + nslab);
+    b.tmem_slot = (uint32_t*)(((uintptr_t)(b.sempty + nslab) + 15) & ~(uintptr_t)15);   // keeps bias_s 16-byte aligned for any slab count
     b.bias_s = (float*)(b.tmem_slot + 4);
     return b;
 }
@@ -805,9 +804,9 @@ __device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& 
             mbar_init(&b.hfull[i], 1);
             mbar_init(&b.hempty[i], issuers);
         }
-        for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
+        for (int i = 0; i < p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
-            mbar_init(&b.sfull[i], p.epi_parts);              // the epilogue warps of one quarter, one arrival each
+            mbar_init(&b.sfull[i], 4 * p.epi_parts);          // every active epilogue warp, one arrival each
             mbar_init(&b.sempty[i], 1);
         }
         fence_barrier_init();
@@ -1168,9 +1167,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo2_kernel(const __grid
             mbar_init(&b.hfull[i], 2);
             mbar_init(&b.hempty[i], 1);
         }
-        for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
+        for (int i = 0; i < p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
-            mbar_init(&b.sfull[i], p.epi_parts);
+            mbar_init(&b.sfull[i], 4 * p.epi_parts);
             mbar_init(&b.sempty[i], 1);
         }
         fence_barrier_init();
@@ -1357,9 +1356,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_pair_kernel(const __grid_
             mbar_init(&b.hfull[i], 1);
             mbar_init(&b.hempty[i], 1);
         }
-        for (int i = 0; i < 4 * p.stg_bufs * p.mt; ++i) {
+        for (int i = 0; i < p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
-            mbar_init(&b.sfull[i], p.epi_parts);
+            mbar_init(&b.sfull[i], 4 * p.epi_parts);
             mbar_init(&b.sempty[i], 1);
         }
         fence_barrier_init();
@@ -2018,7 +2017,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     const uint32_t tile_stg = 128u * row_bytes;
     const uint32_t tail_fixed = 256 /*pipeline barriers + tmem slot*/ + (uint32_t)cout_pad * 4 /*bias*/;
     // slab hand-off barriers: sfull + sempty (+ residual) per quarter and one-tile slab
-    auto slab_bars = [&](int mt, int bufs) { return (uint32_t)((res ? 3 : 2) * 4 * mt * bufs * 8); };
+    auto slab_bars = [&](int mt, int bufs) { return (uint32_t)((res ? 3 : 2) * mt * bufs * 8); };
     const uint32_t avail = 226 * 1024 - 1024 /*align slack*/ - tail_fixed;
 
     // ---- kind, tiles per round, stages, staging buffers ----
@@ -2129,7 +2128,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                 p.epi[n].span = (uint16_t)spans[si];
                 p.epi[n].map = (uint16_t)si;
                 p.epi[n].off = off;
-                off += 32u * spans[si];
+                off += 128u * spans[si];
                 done += spans[si];
                 ++n;
             }
@@ -2249,10 +2248,8 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         uint32_t box[4] = {(uint32_t)(p.bw + 1) * 8u, 2u, (uint32_t)(p.bh + 1), 1u};
         if (encode_map(&p.tmA[0], (void*)src, 4, dims, str, box, 0)) return -1;
     }
-    {   // output / residual sub-box maps: one warp quarter's 32 rows of a tile, one map per chunk width
-        const int rows_per_y = p.bw * p.bn;
-        const uint32_t sbn = (uint32_t)(rows_per_y >= 32 ? 32 / p.bw : p.bn);
-        const uint32_t sbh = (uint32_t)(rows_per_y >= 32 ? 1 : 32 / rows_per_y);
+    {   // output / residual maps: the box is one M tile, one map per chunk width
+        const uint32_t sbn = (uint32_t)p.bn, sbh = (uint32_t)p.bh;
         const uint32_t spans[3] = {128, 64, 32};
         bool used[3] = {false, false, false};
         for (int k = 0; k < p.epi_nchunks; ++k) used[p.epi[k].map] = true;
