@@ -68,7 +68,7 @@ struct __align__(64) ConvTcParams {
     uint32_t rcp_nn, rcp_tx, rcp_ty;   // ceil(2^32 / d) for the tile decode (0 when d == 1)
     int act, out_f32;
     int stages;
-    int kind;             // 0 generic (shifted boxes), 1 halo (3x3 s1, bw == 8), 2 stem (im2col gather), 3 depthwise (halo + diagonal blocks)
+    int kind;             // 0 generic (shifted boxes), 1 halo (3x3 s1, bw == 8), 2 stem (im2col gather), 3 depthwise (halo + diagonal blocks), 4 stride-2 stem through TMA, 5 fused depthwise 3x3 + pointwise 1x1
     int pair;             // 1: CTA-pair kernel (cta_group::2, M = 256 across two SMs)
     int mt;               // M tiles per round (share B stages, one accumulator stage, one epilogue pass)
     int halo_w;           // bw + 2
@@ -86,6 +86,9 @@ struct __align__(64) ConvTcParams {
     int x2;               // 1: split-fp16 storage (B2D_PREC_FP16X2): inputs are [hi x 8 | lo x 8] groups, 16-bit outputs are written that way
     float acc_scale;      // the accumulator is multiplied by this before the bias (1/255 in the stem: its input is the raw pixel value)
     int b_res;            // halo kernel: 1 = all 9 * chunks weight boxes stay resident in the stage slots (loaded once per CTA)
+    const float* dw_w;    // fused depthwise + pointwise kernel: [chunk][tap][64] fp32 depthwise weights, then [chunks * 64] bias (x 0.5 for SiLU)
+    uint32_t dw_off;      // ... their offset in shared memory
+    int dw_act;           // ... SiLU after the depthwise stage
     int rev;              // 1: this op walks its M tiles in descending order (set per op by the engine)
     int rev_last;         // per launch: index of the last M tile when walking backwards, else -1
     int exp;              // timing-ablation flags (trace builds only)
@@ -98,17 +101,22 @@ struct ConvTcPlan {
     int sm_count;
     __nv_bfloat16* w_dev;   // packed weights (owned)
     float* bias_dev;        // owned
+    float* dw_dev;          // owned (fused depthwise + pointwise plans)
     long long* trace_dev;   // owned, debug only
 };
 
+// fused depthwise 3x3 (c channels, source slice) + pointwise 1x1 (c -> cout, destination slice), both with bias and optional SiLU
+struct DwFuse { const __nv_bfloat16* src; int src_cs, src_c0; const float* w; const float* b; int act; };
 int conv_tc_supported(int cin, int ksz, int stride);
 int conv_tc_stem_supported(int src_cs, int cin, int ksz, int stride, int cout, int dst_f32, int has_res);
 int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch,
                  const __nv_bfloat16* src, int src_h, int src_w, int src_cs, int src_c0, int cin,
                  void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32,
                  int ksz, int stride, int act, const float* w_host, const float* b_host,
-                 const __nv_bfloat16* res, int res_cs, int res_c0, int depthwise = 0, int f16 = 0, int x2 = 0, float acc_scale = 1.f);
+                 const __nv_bfloat16* res, int res_cs, int res_c0, int depthwise = 0, int f16 = 0, int x2 = 0, float acc_scale = 1.f,
+                 const DwFuse* fuse = nullptr);
 int conv_tc_dw_supported(int cin, int cout, int ksz, int stride, int dst_f32, int has_res);
+int conv_tc_dwpw_supported(int c, int cout, int dst_f32, int x2);
 int conv_tc_launch(const ConvTcPlan* plan, int n, cudaStream_t stream);
 void conv_tc_free(ConvTcPlan* plan);
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen);

@@ -576,7 +576,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     // With three parts (n_tile a multiple of 48) every warp takes the units part, part + 3, ... and nothing is split.
     const int nunits = n_tile >> 4;
     const bool split_last = nparts == 2 && (nunits & 1) != 0;
-    const int my_units = nparts == 3 ? nunits / 3 : split_last ? (nunits - 1) >> 1 : (nunits - half + 1) >> 1;     // full units half, half + nparts, ...
+    const int my_units = nparts == 1 ? nunits : nparts == 3 ? nunits / 3 : split_last ? (nunits - 1) >> 1 : (nunits - half + 1) >> 1;     // full units half, half + nparts, ...
     const int ipt = my_units + (split_last ? 1 : 0);                                    // work items per tile
     // Swizzled slab address of this lane's row (row q * 32 + lane of the tile) for the 16-column unit starting at byte `b` of the row.
     const uint32_t n128 = g.n128, has64 = g.has64;
@@ -770,7 +770,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
 
 // barrier block shared by all kernels (offsets in 8-byte units from bar_off)
 struct Bars {
-    uint64_t *full, *empty, *tfull, *tempty, *hfull, *hempty, *res, *sfull, *sempty;   // res / sfull / sempty: one per slab (stg_bufs * mt one-tile slabs)
+    uint64_t *full, *empty, *tfull, *tempty, *hfull, *hempty, *afull, *aempty, *res, *sfull, *sempty;   // res / sfull / sempty: one per slab (stg_bufs * mt one-tile slabs); afull / aempty: the fused depthwise + pointwise kernel's A tiles
     uint32_t* tmem_slot;
     float* bias_s;
 };
@@ -782,7 +782,9 @@ __device__ __forceinline__ Bars carve_bars(uint8_t* smem, const ConvTcParams& p)
     b.tempty = b.tfull + 2;
     b.hfull = b.tempty + 2;
     b.hempty = b.hfull + 2;
-    b.res = b.hempty + 2;
+    b.afull = b.hempty + 2;
+    b.aempty = b.afull + 2;
+    b.res = b.aempty + 2;
     const int nslab = p.stg_bufs * p.mt;                // one per slab; the residual barriers exist only for residual layers
     b.sfull = b.res + (p.has_res ? nslab : 0);
     b.sempty = b.sfull + nslab;
@@ -792,7 +794,7 @@ __device__ __forceinline__ Bars carve_bars(uint8_t* smem, const ConvTcParams& p)
 }
 // common prologue: barrier init (warp 1), TMEM allocation (warp 2), bias to smem (everyone)
 __device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& b, int warp, int lane, uint32_t full_count,
-                                             uint32_t issuers = 1) {
+                                             uint32_t issuers = 1, uint32_t hempty_count = 0, uint32_t afull_count = 0) {
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&b.full[i], full_count);
@@ -802,7 +804,11 @@ __device__ __forceinline__ uint32_t prologue(const ConvTcParams& p, const Bars& 
             mbar_init(&b.tfull[i], issuers);
             mbar_init(&b.tempty[i], 4 * p.epi_parts);         // one elected lane of every active epilogue warp
             mbar_init(&b.hfull[i], 1);
-            mbar_init(&b.hempty[i], issuers);
+            mbar_init(&b.hempty[i], hempty_count ? hempty_count : issuers);
+            if (afull_count) {
+                mbar_init(&b.afull[i], afull_count);
+                mbar_init(&b.aempty[i], 1);
+            }
         }
         for (int i = 0; i < p.stg_bufs * p.mt; ++i) {
             if (p.has_res) mbar_init(&b.res[i], 1);
@@ -1831,6 +1837,252 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_stem2_kernel(const __grid
     epilogue_exit(p, tmem_base, warp);
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused depthwise 3x3 + pointwise 1x1 kernel (Ultralytics 8.3.x cls branch: DWConv(c, c, 3) -> Conv(c, c3, 1), each with
+// bias + SiLU).  The depthwise result never leaves the SM: four warps compute it on the CUDA cores straight from the TMA-loaded
+// halo tile of a 64-channel chunk -- thread (x, 4 channels) walks the tile's pixel lines with a three-line register window, fp32
+// FFMA2 accumulation, bias, SiLU -- round it to the 16-bit storage format exactly where the unfused pair rounds its stored
+// intermediate, and write it as the K-major SWIZZLE_128B A operand of the pointwise GEMM, whose weights stream through (or
+// stay in) a ring of 64-channel stages.  Per chunk: TMA halo -> depthwise warps -> A tile -> four K = 16 MMAs into the
+// tile's accumulator; epilogue and stores are the shared ones.  Against the two separate launches this removes one write and
+// one read of the c-channel map (157 MB each at 80 x 80 x 192 x 64 images), the depthwise-as-N=16-MMA kernel that was bound
+// by its single issuing thread, and a launch.
+// Warps: 0 halo producer | 1 MMA issuer | 2 TMEM allocator, then weight producer | 3 store | 4-7 epilogue (one per TMEM lane
+// quarter) | 8-15 depthwise: the depthwise stage is ~1 000 CUDA-core instructions per thread and chunk and a warp issues about one
+// instruction every five cycles, so it gets two warps per scheduler.
+// ---------------------------------------------------------------------------------------------
+template <int F16>
+__device__ __forceinline__ void dw_cvt(uint32_t u, uint64_t& out) {      // two packed 16-bit values -> two fp32
+    if (F16) {
+        const float2 f = __half22float2(*(const __half2*)&u);
+        out = pk2(f.x, f.y);
+    } else {
+        out = pk2u(u << 16, u & 0xFFFF0000u);
+    }
+}
+// the three pixels x .. x + 2 of one halo line, this thread's four channels: six fp32 pairs.  The halo tile is NOT swizzled
+// (rows of 64 channels = 128 bytes; the sixteen lanes of a pixel read one whole row, so the plain layout is conflict-free):
+// `a` = address of pixel x's four channels, the neighbours are +128 and +256 bytes.
+template <int F16>
+__device__ __forceinline__ void dw_load_line(uint32_t a, uint64_t (&r)[6]) {
+    uint32_t u0, u1, u2, u3, u4, u5;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u0), "=r"(u1) : "r"(a));
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+128];" : "=r"(u2), "=r"(u3) : "r"(a));
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+256];" : "=r"(u4), "=r"(u5) : "r"(a));
+    dw_cvt<F16>(u0, r[0]); dw_cvt<F16>(u1, r[1]);
+    dw_cvt<F16>(u2, r[2]); dw_cvt<F16>(u3, r[3]);
+    dw_cvt<F16>(u4, r[4]); dw_cvt<F16>(u5, r[5]);
+}
+// Two output lines (y, y + 1) of this thread's pixel column and four channels from four input lines.  Twelve independent
+// three-FMA chains (2 lines x 2 channel pairs x 3 filter rows), then the sums: one warp per scheduler does this work, so the
+// instruction-level parallelism inside a thread is what hides the FMA and MUFU latencies.
+template <int F16>
+__device__ __forceinline__ uint2 dw_finish(uint64_t a0, uint64_t a1, int act) {
+    if (act) { a0 = silu2_h(a0); a1 = silu2_h(a1); }       // weights and bias carry the halving (see silu2_h)
+    float x0, x1, x2, x3;
+    upk2(a0, x0, x1);
+    upk2(a1, x2, x3);
+    uint2 o;
+    if (F16) {
+        const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
+        o.x = *(const uint32_t*)&h0; o.y = *(const uint32_t*)&h1;
+    } else {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(x2, x3);
+        o.x = *(const uint32_t*)&h0; o.y = *(const uint32_t*)&h1;
+    }
+    return o;
+}
+// filter row kh (weights w[6 kh ..]) over the three pixels of one input line: a three-FMA chain per channel pair, started from `c`
+__device__ __forceinline__ void dw_row(const uint64_t (&l)[6], const uint64_t (&w)[18], int kh, uint64_t c0, uint64_t c1, uint64_t& r0, uint64_t& r1) {
+    r0 = fma2(w[6 * kh], l[0], c0);          r1 = fma2(w[6 * kh + 1], l[1], c1);
+    r0 = fma2(w[6 * kh + 2], l[2], r0);      r1 = fma2(w[6 * kh + 3], l[3], r1);
+    r0 = fma2(w[6 * kh + 4], l[4], r0);      r1 = fma2(w[6 * kh + 5], l[5], r1);
+}
+template <int F16>
+__device__ __forceinline__ void dw_out2(const uint64_t (&la)[6], const uint64_t (&lb)[6], const uint64_t (&lc)[6], const uint64_t (&ld)[6],
+                                        const uint64_t (&w)[18], uint64_t b0, uint64_t b1, int act, uint32_t dst, uint32_t line_bytes) {
+    uint64_t p[12];
+    dw_row(la, w, 0, b0, b1, p[0], p[1]);          // line y: rows a, b, c
+    dw_row(lb, w, 1, 0ull, 0ull, p[2], p[3]);
+    dw_row(lc, w, 2, 0ull, 0ull, p[4], p[5]);
+    dw_row(lb, w, 0, b0, b1, p[6], p[7]);          // line y + 1: rows b, c, d
+    dw_row(lc, w, 1, 0ull, 0ull, p[8], p[9]);
+    dw_row(ld, w, 2, 0ull, 0ull, p[10], p[11]);
+    const uint2 o0 = dw_finish<F16>(add2(add2(p[0], p[2]), p[4]), add2(add2(p[1], p[3]), p[5]), act);
+    const uint2 o1 = dw_finish<F16>(add2(add2(p[6], p[8]), p[10]), add2(add2(p[7], p[9]), p[11]), act);
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(o0.x), "r"(o0.y) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + line_bytes), "r"(o1.x), "r"(o1.y) : "memory");
+}
+// one 64-channel chunk of one tile: halo tile (SWIZZLE_128B rows of 64 channels) -> A tile (128 rows x 64 channels, SWIZZLE_128B).
+// Thread (x, 4 channels) walks its pixel column two lines at a time with a four-line register window (no register moves: the
+// loop body is two steps with the window halves swapped).  bh is even for every 8-pixel-wide tile (bh * bn = 16).
+template <int F16>
+__device__ __forceinline__ void dw_chunk(const ConvTcParams& p, uint32_t halo_base, uint32_t a_base, uint32_t w_addr, uint32_t b_addr, int tid) {
+    const uint32_t c4 = (uint32_t)(tid & 15);
+    const int x = (tid >> 4) & 7;                            // 0 .. 7 (bw == 8)
+    const int seg = tid >> 7;                                // 256 threads: each half takes eight of the tile's sixteen pixel lines
+    const int bn = p.bn, bh = p.bh, act = p.dw_act;
+    const int n_lo = bn >= 2 ? seg * (bn >> 1) : 0, n_hi = bn >= 2 ? n_lo + (bn >> 1) : 1;     // several images: half of them each ...
+    const int y_lo = bn >= 2 ? 0 : seg * (bh >> 1), ny = bn >= 2 ? bh : bh >> 1;               // ... one image: half of its lines each
+    uint64_t w[18], b0, b1;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) lds_b64x2(w_addr + (uint32_t)t * 256u + c4 * 16u, w[2 * t], w[2 * t + 1]);
+    lds_b64x2(b_addr + c4 * 16u, b0, b1);
+    // halo pixel (line l, column x): row l * halo_w + x of 128 bytes; lines y and y + 1 of one image are bn * halo_w rows apart
+    const uint32_t hline = (uint32_t)(p.halo_w * 128), hstep = hline * (uint32_t)bn;
+    const uint32_t src0 = halo_base + (uint32_t)x * 128u + c4 * 8u;
+    // A tile row m = (y * bn + n) * 8 + x: 16-byte piece (c4 >> 1) ^ (m & 7) = (c4 >> 1) ^ x, 8 bytes at (c4 & 1) * 8
+    const uint32_t dst0 = a_base + (uint32_t)x * 128u + ((((c4 >> 1) ^ (uint32_t)x)) << 4) + ((c4 & 1u) << 3);
+    const uint32_t line_bytes = (uint32_t)bn * 1024u;        // A tile bytes between lines y and y + 1 of one image
+    const int steps = ny >> 1;
+    for (int n = n_lo; n < n_hi; ++n) {
+        uint64_t L[4][6];
+        uint32_t src = src0 + (uint32_t)(y_lo * bn + n) * hline;
+        uint32_t dst = dst0 + (uint32_t)(y_lo * bn + n) * 1024u;
+        dw_load_line<F16>(src, L[0]);
+        dw_load_line<F16>(src + hstep, L[1]);
+        src += 2u * hstep;
+#pragma unroll 1
+        for (int st = 0; st < steps; st += 2) {
+            dw_load_line<F16>(src, L[2]);
+            dw_load_line<F16>(src + hstep, L[3]);
+            dw_out2<F16>(L[0], L[1], L[2], L[3], w, b0, b1, act, dst, line_bytes);
+            if (st + 1 < steps) {
+                dw_load_line<F16>(src + 2u * hstep, L[0]);
+                dw_load_line<F16>(src + 3u * hstep, L[1]);
+                dw_out2<F16>(L[2], L[3], L[0], L[1], w, b0, b1, act, dst + 2u * line_bytes, line_bytes);
+            }
+            src += 4u * hstep;
+            dst += 4u * line_bytes;
+        }
+    }
+}
+
+template <int ACT, int OUT>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_dwpw_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const Bars b = carve_bars(smem, p);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.tiles_x * p.tiles_y * ((nimg + p.bn - 1) / p.bn);     // mt == 1, one output-channel tile
+    const int chunks = p.chunks;
+    const uint32_t halo_bytes = p.halo_bytes;
+    const uint32_t smem_h = smem_u32(smem), smem_at = smem_h + 2u * halo_bytes, smem_w = smem_at + 2u * p.a_bytes;
+    const uint32_t smem_dw = smem_u32(smem + p.dw_off);              // [chunk][tap][64] fp32 weights, then [chunks * 64] fp32 bias
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB); }
+    {   // depthwise weights and bias -> shared memory (plain loads: they are constants of the plan, not produced by the previous kernel)
+        const float4* src = (const float4*)p.dw_w;
+        const int n4 = chunks * (9 * 64 + 64) / 4;
+        for (int i = threadIdx.x; i < n4; i += kThreads) {
+            const float4 v = __ldg(src + i);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_dw + (uint32_t)i * 16u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+    }
+    const uint32_t tmem_base = prologue(p, b, warp, lane, 1, 1, 8, 8);    // hempty / afull: one arrival per depthwise warp
+    const uint32_t full_u32 = smem_u32(b.full), empty_u32 = smem_u32(b.empty);
+    const uint32_t hfull_u32 = smem_u32(b.hfull), hempty_u32 = smem_u32(b.hempty);
+    const uint32_t afull_u32 = smem_u32(b.afull), aempty_u32 = smem_u32(b.aempty);
+    const bool perm = p.perm != 0;
+
+    if (warp == 0) {
+        // ===================== halo producer =====================
+        int hb = 0;
+        uint32_t hphase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(p, t);
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait_u32(hempty_u32 + hb * 8, hphase ^ 1);
+                if (elect_one()) {
+                    const uint32_t hbar = hfull_u32 + hb * 8;
+                    mbar_expect_tx_u32(hbar, p.a_tx_bytes);
+                    tma_load_4d(&p.tmA[0], hbar, smem_h + (uint32_t)hb * halo_bytes, ch * 64, tc.x0 - 1, perm ? tc.n0 : tc.y0 - 1, perm ? tc.y0 - 1 : tc.n0);
+                }
+                if (++hb == 2) { hb = 0; hphase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== pointwise-weight producer: one [n_tile x 64] box per chunk through the ring =====================
+        int stage = 0, it = 0;
+        uint32_t phase = 0;
+        const int nstages = p.stages;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            if (p.b_res && it > 0) break;                // resident: the ring holds every chunk and is filled once
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx_u32(full_u32 + stage * 8, p.b_tx_bytes);
+                    tma_load_2d(&p.tmB, full_u32 + stage * 8, smem_w + (uint32_t)stage * p.b_bytes, ch * 64, 0);
+                }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: four K = 16 steps per chunk =====================
+        int stage = 0, ab = 0, it = 0;
+        uint32_t phase = 0, aphase_b = 0;
+        const bool leader = elect_one();
+        const uint32_t hi = desc_hi(1024);
+        const uint32_t a_lo0 = desc_lo(smem_at), b_lo0 = desc_lo(smem_w);
+        const uint32_t a_units = p.a_bytes >> 4, b_units = p.b_bytes >> 4;
+        const uint32_t idesc = p.idesc;
+        const int nstages = p.stages, n_tile = p.n_tile;
+        const uint32_t tfull_u32 = smem_u32(b.tfull), tempty_u32 = smem_u32(b.tempty);
+        const bool b_res = p.b_res != 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1;
+            mbar_wait_u32(tempty_u32 + as * 8, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
+            for (int ch = 0; ch < chunks; ++ch) {
+                if (!b_res || it == 0) mbar_wait_u32(full_u32 + stage * 8, phase);
+                mbar_wait_u32(afull_u32 + ab * 8, aphase_b);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)ab * a_units, b_lo = b_lo0 + (uint32_t)stage * b_units;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, desc64(hi, a_lo + 2 * k), desc64(hi, b_lo + 2 * k), idesc, (uint32_t)((ch | k) != 0));
+                    umma_commit(aempty_u32 + ab * 8);
+                    if (!b_res) umma_commit(empty_u32 + stage * 8);
+                    if (ch == chunks - 1) umma_commit(tfull_u32 + as * 8);
+                }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+                if (++ab == 2) { ab = 0; aphase_b ^= 1; }
+            }
+        }
+    } else if (warp == 3) {
+        store_loop<0, OUT>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
+    } else if (warp >= 8) {
+        // ===================== depthwise warps (8-15) =====================
+        const int tid = threadIdx.x - 256;
+        int hb = 0, ab = 0;
+        uint32_t hphase = 0, aphase_b = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait_u32(hfull_u32 + hb * 8, hphase);                   // the chunk's halo has landed
+                mbar_wait_u32(aempty_u32 + ab * 8, aphase_b ^ 1);            // the MMAs that read this A tile have retired
+                const uint32_t hbase = smem_h + (uint32_t)hb * halo_bytes, abase = smem_at + (uint32_t)ab * p.a_bytes;
+                const uint32_t w_addr = smem_dw + (uint32_t)ch * (9u * 256u), b_addr = smem_dw + (uint32_t)chunks * (9u * 256u) + (uint32_t)ch * 256u;
+                if (p.f16) dw_chunk<1>(p, hbase, abase, w_addr, b_addr, tid);
+                else dw_chunk<0>(p, hbase, abase, w_addr, b_addr, tid);
+                fence_proxy_async();                                         // generic-proxy A tile writes -> visible to the MMA's reads
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_u32(afull_u32 + ab * 8);
+                    mbar_arrive_u32(hempty_u32 + hb * 8);                    // halo buffer read completely by this warp
+                }
+                if (++hb == 2) { hb = 0; hphase ^= 1; }
+                if (++ab == 2) { ab = 0; aphase_b ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        epilogue_loop<ACT, 0, OUT>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
+    }
+    epilogue_exit(p, tmem_base, warp);
+}
+
 // ---- host side ----------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -1944,16 +2196,27 @@ int conv_tc_stem_supported(int src_cs, int cin, int ksz, int stride, int cout, i
     return src_cs == 4 && cin <= 4 && (ksz == 3 || ksz == 1) && (stride == 1 || stride == 2) && cout <= 256 && !dst_f32 && !has_res;
 }
 
+// fused depthwise + pointwise: c a multiple of 64 (whole K chunks), one output-channel tile, 16-bit unsplit storage
+int conv_tc_dwpw_supported(int c, int cout, int dst_f32, int x2) {
+    return c % 64 == 0 && c / 64 <= kMaxStages && cout % 16 == 0 && cout <= 256 && !dst_f32 && !x2;
+}
+
 int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloat16* src, int src_h, int src_w, int src_cs,
                  int src_c0, int cin, void* dst, int dst_h, int dst_w, int dst_cs, int dst_c0, int cout, int dst_f32, int ksz,
                  int stride, int act, const float* w_host, const float* b_host, const __nv_bfloat16* res, int res_cs,
-                 int res_c0, int depthwise, int f16, int x2, float acc_scale) {
+                 int res_c0, int depthwise, int f16, int x2, float acc_scale, const DwFuse* fuse) {
     // Channel arguments are REAL channel counts.  In split-fp16 storage (x2) a 16-bit buffer keeps 2 x 16 bits per channel
     // ([hi x 8 | lo x 8] groups, see split2): the A operand then has K = 2 * cin storage channels against weights packed twice,
     // and 16-bit outputs / residuals are 4 bytes per channel like fp32 ones.  The network input (stem) is never split.
     memset(plan, 0, sizeof(*plan));
     const bool dw = depthwise != 0;
+    const bool fused = fuse != nullptr;       // this 1x1 conv reads the depthwise 3x3 of fuse->src computed in the same kernel (src is unused)
     B2D_CHECK(!x2 || f16, "conv_tc: split storage is fp16");
+    if (fused) {
+        B2D_CHECK(!dw && ksz == 1 && stride == 1 && !res && conv_tc_dwpw_supported(cin, cout, dst_f32, x2), "conv_tc: unsupported fused depthwise + pointwise shape");
+        B2D_CHECK(fuse->src_cs % 8 == 0 && fuse->src_c0 % 8 == 0, "conv_tc: fused source slice must be 16-byte aligned");
+        src = fuse->src; src_cs = fuse->src_cs; src_c0 = fuse->src_c0;
+    }
     if (dw) B2D_CHECK(conv_tc_dw_supported(cin, cout, ksz, stride, dst_f32, res != nullptr), "conv_tc: unsupported depthwise shape");
     const bool stem = !dw && conv_tc_stem_supported(src_cs, cin, ksz, stride, cout, dst_f32, res != nullptr) && src_c0 == 0;
     if (!stem) {
@@ -1981,7 +2244,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // the stride-2 stem is fed by TMA through a space-to-depth view (conv_tc_stem2_kernel) when an 8-pixel-wide one-image
     // tile fits; anything else on the 4-channel input (stride 1, 1x1, odd sizes) keeps the gather kernel
     bool stem2 = stem && ksz == 3 && stride == 2 && src_h % 2 == 0 && src_w % 2 == 0 && env_int("B2D_STEM_S2D", 1) != 0;
-    pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn, dw);
+    pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn, dw || fused);
     if (stem2) {
         int w8, h8, n8;
         pick_tile(dst_w, dst_h, max_batch, &w8, &h8, &n8, true);
@@ -2024,6 +2287,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // halo: 3x3 stride 1 on 8-pixel-wide tiles (uniform (bw+2)-row stride between 8-row groups)
     const bool halo_ok = !stem && ksz == 3 && stride == 1 && p.bw == 8 && (dw || env_int("B2D_HALO", 1) != 0);
     B2D_CHECK(!dw || halo_ok, "conv_tc: depthwise needs an 8-pixel-wide tile");
+    B2D_CHECK(!fused || (p.bw == 8 && p.bh % 2 == 0 && (p.bn == 1 ? p.bh % 4 == 0 : p.bn % 2 == 0)), "conv_tc: fused depthwise + pointwise needs an 8-pixel-wide tile that splits into two even halves");
     if (!stem2) p.halo_w = p.bw + 2;
     p.halo_kh_rows = (uint32_t)(p.bn * p.halo_w);
     const uint32_t halo_rows = (uint32_t)(p.halo_w * p.bn * (p.bh + 2));
@@ -2031,6 +2295,17 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     const int mt_env = env_int("B2D_MT", 0);
     const int mt_cap = stem ? 4 : 2;
     int best_kind = -1, best_mt = 1, best_stages = 0, best_bufs = 1, best_bres = 0;
+    const uint32_t dw_bytes = fused ? (((uint32_t)p.chunks * (9 * 64 + 64) * 4 + 1023u) & ~1023u) : 0u;   // depthwise weights + bias in shared memory
+    if (fused) {
+        // two halo buffers, two A tiles, the depthwise constants, one staging buffer (two if they fit), the rest weight stages
+        const uint32_t fixed = 2u * p.halo_bytes + 2u * p.a_bytes + dw_bytes;
+        B2D_CHECK(avail > fixed + tile_stg + slab_bars(1, 1) + 2u * p.b_bytes, "conv_tc: fused depthwise + pointwise does not fit shared memory (c %d cout %d)", cin, cout);
+        int st = (int)((avail - fixed - tile_stg - slab_bars(1, 1)) / p.b_bytes);
+        if (st >= p.chunks) { st = p.chunks; best_bres = 1; }
+        if (st > kMaxStages) st = kMaxStages;
+        best_bufs = (avail >= fixed + 2u * tile_stg + slab_bars(1, 2) + (uint32_t)st * p.b_bytes && env_int("B2D_STG2", 1) != 0) ? 2 : 1;
+        best_kind = 5; best_mt = 1; best_stages = st;
+    }
     for (int mt = mt_cap; mt >= 1 && best_kind < 0; mt >>= 1) {
         if (mt_env > 0 && mt > mt_env) continue;
         if (mt > 1 && (split > 1 || 2 * mt * p.n_tile > 512)) continue;
@@ -2106,13 +2381,15 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         if (st > 2 * ksteps) st = 2 * ksteps;
         p.stages = st > kMaxStages ? kMaxStages : st;
     }
-    if (best_kind == 1) p.a_tx_bytes = halo_rows * 128u;
+    if (best_kind == 1 || best_kind == 5) p.a_tx_bytes = halo_rows * 128u;
     const uint32_t stg_bytes = (uint32_t)p.stg_bufs * p.mt * tile_stg;
     uint32_t operand_bytes;
     if (p.kind == 0) operand_bytes = (uint32_t)p.stages * ((uint32_t)p.mt * p.a_bytes + p.b_bytes);
     else if (p.kind == 1 || p.kind == 3) operand_bytes = 2u * p.mt * p.halo_bytes + (uint32_t)p.stages * p.b_bytes;
+    else if (p.kind == 5) operand_bytes = 2u * p.halo_bytes + 2u * p.a_bytes + (uint32_t)p.stages * p.b_bytes + dw_bytes;
     else operand_bytes = (uint32_t)p.stages * p.mt * p.a_bytes + p.b_bytes;
     p.stg_off = operand_bytes;                                   // 1 KiB aligned: every operand slot is a multiple of 1 KiB
+    p.dw_off = operand_bytes - dw_bytes;
     p.bar_off = p.stg_off + stg_bytes;
     plan->smem_bytes = (size_t)p.bar_off + tail_fixed + slab_bars(p.mt, p.stg_bufs) + 1024 /*align slack*/;
     B2D_CHECK(plan->smem_bytes <= 227 * 1024, "conv_tc: %zu bytes of shared memory needed", plan->smem_bytes);
@@ -2141,7 +2418,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // the epilogue ran at 3-4.5 outputs per clock per SM against 15 for the same code with eight warps per scheduler
     // (role traces, profiles/r2_role_traces.txt).  A third warp per quarter takes every third 16-column unit when the tile
     // width allows an even split (48, 96, 144, 192 ...); the stem's 16 warps are taken (gather warps).
-    p.epi_parts = ((!stem || stem2) && (p.n_tile >> 4) % 3 == 0 && env_int("B2D_EPI3", 1) != 0) ? 3 : 2;
+    p.epi_parts = fused ? 1 : ((!stem || stem2) && (p.n_tile >> 4) % 3 == 0 && env_int("B2D_EPI3", 1) != 0) ? 3 : 2;   // fused: warps 8-15 compute the depthwise stage
     p.exp = env_int("B2D_EXP", 0);
     p.trace = nullptr;
     if (getenv("B2D_TRACE")) {
@@ -2208,6 +2485,26 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     B2D_CUDA(cudaMemcpy(plan->bias_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
     p.bias = plan->bias_dev;
     p.w_raw = plan->w_dev;
+    if (fused) {
+        // [chunk][tap][64] fp32 then [chunks * 64] bias; values rounded to the 16-bit weight format like every packed weight, and
+        // halved for SiLU layers (silu2_h takes v / 2; the scaling is exact)
+        std::vector<float> dwc((size_t)p.chunks * (9 * 64 + 64), 0.f);
+        const float hs = fuse->act ? 0.5f : 1.0f;
+        for (int c = 0; c < cin; ++c) {
+            for (int t = 0; t < 9; ++t) {
+                const uint16_t v = f16 ? f2h(fuse->w[(size_t)c * 9 + t]) : f2bf(fuse->w[(size_t)c * 9 + t]);
+                float wf;
+                if (f16) { __half h; memcpy(&h, &v, 2); wf = __half2float(h); }
+                else { uint32_t u = (uint32_t)v << 16; memcpy(&wf, &u, 4); }
+                dwc[((size_t)(c / 64) * 9 + t) * 64 + c % 64] = hs * wf;
+            }
+            dwc[(size_t)p.chunks * 9 * 64 + c] = hs * (fuse->b ? fuse->b[c] : 0.f);
+        }
+        B2D_CUDA(cudaMalloc(&plan->dw_dev, dwc.size() * 4));
+        B2D_CUDA(cudaMemcpy(plan->dw_dev, dwc.data(), dwc.size() * 4, cudaMemcpyHostToDevice));
+        p.dw_w = plan->dw_dev;
+        p.dw_act = fuse->act;
+    }
 
     // ---- tensor maps ----
     const bool perm = p.perm != 0;
@@ -2224,9 +2521,9 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
             if (encode_map(&p.tmB, plan->w_dev, 2, dims, str, box, 128)) return -1;
         }
         const uint64_t pix = (uint64_t)src_cs_s * 2, rowb = (uint64_t)src_w * pix, imgb = (uint64_t)src_h * rowb;
-        if (p.kind == 1 || p.kind == 3) {
+        if (p.kind == 1 || p.kind == 3 || p.kind == 5) {
             if (encode_act_map(&p.tmA[0], (void*)(src + src_c0_s), kin, src_w, src_h, max_batch, pix, rowb, imgb, 64u, (uint32_t)p.halo_w,
-                               (uint32_t)(p.bh + 2), (uint32_t)p.bn, perm, 128))
+                               (uint32_t)(p.bh + 2), (uint32_t)p.bn, perm, p.kind == 5 ? 0 : 128))    // fused: read by threads, plain rows
                 return -1;
         } else if (stride == 1) {
             if (encode_act_map(&p.tmA[0], (void*)(src + src_c0_s), kin, src_w, src_h, max_batch, pix, rowb, imgb, 64u, (uint32_t)p.bw, (uint32_t)p.bh,
@@ -2281,6 +2578,7 @@ ConvKernel pick_kernel(int kind, int pair, int act, int res, int out) {
     if (res) return act ? K<1, 1, 0> : K<0, 1, 0>;                         \
     return act ? K<1, 0, 0> : K<0, 0, 0>;
     if (kind == 2) return out == 2 ? (act ? conv_tc_stem_kernel<1, 2> : conv_tc_stem_kernel<0, 2>) : (act ? conv_tc_stem_kernel<1, 0> : conv_tc_stem_kernel<0, 0>);
+    if (kind == 5) return act ? conv_tc_dwpw_kernel<1, 0> : conv_tc_dwpw_kernel<0, 0>;
     if (kind == 4) return out == 2 ? (act ? conv_tc_stem2_kernel<1, 2> : conv_tc_stem2_kernel<0, 2>) : (act ? conv_tc_stem2_kernel<1, 0> : conv_tc_stem2_kernel<0, 0>);
     if (kind == 3) return out == 2 ? (act ? conv_tc_dw_kernel<1, 2> : conv_tc_dw_kernel<0, 2>) : (act ? conv_tc_dw_kernel<1, 0> : conv_tc_dw_kernel<0, 0>);
     if (kind == 1 && pair) { B2D_PICK(conv_tc_halo2_kernel) }
@@ -2361,6 +2659,8 @@ void conv_tc_free(ConvTcPlan* plan) {
     if (plan->w_dev) cudaFree(plan->w_dev);
     if (plan->bias_dev) cudaFree(plan->bias_dev);
     if (plan->trace_dev) cudaFree(plan->trace_dev);
+    if (plan->dw_dev) cudaFree(plan->dw_dev);
+    plan->dw_dev = nullptr;
     plan->trace_dev = nullptr;
     plan->w_dev = nullptr;
     plan->bias_dev = nullptr;
@@ -2368,8 +2668,8 @@ void conv_tc_free(ConvTcPlan* plan) {
 
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
-    static const char* kinds[7] = {"", "-halo", "-stem", "-depthwise", "-halo-pair", "-pair", "-stem-s2d"};
+    static const char* kinds[8] = {"", "-halo", "-stem", "-depthwise", "-halo-pair", "-pair", "-stem-s2d", "-dw3x3+pw"};
     return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d%s stg %d tmem %u smem %zu",
-                    kinds[p.pair ? (p.kind == 0 ? 5 : 4) : p.kind == 4 ? 6 : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
+                    kinds[p.pair ? (p.kind == 0 ? 5 : 4) : p.kind == 4 ? 6 : p.kind == 5 ? 7 : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
                     p.b_res ? " (resident)" : "", p.stg_bufs, p.tmem_cols, plan->smem_bytes);
 }

@@ -95,6 +95,10 @@ struct b2d_engine {
     std::vector<Buffer> bufs;
     std::vector<OpDesc> descs;
     std::vector<Op> ops;
+    // forward() runs a depthwise 3x3 and the 1x1 conv that consumes it as ONE kernel where the pair qualifies (conv_tc_dwpw_kernel):
+    // fused_at[i] = index into fused_plans when ops i and i + 1 are such a pair, else -1.  b2d_run_op always runs the single ops.
+    std::vector<int> fused_at;
+    std::vector<ConvTcPlan> fused_plans;
     HeadDesc head{};
     int head_levels = 0;
     std::vector<TableEntry> tables;
@@ -218,6 +222,13 @@ int launch_op(b2d_engine* e, const Op& op, int n, cudaStream_t s) {
     return -1;
 }
 
+// op i as forward() runs it: the fused pair kernel where one starts at i, nothing for the second op of a pair
+int launch_fwd_op(b2d_engine* e, int i, int n, cudaStream_t s) {
+    if (e->fused_at[i] >= 0) return conv_tc_launch(&e->fused_plans[e->fused_at[i]], n, s);
+    if (i > 0 && e->fused_at[i - 1] >= 0) return 0;
+    return launch_op(e, e->ops[i], n, s);
+}
+
 // Launches every op of the plan into the capture: op i goes to the stream of the dependency it continues, or to another
 // capture stream when that one has moved on, with event edges for every read-after-write, write-after-read and
 // write-after-write between channel ranges of the same buffer.  Independent chains -- the six branches of the
@@ -246,8 +257,16 @@ int capture_ops(b2d_engine* e, int n) {
     std::vector<std::vector<Range>> rd(nops), wr(nops);
     for (int i = 0; i < nops; ++i) {
         const OpDesc& d = e->descs[i];
-        const int owner = e->ops[i].kind == OP_NOP ? e->ops[i].fused_into : i;
         const int cin = d.kind_req == 0 ? d.cin : d.cout;
+        if (e->fused_at[i] >= 0) {                        // depthwise + pointwise pair: reads the depthwise source, writes the pointwise output
+            rd[i].push_back({d.src, d.src_c0, d.src_c0 + cin});
+            continue;
+        }
+        if (i > 0 && e->fused_at[i - 1] >= 0) {
+            wr[i - 1].push_back({d.dst, d.dst_c0, d.dst_c0 + d.cout});
+            continue;
+        }
+        const int owner = e->ops[i].kind == OP_NOP ? e->ops[i].fused_into : i;
         if (owner == i) rd[i].push_back({d.src, d.src_c0, d.src_c0 + cin});
         if (d.res >= 0) rd[owner].push_back({d.res, d.res_c0, d.res_c0 + d.cout});
         wr[owner].push_back({d.dst, d.dst_c0, d.dst_c0 + d.cout});
@@ -258,7 +277,7 @@ int capture_ops(b2d_engine* e, int n) {
     cudaEvent_t fork_ev = e->cap_events[nops];
     B2D_CUDA(cudaEventRecord(fork_ev, e->cap_stream));
     for (int i = 0; i < nops; ++i) {
-        if (e->ops[i].kind == OP_NOP) continue;
+        if (e->ops[i].kind == OP_NOP || (i > 0 && e->fused_at[i - 1] >= 0)) continue;
         std::vector<int> deps;
         for (int j = 0; j < i; ++j) {
             if (where[j] < 0) continue;
@@ -286,7 +305,7 @@ int capture_ops(b2d_engine* e, int n) {
         }
         for (int j : deps)
             if (where[j] != k) B2D_CUDA(cudaStreamWaitEvent(s, e->cap_events[j], 0));
-        if (int r = launch_op(e, e->ops[i], n, s)) return r;
+        if (int r = launch_fwd_op(e, i, n, s)) return r;
         B2D_CUDA(cudaEventRecord(e->cap_events[i], s));
         where[i] = k;
         last_on[k] = i;
@@ -342,6 +361,7 @@ void b2d_destroy(b2d_engine* e) {
     for (auto& op : e->ops) {
         if (op.kind == OP_CONV_TC) conv_tc_free(&op.tc);
     }
+    for (auto& fp : e->fused_plans) conv_tc_free(&fp);
     for (auto& b : e->bufs)
         if (b.ptr) cudaFree(b.ptr);
     for (auto& te : e->tables) {
@@ -523,12 +543,45 @@ int b2d_plan_finalize(b2d_engine* e) {
             op.h = sb.h; op.w = sb.w; op.src_cs = sb.c; op.src_c0 = d.src_c0;
             op.oh = db.h; op.ow = db.w; op.dst_cs = db.c; op.dst_c0 = d.dst_c0; op.c = d.cout; op.k = d.k; op.stride = d.stride;
         }
-        d.w.clear(); d.w.shrink_to_fit();
         if (op.kind == OP_CONV_TC) {        // B2D_REV: 1 (default) odd ops walk backwards, 0 nobody, 2 everybody
             static const int rev_mode = getenv("B2D_REV") ? atoi(getenv("B2D_REV")) : 1;
             op.tc.p.rev = rev_mode == 2 ? 1 : rev_mode == 1 ? (int)(i & 1) : 0;
         }
     }
+    // Depthwise 3x3 followed by the 1x1 conv that is its only reader -> one kernel in forward() (B2D_FUSE_DWPW=0 keeps the pair).
+    e->fused_at.assign(e->descs.size(), -1);
+    e->fused_plans.reserve(e->descs.size());
+    static const bool fuse_dwpw = getenv("B2D_FUSE_DWPW") ? atoi(getenv("B2D_FUSE_DWPW")) != 0 : true;
+    for (size_t i = 0; fuse_dwpw && i + 1 < e->descs.size(); ++i) {
+        const OpDesc& d0 = e->descs[i];
+        const OpDesc& d1 = e->descs[i + 1];
+        if (d0.kind_req != 1 || d1.kind_req != 0 || d1.k != 1 || d1.stride != 1 || d1.res >= 0) continue;
+        if (d1.src != d0.dst || d1.src_c0 != d0.dst_c0 || d1.cin != d0.cout) continue;
+        const Buffer& sb = e->bufs[d0.src];
+        const Buffer& db = e->bufs[d1.dst];
+        if (!conv_tc_dwpw_supported(d0.cout, d1.cout, db.f32, e->x2) || sb.c % 8 != 0 || d0.src_c0 % 8 != 0) continue;
+        if (e->ops[i].tc.p.bw != 8) continue;            // the depthwise plan's tile is the fused kernel's tile
+        bool other_reader = false;                        // the intermediate must have no other consumer
+        for (size_t j = 0; j < e->descs.size(); ++j) {
+            if (j == i + 1) continue;
+            const OpDesc& dj = e->descs[j];
+            const int cj = dj.kind_req == 0 ? dj.cin : dj.cout;
+            if (dj.src == d0.dst && dj.src_c0 < d0.dst_c0 + d0.cout && d0.dst_c0 < dj.src_c0 + cj) other_reader = true;
+            if (dj.res == d0.dst && dj.res_c0 < d0.dst_c0 + d0.cout && d0.dst_c0 < dj.res_c0 + dj.cout) other_reader = true;
+            if (j != i && dj.dst == d0.dst && dj.dst_c0 < d0.dst_c0 + d0.cout && d0.dst_c0 < dj.dst_c0 + dj.cout) other_reader = true;   // or another writer
+        }
+        if (other_reader) continue;
+        DwFuse fz{(const __nv_bfloat16*)sb.ptr, sb.c, d0.src_c0, d0.w.data(), d0.b.data(), d0.act};
+        ConvTcPlan fp;
+        if (conv_tc_plan(&fp, e->sm_count, e->max_batch, nullptr, sb.h, sb.w, 0, 0, d1.cin, db.ptr, db.h, db.w, db.c, d1.dst_c0, d1.cout, 0, 1, 1,
+                         d1.act, d1.w.data(), d1.b.data(), nullptr, 0, 0, 0, e->f16, 0, 1.0f, &fz))
+            return -1;
+        fp.p.rev = e->ops[i].tc.p.rev;
+        e->fused_at[i] = (int)e->fused_plans.size();
+        e->fused_plans.push_back(fp);
+        ++i;
+    }
+    for (auto& d : e->descs) { d.w.clear(); d.w.shrink_to_fit(); }
     // Fuse chains of stride-1 max-pools into one launch: SPPF (mp5 of mp5 of mp5) and SPPCSPC (mp5, mp9, mp13 of one
     // source, which are the same three tensors because max-pooling with -inf padding composes).
     for (size_t i = 0; i + 1 < e->ops.size(); ++i) {
@@ -566,6 +619,7 @@ int b2d_num_kernels_per_forward(b2d_engine* e) {
     if (!e) return -1;
     int k = 0;
     for (const Op& op : e->ops) k += op.kind != OP_NOP;
+    for (int f : e->fused_at) k -= f >= 0;
     return k;
 }
 
@@ -589,6 +643,19 @@ int b2d_run_op(b2d_engine* e, int i, int n, void* stream) {
     return launch_op(e, e->ops[i], n, (cudaStream_t)stream);
 }
 
+int b2d_fused_with_next(b2d_engine* e, int i) {
+    if (!e || !e->finalized || i < 0 || i >= (int)e->fused_at.size()) return -1;
+    return e->fused_at[i] >= 0 ? 1 : 0;
+}
+
+int b2d_run_op_fused(b2d_engine* e, int i, int n, void* stream) {
+    B2D_CHECK(e && e->finalized && i >= 0 && i < (int)e->ops.size(), "run_op_fused: bad index");
+    B2D_CHECK(e->fused_at[i] >= 0, "run_op_fused: op %d does not start a fused pair", i);
+    B2D_CHECK(n > 0 && n <= e->max_batch, "run_op_fused: n=%d outside [1,%d]", n, e->max_batch);
+    B2D_ENTER(e);
+    return conv_tc_launch(&e->fused_plans[e->fused_at[i]], n, (cudaStream_t)stream);
+}
+
 int b2d_forward(b2d_engine* e, int n, void* stream) {
     B2D_CHECK(e && e->finalized, "forward: plan not finalized");
     B2D_CHECK(n > 0 && n <= e->max_batch, "forward: n=%d outside [1,%d]", n, e->max_batch);
@@ -608,8 +675,8 @@ int b2d_forward(b2d_engine* e, int n, void* stream) {
     }
     int rc = 0;
     if (!capture) {
-        for (const Op& op : e->ops)
-            if ((rc = launch_op(e, op, n, st)) != 0) break;
+        for (int i = 0; i < (int)e->ops.size(); ++i)
+            if ((rc = launch_fwd_op(e, i, n, st)) != 0) break;
     } else {
         rc = capture_ops(e, n);
     }
@@ -628,8 +695,8 @@ int b2d_forward(b2d_engine* e, int n, void* stream) {
         if (g) cudaGraphDestroy(g);
         cudaGetLastError();
         B2D_CHECK(rc == 0, "forward: launch failed during graph capture");
-        for (const Op& op : e->ops)                     // capture or instantiation failed: plain launches
-            if (int r = launch_op(e, op, n, st)) return r;
+        for (int i = 0; i < (int)e->ops.size(); ++i)    // capture or instantiation failed: plain launches
+            if (int r = launch_fwd_op(e, i, n, st)) return r;
         return 0;
     }
     return rc;

@@ -181,6 +181,13 @@ class Engine:
     def run_op(self, i: int, n: int) -> None:
         _lib.check(self.lib.b2d_run_op(self.h, i, n, self.stream), f"run_op {i}")
 
+    def fused_with_next(self, i: int) -> bool:
+        """forward() runs op i and op i + 1 (depthwise 3x3 -> 1x1) as one kernel."""
+        return self.lib.b2d_fused_with_next(self.h, i) == 1
+
+    def run_op_fused(self, i: int, n: int) -> None:
+        _lib.check(self.lib.b2d_run_op_fused(self.h, i, n, self.stream), f"run_op_fused {i}")
+
     def decode_rows(self, n: int) -> torch.Tensor:
         rows = torch.empty((n, self.num_rows, 6), dtype=torch.float32, device=self.device)
         _lib.check(self.lib.b2d_decode_rows(self.h, n, _ptr(rows), self.stream), "decode_rows")

@@ -233,6 +233,11 @@ int b2d_set_conf_scale(b2d_engine* e, float scale);
 /* Run a single planned op (index in plan order) -- used by the per-layer parity tests.      */
 int b2d_run_op(b2d_engine* e, int op_index, int n, void* stream);
 int b2d_num_ops(b2d_engine* e);
+/* b2d_forward runs a depthwise 3x3 and the 1x1 conv that is its only consumer (Ultralytics 8.3.x cls branch, the convs inside
+ * `session.run`, _script/gpu_handler.py:165) as one kernel; b2d_run_op still runs the two ops separately.
+ * b2d_fused_with_next: 1 if op i starts such a pair, 0 if not, -1 on a bad index.  b2d_run_op_fused runs the pair kernel.   */
+int b2d_fused_with_next(b2d_engine* e, int op_index);
+int b2d_run_op_fused(b2d_engine* e, int op_index, int n, void* stream);
 /* Describe op i: writes a short text (kernel, tile shape, stages) into buf.                 */
 int b2d_describe_op(b2d_engine* e, int op_index, char* buf, int buflen);
 

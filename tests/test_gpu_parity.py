@@ -167,6 +167,50 @@ def _check_every_op(arch, imgsz, n, precision="bf16"):
     return seen
 
 
+@pytest.mark.parametrize("arch,imgsz,n,precision", [("yolov8m", 128, 3, "bf16"), ("yolov8m", 320, 2, "bf16"), ("yolov8m", 640, 2, "bf16"),
+                                                     ("yolov8m", 640, 8, "bf16"), ("yolov8m", 320, 2, "fp16")])
+def test_fused_depthwise_pointwise_kernel_matches_torch(arch, imgsz, n, precision):
+    """forward() runs DWConv 3x3 -> Conv 1x1 of the cls branch as one kernel (conv_tc_dwpw_kernel): on the engine's own input
+    the pair kernel must equal torch's dwconv -> SiLU -> (rounded to the storage format, as the unfused pair stores it) ->
+    1x1 -> SiLU to one ulp of the storage format, and agree with the two single-op kernels to the same bound."""
+    import torch.nn.functional as F
+    g = G.build(arch, imgsz=imgsz)
+    w = W.make_synthetic_weights(g, 2)
+    eng = _engine(arch, weights=w, max_batch=n, imgsz=imgsz, graph=g, precision=precision)
+    eng.preprocess(torch.from_numpy(synth.make_tiles(n, imgsz, 9)).cuda(), "identity")
+    eng.forward(n)
+    torch.cuda.synchronize()
+    rel16 = {"bf16": 4e-3, "fp16": 5e-4}[precision]
+    store = torch.bfloat16 if precision == "bf16" else torch.float16
+    pairs = [i for i in range(len(g.ops) - 1) if eng.fused_with_next(i)]
+    assert len(pairs) == 6, pairs                      # cv3.{0,1,2}.{0,1}: two pairs per head level
+    for i in pairs:
+        a, b = g.ops[i], g.ops[i + 1]
+        assert a.kind == "dwconv" and b.kind == "conv" and b.k == 1
+        src = eng.buffer(a.src.buf, n).float().cpu()[..., a.src.c0:a.src.c0 + a.src.c].permute(0, 3, 1, 2)
+        wa, ba = (torch.from_numpy(np.ascontiguousarray(x)) for x in G.op_weights(a, w))
+        wb, bb = (torch.from_numpy(np.ascontiguousarray(x)) for x in G.op_weights(b, w))
+        mid = F.conv2d(src, wa, ba, padding=1, groups=a.src.c)
+        mid = (mid * torch.sigmoid(mid)).to(store).float()
+        y = F.conv2d(mid, wb, bb)
+        y = y * torch.sigmoid(y)
+        def out():
+            torch.cuda.synchronize()
+            return eng.buffer(b.dst.buf, n).float().cpu()[..., b.dst.c0:b.dst.c0 + b.dst.c].permute(0, 3, 1, 2).clone()
+        eng.buffer(b.dst.buf, n).zero_()
+        eng.run_op_fused(i, n)
+        fused = out()
+        eng.buffer(b.dst.buf, n).zero_()
+        eng.run_op(i, n)
+        eng.run_op(i + 1, n)
+        single = out()
+        tol = 2 * rel16 * y.abs().max().item() + 1e-5
+        assert (fused - y).abs().max().item() <= tol, (i, eng.describe_op(i), (fused - y).abs().max().item(), tol)
+        assert (fused - single).abs().max().item() <= tol, (i, (fused - single).abs().max().item(), tol)
+    assert eng.num_kernels == sum(1 for _ in g.ops) - 2 - len(pairs), eng.num_kernels     # SPPF pool chain (3 -> 1) and the six pairs
+    eng.close()
+
+
 # ---- whole network vs the oracle -------------------------------------------------------------------
 # Contract (BASELINE.json north_star; the reference's fp32 `session.run`, simple_detector.py:474-481): scores within 1e-3
 # absolute, boxes within 0.5 px, identical keep set away from score ties.  Asserted at 640x640 on C2 tiles (the bench's
