@@ -91,6 +91,7 @@ struct __align__(64) ConvTcParams {
     int dw_act;           // ... SiLU after the depthwise stage
     int rev;              // 1: this op walks its M tiles in descending order (set per op by the engine)
     int rev_last;         // per launch: index of the last M tile when walking backwards, else -1
+    int epi_path;         // epilogue code path (see epilogue_loop; B2D_EPI_PATH, default 2)
     int exp;              // timing-ablation flags (trace builds only)
     long long* trace;     // debug only (B2D_TRACE=1): per-role clock64 stamps of CTA 0, else nullptr
 };

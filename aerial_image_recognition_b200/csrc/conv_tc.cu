@@ -592,7 +592,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
     };
     const uint32_t ubytes = 16u * esize;               // bytes of one unit in a row
     int it = 0;
-    if (my_units <= 2 && !split_last && p.n_tiles_n == 1 && !B2D_EXP(p, 10)) {
+    if (my_units <= 2 && !split_last && p.n_tiles_n == 1 && p.epi_path >= 1) {
         // Narrow tiles (n_tile = 32, 48, 64, 96: the stem, the 160^2 stage, the 96-channel 3x3 layers, the head's box branch): a warp
         // owns the same one or two 16-column units of every tile, so the staging addresses and the bias pointers are loop
         // invariants and a tile is one straight-line block -- TMEM loads of the next tile in flight behind the SiLU of this
@@ -659,6 +659,85 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, int total_t
             if (warp == 4 && lane == 0) trace(p, 2, it, 2);
         }
         (void)rank;
+        return;
+    }
+    if (!split_last && p.epi_path >= 2) {
+        // Tile-structured path (everything except the 8 + 8 split of an odd last unit): a warp's 16-column units are the same
+        // columns of every tile, a tile is one block of straight-line code per pair of units -- bias step of the pair, TMEM loads
+        // of the next pair (of this tile or the next) issued behind it, SiLU + pack + staging stores -- with one slab wait in
+        // front and one hand-off behind.  The item-list form below spends ~180 instructions per 16 columns, most of them
+        // bookkeeping, and a warp issues about one instruction per six cycles.
+        const uint32_t rank = pair ? cluster_ctarank() : 0u;
+        const int rounds = pair ? pair_rounds(p, total_tiles) : (total_tiles + mt - 1) / mt;
+        const int rd0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, rd_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+        const uint32_t tempty_arrive = pair ? mapa_u32(tempty_u32, 0) : tempty_u32;
+        const int f16 = p.f16;
+        const float sc = (ACT ? 0.5f : 1.0f) * p.acc_scale;
+        const uint64_t scale2 = pk2(sc, sc);
+        const uint32_t col0 = (uint32_t)(half * 16), ustep = (uint32_t)nparts * 16u;
+        for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
+            const int as = it & 1;
+            const int t0 = pair ? pair_tile(p, rd, (int)rank, total_tiles) : rd * mt;
+            const int nv = pair ? 1 : min(mt, total_tiles - t0);
+            if (warp == 4 && lane == 0) trace(p, 2, it, 0);
+            mbar_wait_u32(tfull_u32 + as * 8, (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            if (warp == 4 && lane == 0) trace(p, 2, it, 1);
+            const int ch_base = p.n_tiles_n > 1 ? (int)((uint32_t)t0 - __umulhi((uint32_t)t0, p.rcp_nn) * (uint32_t)p.n_tiles_n) * n_tile : 0;   // n_tiles_n > 1 implies mt == 1
+            const uint32_t baddr = bias_base + (uint32_t)ch_base * 4u + col0 * 4u;
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * mt * n_tile) + col0;
+            uint32_t ra[16], rb[16];
+            tmem_ld16(tq, ra);
+            if (my_units > 1) tmem_ld16(tq + ustep, rb);
+#pragma unroll 1
+            for (int m = 0; m < nv; ++m) {
+                const int c = it * mt + m, slab = c & (S - 1);
+                const uint32_t use = (uint32_t)(c >> s_shift);
+                mbar_wait_u32(sempty_u32 + (uint32_t)slab * 8u, (use & 1u) ^ 1u);      // the tile's slab is free ...
+                if (RES) mbar_wait_u32(rbar_u32 + (uint32_t)slab * 8u, use & 1u);     // ... and its residual has landed in it
+                const uint32_t moff = (uint32_t)slab * tile_bytes;
+                const uint32_t tm = tq + (uint32_t)(m * n_tile);
+#pragma unroll 1
+                for (int u = 0; u < my_units; u += 2) {
+                    const bool two = u + 1 < my_units;
+                    uint64_t v0[8], v1[8];
+                    tmem_ld_wait();
+                    epi_bias<ACT, 16>(ra, baddr + (uint32_t)u * ustep * 4u, v0, scale2);
+                    if (two) epi_bias<ACT, 16>(rb, baddr + (uint32_t)(u + 1) * ustep * 4u, v1, scale2);
+                    {   // the next pair's accumulators while this pair's SiLU runs: same tile, or the first pair of the next tile
+                        const bool same = u + 2 < my_units;
+                        const uint32_t tn = same ? tm + (uint32_t)(u + 2) * ustep : tm + (uint32_t)n_tile;
+                        const int un = same ? u + 2 : 0;
+                        if (same || m + 1 < nv) {
+                            tmem_ld16(tn, ra);
+                            if (un + 1 < my_units) tmem_ld16(tn + ustep, rb);
+                        }
+                    }
+                    if (ACT) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v0[i] = silu2_h(v0[i]);
+                    }
+                    epi_store<RES, F32, 16>(v0, unit_base((col0 + (uint32_t)u * ustep) * esize) + moff, 0, f16);
+                    if (two) {
+                        if (ACT) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v1[i] = silu2_h(v1[i]);
+                        }
+                        epi_store<RES, F32, 16>(v1, unit_base((col0 + (uint32_t)(u + 1) * ustep) * esize) + moff, 0, f16);
+                    }
+                }
+                fence_proxy_async();                                                   // generic-proxy slab writes -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0) mbar_arrive_u32(sfull_u32 + (uint32_t)slab * 8u);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (pair) mbar_arrive_cluster(tempty_arrive + as * 8);
+                else mbar_arrive_u32(tempty_u32 + as * 8);
+            }
+            if (warp == 4 && lane == 0) trace(p, 2, it, 2);
+        }
         return;
     }
     // tile walk: a CTA takes rounds blockIdx.x, + gridDim.x, ... of mt tiles; in a CTA pair (mt == 1) the pair takes two
@@ -2420,6 +2499,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // width allows an even split (48, 96, 144, 192 ...); the stem's 16 warps are taken (gather warps).
     p.epi_parts = fused ? 1 : ((!stem || stem2) && (p.n_tile >> 4) % 3 == 0 && env_int("B2D_EPI3", 1) != 0) ? 3 : 2;   // fused: warps 8-15 compute the depthwise stage
     p.exp = env_int("B2D_EXP", 0);
+    p.epi_path = env_int("B2D_EPI_PATH", 2);      // 0: item-list epilogue everywhere, 1: + straight-line path for one- and two-unit warps, 2: + tile-structured path for wide tiles
     p.trace = nullptr;
     if (getenv("B2D_TRACE")) {
         B2D_CUDA(cudaMalloc(&plan->trace_dev, sizeof(long long) * kTraceRoles * kTraceTiles * kTraceEvents));
