@@ -61,6 +61,7 @@ SIGNATURES = {
     "b2d_tta_contrast": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "b2d_colour_convert": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "b2d_set_conf_scale": (c_int, [c_void_p, c_float]),
+    "b2d_segment": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2d_run_op": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "b2d_fused_with_next": (c_int, [c_void_p, c_int]),
     "b2d_run_op_fused": (c_int, [c_void_p, c_int, c_int, c_void_p]),

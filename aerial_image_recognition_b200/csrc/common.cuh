@@ -159,6 +159,7 @@ int candidates_from_rows_launch(const float* rows, int n, int num_rows, int ncol
                                 b2d_det* cand, int* cand_count, int cand_cap, cudaStream_t stream);
 int select_launch(const b2d_det* cand, const int* cand_count, int cand_cap, int n, unsigned long long* keys_scratch,
                   float iou_thr, int top_k, int max_det, b2d_det* out, int* out_count, int cap, cudaStream_t stream);
+int segment_launch(const float* logits, long long npix, int c, int nc, uint8_t* labels, float* conf, cudaStream_t stream);
 int georef_launch(const b2d_det* dets, const int* counts, int n, int cap, int mode, const double* params,
                   b2d_geodet* out, cudaStream_t stream);
 int dedup_launch(const double* x, const double* y, const float* conf, const long long* tiebreak, int count, double thr,

@@ -2316,7 +2316,10 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     const int cout_pad = ceil_div(cout, 16) * 16;
     int split = 1;
     const int n_max = x2 && !dst_f32 ? 128 : 256;      // split outputs are 4 bytes per column: a 256-column staging tile alone would be 128 KB
-    while (cout_pad % split != 0 || (cout_pad / split) % 16 != 0 || cout_pad / split > n_max || (dw && split > 1 && (kmul * cout_pad / split) % 64 != 0)) ++split;
+    while (cout_pad % split != 0 || (cout_pad / split) % 16 != 0 || cout_pad / split > n_max || (dw && split > 1 && (kmul * cout_pad / split) % 64 != 0)) {
+        ++split;
+        B2D_CHECK(split <= cout_pad / 16, "conv_tc: %d output channels cannot be tiled (depthwise layers wider than %d need whole 64-channel chunks)", cout, n_max);
+    }
     p.n_tile = cout_pad / split;
     p.n_tiles_n = split;
     if (dw) p.chunks = ceil_div(kmul * p.n_tile, 64);     // depthwise: storage chunks of one channel tile

@@ -756,6 +756,15 @@ int b2d_postprocess_rows(b2d_engine* e, const float* rows_dev, int n, int num_ro
     return select_launch(e->cand, e->cand_count, e->cand_cap, n, e->keys, iou_thr, top_k, max_det, dets_dev, counts_dev, cap, s);
 }
 
+int b2d_segment(b2d_engine* e, int buf, int n, int nc, uint8_t* labels_dev, float* conf_dev, void* stream) {
+    B2D_CHECK(e && e->finalized && buf >= 0 && buf < (int)e->bufs.size() && labels_dev, "segment: bad arguments");
+    B2D_CHECK(n > 0 && n <= e->max_batch, "segment: n=%d outside [1,%d]", n, e->max_batch);
+    const Buffer& b = e->bufs[buf];
+    B2D_CHECK(b.f32, "segment: buffer %d is not an fp32 logits buffer", buf);
+    B2D_ENTER(e);
+    return segment_launch((const float*)b.ptr, (long long)n * b.h * b.w, b.c, nc, labels_dev, conf_dev, (cudaStream_t)stream);
+}
+
 int b2d_georef(b2d_engine* e, const b2d_det* dets_dev, const int32_t* counts_dev, int n, int cap, int mode, const double* params_dev,
                b2d_geodet* out_dev, void* stream) {
     B2D_CHECK(e && dets_dev && counts_dev && params_dev && out_dev, "georef: bad arguments");

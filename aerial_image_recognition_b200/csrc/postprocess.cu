@@ -595,3 +595,48 @@ int georef_launch(const b2d_det* dets, const int* counts, int n, int cap, int mo
     B2D_LAUNCH_CHECK();
     return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Segmentation head (config C5): per-pixel argmax + softmax probability over nc <= 8 fp32 logits of an NHWC buffer with c
+// channels per pixel (c * 4 bytes a multiple of 16).  HBM-bound: 16 bytes read and 1 (+4) written per pixel.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void segment_kernel(const float4* __restrict__ logits, long long npix, int c4, int nc, uint8_t* __restrict__ labels,
+                               float* __restrict__ conf) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j < c4) {
+                const float4 q = __ldg(logits + i * c4 + j);
+                v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+            }
+        }
+        int best = 0;
+        float m = v[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+            if (k < nc && v[k] > m) { m = v[k]; best = k; }
+        labels[i] = (uint8_t)best;
+        if (conf) {
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < nc) sum += expf(v[k] - m);
+            conf[i] = 1.0f / sum;
+        }
+    }
+}
+}  // namespace
+
+int segment_launch(const float* logits, long long npix, int c, int nc, uint8_t* labels, float* conf, cudaStream_t stream) {
+    B2D_CHECK(c % 4 == 0 && c <= 8 && nc >= 1 && nc <= c, "segment: %d classes in %d channels not supported", nc, c);
+    if (npix <= 0) return 0;
+    const int threads = 256;
+    long long blocks = (npix + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    segment_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const float4*)logits, npix, c / 4, nc, labels, conf);
+    B2D_LAUNCH_CHECK();
+    return 0;
+}

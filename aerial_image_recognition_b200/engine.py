@@ -101,7 +101,7 @@ class Engine:
             else:
                 raise ValueError(op.kind)
             self.op_names.append(op.tag or op.weight)
-        kind = 0 if g.head["kind"] == "v8_dfl" else 1
+        kind = 0 if g.head["kind"] == "v8_dfl" else 1            # "seg" (config C5) has no detection levels: see segment()
         for lv in g.head["levels"]:
             anc = None
             if "anchors" in lv:
@@ -187,6 +187,18 @@ class Engine:
 
     def run_op_fused(self, i: int, n: int) -> None:
         _lib.check(self.lib.b2d_run_op_fused(self.h, i, n, self.stream), f"run_op_fused {i}")
+
+    def segment(self, n: int, with_conf: bool = True):
+        """Per-pixel class of the segmentation stand-in (config C5): argmax over the ``nc`` fp32 logits of the head buffer (first
+        maximum wins, like ``numpy.argmax``) as uint8 ``[n, H, W]`` and, optionally, the softmax probability of that class."""
+        g = self.graph
+        if g.head.get("kind") != "seg":
+            raise ValueError("segment() needs a segmentation graph (arch='xunet')")
+        b = g.bufs[g.head["buf"]]
+        labels = torch.empty((n, b.h, b.w), dtype=torch.uint8, device=self.device)
+        conf = torch.empty((n, b.h, b.w), dtype=torch.float32, device=self.device) if with_conf else None
+        _lib.check(self.lib.b2d_segment(self.h, self.buf_id[g.head["buf"]], n, g.nc, _ptr(labels), _ptr(conf), self.stream), "b2d_segment")
+        return (labels, conf) if with_conf else labels
 
     def decode_rows(self, n: int) -> torch.Tensor:
         rows = torch.empty((n, self.num_rows, 6), dtype=torch.float32, device=self.device)

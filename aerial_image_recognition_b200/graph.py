@@ -7,13 +7,16 @@ The reference never builds a graph itself: it hands an ``.onnx`` file to
 to be stated somewhere; this module states it as data that the C-ABI plan
 builder (``engine.py`` -> ``b2d_plan_*``) consumes one op at a time.
 
-Two architectures are described:
+Three architectures are described:
 
 * ``yolov8m`` with ``nc=2`` and the Ultralytics 8.3.x depthwise cls branch -- the
   "tokyo" checkpoint, recovered from the training log in
   ``x_arch/01_train_tokyo.ipynb:1 (cell 15 output)``.
 * ``yolov7`` canonical deploy graph -- the stand-in for the missing ITCVD
   model named at ``_script/config.py:25``.
+
+* ``xunet`` -- a stated EfficientNet-B0-shaped U-Net stand-in for the "ramp XUnet 256" blob of BASELINE config C5, of which the
+  reference holds only the name (``build_xunet``).
 
 Design rules (B200-first, not ONNX-shaped):
 
@@ -385,9 +388,93 @@ def build_yolov7(nc: int = 1, imgsz: int = 640) -> Graph:
     return g
 
 
+# EfficientNet-B0 stage table (expand ratio, output channels, repeats, stride) with the widths of stages 2-5 rounded up to
+# multiples of 32 (24 -> 32, 40 -> 64, 80 -> 96, 112 -> 128) so that every 6x expanded width is a whole number of the engine's
+# 64-channel K chunks (the depthwise kernel tiles wide layers by chunk).
+XUNET_STAGES = ((1, 16, 1, 1), (6, 32, 2, 2), (6, 64, 2, 2), (6, 96, 3, 2), (6, 128, 3, 1), (6, 192, 4, 2), (6, 320, 1, 1))
+XUNET_DECODER = (256, 128, 64, 32, 16)
+
+
+def build_xunet(nc: int = 4, imgsz: int = 256) -> Graph:
+    """Encoder-decoder segmentation stand-in for BASELINE config C5 ("ramp XUnet 256").
+
+    The reference holds only the blob's name (``.MISSING_LARGE_BLOBS:3``) -- no code, no architecture.
+    [EXT] ramp's model is an EfficientNet-B0-encoder U-Net with a 4-class softmax on 256 x 256 tiles; this graph is a STATED
+    stand-in of that shape built from the ops the engine has, not a reproduction:
+
+    * encoder: stem 3x3 s2 -> 32, then the seven EfficientNet-B0 stages as MBConv blocks (1x1 expand + SiLU, depthwise 3x3 + SiLU,
+      1x1 linear projection, identity shortcut where shapes allow).  Differences from B0, all forced by the op set: stage widths
+      rounded up to multiples of 32, every depthwise kernel is 3x3 (B0 mixes 3x3 and 5x5), a stride-2 block runs its depthwise conv at
+      stride 1 followed by a 2x2 max-pool, no squeeze-and-excitation;
+    * decoder: the segmentation_models U-Net -- five blocks of nearest 2x upsample, concat with the encoder skip (a channel
+      offset, never a copy), two 3x3 convs (SiLU instead of BatchNorm + ReLU) with 256 / 128 / 64 / 32 / 16 channels;
+    * head: 3x3 conv to ``nc`` logits (fp32 NHWC, padded to 4 channels = 16 bytes); argmax / softmax are the segment kernel's.
+    """
+    assert imgsz % 32 == 0
+    g = Graph("xunet", nc, imgsz)
+    g.buf("input", imgsz, imgsz, 4)
+    hw = imgsz // 2
+    # decoder concat buffers [upsampled | skip], allocated first so the encoder can write its skips into them
+    skips_c = tuple(XUNET_STAGES[i][1] for i in (0, 1, 2, 4))     # encoder outputs at imgsz / 2, / 4, / 8, / 16: 16, 32, 64, 128
+    dec_in = (XUNET_STAGES[-1][1],) + XUNET_DECODER[:-1]          # channels arriving from below: 320, 256, 128, 64, 32
+    cats = []
+    for lvl in range(4):                            # lvl 0 = imgsz / 16 ... lvl 3 = imgsz / 2
+        size = imgsz // (16 >> lvl)
+        cats.append(g.buf(f"dec{lvl}.cat", size, size, dec_in[lvl] + skips_c[3 - lvl]))
+    skip_ref = {imgsz // 2: Ref(cats[3], dec_in[3], skips_c[0]), imgsz // 4: Ref(cats[2], dec_in[2], skips_c[1]),
+                imgsz // 8: Ref(cats[1], dec_in[1], skips_c[2]), imgsz // 16: Ref(cats[0], dec_in[0], skips_c[3])}
+    x = Ref(g.buf("enc.stem", hw, hw, 32), 0, 32)
+    g.conv("encoder.stem", Ref("input", 0, 4), x, 3, 2)
+    last_of_size = {1: 0, 2: 1, 3: 2, 5: 4}         # stage index (1-based) whose output is the skip of its resolution
+    for si, (e, c, r, s) in enumerate(XUNET_STAGES, start=1):
+        for bi in range(r):
+            name = f"encoder.s{si}.b{bi}"
+            cin, stride = x.c, (s if bi == 0 else 1)
+            mid = cin * e
+            t = x
+            if e != 1:
+                t = Ref(g.buf(f"{name}.exp", hw, hw, mid), 0, mid)
+                g.conv(f"{name}.expand", x, t, 1, 1)
+            d = Ref(g.buf(f"{name}.dw", hw, hw, mid), 0, mid)
+            g.conv(f"{name}.dw", t, d, 3, 1, groups=mid)
+            if stride == 2:
+                hw //= 2
+                pd = Ref(g.buf(f"{name}.pool", hw, hw, mid), 0, mid)
+                g.maxpool(d, pd, 2, 2, tag=f"{name}.pool")
+                d = pd
+            is_skip = si in last_of_size and bi == r - 1
+            out = skip_ref[hw] if is_skip else Ref(g.buf(f"{name}.out", hw, hw, c), 0, c)
+            g.conv(f"{name}.project", d, out, 1, 1, act=ACT_NONE, res=x if (stride == 1 and cin == c) else None)
+            x = out
+    # decoder
+    for lvl in range(5):
+        name = f"decoder.b{lvl}"
+        cdec = XUNET_DECODER[lvl]
+        hw *= 2
+        if lvl < 4:
+            g.upsample(x, Ref(cats[lvl], 0, x.c), tag=f"{name}.up")
+            src = Ref(cats[lvl], 0, g.bufs[cats[lvl]].c)
+        else:
+            up = g.buf(f"{name}.up", hw, hw, x.c)
+            g.upsample(x, Ref(up, 0, x.c), tag=f"{name}.up")
+            src = Ref(up, 0, x.c)
+        a = Ref(g.buf(f"{name}.c1", hw, hw, cdec), 0, cdec)
+        g.conv(f"{name}.conv1", src, a, 3, 1)
+        b = Ref(g.buf(f"{name}.c2", hw, hw, cdec), 0, cdec)
+        g.conv(f"{name}.conv2", a, b, 3, 1)
+        x = b
+    hc = ((nc + 3) // 4) * 4
+    logits = g.buf("logits", imgsz, imgsz, hc, f32=True)
+    g.conv("segmentation_head", x, Ref(logits, 0, nc), 3, 1, act=ACT_NONE)
+    g.head = {"kind": "seg", "levels": [], "buf": logits, "nc": nc, "c": hc, "anchors_total": 0}
+    return g
+
+
 def build(arch: str, nc: Optional[int] = None, imgsz: int = 640) -> Graph:
     if arch in ("yolov8m", "v8", "yolov8m_tokyo"):
         return build_yolov8m(2 if nc is None else nc, imgsz)
     if arch in ("yolov7", "v7", "yolov7_itcvd"):
         return build_yolov7(1 if nc is None else nc, imgsz)
+    if arch in ("xunet", "ramp_xunet"):
+        return build_xunet(4 if nc is None else nc, 256 if imgsz == 640 else imgsz)
     raise ValueError(f"unknown architecture {arch!r}")

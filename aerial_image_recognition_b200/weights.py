@@ -70,6 +70,8 @@ def _snap(v, bits: int = 12):
 
 
 def _final_layers(graph: Graph):
+    if graph.head["kind"] == "seg":        # segmentation stand-in: the logits layer is scaled like every other conv
+        return set(), set()
     if graph.head["kind"] == "v8_dfl":
         return {f"model.22.cv2.{i}.2" for i in range(3)}, {f"model.22.cv3.{i}.2" for i in range(3)}
     return set(), {f"model.105.m.{i}" for i in range(3)}
@@ -162,10 +164,11 @@ def _calibrate_single_thread(graph: Graph, w: Dict[str, np.ndarray], seed: int) 
     from .graph import build
     from .synth import make_tiles
 
-    g = build(graph.arch, graph.nc, CAL_SIZE)
+    g = build(graph.arch, graph.nc, 256 if graph.arch == "xunet" else CAL_SIZE)
+    cal_size = g.imgsz
     box_final, cls_final = _final_layers(g)
     v8 = g.head["kind"] == "v8_dfl"
-    x = torch.from_numpy(make_tiles(CAL_TILES, CAL_SIZE, seed=seed + 7919).astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+    x = torch.from_numpy(make_tiles(CAL_TILES, cal_size, seed=seed + 7919).astype(np.float32) / 255.0).permute(0, 3, 1, 2)
     bufs = {n: torch.zeros(CAL_TILES, b.c, b.h, b.w) for n, b in g.bufs.items()}
     bufs["input"][:, :3] = x
     inv = lambda op, a: a if op.out_perm is None else a[np.argsort(np.asarray(op.out_perm))]    # buffer order -> model order

@@ -229,6 +229,12 @@ int b2d_colour_convert(b2d_engine* e, const uint8_t* src_dev, long long npix, in
  * b2d_postprocess_rows multiplies the confidence by `scale` (float32) first.  1.0 (the default) is exact.    */
 int b2d_set_conf_scale(b2d_engine* e, float scale);
 
+/* Segmentation head (BASELINE config C5, "ramp XUnet 256": the reference holds only the blob's name,
+ * /root/reference/.MISSING_LARGE_BLOBS:3; [EXT] ramp post-processes its 4-class softmax output with a per-pixel argmax).
+ * Reads the fp32 NHWC logits of planned buffer `buf` ([n, H, W, c], the first `nc` channels), writes the class with the largest
+ * logit (first maximum wins) as uint8 [n, H, W] and, if conf_dev is not NULL, its softmax probability as float32 [n, H, W].  */
+int b2d_segment(b2d_engine* e, int buf, int n, int nc, uint8_t* labels_dev, float* conf_dev, void* stream);
+
 /* Debug / test hooks ---------------------------------------------------------------------- */
 /* Run a single planned op (index in plan order) -- used by the per-layer parity tests.      */
 int b2d_run_op(b2d_engine* e, int op_index, int n, void* stream);

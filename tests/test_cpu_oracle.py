@@ -48,6 +48,26 @@ def test_offset_write_graph_equals_conventional_oracle(arch):
             assert err < (5e-2 if emu else 1e-4), (arch, emu, i, err)
 
 
+def test_xunet_stand_in_graph_equals_conventional_oracle():
+    """Config C5's declared stand-in (graph.build_xunet): the offset-write op list (skips written straight into the decoder's
+    concat buffers, stride 2 as depthwise + max-pool) against the conventionally written NCHW module of oracle/xunet_torch.py."""
+    from oracle.xunet_torch import XUnetOracle
+    g = G.build("xunet", imgsz=64)
+    assert g.head["kind"] == "seg" and g.bufs["logits"].f32 and sum(op.kind == "dwconv" for op in g.ops) == 16
+    full = G.build("xunet")
+    assert full.imgsz == 256 and full.macs_per_tile() == 3124379648 and full.fused_param_count() == 5472372
+    w = W.make_synthetic_weights(g, 1)
+    x = torch.from_numpy(synth.make_tiles(2, 64, 3).astype(np.float32) / 255).permute(0, 3, 1, 2)
+    for emu in (False, True):
+        ref = XUnetOracle(w, emulate_bf16=emu).logits(x)
+        got = run_graph_cpu(g, w, x, emulate_bf16=emu)["logits"][:, :4]
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        assert err < (5e-2 if emu else 1e-4), (emu, err)
+    labels, conf = XUnetOracle(w).forward(x)
+    assert labels.shape == (2, 64, 64) and labels.dtype == torch.uint8 and int(labels.max()) <= 3
+    assert float(conf.min()) >= 0.25 - 1e-6 and float(conf.max()) <= 1.0 + 1e-6          # softmax maximum of four classes
+
+
 def test_weights_are_deterministic_and_bf16_representable():
     g = G.build("yolov8m", imgsz=64)
     a = W.make_synthetic_weights(g, 0)

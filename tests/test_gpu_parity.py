@@ -211,6 +211,42 @@ def test_fused_depthwise_pointwise_kernel_matches_torch(arch, imgsz, n, precisio
     eng.close()
 
 
+# ---- config C5: the segmentation stand-in ("ramp XUnet 256") -------------------------------------------
+def test_xunet_every_planned_op_matches_torch():
+    seen = _check_every_op("xunet", 128, 3)
+    assert any("stem-s2d" in d for d in seen) and any("depthwise" in d for d in seen)
+    _check_every_op("xunet", 256, 2)
+
+
+def test_xunet_logits_and_labels_vs_oracle():
+    """Whole stand-in network at 256 x 256: logits against the oracle with the same storage rounding (kernels' arithmetic) and against
+    the fp32 oracle (storage format's deviation), labels / softmax kernel exact on the engine's own logits, and label agreement."""
+    from oracle.xunet_torch import XUnetOracle
+    n = 3
+    g = G.build("xunet")
+    w = W.make_synthetic_weights(g, 0)
+    tiles = synth.make_tiles(n, 256, 77)
+    x = torch.from_numpy(tiles.astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+    ref16 = XUnetOracle(w, emulate_bf16=True).logits(x)
+    ref32 = XUnetOracle(w, emulate_bf16=False).logits(x)
+    eng = _engine("xunet", weights=w, max_batch=n, graph=g)
+    eng.preprocess(torch.from_numpy(tiles).cuda(), "identity")
+    eng.forward(n)
+    z = eng.buffer("logits", n).float().cpu()[..., :4].permute(0, 3, 1, 2)
+    scale = ref32.abs().max().item()
+    e16, e32 = (z - ref16).abs().max().item() / scale, (z - ref32).abs().max().item() / scale
+    print(f"xunet logits: max |d| / max |z| = {e16:.2e} vs bf16-emulating oracle, {e32:.2e} vs fp32 oracle")
+    assert e16 < 3e-2 and e32 < 6e-2, (e16, e32)
+    labels, conf = eng.segment(n)
+    torch.cuda.synchronize()
+    zz = eng.buffer("logits", n).float()[:n, ..., :4]
+    assert torch.equal(labels.cpu(), zz.argmax(-1).to(torch.uint8).cpu())                # first maximum wins, like argmax
+    assert (conf.cpu() - torch.softmax(zz, -1).amax(-1).cpu()).abs().max().item() < 1e-6
+    agree = (labels.cpu() == ref32.argmax(1).to(torch.uint8)).float().mean().item()
+    assert agree > 0.97, agree
+    eng.close()
+
+
 # ---- whole network vs the oracle -------------------------------------------------------------------
 # Contract (BASELINE.json north_star; the reference's fp32 `session.run`, simple_detector.py:474-481): scores within 1e-3
 # absolute, boxes within 0.5 px, identical keep set away from score ties.  Asserted at 640x640 on C2 tiles (the bench's
