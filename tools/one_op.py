@@ -13,7 +13,7 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--arch", default="yolov8m")
 a = ap.parse_args()
 eng = Engine(a.arch, max_batch=a.batch)
-t = torch.from_numpy(synth.make_tiles(4, 640, 5)).cuda().repeat(a.batch // 4, 1, 1, 1).contiguous()
+t = torch.from_numpy(synth.make_tiles(4, eng.imgsz, 5)).cuda().repeat(a.batch // 4, 1, 1, 1).contiguous()
 eng.preprocess(t, "identity")
 eng.forward(a.batch)
 torch.cuda.synchronize()
