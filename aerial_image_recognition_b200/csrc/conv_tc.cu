@@ -2448,8 +2448,10 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // tile is a large share of a short round's operand traffic), K >= 576 loses 1-6 % (the leader's barrier round trip through
     // the cluster per K step is no longer hidden), so the planner pairs only the short ones.
     const int k_total = cin * p.taps;
-    const bool pair_short_k = k_total < env_int("B2D_PAIRG_MAX_K", 576) || (stride == 2 && cin <= 96);
-    if (p.kind == 0 && !stem && p.n_tile >= env_int("B2D_PAIRG_MIN_N", 128) && p.n_tile % 32 == 0 && p.mt == 1 &&
+    // ... and the 3x3 stride-1 layers that run here because their tiles are not 8 pixels wide (288 -> 288 at 20 x 20, two N = 144
+    // tiles): 41.6 -> 35 us each with the pair's halved weight traffic (gpurun_out/r2bg), N / 2 = 72 rows per CTA.
+    const bool pair_short_k = k_total < env_int("B2D_PAIRG_MAX_K", 576) || (stride == 2 && cin <= 96) || (ksz == 3 && stride == 1 && env_int("B2D_PAIRG_3X3", 1) != 0);
+    if (p.kind == 0 && !stem && p.n_tile >= env_int("B2D_PAIRG_MIN_N", 128) && p.n_tile % 16 == 0 && p.mt == 1 &&
         (pair_short_k || env_int("B2D_PAIR", 1) == 2) &&
         (total_tiles >= 2 * sm_count || env_int("B2D_PAIR", 1) == 2) && env_int("B2D_PAIR", 1) != 0 && env_int("B2D_PAIRG", 1) != 0) {
         p.pair = 1;
