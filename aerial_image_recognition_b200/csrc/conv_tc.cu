@@ -2162,6 +2162,122 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_dwpw_kernel(const __grid_
     epilogue_exit(p, tmem_base, warp);
 }
 
+// ---------------------------------------------------------------------------------------------
+// stride-2 halo kernel: 3x3 stride-2 convs with one K chunk (cin <= 64) on 8-pixel-wide one-image tiles, weights resident.
+// The generic kernel feeds a stride-2 layer nine shifted boxes per tile -- every input pixel 2.25 times -- plus the nine weight
+// boxes of every round, and ncu shows model.1 (48 -> 96 at 160 x 160) pulling 2.6 GB through L2 for 0.31 GB of input: it runs
+// at the 11 TB/s the L2 delivers, not at the HBM rate.  Here a tile fetches each of the four even / odd phase maps ONCE as a
+// (bw + 1) x (bh + 1) halo box (input row 2 oy + kh - 1 is row oy - 1 or oy of the odd-row phase, row oy of the even one) and
+// the nine taps are descriptor offsets into the box of their phase, exactly as in the stride-1 halo kernel; the 9 weight
+// boxes are loaded once per CTA.  Operand traffic per tile: 4 x 153 rows instead of 9 x 128 + 9 weight boxes.
+// Ring of phase boxes in the order P11, P10, P01, P00 (taps: 4, 2, 2, 1); a slot is released as soon as its taps have retired.
+// Warps: 0 phase-box producer | 1 MMA issuer | 2 TMEM allocator, then the one-time weight load | 3 store | 4-15 epilogue.
+// ---------------------------------------------------------------------------------------------
+template <int ACT, int RES, int F32>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_s2halo_kernel(const __grid_constant__ ConvTcParams p, int nimg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const Bars b = carve_bars(smem, p);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.tiles_x * p.tiles_y * nimg;            // bn == 1, mt == 1, one output-channel tile
+    const int nslots = p.stages;
+    const uint32_t box_bytes = p.halo_bytes;
+    const uint32_t smem_a = smem_u32(smem), smem_w = smem_a + (uint32_t)nslots * box_bytes;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
+        tma_prefetch_desc(&p.tmB);
+    }
+    const uint32_t tmem_base = prologue(p, b, warp, lane, 1);
+    const uint32_t full_u32 = smem_u32(b.full), empty_u32 = smem_u32(b.empty);
+    const uint32_t wbar = smem_u32(b.hfull);                          // "weights have landed"
+
+    if (warp == 0) {
+        // ===================== phase-box producer =====================
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(p, t);
+#pragma unroll 1
+            for (int ph = 0; ph < 4; ++ph) {                          // P11, P10, P01, P00
+                mbar_wait_u32(empty_u32 + slot * 8, phase ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = full_u32 + slot * 8;
+                    mbar_expect_tx_u32(fb, p.a_tx_bytes);
+                    tma_load_4d(&p.tmA[3 - ph], fb, smem_a + (uint32_t)slot * box_bytes, 0, tc.x0 - 1, tc.y0 - 1, tc.n0);
+                }
+                if (++slot == nslots) { slot = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== resident weights: nine boxes, once =====================
+        if (elect_one()) {
+            mbar_expect_tx_u32(wbar, 9u * p.b_tx_bytes);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(&p.tmB, wbar, smem_w + (uint32_t)tap * p.b_bytes, tap * 64, 0);
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int slot = 0, it = 0;
+        uint32_t phase = 0;
+        const bool leader = elect_one();
+        const uint32_t hi_b = desc_hi(1024), hi_a = desc_hi((uint32_t)p.halo_w * 128u);
+        const uint32_t a_lo0 = desc_lo(smem_a), b_lo0 = desc_lo(smem_w);
+        const uint32_t box_units = box_bytes >> 4, b_units = p.b_bytes >> 4, row_units = ((uint32_t)p.halo_w * 128u) >> 4;
+        const uint32_t idesc = p.idesc;
+        const int n_tile = p.n_tile;
+        const int kmmas = (p.cin + 15) >> 4;
+        const uint32_t tfull_u32 = smem_u32(b.tfull), tempty_u32 = smem_u32(b.tempty);
+        mbar_wait_u32(wbar, 0);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1;
+            mbar_wait_u32(tempty_u32 + as * 8, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * n_tile);
+            auto tile = [&](auto KM) {
+                bool first = true;
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph) {
+                    // phase ph = (py, px) = (1,1), (1,0), (0,1), (0,0): filter rows kh with (kh + 1) & 1 == py ... i.e. py = 1: kh in {0, 2}, py = 0: kh = 1
+                    const int py = ph < 2 ? 1 : 0, px = (ph & 1) ? 0 : 1;
+                    mbar_wait_u32(full_u32 + slot * 8, phase);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t a_box = a_lo0 + (uint32_t)slot * box_units;
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            if (((kh + 1) & 1) != py) continue;
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+                                if (((kw + 1) & 1) != px) continue;
+                                const uint32_t dy = kh == 0 ? 0u : 1u, dx = kw == 0 ? 0u : 1u;
+                                const uint32_t a_lo = a_box + dy * row_units + dx * 8u;
+                                const uint32_t b_lo = b_lo0 + (uint32_t)(kh * 3 + kw) * b_units;
+#pragma unroll
+                                for (int k = 0; k < decltype(KM)::value; ++k)
+                                    umma_bf16(d_tmem, desc64(hi_a, a_lo + 2 * k), desc64(hi_b, b_lo + 2 * k), idesc, (first && k == 0) ? 0u : 1u);
+                                first = false;
+                            }
+                        }
+                        umma_commit(empty_u32 + slot * 8);
+                        if (ph == 3) umma_commit(tfull_u32 + as * 8);
+                    }
+                    if (++slot == nslots) { slot = 0; phase ^= 1; }
+                }
+            };
+            if (kmmas == 4) tile(KConst<4>{});
+            else if (kmmas == 3) tile(KConst<3>{});
+            else if (kmmas == 2) tile(KConst<2>{});
+            else tile(KConst<1>{});
+        }
+    } else if (warp == 3) {
+        store_loop<RES, F32>(p, total_tiles, b.sfull, b.sempty, b.res, smem + p.stg_off, lane);
+    } else if (warp >= 4) {
+        epilogue_loop<ACT, RES, F32>(p, total_tiles, tmem_base, b.bias_s, b.tfull, b.tempty, b.sfull, b.sempty, b.res, smem + p.stg_off, warp, lane);
+    }
+    epilogue_exit(p, tmem_base, warp);
+}
+
 // ---- host side ----------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -2327,6 +2443,15 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     // tile fits; anything else on the 4-channel input (stride 1, 1x1, odd sizes) keeps the gather kernel
     bool stem2 = stem && ksz == 3 && stride == 2 && src_h % 2 == 0 && src_w % 2 == 0 && env_int("B2D_STEM_S2D", 1) != 0;
     pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn, dw || fused);
+    // 3x3 stride-2 layers with one K chunk: the stride-2 halo kernel when an 8-pixel-wide one-image tile fits (decided below with the
+    // shared-memory budget: its nine weight boxes stay resident)
+    bool s2halo = !stem && !dw && !fused && ksz == 3 && stride == 2 && kin <= 64 && cout_pad <= 256 && env_int("B2D_S2HALO", 1) != 0;
+    if (s2halo) {
+        int w8, h8, n8;
+        pick_tile(dst_w, dst_h, max_batch, &w8, &h8, &n8, true);
+        if (n8 == 1) { p.bw = w8; p.bh = h8; p.bn = n8; }
+        else s2halo = false;
+    }
     if (stem2) {
         int w8, h8, n8;
         pick_tile(dst_w, dst_h, max_batch, &w8, &h8, &n8, true);
@@ -2378,6 +2503,28 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     const int mt_cap = stem ? 4 : 2;
     int best_kind = -1, best_mt = 1, best_stages = 0, best_bufs = 1, best_bres = 0;
     const uint32_t dw_bytes = fused ? (((uint32_t)p.chunks * (9 * 64 + 64) * 4 + 1023u) & ~1023u) : 0u;   // depthwise weights + bias in shared memory
+    if (s2halo) {
+        // resident weights (nine boxes), two staging buffers if they fit, the rest phase-box slots (at least the four of one tile)
+        const uint32_t box = ((uint32_t)((p.bw + 1) * (p.bh + 1)) * 128u + 1023u) & ~1023u;
+        const uint32_t wres = 9u * p.b_bytes;
+        int bufs = env_int("B2D_STG2", 1) != 0 ? 2 : 1;
+        while (bufs >= 1 && avail < wres + (uint32_t)bufs * tile_stg + slab_bars(1, bufs) + 4u * box) --bufs;
+        if (bufs >= 1 && split == 1) {
+            int slots = (int)((avail - wres - (uint32_t)bufs * tile_stg - slab_bars(1, bufs)) / box);
+            if (slots > 8) slots = 8;
+            best_kind = 6; best_mt = 1; best_stages = slots; best_bufs = bufs; best_bres = 1;
+            p.halo_w = p.bw + 1;
+            p.halo_bytes = box;
+        } else {
+            s2halo = false;                      // does not fit: the generic kernel runs the layer (its tile choice is redone here)
+            pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn, false);
+            p.perm = p.bn > 1 ? 1 : 0;
+            p.tiles_x = ceil_div(dst_w, p.bw);
+            p.tiles_y = ceil_div(dst_h, p.bh);
+            p.rcp_tx = rcp32(p.tiles_x);
+            p.rcp_ty = rcp32(p.tiles_y);
+        }
+    }
     if (fused) {
         // two halo buffers, two A tiles, the depthwise constants, one staging buffer (two if they fit), the rest weight stages
         const uint32_t fixed = 2u * p.halo_bytes + 2u * p.a_bytes + dw_bytes;
@@ -2466,11 +2613,13 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         p.stages = st > kMaxStages ? kMaxStages : st;
     }
     if (best_kind == 1 || best_kind == 5) p.a_tx_bytes = halo_rows * 128u;
+    if (best_kind == 6) p.a_tx_bytes = (uint32_t)((p.bw + 1) * (p.bh + 1)) * 128u;
     const uint32_t stg_bytes = (uint32_t)p.stg_bufs * p.mt * tile_stg;
     uint32_t operand_bytes;
     if (p.kind == 0) operand_bytes = (uint32_t)p.stages * ((uint32_t)p.mt * p.a_bytes + p.b_bytes);
     else if (p.kind == 1 || p.kind == 3) operand_bytes = 2u * p.mt * p.halo_bytes + (uint32_t)p.stages * p.b_bytes;
     else if (p.kind == 5) operand_bytes = 2u * p.halo_bytes + 2u * p.a_bytes + (uint32_t)p.stages * p.b_bytes + dw_bytes;
+    else if (p.kind == 6) operand_bytes = (uint32_t)p.stages * p.halo_bytes + 9u * p.b_bytes;
     else operand_bytes = (uint32_t)p.stages * p.mt * p.a_bytes + p.b_bytes;
     p.stg_off = operand_bytes;                                   // 1 KiB aligned: every operand slot is a multiple of 1 KiB
     p.dw_off = operand_bytes - dw_bytes;
@@ -2615,11 +2764,12 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                                (uint32_t)p.bn, perm, 128))
                 return -1;
         } else {
+            const uint32_t hb = p.kind == 6 ? 1u : 0u;           // stride-2 halo kernel: one more column and row per phase box
             for (int py = 0; py < 2; ++py)
                 for (int px = 0; px < 2; ++px) {
                     const __nv_bfloat16* base = src + ((size_t)py * src_w + px) * src_cs_s + src_c0_s;
                     if (encode_act_map(&p.tmA[py * 2 + px], (void*)base, kin, src_w / 2, src_h / 2, max_batch, 2 * pix, 2 * rowb, imgb, 64u,
-                                       (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, perm, 128))
+                                       (uint32_t)p.bw + hb, (uint32_t)p.bh + hb, (uint32_t)p.bn, perm, 128))
                         return -1;
                 }
         }
@@ -2663,6 +2813,7 @@ ConvKernel pick_kernel(int kind, int pair, int act, int res, int out) {
     if (res) return act ? K<1, 1, 0> : K<0, 1, 0>;                         \
     return act ? K<1, 0, 0> : K<0, 0, 0>;
     if (kind == 2) return out == 2 ? (act ? conv_tc_stem_kernel<1, 2> : conv_tc_stem_kernel<0, 2>) : (act ? conv_tc_stem_kernel<1, 0> : conv_tc_stem_kernel<0, 0>);
+    if (kind == 6) { B2D_PICK(conv_tc_s2halo_kernel) }
     if (kind == 5) return act ? conv_tc_dwpw_kernel<1, 0> : conv_tc_dwpw_kernel<0, 0>;
     if (kind == 4) return out == 2 ? (act ? conv_tc_stem2_kernel<1, 2> : conv_tc_stem2_kernel<0, 2>) : (act ? conv_tc_stem2_kernel<1, 0> : conv_tc_stem2_kernel<0, 0>);
     if (kind == 3) return out == 2 ? (act ? conv_tc_dw_kernel<1, 2> : conv_tc_dw_kernel<0, 2>) : (act ? conv_tc_dw_kernel<1, 0> : conv_tc_dw_kernel<0, 0>);
@@ -2753,8 +2904,8 @@ void conv_tc_free(ConvTcPlan* plan) {
 
 int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
-    static const char* kinds[8] = {"", "-halo", "-stem", "-depthwise", "-halo-pair", "-pair", "-stem-s2d", "-dw3x3+pw"};
+    static const char* kinds[9] = {"", "-halo", "-stem", "-depthwise", "-halo-pair", "-pair", "-stem-s2d", "-dw3x3+pw", "-s2halo"};
     return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d%s stg %d tmem %u smem %zu",
-                    kinds[p.pair ? (p.kind == 0 ? 5 : 4) : p.kind == 4 ? 6 : p.kind == 5 ? 7 : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
+                    kinds[p.pair ? (p.kind == 0 ? 5 : 4) : p.kind == 4 ? 6 : p.kind == 5 ? 7 : p.kind == 6 ? 8 : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
                     p.b_res ? " (resident)" : "", p.stg_bufs, p.tmem_cols, plan->smem_bytes);
 }
