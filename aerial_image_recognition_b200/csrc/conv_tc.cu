@@ -1839,12 +1839,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_stem2_kernel(const __grid
     uint8_t* wres = smem + (size_t)p.stages * stage_bytes;               // resident weights [n_tile][64] 16-bit, SWIZZLE_128B
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&p.tmA[0]);
+    const bool s1 = p.stride == 1;                                        // pair-pixel form of the stride-1 stem (see conv_tc_plan)
+    const int wchunks = s1 ? 2 : 1;
+    const uint32_t wchunk_bytes = p.b_bytes / (uint32_t)wchunks;
     {
         const uint4* wg = (const uint4*)p.w_raw;
         const uint32_t wbase = smem_u32(wres);
-        for (int i = threadIdx.x; i < p.n_tile * 8; i += kThreads) {
-            const int n = i >> 3, j = i & 7;
-            sts128(wbase + (uint32_t)n * 128u + (uint32_t)((j ^ (n & 7)) << 4), __ldg(wg + i));
+        const int per_chunk = p.n_tile * 8;
+        for (int i = threadIdx.x; i < per_chunk * wchunks; i += kThreads) {
+            const int ch = i >= per_chunk ? 1 : 0, r = i - ch * per_chunk, n = r >> 3, j = r & 7;
+            sts128(wbase + (uint32_t)ch * wchunk_bytes + (uint32_t)n * 128u + (uint32_t)((j ^ (n & 7)) << 4), __ldg(wg + n * 8 * wchunks + ch * 8 + j));
         }
         fence_proxy_async();
     }
@@ -1866,7 +1870,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_stem2_kernel(const __grid
                 mbar_expect_tx_u32(fb, (uint32_t)nv * p.a_tx_bytes);
                 for (int m = 0; m < nv; ++m) {
                     const TileCoord tc = decode_tile(p, t0 + m);
-                    tma_load_4d(&p.tmA[0], fb, sa + (uint32_t)m * tile_bytes, (tc.x0 - 1) * 8, 0, tc.y0 - 1, tc.n0);
+                    if (s1) tma_load_4d(&p.tmA[0], fb, sa + (uint32_t)m * tile_bytes, (2 * tc.x0 - 2) * 4, tc.y0 - 1, tc.n0, 0);
+                    else tma_load_4d(&p.tmA[0], fb, sa + (uint32_t)m * tile_bytes, (tc.x0 - 1) * 8, 0, tc.y0 - 1, tc.n0);
                 }
             }
             trace(p, 0, pit, 1);
@@ -1877,7 +1882,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_stem2_kernel(const __grid
         int stage = 0, it = 0;
         uint32_t phase = 0;
         const bool leader = elect_one();
-        const uint32_t lbo = (uint32_t)p.halo_w * 16u, sbo = 2u * lbo;
+        const uint32_t lbo = s1 ? 16u : (uint32_t)p.halo_w * 16u, sbo = s1 ? (uint32_t)p.halo_w * 8u : 2u * lbo;
+        const uint32_t wchunk_units = wchunk_bytes >> 4;
         const uint32_t hi_a = desc_hi_ns(sbo), hi_b = desc_hi(1024);
         const uint32_t b_lo = desc_lo(smem_u32(wres));
         const uint32_t idesc = p.idesc;
@@ -1897,10 +1903,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_stem2_kernel(const __grid
                 const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                 for (int m = 0; m < nv; ++m) {
                     const uint32_t a0 = sa + (uint32_t)m * tile_bytes;
+                    if (s1) {            // filter row kh = t >> 1, K half t & 1: input pixels x - 2 .. x + 1 / x + 2 .. x + 5 of box line y + kh
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        umma_bf16(d_tmem + (uint32_t)(m * n_tile), desc64(hi_a, desc_lo_ns(a0 + (uint32_t)(t >> 1) * sbo + (uint32_t)(t & 1) * 16u, lbo)),
-                                  desc64(hi_b, b_lo + 2 * t), idesc, (uint32_t)(t != 0));
+                        for (int t = 0; t < 6; ++t)
+                            umma_bf16(d_tmem + (uint32_t)(m * n_tile), desc64(hi_a, desc_lo_ns(a0 + (uint32_t)(t >> 1) * sbo + (uint32_t)(t & 1) * 32u, lbo)),
+                                      desc64(hi_b, b_lo + (uint32_t)(t >> 2) * wchunk_units + 2 * (t & 3)), idesc, (uint32_t)(t != 0));
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            umma_bf16(d_tmem + (uint32_t)(m * n_tile), desc64(hi_a, desc_lo_ns(a0 + (uint32_t)(t >> 1) * sbo + (uint32_t)(t & 1) * 16u, lbo)),
+                                      desc64(hi_b, b_lo + 2 * t), idesc, (uint32_t)(t != 0));
+                    }
                 }
                 umma_commit(empty_u32 + stage * 8);
                 umma_commit(tfull_u32 + as * 8);
@@ -2419,6 +2432,16 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         B2D_CHECK(src_cs % 8 == 0 && src_c0 % 8 == 0, "conv_tc: source slice must be 16-byte aligned (cs=%d c0=%d)", src_cs, src_c0);
         B2D_CHECK(stride == 1 || (src_h % 2 == 0 && src_w % 2 == 0), "conv_tc: stride-2 input must have even size");
     }
+    // Stride-1 3x3 stem (YOLOv7 model.0) through TMA: two horizontally adjacent output pixels form ONE GEMM row.  For an even x the
+    // inputs of pixels x and x + 1 (input pixels x - 1 .. x + 2) lie inside the 64 contiguous, 16-byte-aligned bytes of input pixels
+    // x - 2 .. x + 5 of each of the three input rows, consecutive pairs are 16 bytes apart -- the no-swizzle K-major layout again
+    // (a core matrix = 8 pairs x 16 B, LBO = 16 B, SBO = one box line) -- and the pair's outputs, 2 x cout channels, are contiguous
+    // in the NHWC output.  So the layer is planned as a conv with N = 2 * cout over an image of W / 2 pair-pixels: six K = 16 MMAs
+    // per tile (3 filter rows x 32 input values) against weights that hold every filter tap twice, once per pixel of the pair.
+    const int cout_real = cout;
+    const bool stem1 = stem && ksz == 3 && stride == 1 && dst_c0 == 0 && dst_cs == cout && dst_w % 2 == 0 && 2 * cout <= (x2 ? 128 : 256) &&
+                       cout % 8 == 0 && env_int("B2D_STEM_S1", 1) != 0;
+    if (stem1) { cout *= 2; dst_cs *= 2; dst_w /= 2; }
     ConvTcParams& p = plan->p;
     plan->sm_count = sm_count;
     const int kmul = (x2 && !stem) ? 2 : 1;        // storage channels per real input channel
@@ -2441,7 +2464,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     if (dw) p.chunks = ceil_div(kmul * p.n_tile, 64);     // depthwise: storage chunks of one channel tile
     // the stride-2 stem is fed by TMA through a space-to-depth view (conv_tc_stem2_kernel) when an 8-pixel-wide one-image
     // tile fits; anything else on the 4-channel input (stride 1, 1x1, odd sizes) keeps the gather kernel
-    bool stem2 = stem && ksz == 3 && stride == 2 && src_h % 2 == 0 && src_w % 2 == 0 && env_int("B2D_STEM_S2D", 1) != 0;
+    bool stem2 = stem1 || (stem && ksz == 3 && stride == 2 && src_h % 2 == 0 && src_w % 2 == 0 && env_int("B2D_STEM_S2D", 1) != 0);
     pick_tile(dst_w, dst_h, max_batch, &p.bw, &p.bh, &p.bn, dw || fused);
     // 3x3 stride-2 layers with one K chunk: the stride-2 halo kernel when an 8-pixel-wide one-image tile fits (decided below with the
     // shared-memory budget: its nine weight boxes stay resident)
@@ -2456,7 +2479,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
         int w8, h8, n8;
         pick_tile(dst_w, dst_h, max_batch, &w8, &h8, &n8, true);
         if (n8 == 1) { p.bw = w8; p.bh = h8; p.bn = n8; }
-        else stem2 = false;
+        else { B2D_CHECK(!stem1, "conv_tc: the stride-1 stem needs a one-image tile"); stem2 = false; }
     }
     p.perm = p.bn > 1 ? 1 : 0;
     p.tiles_x = ceil_div(dst_w, p.bw);
@@ -2468,13 +2491,19 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
     const int total_tiles = p.tiles_x * p.tiles_y * ceil_div(max_batch, p.bn) * split;
     p.a_bytes = kTileM * 64 * 2;
     p.a_tx_bytes = p.a_bytes;
-    if (stem2) {        // one tile's box: (bh + 1) block rows x 2 row phases x (bw + 1) block columns x 16 bytes
+    if (stem1) {        // one tile's box: (bh + 2) input rows x (2 bw + 6) pixels x 8 bytes (the last pair's K = 32 run ends at pixel
+                        // x + 5: its two zero-weighted pixels must still be finite numbers, so they are fetched); two 64-value weight chunks
+        p.halo_w = 2 * p.bw + 6;
+        p.a_tx_bytes = (uint32_t)((p.bh + 2) * p.halo_w * 8);
+        p.a_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+    } else if (stem2) {        // one tile's box: (bh + 1) block rows x 2 row phases x (bw + 1) block columns x 16 bytes
         p.halo_w = p.bw + 1;
         p.a_tx_bytes = (uint32_t)((p.bh + 1) * 2 * (p.bw + 1) * 16);
         p.a_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
     }
     p.b_tx_bytes = dw ? 144 * 128 : p.n_tile * 64 * 2;      // depthwise: [9 taps][16 rows] x 128 B per 64-channel chunk
     p.b_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
+    if (stem1) p.b_bytes *= 2;                              // two 64-value weight chunks per output row
     const int esize = (dst_f32 || x2) ? 4 : 2;     // bytes per output column in the destination buffer
     const int esize_r = x2 ? 4 : 2;                // ... and per residual column
     B2D_CHECK(!(dst_f32 && res), "conv_tc: residual with fp32 output is not supported");
@@ -2669,7 +2698,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
 
     // ---- weights: fp32 [cout][cin][k][k] -> bf16 [cout_pad][kh][kw][cin_pad] (zero padded) ----
     const int cin_pad = p.chunks * 64;
-    const size_t ktot = stem ? 64 : (size_t)p.taps * cin_pad;     // stem: k = tap * 4 + c, one 128-byte row per output channel
+    const size_t ktot = stem1 ? 128 : stem ? 64 : (size_t)p.taps * cin_pad;     // stem: k = tap * 4 + c, one 128-byte row per output channel
     const int dw_chunks = p.chunks * split;                       // depthwise: 64-channel chunks over all channels
     std::vector<uint16_t> wp(dw ? (size_t)dw_chunks * 9 * 16 * 64 : (size_t)cout_pad * ktot, 0);
     if (dw && x2) {
@@ -2692,11 +2721,15 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                 wp[row * 64 + g * 16 + d] = f16 ? f2h(w_host[(size_t)c * 9 + t]) : f2bf(w_host[(size_t)c * 9 + t]);
             }
     } else {
-        for (int o = 0; o < cout; ++o)
+        for (int o = 0; o < cout_real; ++o)
             for (int c = 0; c < cin; ++c)
                 for (int t = 0; t < p.taps; ++t) {
                     const uint16_t v = f16 ? f2h(w_host[((size_t)o * cin + c) * p.taps + t]) : f2bf(w_host[((size_t)o * cin + c) * p.taps + t]);
-                    if (stem2) {      // tap (kh, kw) -> block (di, dj), phase (rp, px): k = (di * 2 + dj) * 16 + rp * 8 + px * 4 + c
+                    if (stem1) {      // row half * cout + o (half = pixel of the pair), k = kh * 32 + (kw + 1 + half) * 4 + c
+                        const int kh = t / 3, kw = t % 3;
+                        for (int half = 0; half < 2; ++half)
+                            wp[(size_t)(half * cout_real + o) * ktot + (size_t)(kh * 32 + (kw + 1 + half) * 4 + c)] = v;
+                    } else if (stem2) {      // tap (kh, kw) -> block (di, dj), phase (rp, px): k = (di * 2 + dj) * 16 + rp * 8 + px * 4 + c
                         const int kh = t / 3, kw = t % 3;
                         const int di = kh == 0 ? 0 : 1, rp = kh == 1 ? 0 : 1, dj = kw == 0 ? 0 : 1, px = kw == 1 ? 0 : 1;
                         wp[(size_t)o * ktot + (size_t)((di * 2 + dj) * 16 + rp * 8 + px * 4 + c)] = v;
@@ -2712,7 +2745,7 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                 }
     }
     std::vector<float> bp(cout_pad, 0.f);
-    for (int o = 0; o < cout; ++o) bp[o] = b_host ? b_host[o] : 0.f;
+    for (int o = 0; o < cout; ++o) bp[o] = b_host ? b_host[o % cout_real] : 0.f;      // stride-1 stem: both pixels of a pair
     B2D_CUDA(cudaMalloc(&plan->w_dev, wp.size() * 2));
     B2D_CUDA(cudaMemcpy(plan->w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
     B2D_CUDA(cudaMalloc(&plan->bias_dev, bp.size() * 4));
@@ -2774,7 +2807,12 @@ int conv_tc_plan(ConvTcPlan* plan, int sm_count, int max_batch, const __nv_bfloa
                 }
         }
     }
-    if (stem2) {        // (8-byte pixels of one input row as 16-bit elements | row phase | block row | image), un-swizzled box
+    if (stem1) {        // (8-byte pixels of an input row as 16-bit elements | row | image | 1), un-swizzled box of (bh + 2) rows
+        uint64_t dims[4] = {(uint64_t)src_w * 4, (uint64_t)src_h, (uint64_t)max_batch, 1u};
+        uint64_t str[3] = {(uint64_t)src_w * 8, (uint64_t)src_h * src_w * 8, (uint64_t)src_h * src_w * 8 * (uint64_t)max_batch};
+        uint32_t box[4] = {(uint32_t)p.halo_w * 4u, (uint32_t)(p.bh + 2), 1u, 1u};
+        if (encode_map(&p.tmA[0], (void*)src, 4, dims, str, box, 0)) return -1;
+    } else if (stem2) {        // (8-byte pixels of one input row as 16-bit elements | row phase | block row | image), un-swizzled box
         uint64_t dims[4] = {(uint64_t)src_w * 4, 2u, (uint64_t)src_h / 2, (uint64_t)max_batch};
         uint64_t str[3] = {(uint64_t)src_w * 8, (uint64_t)src_w * 16, (uint64_t)src_h * src_w * 8};
         uint32_t box[4] = {(uint32_t)(p.bw + 1) * 8u, 2u, (uint32_t)(p.bh + 1), 1u};
@@ -2906,6 +2944,6 @@ int conv_tc_describe(const ConvTcPlan* plan, char* buf, int buflen) {
     const ConvTcParams& p = plan->p;
     static const char* kinds[9] = {"", "-halo", "-stem", "-depthwise", "-halo-pair", "-pair", "-stem-s2d", "-dw3x3+pw", "-s2halo"};
     return snprintf(buf, buflen, "tcgen05%s conv k%d s%d cin %d cout %d -> %dx%d | tile %dx%dx%d x%d n_tile %d x%d stages %d%s stg %d tmem %u smem %zu",
-                    kinds[p.pair ? (p.kind == 0 ? 5 : 4) : p.kind == 4 ? 6 : p.kind == 5 ? 7 : p.kind == 6 ? 8 : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
+                    p.kind == 4 && p.stride == 1 ? "-stem-pairs" : kinds[p.pair ? (p.kind == 0 ? 5 : 4) : p.kind == 4 ? 6 : p.kind == 5 ? 7 : p.kind == 6 ? 8 : p.kind], p.ksz, p.stride, (p.x2 && p.kind != 2) ? p.cin / 2 : p.cin, p.cout, p.H, p.W, p.bw, p.bh, p.bn, p.mt, p.n_tile, p.n_tiles_n, p.stages,
                     p.b_res ? " (resident)" : "", p.stg_bufs, p.tmem_cols, plan->smem_bytes);
 }
