@@ -529,7 +529,17 @@ __device__ __forceinline__ void store_loop(const ConvTcParams& p, int total_tile
             if (rd < rounds && m < valid_tiles(rd)) tile_io(first_tile(rd) + m, c, true);
         }
     }
+    // Layers without a residual keep one store group in flight: tile c's stores are issued before the lane waits for tile c - 1's
+    // slab to be read, so the read latency of the TMA unit is not paid once per tile (stem 180 -> 147 us).
     int it = 0;
+    int pend_slab = -1, pend_next = -1;                                        // slab whose stores are in flight; residual tile to load into it (or -1)
+    auto release = [&](bool last) {
+        if (pend_slab < 0) return;
+        if (!no_store) { if (last) tma_store_wait_read0(); else tma_store_wait_read1(); }      // the TMA unit has read the pending slab
+        mbar_arrive_u32(sempty_u32 + (uint32_t)pend_slab * 8u);
+        if (RES && pend_next >= 0) tile_io(pend_next, pend_slab, true);
+        pend_slab = -1;
+    };
     for (int rd = rd0; rd < rounds; rd += rd_step, ++it) {
         const int t0 = first_tile(rd), nv = valid_tiles(rd);
         const int rdn = rd + g.nb * rd_step;                                   // the round whose tile m reuses tile m's slab
@@ -541,12 +551,19 @@ __device__ __forceinline__ void store_loop(const ConvTcParams& p, int total_tile
             if (!no_store) {
                 tile_io(t0 + m, slab, false);
                 tma_store_commit();
-                tma_store_wait_read0();                  // the TMA unit has read the slab
             }
-            mbar_arrive_u32(sempty_u32 + (uint32_t)slab * 8u);
-            if (RES && m < nvn) tile_io(first_tile(rdn) + m, slab, true);
+            if (RES || S < 4) {                          // residual layers: the slab's next residual must start loading as early as possible
+                pend_slab = slab;                        // (measured: +11 us on the 96-channel residual layers when it waits a tile longer);
+                pend_next = (RES && m < nvn) ? first_tile(rdn) + m : -1;       // with fewer than four slabs a pending one starves the epilogue (+2-4 us)
+                release(true);
+            } else {
+                release(false);
+                pend_slab = slab;
+                pend_next = -1;
+            }
         }
     }
+    release(true);
     tma_store_wait_all();
 }
 
