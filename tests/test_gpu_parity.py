@@ -98,7 +98,8 @@ def test_session_input_path_equals_preprocess_path(eng640, tiles4):
 
 
 # ---- K2/K3: every op of the graph against torch on the engine's own inputs -------------------------
-@pytest.mark.parametrize("arch,imgsz,n", [("yolov8m", 128, 3), ("yolov8m", 320, 2), ("yolov7", 128, 2)])
+@pytest.mark.parametrize("arch,imgsz,n", [("yolov8m", 128, 3), ("yolov8m", 320, 2), ("yolov7", 128, 2),
+                                          ("yolov8m", 224, 3), ("yolov7", 160, 2), ("xunet", 96, 2)])     # the last three: partial tiles in x and y
 def test_every_planned_op_matches_torch(arch, imgsz, n):
     _check_every_op(arch, imgsz, n)
 
