@@ -750,7 +750,7 @@ def main():
                     "plugin_api": plugin},
             "gpu_launches": K * (eng.num_kernels + 5),     # per timed K-step run     # graph kernels + preprocess, decode/compact, key sort, select/NMS, georef
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_* family (tcgen05 implicit-GEMM conv+bias+SiLU: generic, halo, halo-pair, stem, depthwise)",
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_* family (tcgen05 implicit-GEMM conv+bias+SiLU: generic, pair, halo, halo-pair, stride-2 halo, TMA-fed stem, depthwise, fused depthwise + pointwise)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "frac_of_burst_peak": achieved / peak_burst, "burst_peak": peak_burst,
                          "traffic": traffic, "traffic_source": traffic_meta,
