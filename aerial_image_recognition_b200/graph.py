@@ -226,7 +226,9 @@ def build_yolov8m(nc: int = 2, imgsz: int = 640) -> Graph:
     levels = []
     c2, c3 = 64, 192
     for i, (feat, ch, hw, stride) in enumerate(((x15, 192, s3, 8), (x18, 384, s4, 16), (x21, 576, s5, 32))):
-        hc = 64 + ((nc + 3) // 4) * 4            # box 64 | cls nc, padded to 16 B
+        # box 64 | cls nc | padding up to a multiple of 32 fp32 channels: a pixel is then a whole number of 128-byte lines and the box
+        # branch's 256-byte rows start on a line (with 68 channels = 272 bytes every store straddled three lines: cv2.0.2 50 -> 35 us)
+        hc = ((64 + nc + 31) // 32) * 32
         out = g.buf(f"head{i}", hw, hw, hc, f32=True)
         a = g.buf(f"h{i}.b0", hw, hw, c2)
         b = g.buf(f"h{i}.b1", hw, hw, c2)
