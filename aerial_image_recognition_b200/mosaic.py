@@ -217,9 +217,10 @@ class MosaicDetector:
             return time.perf_counter()
         return t0
 
-    def seam_split(self, x, y, conf, cls, wid, slot, py, rank: int, covers):
+    def seam_split(self, x, y, conf, cls, wid, slot, py, rank: int, covers, pack: bool = True):
         """Dedup everything that cannot interact with another shard; return (local survivors,
-        records [k, RECORD_WORDS] float64 on device that must be exchanged)."""
+        records [k, RECORD_WORDS] float64 on device that must be exchanged).  ``pack=False`` leaves the local survivors on the
+        device as the column tuple ``_pack`` takes (``dedup`` packs them together with the seam survivors: one read-back)."""
         import torch
         eng = self.eng
         import time
@@ -237,24 +238,26 @@ class MosaicDetector:
         lkeep = eng.dedup(lx, ly, lc, self.dedup_thr, True, tiebreak=lk)
         t0 = self._tick("local_dedup", t0)
         kept = li[lkeep.bool().nonzero().squeeze(1)]
-        local = self._pack(x[kept], y[kept], conf[kept], cls[kept], wid[kept], slot[kept])
+        cols = (x[kept], y[kept], conf[kept], cls[kept], wid[kept], slot[kept])
+        local = self._pack(*cols) if pack else cols
         rec = pack_records(x[si], y[si], conf[si], cls[si], key[si])
         self._tick("pack", t0)
         return local, rec
 
-    def seam_merge(self, parts, origin: np.ndarray, rank: int) -> np.ndarray:
+    def seam_merge(self, parts, origin: np.ndarray, rank: int, pack: bool = True):
         """The identical greedy pass every rank runs on the gathered seam records; returns the
-        survivors that originated on ``rank``."""
+        survivors that originated on ``rank`` (``pack=False``: as device columns, see ``seam_split``)."""
         import torch
         eng = self.eng
         allrec = torch.cat([torch.as_tensor(p).to(eng.device) for p in parts]) if parts else torch.zeros((0, RECORD_WORDS), dtype=torch.int64, device=eng.device)
         self.last_seam_records = int(allrec.shape[0])
         if not allrec.shape[0]:
-            return np.zeros(0, self.OUT_DTYPE)
+            return np.zeros(0, self.OUT_DTYPE) if pack else None
         gx, gy, gc, gcls, gk = unpack_records(allrec)
         gkeep = eng.dedup(gx, gy, gc, self.dedup_thr, True, tiebreak=gk).bool()
         mine = (gkeep & torch.from_numpy(origin == rank).to(eng.device)).nonzero().squeeze(1)
-        return self._pack(gx[mine], gy[mine], gc[mine], gcls[mine], gk[mine] >> 16, (gk[mine] & 0xFFFF).int())
+        cols = (gx[mine], gy[mine], gc[mine], gcls[mine], gk[mine] >> 16, (gk[mine] & 0xFFFF).int())
+        return self._pack(*cols) if pack else cols
 
     def dedup(self, x, y, conf, cls, wid, slot, py, rank: int, world: int, covers, group=None):
         import torch
@@ -263,7 +266,7 @@ class MosaicDetector:
         if world == 1:
             keep = eng.dedup(x, y, conf, self.dedup_thr, True, tiebreak=self.order_key(wid, slot)).bool().nonzero().squeeze(1)
             return self._pack(x[keep], y[keep], conf[keep], cls[keep], wid[keep], slot[keep])
-        local, rec = self.seam_split(x, y, conf, cls, wid, slot, py, rank, covers)
+        local, rec = self.seam_split(x, y, conf, cls, wid, slot, py, rank, covers, pack=False)     # survivors stay on the device ...
 
         # seam part: NCCL all-gather over NVLink -- the counts as one [world] tensor read back once, then the padded payload
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -286,10 +289,15 @@ class MosaicDetector:
         t0 = time.perf_counter()
         parts, origin = exchange_seam(rec, world, gather_counts, gather_padded)
         t0 = self._tick("exchange", t0)
-        merged = self.seam_merge(parts, origin, rank)
-        self._tick("merge", t0)
-        self.last_allgather_us = ev[0].elapsed_time(ev[1]) * 1e3      # both events have completed: seam_merge read its result back
-        return np.concatenate([local, merged])
+        merged = self.seam_merge(parts, origin, rank, pack=False)
+        t0 = self._tick("merge", t0)
+        # ... and come back in ONE packed read-back (local survivors first, then this rank's seam survivors): the exchange and the merge
+        # are queued behind the local dedup without a host synchronisation in between
+        cols = local if merged is None else tuple(torch.cat([a, b.to(a.dtype)]) for a, b in zip(local, merged))
+        out = self._pack(*cols)
+        self._tick("read_back", t0)
+        self.last_allgather_us = ev[0].elapsed_time(ev[1]) * 1e3      # both events have completed: the read-back synchronised the stream
+        return out
 
     def _pack(self, x, y, conf, cls, wid, slot) -> np.ndarray:
         """Device columns -> one structured host array, through ONE device->host copy of 32-byte records."""
