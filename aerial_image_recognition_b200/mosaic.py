@@ -289,14 +289,22 @@ class MosaicDetector:
         t0 = time.perf_counter()
         parts, origin = exchange_seam(rec, world, gather_counts, gather_padded)
         t0 = self._tick("exchange", t0)
+        out = self.finish(local, parts, origin, rank)
+        self.last_allgather_us = ev[0].elapsed_time(ev[1]) * 1e3      # both events have completed: the read-back synchronised the stream
+        return out
+
+    def finish(self, local, parts, origin: np.ndarray, rank: int) -> np.ndarray:
+        """Second half of the sharded dedup: ``local`` = the device columns ``seam_split(..., pack=False)`` left, ``parts`` /
+        ``origin`` = the gathered seam records.  The merge is queued behind the local dedup without a host synchronisation in
+        between, and everything comes back in ONE packed read-back (local survivors first, then this rank's seam survivors)."""
+        import time
+        import torch
+        t0 = time.perf_counter()
         merged = self.seam_merge(parts, origin, rank, pack=False)
         t0 = self._tick("merge", t0)
-        # ... and come back in ONE packed read-back (local survivors first, then this rank's seam survivors): the exchange and the merge
-        # are queued behind the local dedup without a host synchronisation in between
         cols = local if merged is None else tuple(torch.cat([a, b.to(a.dtype)]) for a, b in zip(local, merged))
         out = self._pack(*cols)
         self._tick("read_back", t0)
-        self.last_allgather_us = ev[0].elapsed_time(ev[1]) * 1e3      # both events have completed: the read-back synchronised the stream
         return out
 
     def _pack(self, x, y, conf, cls, wid, slot) -> np.ndarray:

@@ -144,3 +144,29 @@ def test_shapefile_round_trip_and_header_bounds(tmp_path):
     assert U.read_shapefile(str(tmp_path / "fc")) == back
     U.write_shapefile([], str(tmp_path / "empty"))
     assert U.read_shapefile(str(tmp_path / "empty")) == []
+
+
+def test_rgbx_view_of_a_pil_image_is_its_pixels_without_a_copy(tmp_path):
+    """``GPUHandler.process_batch`` stages PIL RGB tiles as Pillow's own 4-byte pixels (gpu_handler._rgbx_view): the view
+    must hold exactly ``np.asarray(img)`` in its first three bytes, for images built in memory and for lazily opened
+    files, and must decline (None -> the np.asarray route) for every other mode."""
+    from PIL import Image
+    from aerial_image_recognition_b200.gpu_handler import _rgbx_view, _as_u8_hwc, _shape_of
+    rng = np.random.default_rng(3)
+    for h, w in ((640, 640), (864, 864), (333, 641), (1, 1)):
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        img = Image.fromarray(a)
+        v = _rgbx_view(img)
+        assert v is not None and v.shape == (h, w, 4) and v.dtype == np.uint8
+        assert np.array_equal(v[..., :3], a) and _shape_of(img) == (h, w, 3)
+    lazy = Image.open(os.path.join(os.path.dirname(__file__), "golden", "test_tile_864.png"))     # not loaded yet
+    v = _rgbx_view(lazy) if lazy.mode == "RGB" else None
+    if lazy.mode == "RGB":
+        assert np.array_equal(v[..., :3], np.asarray(lazy))
+    for mode in ("L", "RGBA", "P", "I;16", "F"):
+        assert _rgbx_view(Image.new(mode, (8, 8))) is None
+    assert _rgbx_view(rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)) is None            # arrays are not PIL images
+    big = Image.new("RGB", (5000, 4000), (1, 2, 3))                                       # 80 MB: several storage blocks
+    v = _rgbx_view(big)
+    assert v is None or (v.shape == (4000, 5000, 4) and (v[..., :3] == (1, 2, 3)).all())
+    assert np.array_equal(_as_u8_hwc(big)[0, 0], (1, 2, 3))

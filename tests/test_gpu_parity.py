@@ -575,16 +575,20 @@ def test_sharded_mosaic_equals_single_rank(eng640):
     key = lambda a: np.sort(a, order=["window", "slot"])
     for world in (2, 3):
         covers = [M.shard_windows(H, W_, r, world)[2] for r in range(world)]
-        locals_, recs = [], []
+        locals_, recs, cols_ = [], [], []
         for r in range(world):
             wins, ids, _ = M.shard_windows(H, W_, r, world)
             lo, hi = covers[r]
             band = mosaic[lo:hi].contiguous()                      # each rank holds only its band (+ overlap)
             out = det.detect_windows(band, wins, ids, y_offset=lo)
             loc, rec = det.seam_split(*out, r, covers)
-            locals_.append(loc); recs.append(rec)
+            cols, rec2 = det.seam_split(*out, r, covers, pack=False)   # the form `dedup` uses under torchrun: columns stay on the device
+            assert torch.equal(rec, rec2)
+            locals_.append(loc); recs.append(rec); cols_.append(cols)
         origin = np.concatenate([np.full(len(rc), r, np.int64) for r, rc in enumerate(recs)])
         merged = [np.concatenate([locals_[r], det.seam_merge(recs, origin, r)]) for r in range(world)]
+        for r in range(world):                                      # ... and its one packed read-back gives the same records
+            assert np.array_equal(det.finish(cols_[r], recs, origin, r), merged[r])
         union = np.concatenate(merged)
         assert len(union) == len(single)
         a, b = key(union), key(single)
