@@ -256,7 +256,8 @@ int closure_launch(const double* x, const double* y, int count, double thr, int 
     const int blocks = (count + 255) / 256;
     closure_init_kernel<<<blocks, 256, 0, stream>>>(label, comp, count);
     int h_flag[2] = {1, 0};
-    for (int round = 0; h_flag[0] != 0; ++round) {
+    int closure_rounds = 0;
+    for (int round = 0; h_flag[0] != 0; ++round, ++closure_rounds) {
         B2D_CUDA(cudaMemsetAsync(t.flag, 0, sizeof(int), stream));
         closure_hook_kernel<<<blocks, 256, 0, stream>>>(t, x, y, count, inv_cell, thr * thr, inclusive, label);
         closure_jump_kernel<<<blocks, 256, 0, stream>>>(label, count);
@@ -266,6 +267,7 @@ int closure_launch(const double* x, const double* y, int count, double thr, int 
         B2D_CHECK(h_flag[1] == 0, "closure: a coordinate / thr is outside the grid's +-2^31 cells (or not finite)");
         B2D_CHECK(round <= count + 8, "closure: did not converge");
     }
+    if (getenv("B2D_VERBOSE")) fprintf(stderr, "b2det: seam closure of %d points: %d rounds\n", count, closure_rounds);
     closure_mark_kernel<<<blocks, 256, 0, stream>>>(label, flag, comp, count);
     closure_apply_kernel<<<blocks, 256, 0, stream>>>(label, comp, flag, count);
     B2D_LAUNCH_CHECK();
@@ -283,7 +285,8 @@ int dedup_launch(const double* x, const double* y, const float* conf, const long
     // Rounds: every round decides at least the highest-priority undecided point, so the loop ends;
     // real data needs a handful of rounds.  The host reads the undecided count back every 4 rounds.
     int h_flag[2] = {1, 0};
-    for (int round = 0; h_flag[0] != 0; ++round) {
+    int rounds_run = 0;
+    for (int round = 0; h_flag[0] != 0; ++round, ++rounds_run) {
         B2D_CUDA(cudaMemsetAsync(t.flag, 0, sizeof(int), stream));
         dedup_round_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, x, y, conf, tiebreak, count, inv_cell, thr2, inclusive);
         B2D_LAUNCH_CHECK();
@@ -296,6 +299,7 @@ int dedup_launch(const double* x, const double* y, const float* conf, const long
     }
     dedup_finish_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(t, count, keep);
     B2D_LAUNCH_CHECK();
+    if (getenv("B2D_VERBOSE")) fprintf(stderr, "b2det: dedup of %d points: %d rounds\n", count, rounds_run);
     return 0;
 }
 

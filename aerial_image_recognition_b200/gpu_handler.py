@@ -16,6 +16,7 @@ front of the C-ABI engine instead of an onnxruntime session:
 from __future__ import annotations
 
 import gc
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -61,6 +62,58 @@ def _shape_of(img):
     return (a.shape[0], a.shape[1], 3)
 
 
+class TileStager:
+    """Host images -> one device batch ``uint8 [n, h, w, 3]`` through reused page-locked buffers (no ``np.stack`` +
+    ``pin_memory`` per batch: allocating pinned memory costs more than the copy).  PIL RGB images are staged as the 4-byte
+    pixels Pillow holds (``_rgbx_view``: one memcpy per image, no re-packing on the host) and the pad byte is dropped on the
+    device; anything else goes through ``np.asarray`` into a 3-byte buffer.  Two buffers per shape alternate, each guarded by
+    the event of the copy that last read it, so the host fills batch i+1 while batch i is in flight."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self._stage = {}            # (h, w, channels) -> two pinned uint8 [max_batch, h, w, channels] buffers
+        self._free = {}             # same key -> the events after which they may be overwritten
+        self._turn = 0
+        self.threads = max(1, int(os.environ.get("B2D_STAGE_THREADS", "4")))      # host threads copying images into the pinned buffer
+        self._pool = None
+
+    def _executor(self):
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(self.threads, thread_name_prefix="b2d-stage")
+        return self._pool
+
+    def upload(self, imgs, shape) -> torch.Tensor:
+        eng = self.engine
+        n = len(imgs)
+        assert 0 < n <= eng.max_batch
+        views = [_rgbx_view(im) for im in imgs]
+        rgbx = all(v is not None for v in views)
+        key = (int(shape[0]), int(shape[1]), 4 if rgbx else 3)
+        if key not in self._stage:
+            self._stage[key] = [torch.empty((eng.max_batch,) + key, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._free[key] = [None, None]
+        slot = self._turn % 2
+        self._turn += 1
+        host, free = self._stage[key][slot], self._free[key]
+        if free[slot] is not None:
+            free[slot].synchronize()                    # the copy that last read this buffer has finished
+        hv = host.numpy()
+        if rgbx and n >= 2 * self.threads and self.threads > 1:
+            # plain memcpys of 1.6 MB each: NumPy releases the GIL for them, so a few threads copy at several times one core's rate
+            def copy(t):
+                for k in range(t, n, self.threads):
+                    hv[k] = views[k]
+            list(self._executor().map(copy, range(self.threads)))
+        else:
+            for k in range(n):
+                hv[k] = views[k] if rgbx else _as_u8_hwc(imgs[k])
+        tiles = host[:n].to(eng.device, non_blocking=True)
+        free[slot] = torch.cuda.Event()
+        free[slot].record()
+        return tiles[..., :3].contiguous() if rgbx else tiles
+
+
 class GPUHandler:
     def __init__(self, model_path, max_gpu_memory=5.0, confidence_threshold=0.3, output_dir=None, *,
                  arch: Optional[str] = None, weights=None, max_batch: int = 64,
@@ -79,18 +132,8 @@ class GPUHandler:
         weights = resolve_weights(model_path, arch, weights)     # FileNotFoundError unless weights="synthetic" (session.py)
         self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, precision=precision)
         self.session = InferenceSession(engine=self.engine)
-        self._stage = {}                    # (h, w) -> two pinned uint8 [max_batch, h, w, 3] staging buffers, reused across calls
-        self._stage_free = {}
-
-    def _staging(self, shape, k, channels=3):
-        """Pinned host buffer ``k % 2`` for tiles of ``shape`` plus the event after which it may be overwritten: images are
-        copied straight into page-locked memory (no ``np.stack`` + ``pin_memory`` per batch), and two buffers let the host
-        fill batch i+1 while batch i is still in flight.  ``channels=4`` is the buffer for Pillow's own RGBX pixels."""
-        key = tuple(shape[:2]) + (channels,)
-        if key not in self._stage:
-            self._stage[key] = [torch.empty((self.engine.max_batch, shape[0], shape[1], channels), dtype=torch.uint8).pin_memory() for _ in range(2)]
-            self._stage_free[key] = [None, None]
-        return self._stage[key][k % 2], self._stage_free[key], k % 2
+        self._stager = TileStager(self.engine)      # pinned input staging, reused across calls
+        self._stage = {}                            # ("out", cap) -> two pinned result buffers
 
     def _result_staging(self, cap, k):
         key = ("out", cap)
@@ -152,21 +195,7 @@ class GPUHandler:
             while j < len(items) and j - i < eng.max_batch and shapes[j] == shape:
                 j += 1
             n = j - i
-            # PIL RGB images are staged as the 4-byte pixels Pillow holds (one memcpy per image, no re-packing on the host);
-            # the pad byte is dropped on the device.  Anything else goes through np.asarray into a 3-byte buffer.
-            views = [_rgbx_view(items[i + k][0]) for k in range(n)]
-            rgbx = all(v is not None for v in views)
-            host, free, slot = self._staging(shape, b, 4 if rgbx else 3)
-            if free[slot] is not None:
-                free[slot].synchronize()                # the copy that last read this buffer has finished
-            hv = host.numpy()
-            for k in range(n):
-                hv[k] = views[k] if rgbx else _as_u8_hwc(items[i + k][0])
-            tiles = host[:n].to(eng.device, non_blocking=True)
-            if rgbx:
-                tiles = tiles[..., :3].contiguous()
-            free[slot] = torch.cuda.Event()
-            free[slot].record()
+            tiles = self._stager.upload([it[0] for it in items[i:j]], shape)
             S = eng.imgsz
             mode = "identity" if shape[:2] == (S, S) else "cv2_linear"
             dets, counts = eng.infer(tiles, mode, self.bgr, self.confidence_threshold, True, 0.0, self.top_k)
@@ -204,8 +233,7 @@ class GPUHandler:
             params[:, :4] = bb[i:i + n]
             geo = eng.georef(dets, counts, torch.from_numpy(params).to(eng.device), "gpuhandler")
             for g in geodets_to_numpy(geo, counts):
-                for r in g:
-                    out.append({"lon": float(r["x"]), "lat": float(r["y"]), "confidence": float(r["conf"])})
+                out.extend({"lon": x, "lat": y, "confidence": c} for x, y, c in zip(g["x"].tolist(), g["y"].tolist(), g["conf"].tolist()))
         return out
 
     # -- test-time augmentation: gpu_handler.py:94-149, :220-285 ------------------------------
@@ -264,8 +292,9 @@ class GPUHandler:
         out: List[dict] = []
         for t, (v, _) in enumerate(tiles):
             for i in range(len(v)):
-                for r in per[(t, i)]:
-                    out.append({"lon": float(np.float32(r["x"])), "lat": float(np.float32(r["y"])), "confidence": float(r["conf"])})
+                g = per[(t, i)]                      # lon / lat are float32 in this path (gpu_handler.py:247-253), widened on output
+                out.extend({"lon": x, "lat": y, "confidence": c} for x, y, c in
+                           zip(g["x"].astype(np.float32).tolist(), g["y"].astype(np.float32).tolist(), g["conf"].tolist()))
         return out
 
     def process_batch_tta(self, images, views=None):
@@ -303,8 +332,9 @@ class GPUHandler:
         out: List[dict] = []
         for t in range(len(items)):
             for i in range(len(views)):
-                for r in per[(t, i)]:
-                    out.append({"lon": float(np.float32(r["x"])), "lat": float(np.float32(r["y"])), "confidence": float(r["conf"])})
+                g = per[(t, i)]                      # lon / lat are float32 in this path (gpu_handler.py:247-253), widened on output
+                out.extend({"lon": x, "lat": y, "confidence": c} for x, y, c in
+                           zip(g["x"].astype(np.float32).tolist(), g["y"].astype(np.float32).tolist(), g["conf"].tolist()))
         return out
 
     def cleanup(self):

@@ -144,7 +144,11 @@ class MosaicDetector:
     """Runs config C4 on one rank; ``run`` returns this rank's share of the globally deduplicated
     detections as a structured array (x, y, conf, cls, window, slot)."""
 
-    OUT_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("conf", "<f4"), ("cls", "<i4"), ("window", "<i8"), ("slot", "<i4")])
+    # one result record = five 8-byte words, laid out so that the device writes it and the host only re-labels it (no per-field
+    # unpacking of up to a million records): x | y | conf, cls | window | slot, 4 bytes of padding
+    OUT_DTYPE = np.dtype({"names": ["x", "y", "conf", "cls", "window", "slot"], "formats": ["<f8", "<f8", "<f4", "<i4", "<i8", "<i4"],
+                          "offsets": [0, 8, 16, 20, 24, 32], "itemsize": 40})
+    OUT_WORDS = 5
 
     def __init__(self, engine, geotransform: Sequence[float], win: int = 640, stride: int = 512, conf: float = 0.4,
                  nms_conf: float = 0.25, iou: float = 0.7, max_det: int = 300, dedup_thr: float = 1.0, fill: int = 114):
@@ -308,27 +312,23 @@ class MosaicDetector:
         return out
 
     def _pack(self, x, y, conf, cls, wid, slot) -> np.ndarray:
-        """Device columns -> one structured host array, through ONE device->host copy of 32-byte records."""
+        """Device columns -> one structured host array, through ONE device->host copy of 40-byte records that already have
+        ``OUT_DTYPE``'s layout (the host side is a view plus one copy out of the reused pinned buffer)."""
         import torch
         n = int(x.numel())
-        rec = torch.empty((n, 4), dtype=torch.int64, device=x.device)
+        W = self.OUT_WORDS
+        rec = torch.empty((n, W), dtype=torch.int64, device=x.device)
         rec[:, 0] = x.contiguous().view(torch.int64)
         rec[:, 1] = y.contiguous().view(torch.int64)
         rec[:, 2] = (conf.contiguous().view(torch.int32).long() & 0xFFFFFFFF) | (cls.long() << 32)
-        rec[:, 3] = (wid.long() << 16) | slot.long()
+        rec[:, 3] = wid.long()
+        rec[:, 4] = slot.long() & 0xFFFFFFFF
         stage = getattr(self, "_pack_stage", None)          # pinned staging: the copy runs at PCIe rate instead of through pageable memory
         if stage is None or stage.shape[0] < n:
-            stage = self._pack_stage = torch.empty((max(n, 1 << 16), 4), dtype=torch.int64).pin_memory()
+            stage = self._pack_stage = torch.empty((max(n, 1 << 16), W), dtype=torch.int64).pin_memory()
         stage[:n].copy_(rec, non_blocking=True)
         torch.cuda.current_stream(x.device).synchronize()
-        host = stage[:n].numpy()
-        out = np.empty(n, dtype=self.OUT_DTYPE)
-        out["x"] = host[:, 0].view(np.float64); out["y"] = host[:, 1].view(np.float64)
-        out["conf"] = (host[:, 2] & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
-        out["cls"] = (host[:, 2] >> 32).astype(np.int32)
-        out["window"] = host[:, 3] >> 16
-        out["slot"] = (host[:, 3] & 0xFFFF).astype(np.int32)
-        return out
+        return stage[:n].numpy().view(self.OUT_DTYPE).reshape(n).copy()
 
     def run(self, mosaic, height: int, width: int, rank: int = 0, world: int = 1, y_offset: int = 0, group=None) -> np.ndarray:
         windows, ids, _ = shard_windows(height, width, rank, world, self.win, self.stride)

@@ -23,17 +23,8 @@ import numpy as np
 import torch
 
 from .engine import GEO_PARAMS, Engine, geodets_to_numpy
+from .gpu_handler import TileStager, _as_u8_hwc, _shape_of  # noqa: F401  (host image staging shared with GPUHandler)
 from .session import InferenceSession, arch_from_model_path, resolve_weights
-
-
-def _as_u8_hwc(img) -> np.ndarray:
-    a = np.asarray(img)
-    if a.ndim == 2:
-        a = np.repeat(a[..., None], 3, 2)
-    if a.shape[2] == 4:
-        a = a[..., :3]
-    a = np.ascontiguousarray(a, dtype=np.uint8)
-    return a if a.flags.writeable else a.copy()      # np.asarray(PIL image) is read-only; torch.from_numpy wants a writable array
 
 
 class SimpleDetector:
@@ -52,6 +43,7 @@ class SimpleDetector:
         self.engine = Engine(arch, weights=weights, max_batch=max_batch, device=device, seed=seed, imgsz=self.model_size,
                              precision=precision)
         self.model = InferenceSession(engine=self.engine)
+        self._stager = TileStager(self.engine)
 
     # -- simple_detector.py:456-504 ----------------------------------------------------------
     def detect(self, image, preview_info):
@@ -65,17 +57,17 @@ class SimpleDetector:
         eng = self.engine
         if isinstance(images, torch.Tensor):
             return self._detect_device_tiles(images, preview_infos)
-        arrs = [_as_u8_hwc(im) for im in images]
+        images = list(images)
+        shapes = [_shape_of(im) for im in images]
         out: List[dict] = []
         i = 0
-        while i < len(arrs):
-            shape = arrs[i].shape
+        while i < len(images):
+            shape = shapes[i]
             j = i
-            while j < len(arrs) and j - i < eng.max_batch and arrs[j].shape == shape:
+            while j < len(images) and j - i < eng.max_batch and shapes[j] == shape:
                 j += 1
             n = j - i
-            host = torch.from_numpy(np.stack(arrs[i:j])).pin_memory()
-            tiles = host.to(eng.device, non_blocking=True)
+            tiles = self._stager.upload(images[i:j], shape)        # reused pinned staging; PIL RGB pixels without re-packing
             mode = "identity" if shape[:2] == (self.model_size, self.model_size) else "pil_bicubic"
             dets, counts = eng.infer(tiles, mode, False, self.confidence_threshold, True)
             params = np.zeros((n, GEO_PARAMS), dtype=np.float64)
@@ -113,9 +105,11 @@ class SimpleDetector:
 
     @staticmethod
     def _records(g) -> List[dict]:
-        return [{"lon": float(r["x"]), "lat": float(r["y"]), "confidence": float(r["conf"]),
-                 "image": {"x": float(r["x_img"]), "y": float(r["y_img"])},
-                 "yolo": {"x": float(r["x_yolo"]), "y": float(r["y_yolo"])}} for r in g]
+        # whole columns -> Python floats at once (``ndarray.tolist``: the same float64 values ``float(record[field])`` gives);
+        # converting record by record was 7 NumPy scalar extractions per detection, 2 of the 4 ms of a C1 call
+        cols = [g[k].tolist() for k in ("x", "y", "conf", "x_img", "y_img", "x_yolo", "y_yolo")]
+        return [{"lon": x, "lat": y, "confidence": c, "image": {"x": xi, "y": yi}, "yolo": {"x": xy, "y": yy}}
+                for x, y, c, xi, yi, xy, yy in zip(*cols)]
 
     # -- simple_detector.py:506-538 ----------------------------------------------------------
     def _process_detections(self, boxes, preview_info):
