@@ -417,9 +417,11 @@ def leg_c4(eng, rank, world, size, repeat):
     e0, e1 = _events()
     d0, d1 = _events()
     e0.record()
-    dedup_ms = 0.0
+    dedup_ms = detect_ms = 0.0
+    c0 = torch.cuda.Event(enable_timing=True)
     for _ in range(repeat):
         covers = [M.shard_windows(H, W, r, world)[2] for r in range(world)]
+        c0.record()
         cols = det.detect_windows(band, windows, ids, cover[0])
         det.last_raw = int(cols[0].numel())
         d0.record()
@@ -427,6 +429,7 @@ def leg_c4(eng, rank, world, size, repeat):
         d1.record()
         torch.cuda.synchronize()
         dedup_ms += d0.elapsed_time(d1)
+        detect_ms += c0.elapsed_time(d0)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / repeat
@@ -443,7 +446,9 @@ def leg_c4(eng, rank, world, size, repeat):
                           float(getattr(det, "last_seam_records", 0) if rank == 0 else 0), float(np.sum(key % 1000003)),
                           float(np.sum(out["x"] - GT[0])), float(np.sum(GT[3] - out["y"]))], dtype=torch.float64, device=eng.device)
     mx = stats.clone()
+    dt = torch.tensor([detect_ms / repeat, -detect_ms / repeat], dtype=torch.float64, device=eng.device)     # max and -min over ranks
     if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     del band, pool
@@ -452,10 +457,11 @@ def leg_c4(eng, rank, world, size, repeat):
     return {"workload": f"C4: synthetic {H}x{W} mosaic (procedural, resident in HBM, one band per rank), window 640 stride 512 (20 % overlap), {nwin} windows, "
                         f"YOLOv8m (seeded synthetic weights), conf > 0.4, 1 m inclusive dedup, {world} band(s) of window rows",
             "scaling": "strong", "n_gpus": world, "windows": nwin, "ms_per_mosaic": float(mx[0]), "windows_per_s": nwin / (float(mx[0]) * 1e-3),
+            "detect_ms_slowest_rank": float(dt[0]), "detect_ms_fastest_rank": -float(dt[1]),
             "dedup_ms": float(mx[1]), "dedup_phases_ms_rank0": phases, "allgather_us": float(mx[2]), "seam_records": int(stats[5]), "seam_record_bytes": 8 * M.RECORD_WORDS,
             "detections_raw": int(stats[4]), "detections_after_dedup": int(stats[3]),
             "checksum": {"keys_mod": int(stats[6]), "sum_dx_m": round(float(stats[7]), 3), "sum_dy_m": round(float(stats[8]), 3)},
-            "timing": "CUDA events around cut windows -> preprocess -> network -> NMS -> georef -> local dedup -> seam all-gather -> merge, max over ranks; dedup_ms includes the exchange"}
+            "timing": "CUDA events around cut windows -> preprocess -> network -> NMS -> georef -> local dedup -> seam all-gather -> merge, max over ranks; dedup_ms includes the exchange and, with it, the wait for the slowest rank's detection (detect_ms_*: this rank's windows, cut -> georef); dedup_phases_ms_rank0 is one extra, synchronised pass outside the timed region"}
 
 
 def leg_plugin_api(eng_weights_seed, local_rank, calls=4):
