@@ -170,3 +170,50 @@ def test_rgbx_view_of_a_pil_image_is_its_pixels_without_a_copy(tmp_path):
     v = _rgbx_view(big)
     assert v is None or (v.shape == (4000, 5000, 4) and (v[..., :3] == (1, 2, 3)).all())
     assert np.array_equal(_as_u8_hwc(big)[0, 0], (1, 2, 3))
+
+
+def test_detection_records_from_columns_equal_the_per_record_form():
+    """``SimpleDetector._records`` builds the reference's record dicts (simple_detector.py:496-502) from whole columns; the
+    values must be exactly what converting record by record (``float(record[field])``) gives."""
+    from aerial_image_recognition_b200.engine import GEODET_DTYPE
+    from aerial_image_recognition_b200.simple_detector import SimpleDetector
+    rng = np.random.default_rng(5)
+    g = np.zeros(257, GEODET_DTYPE)
+    for name in g.dtype.names:
+        g[name] = (rng.normal(size=len(g)) * 1e3).astype(g.dtype[name])
+    ref = [{"lon": float(r["x"]), "lat": float(r["y"]), "confidence": float(r["conf"]),
+            "image": {"x": float(r["x_img"]), "y": float(r["y_img"])},
+            "yolo": {"x": float(r["x_yolo"]), "y": float(r["y_yolo"])}} for r in g]
+    got = SimpleDetector._records(g)
+    assert got == ref and all(type(v) is float for v in got[0].values() if not isinstance(v, dict))
+    assert SimpleDetector._records(g[:0]) == []
+
+
+def test_mosaic_result_record_layout_is_what_the_device_writes():
+    """``MosaicDetector._pack`` writes five 8-byte words per detection on the device and re-labels them on the host as
+    ``OUT_DTYPE``; this restates the packing with CPU tensors and checks every field, including negative coordinates, the
+    sign bit of the confidence's bit pattern, and the largest window id / slot of config C4."""
+    import torch
+    from aerial_image_recognition_b200.mosaic import MosaicDetector as MD, pack_records, unpack_records
+    assert MD.OUT_DTYPE.itemsize == 8 * MD.OUT_WORDS
+    n = 4096
+    rng = np.random.default_rng(9)
+    x = torch.from_numpy(rng.normal(size=n) * 1e7)
+    y = torch.from_numpy(-np.abs(rng.normal(size=n)) * 1e7)
+    conf = torch.from_numpy((rng.random(n) * 2 - 1).astype(np.float32))                 # negative values exercise bit 31
+    cls = torch.from_numpy(rng.integers(0, 2, n).astype(np.int32))
+    wid = torch.from_numpy(rng.integers(0, 6241, n)); wid[0] = 6240
+    slot = torch.from_numpy(rng.integers(0, 300, n).astype(np.int32)); slot[0] = 299
+    rec = torch.empty((n, MD.OUT_WORDS), dtype=torch.int64)
+    rec[:, 0] = x.view(torch.int64); rec[:, 1] = y.view(torch.int64)
+    rec[:, 2] = (conf.view(torch.int32).long() & 0xFFFFFFFF) | (cls.long() << 32)
+    rec[:, 3] = wid.long(); rec[:, 4] = slot.long() & 0xFFFFFFFF
+    out = rec.numpy().view(MD.OUT_DTYPE).reshape(n).copy()
+    for name, col in (("x", x), ("y", y), ("conf", conf), ("cls", cls), ("window", wid), ("slot", slot)):
+        assert np.array_equal(out[name], col.numpy()), name
+    both = np.concatenate([out, np.zeros(0, MD.OUT_DTYPE), out[:3]])                      # what callers do with per-rank parts
+    assert len(both) == n + 3 and np.array_equal(np.sort(both, order=["window", "slot"])["window"], np.sort(both["window"]))
+    # the exchanged 32-byte seam record round-trips the same columns (key = window * 65536 + slot)
+    key = wid * 65536 + slot.long()
+    ux, uy, uc, ucls, uk = unpack_records(pack_records(x, y, conf, cls, key))
+    assert torch.equal(ux, x) and torch.equal(uy, y) and torch.equal(uc, conf) and torch.equal(ucls, cls) and torch.equal(uk, key)
